@@ -1,0 +1,104 @@
+"""Seeded parity cases shared by tests/golden/make_golden.py and tests/ (TEST INFRASTRUCTURE).
+
+Inputs and weights are regenerated from these seeds on both sides, so the committed fixtures only hold
+the reference's outputs.  CPU torch RNG is deterministic for a fixed torch build (same image on the GPU box).
+"""
+import math
+import zlib
+
+import torch
+
+STATE_SEED = 7
+GA_LAM = -0.8          # --GA_lam used by the published recipe (GA/README.md:26)
+GA_MODEL_CASES = [('ga_convnext_tiny_688', 2)]
+PARAM_COUNTS = {
+    'ga_convnext_tiny_688': 47821324, 'ga_convnext_tiny_768': 54354584,
+    'ga_convnext_small_688': 70116364, 'ga_convnext_small_768': 76726424,
+    'ga_convnext_base_976': 123688396, 'ga_convnext_base_1024': 128839176,
+}
+
+# name -> (C, H(=W), B)
+BLOCK_CASES = {'c32_h9': (32, 9, 2), 'c96_h14': (96, 14, 2), 'c192_h14': (192, 14, 1), 'c688_h7': (688, 7, 1)}
+GRAM_CASES = {'c192_h14': (192, 14, 3), 'c24_h5': (24, 5, 2)}
+# name -> (C, dim_embed, N tokens, B)
+CLASSATTN_CASES = {'c688_e168': (688, 168, 196, 2), 'c64_e32': (64, 32, 10, 3)}
+
+
+def _gen(seed, name):
+    return torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
+
+
+def _fill(shapes, seed):
+    P = {}
+    for name, (shape, kind) in shapes.items():
+        g = _gen(seed, name)
+        if kind == 'w':
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            P[name] = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+        elif kind == 'b':
+            P[name] = torch.randn(shape, generator=g) * 0.1
+        else:
+            P[name] = 0.5 + torch.rand(shape, generator=g)
+    return P
+
+
+def ga_inputs(B, seed=42, size=224):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 3, size, size, generator=g), torch.randint(0, 1000, (B,), generator=g)
+
+
+def block_state(C, seed=STATE_SEED):
+    return _fill({'conv_dw.weight': ((C, 1, 7, 7), 'w'), 'conv_dw.bias': ((C,), 'b'),
+                  'norm.weight': ((C,), 'g'), 'norm.bias': ((C,), 'b'),
+                  'mlp.fc1.weight': ((4 * C, C), 'w'), 'mlp.fc1.bias': ((4 * C,), 'b'),
+                  'mlp.fc2.weight': ((C, 4 * C), 'w'), 'mlp.fc2.bias': ((C,), 'b'),
+                  'gamma': ((C,), 'g')}, seed)
+
+
+def block_inputs(C, H, B, seed=11):
+    g = torch.Generator().manual_seed(seed + C * 131 + H)
+    return torch.randn(B, C, H, H, generator=g), torch.randn(B, C, H, H, generator=g)
+
+
+def gram_input(C, H, B, seed=13):
+    g = torch.Generator().manual_seed(seed + C)
+    return torch.randn(B, C, H, H, generator=g)
+
+
+def ga_block_state(C, E, seed=STATE_SEED, groups=4):
+    return _fill({'norm1.weight': ((C,), 'g'), 'norm1.bias': ((C,), 'b'),
+                  'attn.q.weight': ((E, C), 'w'), 'attn.k.weight': ((E, C), 'w'), 'attn.v.weight': ((E, C), 'w'),
+                  'attn.proj.weight': ((C, E), 'w'), 'attn.proj.bias': ((C,), 'b'),
+                  'norm2.weight': ((C,), 'g'), 'norm2.bias': ((C,), 'b'),
+                  'mlp.fc1.weight': ((4 * C, C // groups, 1, 1), 'w'), 'mlp.fc1.bias': ((4 * C,), 'b'),
+                  'mlp.fc2.weight': ((C, 4 * C // groups, 1, 1), 'w'), 'mlp.fc2.bias': ((C,), 'b'),
+                  'gamma_1': ((C,), 'g'), 'gamma_2': ((C,), 'g')}, seed)
+
+
+def ga_block_inputs(C, N, B, seed=17):
+    g = torch.Generator().manual_seed(seed + C)
+    return (torch.randn(B, N, C, generator=g), torch.randn(B, C, generator=g), torch.randn(B, C, generator=g))
+
+
+def digest(t, n=2048):
+    """(L2 norm, strided sample) of a tensor: the committed form of large reference gradients."""
+    flat = t.detach().reshape(-1)
+    stride = max(1, flat.numel() // n)
+    return (flat.double().norm().item(), flat[::stride][:n].clone().float(), stride)
+
+
+def digest_close(t, dig, rtol, atol=3e-4):
+    """Compare a tensor with a digest made by digest(): norm and sampled entries.
+
+    atol absorbs parameters whose true gradient is exactly zero (conv biases feeding a train-mode
+    BatchNorm): both sides then hold rounding noise only.
+    """
+    norm, sample, stride = dig
+    flat = t.detach().reshape(-1).float().cpu()
+    mine = flat[::stride][:sample.numel()]
+    err = (mine.double() - sample.double()).norm().item()
+    ok_sample = err <= rtol * sample.double().norm().item() + atol
+    ok_norm = abs(flat.double().norm().item() - norm) <= rtol * norm + atol
+    return ok_sample and ok_norm

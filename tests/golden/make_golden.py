@@ -1,0 +1,178 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
+The reference modules are imported from where they lie (never copied) through `oracle/timm_shim`.
+For each case the script
+  1. builds the reference module, loads `oracle.make_state(...)` with strict=True (pins key names/shapes),
+  2. runs the reference forward / backward on seeded inputs,
+  3. asserts the oracle restatement agrees (<= 2e-5 relative), and
+  4. stores the REFERENCE outputs (not the oracle's) in tests/golden/*.pt.
+Inputs and weights are regenerated from seeds on the test side, so fixtures hold outputs only.
+"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'timm_shim'))
+sys.path.insert(0, '/root/reference/GA')
+sys.path.insert(0, '/root/reference/MAP')
+
+from oracle import ga_convnext_oracle as O  # noqa: E402
+from oracle import cases  # noqa: E402
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def grad_digest(named_grads):
+    """Per-tensor (L2 norm, strided sample of <=2048 values): small enough to commit, sharp enough to catch errors."""
+    return {k: cases.digest(g) for k, g in named_grads.items()}
+
+
+def close(a, b, rtol, atol=3e-4):
+    """||a-b|| <= rtol*||b|| + atol.  atol absorbs parameters whose true gradient is exactly zero
+    (conv biases feeding a train-mode BatchNorm), where both sides only hold rounding noise."""
+    return (a.double() - b.double()).norm().item() <= rtol * b.double().norm().item() + atol
+
+
+def golden_ga_model():
+    import ga_convnext as R
+    import timm
+    out = {}
+    for name, B in cases.GA_MODEL_CASES:
+        spec = O.SPECS[name]
+        torch.manual_seed(0)
+        ref = timm.create_model(name)
+        P = O.make_state(spec, seed=cases.STATE_SEED)
+        missing = ref.load_state_dict(P, strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        assert sum(p.numel() for p in ref.parameters()) == cases.PARAM_COUNTS[name]
+        x, y = cases.ga_inputs(B)
+        # ---- eval
+        ref.eval()
+        with torch.no_grad():
+            r_eval = ref(x)
+            o_eval = O.forward({k: v.clone() for k, v in P.items()}, spec, x, training=False)
+        for a, b in zip(o_eval, r_eval):
+            assert rel(a, b) < 2e-5, rel(a, b)
+        # ---- train (drop rates 0): forward, GA loss (CE, lam=-0.8), backward
+        ref.train()
+        r_train = ref(x)
+        # the exact expression of GA/train.py:735-745
+        output, loss = 0, 0
+        for o in r_train:
+            loss = loss + F.cross_entropy(o, y)
+            output = output + o.data
+        for o in r_train:
+            loss = loss + F.kl_div(F.log_softmax(o + 0), F.log_softmax((output.detach() / len(r_train)) + 0),
+                                   reduction='mean', log_target=True) * cases.GA_LAM
+        loss.backward()
+        r_grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+        r_state = {k: v.detach().clone() for k, v in ref.state_dict().items() if 'running' in k}
+
+        Po = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone())
+              for k, v in P.items()}
+        o_train = O.forward(Po, spec, x, training=True)
+        o_loss = O.ga_loss(o_train, y, cases.GA_LAM)
+        o_loss.backward()
+        assert rel(o_loss.detach(), loss.detach()) < 1e-6
+        for a, b in zip(o_train, r_train):
+            assert rel(a.detach(), b.detach()) < 2e-5, rel(a.detach(), b.detach())
+        for k, g in r_grads.items():
+            assert close(Po[k].grad, g, 5e-5), (k, rel(Po[k].grad, g))
+        worst = max(rel(Po[k].grad, g) for k, g in r_grads.items() if g.norm() > 1e-2)
+        for k, v in r_state.items():
+            assert rel(Po[k], v) < 1e-5, k
+        print(f'{name} B={B}: oracle==reference  (loss {loss.item():.6f}, worst grad rel {worst:.2e})')
+        out[f'{name}/B{B}'] = dict(
+            eval_logits=[t.clone() for t in r_eval], train_logits=[t.detach().clone() for t in r_train],
+            loss=loss.detach().clone(), grads=grad_digest(r_grads), running=r_state)
+    torch.save(out, os.path.join(HERE, 'ga_convnext_model.pt'))
+
+
+def golden_ga_modules():
+    """Small-shape module-level vectors from the reference classes (kernel-level parity fixtures)."""
+    import ga_convnext as R
+    out = {}
+    for cname, (C, H, B) in cases.BLOCK_CASES.items():
+        blk = R.ConvNeXtBlock(C, ls_init_value=1.0)
+        P = cases.block_state(C, seed=cases.STATE_SEED)
+        blk.load_state_dict(P, strict=True)
+        x, dy = cases.block_inputs(C, H, B)
+        x.requires_grad_(True)
+        yv = blk(x)
+        yv.backward(dy)
+        grads = {k: p.grad.clone() for k, p in blk.named_parameters()}
+        Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        xo = x.detach().clone().requires_grad_(True)
+        yo = O.convnext_block(Po, '', xo)
+        yo.backward(dy)
+        assert rel(yo.detach(), yv.detach()) < 1e-5
+        assert rel(xo.grad, x.grad) < 1e-5
+        for k in grads:
+            assert rel(Po[k].grad, grads[k]) < 1e-5, k
+        out[cname] = dict(y=yv.detach().clone(), dx=x.grad.clone(), grads=grad_digest(grads))
+        print(f'block {cname}: oracle==reference')
+
+    # get_gram on a fake `self` (training / eval branches), ga_convnext.py:452-467
+    class _G:
+        pass
+    for cname, (C, H, B) in cases.GRAM_CASES.items():
+        x = cases.gram_input(C, H, B)
+        for training in (False, True):
+            g = _G()
+            g.training = training
+            import numpy as np
+            idx = np.zeros(((C + 1) * C // 2))
+            n = 0
+            for i in range(C):
+                for j in range(C):
+                    if j >= i:
+                        idx[n] = i * C + j
+                        n += 1
+            g.gram_index = idx
+            r = R.GA_ConvNeXt.get_gram(g, x, B, C)
+            o = O.gram_vector(x, training)
+            assert rel(o, r) < 1e-6
+            out[f'{cname}/train{int(training)}'] = r.clone()
+        print(f'gram {cname}: oracle==reference')
+
+    # ClassAttn + LayerScaleBlockClassAttn
+    for cname, (C, E, N, B) in cases.CLASSATTN_CASES.items():
+        m = R.LayerScaleBlockClassAttn(C, num_heads=8, mlp_block_groups=4, dim_embed=E)
+        P = cases.ga_block_state(C, E, seed=cases.STATE_SEED)
+        m.load_state_dict(P, strict=True)
+        tokens, cls, dy = cases.ga_block_inputs(C, N, B)
+        tokens.requires_grad_(True)
+        cls.requires_grad_(True)
+        r = m(tokens, cls[:, None, :])[:, 0]
+        r.backward(dy)
+        spec = O.GASpec((1,), (C,), E, 0)
+        Po = {'ga.0.' + k: v.clone().requires_grad_(True) for k, v in P.items()}
+        to, co = tokens.detach().clone().requires_grad_(True), cls.detach().clone().requires_grad_(True)
+        o = O.ga_block(Po, spec, 0, to, co)
+        o.backward(dy)
+        assert rel(o.detach(), r.detach()) < 1e-5
+        assert rel(to.grad, tokens.grad) < 1e-5 and rel(co.grad, cls.grad) < 1e-5
+        grads = {k: p.grad.clone() for k, p in m.named_parameters()}
+        for k in grads:
+            assert rel(Po['ga.0.' + k].grad, grads[k]) < 2e-5, k
+        out[cname] = dict(y=r.detach().clone(), dtokens=tokens.grad.clone(), dcls=cls.grad.clone(), grads=grad_digest(grads))
+        print(f'ga_block {cname}: oracle==reference')
+    torch.save(out, os.path.join(HERE, 'ga_convnext_modules.pt'))
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ['modules', 'model']
+    if 'modules' in which:
+        golden_ga_modules()
+    if 'model' in which:
+        golden_ga_model()
