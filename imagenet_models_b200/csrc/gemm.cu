@@ -1,0 +1,548 @@
+// GEMM with fused epilogue for every Linear / 1x1 / k=s conv on the GA / MAP hot path.
+//   bf16 operands : tcgen05.mma (cta_group::1, M=128) fed by TMA (SWIZZLE_128B), fp32 accumulators in TMEM,
+//                   warp-specialised {TMA producer, MMA issuer, 4 epilogue warps}, smem-staged coalesced epilogue.
+//                   Operands may be K-major or MN-major (wgrad / dgrad read activations and weights in place).
+//   fp32 operands : register-tiled SIMT kernel (exact fp32 FMA; the 1e-5 parity path and odd-shape fallback).
+// Replaces the cuBLAS(Lt)/cuDNN calls behind ga_convnext.py:107-111,127,357,260-282,407,418,163-167,202-205,422,460.
+#include "common.cuh"
+#include "../../include/ga_sm100.h"
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+
+
+
+// ------------------------------------------------------------------------------------------------ epilogue
+struct EpiArgs {
+  void* D; long long ldd, d_bs, d_cs;
+  int out_f32, accumulate;
+  float alpha;
+  const float* bias; long long bias_bs;
+  int act;
+  void* Z;
+  const float* colscale; long long colscale_bs;
+  const float* rowscale; int rows_per_scale;
+  const void* R; long long ldr, r_bs;
+  const void* Zin; long long ldz, z_bs; int zmode;
+  int M, N;
+};
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+  if (act == GA_ACT_GELU) return gelu_f(v);
+  if (act == GA_ACT_RELU) return fmaxf(v, 0.f);
+  return v;
+}
+
+// one element (generic / tail path)
+__device__ __forceinline__ void epi_store1(const EpiArgs& e, int b, int m, int n, float acc) {
+  float v = acc * e.alpha;
+  long long off = (long long)b * e.d_bs + (long long)m * e.ldd + (long long)n * e.d_cs;
+  if (e.Zin) {
+    long long zo = (long long)b * e.z_bs + (long long)m * e.ldz + n;
+    float z = e.out_f32 ? ((const float*)e.Zin)[zo] : __bfloat162float(((const bf16*)e.Zin)[zo]);
+    v *= (e.zmode == GA_ACT_GELU) ? gelu_grad_f(z) : (z > 0.f ? 1.f : 0.f);
+  } else {
+    if (e.bias) v += e.bias[(long long)b * e.bias_bs + n];
+    if (e.Z) { if (e.out_f32) ((float*)e.Z)[off] = v; else ((bf16*)e.Z)[off] = __float2bfloat16_rn(v); }
+    v = epi_act(v, e.act);
+    if (e.colscale) v *= e.colscale[(long long)b * e.colscale_bs + n];
+    if (e.rowscale) v *= e.rowscale[m / e.rows_per_scale];
+    if (e.R) {
+      long long ro = (long long)b * e.r_bs + (long long)m * e.ldr + n;
+      v += e.out_f32 ? ((const float*)e.R)[ro] : __bfloat162float(((const bf16*)e.R)[ro]);
+    }
+  }
+  if (e.accumulate) atomicAdd(((float*)e.D) + off, v);
+  else if (e.out_f32) ((float*)e.D)[off] = v;
+  else ((bf16*)e.D)[off] = __float2bfloat16_rn(v);
+}
+
+// four consecutive columns n..n+3 (requires N%4==0, ld%4==0, 16B-aligned bases): coalesced vector path
+__device__ __forceinline__ void epi_store4(const EpiArgs& e, int b, int m, int n, float4 acc) {
+  float v[4] = {acc.x * e.alpha, acc.y * e.alpha, acc.z * e.alpha, acc.w * e.alpha};
+  long long off = (long long)b * e.d_bs + (long long)m * e.ldd + n;
+  if (e.Zin) {
+    long long zo = (long long)b * e.z_bs + (long long)m * e.ldz + n;
+    float4 z = e.out_f32 ? ld4((const float*)e.Zin + zo) : ld4((const bf16*)e.Zin + zo);
+    float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= (e.zmode == GA_ACT_GELU) ? gelu_grad_f(zz[i]) : (zz[i] > 0.f ? 1.f : 0.f);
+  } else {
+    if (e.bias) {
+      float4 bb = *reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bs + n);
+      v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+    }
+    if (e.Z) {
+      float4 zv = make_float4(v[0], v[1], v[2], v[3]);
+      if (e.out_f32) st4((float*)e.Z + off, zv); else st4((bf16*)e.Z + off, zv);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = epi_act(v[i], e.act);
+    if (e.colscale) {
+      float4 cs = *reinterpret_cast<const float4*>(e.colscale + (long long)b * e.colscale_bs + n);
+      v[0] *= cs.x; v[1] *= cs.y; v[2] *= cs.z; v[3] *= cs.w;
+    }
+    if (e.rowscale) {
+      float rs = e.rowscale[m / e.rows_per_scale];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] *= rs;
+    }
+    if (e.R) {
+      long long ro = (long long)b * e.r_bs + (long long)m * e.ldr + n;
+      float4 r = e.out_f32 ? ld4((const float*)e.R + ro) : ld4((const bf16*)e.R + ro);
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    }
+  }
+  if (e.accumulate) {
+    float* d = (float*)e.D + off;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(d + i, v[i]);
+  } else {
+    float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    if (e.out_f32) st4((float*)e.D + off, o); else st4((bf16*)e.D + off, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SIMT kernel
+// 64x64 tile, BK=16, 256 threads, 4x4 micro-tile, arbitrary element strides, fp32 or bf16 inputs.
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A, long long a_rs, long long a_cs, long long a_bs,
+                                                        const T* __restrict__ Bm, long long b_rs, long long b_cs, long long b_bs,
+                                                        int K, EpiArgs e) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16x16 threads, each 4x4
+  A += (long long)b * a_bs;
+  Bm += (long long)b * b_bs;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // loader mapping: choose the fast index along the contiguous dimension
+  const bool a_kfast = (a_cs == 1);
+  const bool b_kfast = (b_cs == 1);
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      int idx = tid + it * 256;  // 0..1023
+      int mm, kk;
+      if (a_kfast) { kk = idx & 15; mm = idx >> 4; } else { mm = idx & 63; kk = idx >> 6; }
+      int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < e.M && gk < K) v = ld_f(A + (long long)gm * a_rs + (long long)gk * a_cs);
+      As[kk][mm] = v;
+      int nn;
+      if (b_kfast) { kk = idx & 15; nn = idx >> 4; } else { nn = idx & 63; kk = idx >> 6; }
+      int gn = n0 + nn; gk = k0 + kk;
+      v = 0.f;
+      if (gn < e.N && gk < K) v = ld_f(Bm + (long long)gn * b_rs + (long long)gk * b_cs);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float a_[4] = {av.x, av.y, av.z, av.w}, b_[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= e.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < e.N) epi_store1(e, b, m, n, acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ tcgen05 kernel
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int EPI_N = 64;       // epilogue column chunk staged through smem
+constexpr int STAGE_LD = EPI_N + 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread = its own TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B.  K-major: 8-row groups 1024 B apart (SBO), LBO unused(=1).
+// MN-major: 64-element MN chunks `lbo` bytes apart, 8-k groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+struct Params {
+  int M, N, K;
+  int kb_total, kb_per_split, splits;
+  int stages;
+  uint32_t idesc;
+  uint32_t lbo_a, sbo_a, lbo_b, sbo_b;  // descriptor byte offsets (host-selected so they can be probed)
+};
+
+// grid: (m tiles, n tiles, batch*splits).  192 threads: warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue.
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, Params p, EpiArgs e) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-B aligned carve-up (SWIZZLE_128B atoms)
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint8_t* stage_base = smem;
+  float* staging = (float*)(smem + (size_t)p.stages * STAGE_BYTES);          // 4 warps x 32 x STAGE_LD floats
+  uint64_t* full_bar = (uint64_t*)((uint8_t*)staging + 4 * 32 * STAGE_LD * 4);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full = empty_bar + 8;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int batch = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int kb_begin = split * p.kb_per_split;
+  int kb_end = kb_begin + p.kb_per_split;
+  if (kb_end > p.kb_total) kb_end = p.kb_total;
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        uint8_t* sa = stage_base + (size_t)s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        const int k0 = (kb_begin + i) * BK;
+        if (!A_MN) {
+          tma_load_3d(sa, &tmA, &full_bar[s], k0, m0, batch);
+        } else {
+          tma_load_3d(sa, &tmA, &full_bar[s], m0, k0, batch);
+          tma_load_3d(sa + 64 * BK * 2, &tmA, &full_bar[s], m0 + 64, k0, batch);
+        }
+        if (!B_MN) {
+          tma_load_3d(sb, &tmB, &full_bar[s], k0, n0, batch);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 64 * BK * 2, &tmB, &full_bar[s], n0 + 64 * j, k0, batch);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (i / p.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+        const uint64_t adesc = make_desc(sa, p.lbo_a, p.sbo_a);
+        const uint64_t bdesc = make_desc(sb, p.lbo_b, p.sbo_b);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 K-elements: K-major = 32 B inside the swizzle atom; MN-major = 16 rows of 128 B
+          const uint64_t ka = A_MN ? (uint64_t)((k * 16 * 128) >> 4) : (uint64_t)((k * 32) >> 4);
+          const uint64_t kb = B_MN ? (uint64_t)((k * 16 * 128) >> 4) : (uint64_t)((k * 32) >> 4);
+          umma_bf16(tmem_base, adesc + ka, bdesc + kb, p.idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees this smem stage when the MMAs above retire
+      }
+      umma_commit(tmem_full);        // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> smem (transpose) -> coalesced global stores
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    float* st = staging + (size_t)(warp - 2) * 32 * STAGE_LD;
+    if (nkb > 0) {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+    }
+    const bool vec_ok = ((e.N & 3) == 0) && ((e.ldd & 3) == 0) && (!e.R || (e.ldr & 3) == 0) && (!e.Zin || (e.ldz & 3) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / EPI_N; ++c) {
+      if (n0 + c * EPI_N >= e.N) break;
+#pragma unroll
+      for (int h = 0; h < EPI_N / 32; ++h) {
+        uint32_t r[32];
+        if (nkb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * EPI_N + h * 32), r);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+        float* row = st + lane * STAGE_LD + h * 32;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(row + 4 * i) =
+              make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                          __uint_as_float(r[4 * i + 3]));
+      }
+      __syncwarp();
+      const int cl = (lane & 15) * 4;
+      const int n = n0 + c * EPI_N + cl;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int rl = 2 * i + (lane >> 4);
+        const int m = m0 + q * 32 + rl;
+        if (m < e.M && n < e.N) {
+          float4 acc = *reinterpret_cast<const float4*>(st + rl * STAGE_LD + cl);
+          if (vec_ok) {
+            epi_store4(e, batch, m, n, acc);
+          } else {
+            float a_[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < e.N) epi_store1(e, batch, m, n + j, a_[j]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// ---- host: tensor maps (shared cache in runtime.cu) -------------------------------------------------------
+// 3-D bf16 tensor map: dims {d0 (contiguous), d1, d2}, strides in elements, box {b0, b1, 1}, SWIZZLE_128B
+static int get_map(const void* ptr, long long d0, long long d1, long long d2, long long s1, long long s2, int b0, int b1,
+                   CUtensorMap* out) {
+  uint64_t dims[3] = {(uint64_t)d0, (uint64_t)d1, (uint64_t)d2};
+  uint64_t strides[2] = {(uint64_t)s1 * 2, (uint64_t)(d2 > 1 ? s2 : s1 * d1) * 2};
+  uint32_t box[3] = {(uint32_t)b0, (uint32_t)b1, 1};
+  return ga_tensor_map(out, GA_BF16, 3, ptr, dims, strides, box, /*swizzle128=*/1);
+}
+
+static uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                     // D format f32
+  d |= 1u << 7;                     // A bf16
+  d |= 1u << 10;                    // B bf16
+  d |= (a_mn ? 1u : 0u) << 15;      // A major (0 = K-major)
+  d |= (b_mn ? 1u : 0u) << 16;      // B major
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  int rc;
+  // A
+  if (!A_MN) rc = get_map(g->A, g->K, g->M, g->batch, g->a_rs, g->a_bs, BK, BM, &ma);
+  else rc = get_map(g->A, g->M, g->K, g->batch, g->a_cs, g->a_bs, 64, BK, &ma);
+  if (rc) return rc;
+  if (!B_MN) rc = get_map(g->B, g->K, g->N, g->batch, g->b_rs, g->b_bs, BK, BN, &mb);
+  else rc = get_map(g->B, g->N, g->K, g->batch, g->b_cs, g->b_bs, 64, BK, &mb);
+  if (rc) return rc;
+
+  Params p;
+  p.M = g->M; p.N = g->N; p.K = g->K;
+  p.kb_total = (g->K + BK - 1) / BK;
+  int mt = (g->M + BM - 1) / BM, nt = (g->N + BN - 1) / BN;
+  int splits = 1;
+  if (g->accumulate) {
+    splits = g->splits;
+    if (splits <= 0) {
+      long long tiles = (long long)mt * nt * g->batch;
+      int sms = ga_num_sms();
+      splits = (int)((2LL * sms + tiles - 1) / tiles);
+      int maxs = p.kb_total / 4; if (maxs < 1) maxs = 1;
+      if (splits > maxs) splits = maxs;
+      if (splits < 1) splits = 1;
+    }
+    if (splits > p.kb_total) splits = p.kb_total > 0 ? p.kb_total : 1;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  if (p.kb_per_split < 1) p.kb_per_split = 1;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  constexpr int STAGE_BYTES = (BM + BN) * BK * 2;
+  static int stages_env = -1;
+  if (stages_env < 0) { const char* sv = getenv("GA_GEMM_STAGES"); stages_env = sv ? atoi(sv) : 0; }
+  int stages = stages_env > 0 ? stages_env : (BN <= 128 ? 2 : 3);
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  p.idesc = make_idesc(BM, BN, A_MN, B_MN);
+  p.lbo_a = A_MN ? 64 * BK * 2 : 16; p.sbo_a = 1024;
+  p.lbo_b = B_MN ? 64 * BK * 2 : 16; p.sbo_b = 1024;
+  size_t smem = 1024 + (size_t)stages * STAGE_BYTES + 4 * 32 * STAGE_LD * 4 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  dim3 grid(mt, nt, g->batch * splits);
+  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, 192, smem, st>>>(ma, mb, p, e);
+  ga_count_launch();
+  return ga_check_launch("gemm_tc");
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------ entry point
+static int g_last_backend = 0;
+extern "C" int ga_gemm_last_backend(void) { return g_last_backend; }
+
+static bool tc_eligible(const GaGemm* g, bool* a_mn, bool* b_mn) {
+  if (g->in_dtype != GA_BF16) return false;
+  if (g->M < 1 || g->N < 1 || g->K < 1) return false;
+  auto ok_ptr = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (!ok_ptr(g->A) || !ok_ptr(g->B)) return false;
+  if (g->batch > 1 && ((g->a_bs & 7) || (g->b_bs & 7))) return false;
+  if (g->a_cs == 1 && (g->a_rs & 7) == 0 && g->a_rs >= g->K) *a_mn = false;
+  else if (g->a_rs == 1 && (g->a_cs & 7) == 0 && g->a_cs >= g->M) *a_mn = true;
+  else return false;
+  if (g->b_cs == 1 && (g->b_rs & 7) == 0 && g->b_rs >= g->K) *b_mn = false;
+  else if (g->b_rs == 1 && (g->b_cs & 7) == 0 && g->b_cs >= g->N) *b_mn = true;
+  else return false;
+  // MN-major operands are loaded in 64-wide chunks: the contiguous extent must cover whole 16-byte rows (checked above)
+  return true;
+}
+
+extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
+  cudaStream_t st = (cudaStream_t)s;
+  GA_REQUIRE(g && g->A && g->B && g->D, GA_ERR_SHAPE, "ga_gemm: null operand");
+  GA_REQUIRE(g->M >= 0 && g->N >= 0 && g->K >= 0 && g->batch >= 1, GA_ERR_SHAPE, "ga_gemm: bad sizes M=%d N=%d K=%d batch=%d",
+             g->M, g->N, g->K, g->batch);
+  GA_REQUIRE(!g->accumulate || g->out_dtype == GA_F32, GA_ERR_UNSUPPORTED, "ga_gemm: accumulate needs fp32 D");
+  if (g->M == 0 || g->N == 0) return GA_OK;
+  EpiArgs e;
+  e.D = g->D; e.ldd = g->ldd; e.d_bs = g->d_bs; e.d_cs = g->d_cs > 0 ? g->d_cs : 1;
+  e.out_f32 = (g->out_dtype == GA_F32); e.accumulate = g->accumulate;
+  e.alpha = g->alpha;
+  e.bias = g->bias; e.bias_bs = g->bias_bs; e.act = g->act; e.Z = g->Z;
+  e.colscale = g->colscale; e.colscale_bs = g->colscale_bs;
+  e.rowscale = g->rowscale; e.rows_per_scale = g->rows_per_scale > 0 ? g->rows_per_scale : 1;
+  e.R = g->R; e.ldr = g->ldr; e.r_bs = g->r_bs;
+  e.Zin = g->Zin; e.ldz = g->ldz; e.z_bs = g->z_bs; e.zmode = g->zmode;
+  e.M = g->M; e.N = g->N;
+
+  bool a_mn = false, b_mn = false;
+  GA_REQUIRE(!g->accumulate || (!g->bias && !g->act && !g->R && !g->Zin && !g->Z), GA_ERR_UNSUPPORTED,
+             "ga_gemm: accumulate mode takes no bias/act/residual/Zin");
+  bool use_tc = (g->backend != GA_BACKEND_SIMT) && e.d_cs == 1 && tc_eligible(g, &a_mn, &b_mn);
+  if (g->backend == GA_BACKEND_TCGEN05)
+    GA_REQUIRE(use_tc, GA_ERR_ALIGN, "ga_gemm: operands not eligible for the tcgen05 path (bf16, 16B-aligned, unit stride)");
+  if (use_tc) {
+    g_last_backend = GA_BACKEND_TCGEN05;
+    const bool wide = g->N > 64;
+#define GA_TC_CASE(AM, BM_)                                                        \
+  if (a_mn == AM && b_mn == BM_)                                                    \
+    return wide ? tc::launch<128, AM, BM_>(g, e, st) : tc::launch<64, AM, BM_>(g, e, st);
+    GA_TC_CASE(false, false)
+    GA_TC_CASE(false, true)
+    GA_TC_CASE(true, false)
+    GA_TC_CASE(true, true)
+#undef GA_TC_CASE
+  }
+  g_last_backend = GA_BACKEND_SIMT;
+  dim3 grid((g->M + 63) / 64, (g->N + 63) / 64, g->batch);
+  GA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, GA_ERR_SHAPE, "ga_gemm(simt): grid too large");
+  if (g->in_dtype == GA_F32)
+    gemm_simt_kernel<float><<<grid, 256, 0, st>>>((const float*)g->A, g->a_rs, g->a_cs, g->a_bs, (const float*)g->B, g->b_rs,
+                                                  g->b_cs, g->b_bs, g->K, e);
+  else
+    gemm_simt_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)g->A, g->a_rs, g->a_cs, g->a_bs, (const bf16*)g->B, g->b_rs,
+                                                 g->b_cs, g->b_bs, g->K, e);
+  ga_count_launch();
+  return ga_check_launch("gemm_simt");
+}

@@ -1,0 +1,147 @@
+// K7: fused multi-tensor AdamW + EMA over flat fp32 buffers, and the GA multi-branch loss (forward + gradient).
+// Reference: create_optimizer_v2(... 'adamw') + ModelEmaV2.update (GA/train.py:466,499,760-761) and the loss
+// expression at GA/train.py:735-745.  Both are pure HBM streams: 128-bit accesses, grid = k x SM count.
+#include "common.cuh"
+
+static inline int launch_ok(const char* n) { ga_count_launch(); return ga_check_launch(n); }
+
+// torch.optim.AdamW (decoupled decay, eps outside the bias-corrected sqrt):
+//   p *= 1 - lr*wd ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+// timm ModelEmaV2: ema = d*ema + (1-d)*p (after the step).  decay_flag is per 2^seg_shift-element segment.
+__global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, float* __restrict__ ema, bf16* __restrict__ p16,
+                                                        const unsigned char* __restrict__ decay_flag, int seg_shift, long long n4,
+                                                        float lr, float b1, float b2, float eps, float wd, float inv_bc1,
+                                                        float inv_sqrt_bc2, float ema_decay, float grad_scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    const float decay = (decay_flag == nullptr || decay_flag[(i * 4) >> seg_shift]) ? (1.f - lr * wd) : 1.f;
+    float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w}, ma[4] = {mm.x, mm.y, mm.z, mm.w},
+          va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = ga[k] * grad_scale;
+      pa[k] *= decay;
+      ma[k] = b1 * ma[k] + (1.f - b1) * gk;
+      va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+      const float denom = sqrtf(va[k]) * inv_sqrt_bc2 + eps;
+      pa[k] -= lr * inv_bc1 * ma[k] / denom;
+    }
+    reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+    reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+    reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+    if (ema) {
+      float4 ee = reinterpret_cast<float4*>(ema)[i];
+      ee.x = ema_decay * ee.x + (1.f - ema_decay) * pa[0]; ee.y = ema_decay * ee.y + (1.f - ema_decay) * pa[1];
+      ee.z = ema_decay * ee.z + (1.f - ema_decay) * pa[2]; ee.w = ema_decay * ee.w + (1.f - ema_decay) * pa[3];
+      reinterpret_cast<float4*>(ema)[i] = ee;
+    }
+    if (p16) {
+      uint2 u; u.x = pack_bf16(pa[0], pa[1]); u.y = pack_bf16(pa[2], pa[3]);
+      reinterpret_cast<uint2*>(p16)[i] = u;
+    }
+  }
+}
+
+extern "C" int ga_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16,
+                            const unsigned char* decay_flag, int seg_shift, long long n, float lr, float beta1, float beta2,
+                            float eps, float wd, float bias_c1, float bias_c2, float ema_decay, float grad_scale, ga_stream_t s) {
+  GA_REQUIRE(p && g && m && v && n >= 0 && (n & 3) == 0, GA_ERR_ALIGN, "ga_adamw_ema: n=%lld must be a multiple of 4", n);
+  GA_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) & 15) == 0, GA_ERR_ALIGN,
+             "ga_adamw_ema: buffers must be 16-byte aligned");
+  GA_REQUIRE(seg_shift >= 2, GA_ERR_SHAPE, "ga_adamw_ema: segments must hold >= 4 elements");
+  if (n == 0) return GA_OK;
+  const long long n4 = n >> 2;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)ga_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  adamw_ema_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(p, g, m, v, ema, (bf16*)p_bf16, decay_flag, seg_shift, n4, lr, beta1,
+                                                                   beta2, eps, wd, 1.f / bias_c1, rsqrtf(bias_c2), ema_decay, grad_scale);
+  return launch_ok("adamw_ema");
+}
+
+// ema = d*ema + (1-d)*src over a flat buffer (buffers such as BatchNorm running statistics)
+__global__ void ema_lerp_kernel(float* __restrict__ ema, const float* __restrict__ src, long long n, float d) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    ema[i] = d * ema[i] + (1.f - d) * src[i];
+}
+extern "C" int ga_ema_lerp(float* ema, const float* src, long long n, float decay, ga_stream_t s) {
+  if (n == 0) return GA_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ema_lerp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(ema, src, n, decay);
+  return launch_ok("ema_lerp");
+}
+
+// ---------------------------------------------------------------------------------------------- GA loss
+// logits [nb][B][ncls] fp32.  loss = sum_k mean_b CE(out_k[b], y_b) + lam * sum_k mean_{b,c} KL term
+//   KL_mean(logp_k || logq) with log_target: mean over B*ncls of  q*(logq - logp_k),  q = softmax(mean_k out) (detached)
+// One CTA per sample: nb+1 log-softmaxes kept in smem; writes dlogits and atomically adds the sample's loss.
+__global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                                      float* __restrict__ loss, float* __restrict__ dlogits, int nb, int B, int ncls,
+                                                      float lam, float grad_scale) {
+  extern __shared__ float sm[];  // [(nb+1)][ncls] log-probs
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float* lq = sm + (size_t)nb * ncls;
+  // mean logits
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < nb; ++k) {
+      const float v = logits[((size_t)k * B + b) * ncls + c];
+      sm[(size_t)k * ncls + c] = v;
+      a += v;
+    }
+    lq[c] = a / (float)nb;
+  }
+  __syncthreads();
+  // log-softmax of each of the nb+1 rows
+  for (int k = 0; k <= nb; ++k) {
+    float* row = sm + (size_t)k * ncls;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) mx = fmaxf(mx, row[c]);
+    mx = warp_max(mx);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+    float se = 0.f;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) se += expf(row[c] - mx);
+    se = block_sum(se, red);
+    const float lse = mx + logf(se);
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) row[c] -= lse;
+    __syncthreads();
+  }
+  const int y = (int)target[b];
+  const float invB = 1.f / (float)B, inv_bc = 1.f / ((float)B * (float)ncls);
+  float local = 0.f;
+  for (int k = 0; k < nb; ++k) {
+    const float* lp = sm + (size_t)k * ncls;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+      const float p = expf(lp[c]), qv = expf(lq[c]);
+      local += lam * inv_bc * qv * (lq[c] - lp[c]);
+      if (c == y) local += -lp[c] * invB;
+      if (dlogits) {
+        // dCE/dz = (p - onehot)/B ; d/dz_k of -lam/(B C) * sum_c q_c logp_k,c = -lam/(B C) * (q_c - p_c)
+        const float gce = (p - (c == y ? 1.f : 0.f)) * invB;
+        const float gkl = -lam * inv_bc * (qv - p);
+        dlogits[((size_t)k * B + b) * ncls + c] = (gce + gkl) * grad_scale;
+      }
+    }
+  }
+  local = block_sum(local, red);
+  if (threadIdx.x == 0) atomicAdd(loss, local);
+}
+extern "C" int ga_loss_fwd_bwd(const float* logits, const long long* target, float* loss, float* dlogits, int nb, int B, int ncls,
+                               float lam, float grad_scale, ga_stream_t s) {
+  GA_REQUIRE(logits && target && loss && nb > 0 && B > 0 && ncls > 0, GA_ERR_SHAPE, "ga_loss_fwd_bwd: bad arguments");
+  const size_t smem = (size_t)(nb + 1) * ncls * sizeof(float);
+  GA_REQUIRE(smem <= 200 * 1024, GA_ERR_UNSUPPORTED, "ga_loss_fwd_bwd: (nb+1)*ncls too large for shared memory");
+  cudaFuncSetAttribute(ga_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ga_loss_kernel<<<B, 256, smem, (cudaStream_t)s>>>(logits, target, loss, dlogits, nb, B, ncls, lam, grad_scale);
+  return launch_ok("ga_loss");
+}

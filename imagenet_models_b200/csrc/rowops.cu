@@ -1,0 +1,659 @@
+// Row / column kernels over NHWC activation matrices [M, C]: LayerNorm, BatchNorm statistics + apply, patch
+// gathers, casts.  All are HBM-bound: 128-bit (4-element) accesses, one warp per row for row reductions,
+// column-strip CTAs with partial buffers for column reductions (no atomics on the result).
+#include "common.cuh"
+
+#define DISPATCH_T(dtype, ...)                         \
+  if ((dtype) == GA_BF16) { typedef bf16 T; __VA_ARGS__; } \
+  else { typedef float T; __VA_ARGS__; }
+
+static inline int launch_ok(const char* n) { ga_count_launch(); return ga_check_launch(n); }
+
+// ---------------------------------------------------------------------------------------------- LayerNorm rows
+// one warp per row; row cached in registers (C <= 32*4*MAXV)
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, T* __restrict__ y,
+                                                            float* __restrict__ mean_o, float* __restrict__ rstd_o,
+                                                            long long M, int C, long long ldx, long long ldy, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const T* xr = x + row * ldx;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    v[i] = (c < C) ? ld4(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < C) {
+      float a = v[i].x - mean, bb = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + bb * bb + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  if (lane == 0) { if (mean_o) mean_o[row] = mean; if (rstd_o) rstd_o[row] = rstd; }
+  T* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < C) {
+      float4 o = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
+      if (w) {
+        float4 ww = *reinterpret_cast<const float4*>(w + c), bb = *reinterpret_cast<const float4*>(b + c);
+        o.x = o.x * ww.x + bb.x; o.y = o.y * ww.y + bb.y; o.z = o.z * ww.z + bb.z; o.w = o.w * ww.w + bb.w;
+      }
+      st4(yr + c, o);
+    }
+  }
+}
+
+extern "C" int ga_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, long long M,
+                                int C, long long ldx, long long ldy, float eps, int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && y && M >= 0 && C > 0 && (C & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0, GA_ERR_ALIGN,
+             "ga_layernorm_fwd: C=%d ldx=%lld ldy=%lld must be multiples of 4", C, ldx, ldy);
+  GA_REQUIRE(C <= 2048, GA_ERR_UNSUPPORTED, "ga_layernorm_fwd: C=%d > 2048", C);
+  if (M == 0) return GA_OK;
+  const unsigned grid = (unsigned)((M + 7) / 8);
+  DISPATCH_T(dtype, {
+    if (C <= 512) layernorm_fwd_kernel<T, 4><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, mean, rstd, M, C, ldx, ldy, eps);
+    else if (C <= 1024) layernorm_fwd_kernel<T, 8><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, mean, rstd, M, C, ldx, ldy, eps);
+    else layernorm_fwd_kernel<T, 16><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, mean, rstd, M, C, ldx, ldy, eps);
+  });
+  return launch_ok("layernorm_fwd");
+}
+
+// backward.  xhat either given directly (x_is_hat) or recomputed from x, mean, rstd.
+// dx = rstd * (g - mean(g) - xhat*mean(g*xhat)),  g = dy*w ; per-CTA partial dw/db -> partial[blockIdx][2][C]
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                            const float* __restrict__ w, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, T* __restrict__ dx,
+                                                            float* __restrict__ partial, long long M, int C, long long lddy,
+                                                            long long ldx, long long lddx, int x_is_hat, int rows_per_cta) {
+  extern __shared__ float sacc[];  // [2][C] per CTA when partial != NULL
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (partial) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+  }
+  float4 dwv[MAXV], dbv[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { dwv[i] = make_float4(0, 0, 0, 0); dbv[i] = make_float4(0, 0, 0, 0); }
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  for (long long row = r0 + wid; row < r0 + rows_per_cta && row < M; row += nw) {
+    const float mu = x_is_hat ? 0.f : mean[row];
+    const float rs = rstd[row];
+    float4 g[MAXV], xh[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        float4 d = ld4(dy + row * lddy + c);
+        float4 xv = ld4(x + row * ldx + c);
+        if (!x_is_hat) { xv.x = (xv.x - mu) * rs; xv.y = (xv.y - mu) * rs; xv.z = (xv.z - mu) * rs; xv.w = (xv.w - mu) * rs; }
+        if (partial) {
+          dwv[i].x += d.x * xv.x; dwv[i].y += d.y * xv.y; dwv[i].z += d.z * xv.z; dwv[i].w += d.w * xv.w;
+          dbv[i].x += d.x; dbv[i].y += d.y; dbv[i].z += d.z; dbv[i].w += d.w;
+        }
+        if (w) { float4 ww = *reinterpret_cast<const float4*>(w + c); d.x *= ww.x; d.y *= ww.y; d.z *= ww.z; d.w *= ww.w; }
+        g[i] = d; xh[i] = xv;
+        s1 += d.x + d.y + d.z + d.w;
+        s2 += d.x * xv.x + d.y * xv.y + d.z * xv.z + d.w * xv.w;
+      } else { g[i] = make_float4(0, 0, 0, 0); xh[i] = g[i]; }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        float4 o = make_float4(rs * (g[i].x - s1 - xh[i].x * s2), rs * (g[i].y - s1 - xh[i].y * s2),
+                               rs * (g[i].z - s1 - xh[i].z * s2), rs * (g[i].w - s1 - xh[i].w * s2));
+        st4(dx + row * lddx + c, o);
+      }
+    }
+  }
+  if (partial) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        atomicAdd(&sacc[c], dwv[i].x); atomicAdd(&sacc[c + 1], dwv[i].y); atomicAdd(&sacc[c + 2], dwv[i].z); atomicAdd(&sacc[c + 3], dwv[i].w);
+        atomicAdd(&sacc[C + c], dbv[i].x); atomicAdd(&sacc[C + c + 1], dbv[i].y); atomicAdd(&sacc[C + c + 2], dbv[i].z); atomicAdd(&sacc[C + c + 3], dbv[i].w);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * C + i] = sacc[i];
+  }
+}
+
+// out0[j] += sum_p partial[p][j] (j < n0), out1[j-n0] += ... (j >= n0)
+__global__ void reduce_parts2_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out0, int n0,
+                                     float* __restrict__ out1, int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n + j];
+  float* o = (j < n0) ? (out0 ? out0 + j : nullptr) : (out1 ? out1 + (j - n0) : nullptr);
+  if (o) *o = accumulate ? (*o + s) : s;
+}
+
+static inline int row_parts(long long M) {
+  long long p = (M + 63) / 64;  // >= 64 rows per CTA
+  const long long cap = 2LL * 148;
+  if (p > cap) p = cap;
+  if (p < 1) p = 1;
+  return (int)p;
+}
+extern "C" int ga_layernorm_bwd_parts(long long M, int C) { return row_parts(M); }
+
+extern "C" int ga_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd, void* dx,
+                                float* dw, float* db, float* partial, long long M, int C, long long lddy, long long ldx,
+                                long long lddx, int dtype, ga_stream_t s) {
+  GA_REQUIRE(dy && x && rstd && dx && (C & 3) == 0 && (lddy & 3) == 0 && (ldx & 3) == 0 && (lddx & 3) == 0, GA_ERR_ALIGN,
+             "ga_layernorm_bwd: bad arguments (C=%d)", C);
+  GA_REQUIRE(C <= 2048, GA_ERR_UNSUPPORTED, "ga_layernorm_bwd: C=%d > 2048", C);
+  if (M == 0) return GA_OK;
+  const bool want_param = (dw || db);
+  GA_REQUIRE(!want_param || partial, GA_ERR_SHAPE, "ga_layernorm_bwd: parameter gradients need the partial workspace");
+  const int parts = row_parts(M);
+  const int rows_per_cta = (int)((M + parts - 1) / parts);
+  const size_t smem = want_param ? (size_t)2 * C * sizeof(float) : 0;
+  const int x_is_hat = (mean == nullptr);
+  DISPATCH_T(dtype, {
+    if (C <= 512) layernorm_bwd_kernel<T, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
+    else if (C <= 1024) layernorm_bwd_kernel<T, 8><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
+    else layernorm_bwd_kernel<T, 16><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
+  });
+  int rc = launch_ok("layernorm_bwd");
+  if (rc || !want_param) return rc;
+  reduce_parts2_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, dw, C, db, 1);
+  return launch_ok("layernorm_bwd_reduce");
+}
+
+extern "C" int ga_ln_bwd_rows(const void* dxhat, const void* xhat, const float* rstd, void* dconv, long long M, int C, int dtype,
+                              ga_stream_t s) {
+  return ga_layernorm_bwd(dxhat, xhat, nullptr, nullptr, rstd, dconv, nullptr, nullptr, nullptr, M, C, C, C, C, dtype, s);
+}
+
+// ---------------------------------------------------------------------------------------------- patch gathers
+// k == stride patches of an NHWC tensor: out row (b, oy, ox), column ((ky*k + kx)*C + c).  inverse: scatter back.
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int k, int inverse) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long p = i / C4;
+    const int xx = (int)(p % W); p /= W;
+    const int yy = (int)(p % H);
+    const int b = (int)(p / H);
+    const int oy = yy / k, ky = yy - oy * k, ox = xx / k, kx = xx - ox * k;
+    const long long row = ((long long)b * (H / k) + oy) * (W / k) + ox;
+    const long long po = row * ((long long)k * k * C) + (long long)(ky * k + kx) * C + c4 * 4;
+    const long long xo = i * 4;
+    if (!inverse) st4(y + po, ld4(x + xo)); else st4(y + xo, ld4(x + po));
+  }
+}
+extern "C" int ga_patchify(const void* x, void* y, int B, int H, int W, int C, int k, int inverse, int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && y && (C & 3) == 0 && H % k == 0 && W % k == 0, GA_ERR_SHAPE, "ga_patchify: bad shape H=%d W=%d C=%d k=%d", H, W, C, k);
+  const long long total = (long long)B * H * W * (C >> 2);
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, { patchify_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, B, H, W, C, k, inverse); });
+  return launch_ok("patchify");
+}
+
+// stem: fp32 image [B,3,H,W] with arbitrary element strides (NCHW or channels_last storage) -> rows (b, oy, ox),
+// columns (ky, kx, c)
+template <typename T>
+__global__ void stem_patchify_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int H, int W, int k, long long sb,
+                                     long long sc, long long sy, long long sx) {
+  const int Ho = H / k, Wo = W / k, KK = k * k * 3;
+  const long long total = (long long)B * Ho * Wo * KK;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % KK);
+    long long p = i / KK;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const int c = col % 3, kx = (col / 3) % k, ky = col / (3 * k);
+    st_f(y + i, x[b * sb + c * sc + (long long)(oy * k + ky) * sy + (long long)(ox * k + kx) * sx]);
+  }
+}
+extern "C" int ga_stem_patchify(const float* x, void* y, int B, int H, int W, int k, long long sb, long long sc, long long sy,
+                                long long sx, int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && y && H % k == 0 && W % k == 0, GA_ERR_SHAPE, "ga_stem_patchify: bad shape");
+  const long long total = (long long)B * (H / k) * (W / k) * k * k * 3;
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, { stem_patchify_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>(x, (T*)y, B, H, W, k, sb, sc, sy, sx); });
+  return launch_ok("stem_patchify");
+}
+
+// 3x3, pad 1, stride 1 im2col (forward) and its adjoint in gather form (inverse): C % 4 == 0
+template <typename T>
+__global__ void im2col3_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, long long ldx,
+                               long long ldy, int inverse) {
+  const int C4 = C >> 2;
+  if (!inverse) {
+    const long long total = (long long)B * H * W * 9 * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int c4 = (int)(i % C4);
+      long long p = i / C4;
+      const int tap = (int)(p % 9); p /= 9;
+      const int xx = (int)(p % W); p /= W;
+      const int yy = (int)(p % H);
+      const int b = (int)(p / H);
+      const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+      float4 v = make_float4(0, 0, 0, 0);
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = ld4(x + (((long long)b * H + sy) * W + sx) * ldx + c4 * 4);
+      st4(y + (((long long)b * H + yy) * W + xx) * ldy + tap * C + c4 * 4, v);
+    }
+  } else {
+    // x = d(col) [B*H*W, ldx>=9C] ; y = d(image) [B*H*W, ldy]: pixel (yy,xx) gathers tap t from output pixel (yy - dy, xx - dx)
+    const long long total = (long long)B * H * W * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int c4 = (int)(i % C4);
+      long long p = i / C4;
+      const int xx = (int)(p % W); p /= W;
+      const int yy = (int)(p % H);
+      const int b = (int)(p / H);
+      float4 a = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int oy = yy - (tap / 3 - 1), ox = xx - (tap % 3 - 1);
+        if (oy >= 0 && oy < H && ox >= 0 && ox < W) {
+          float4 v = ld4(x + (((long long)b * H + oy) * W + ox) * ldx + tap * C + c4 * 4);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+      }
+      st4(y + (((long long)b * H + yy) * W + xx) * ldy + c4 * 4, a);
+    }
+  }
+}
+extern "C" int ga_im2col3(const void* x, void* y, int B, int H, int W, int C, long long ldx, long long ldy, int inverse,
+                          int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && y && (C & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0, GA_ERR_ALIGN, "ga_im2col3: C/ld must be multiples of 4");
+  const long long total = (long long)B * H * W * (C >> 2) * (inverse ? 1 : 9);
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, { im2col3_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, B, H, W, C, ldx, ldy, inverse); });
+  return launch_ok("im2col3");
+}
+
+// ---------------------------------------------------------------------------------------------- column statistics
+// CTA (strip of 128 columns as 32 lanes x 4, row slice): 8 warps stride rows; result -> partial[slice][2][C]
+// MODE 0: s1 = sum x, s2 = sum x^2
+// MODE 1: BN backward: d = dy * (relu ? y>0 : 1); s1 = sum d; s2 = sum d * (x-mean)*invstd
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ yact,
+                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                       float* __restrict__ partial, long long M, int C, long long ldx,
+                                                       long long lddy, long long ldy, int rows_per_cta, int relu) {
+  __shared__ float4 sh[2][8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  float4 a = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+  if (c < C) {
+    float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
+    if (MODE == 1) { mu = *reinterpret_cast<const float4*>(mean + c); is = *reinterpret_cast<const float4*>(invstd + c); }
+    for (long long r = r0 + wid; r < r0 + rows_per_cta && r < M; r += 8) {
+      float4 v = ld4(x + r * ldx + c);
+      if (MODE == 0) {
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+      } else {
+        float4 d = ld4(dy + r * lddy + c);
+        if (relu) {
+          float4 yy = ld4(yact + r * ldy + c);
+          d.x = yy.x > 0.f ? d.x : 0.f; d.y = yy.y > 0.f ? d.y : 0.f; d.z = yy.z > 0.f ? d.z : 0.f; d.w = yy.w > 0.f ? d.w : 0.f;
+        }
+        a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+        q.x += d.x * (v.x - mu.x) * is.x; q.y += d.y * (v.y - mu.y) * is.y; q.z += d.z * (v.z - mu.z) * is.z; q.w += d.w * (v.w - mu.w) * is.w;
+      }
+    }
+  }
+  sh[0][wid][lane] = a; sh[1][wid][lane] = q;
+  __syncthreads();
+  if (wid < 2 && c < C) {
+    float4 t = sh[wid][0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { float4 u = sh[wid][k][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    *reinterpret_cast<float4*>(partial + ((size_t)blockIdx.y * 2 + wid) * C + c) = t;
+  }
+}
+
+extern "C" int ga_colstats_parts(long long M, int C) {
+  const int strips = (C + 127) / 128;
+  long long p = (2LL * 148 + strips - 1) / strips;
+  const long long maxp = (M + 63) / 64;
+  if (p > maxp) p = maxp;
+  if (p < 1) p = 1;
+  return (int)p;
+}
+
+extern "C" int ga_colstats(const void* x, float* sum, float* sumsq, float* partial, long long M, int C, long long ldx,
+                           int accumulate, int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && partial && (C & 3) == 0 && (ldx & 3) == 0, GA_ERR_ALIGN, "ga_colstats: C=%d ldx=%lld must be multiples of 4", C, ldx);
+  const int parts = ga_colstats_parts(M, C);
+  const int rows_per_cta = (int)((M + parts - 1) / parts);
+  dim3 grid((C + 127) / 128, parts);
+  DISPATCH_T(dtype, { colstats_kernel<T, 0><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, partial, M, C, ldx, 0, 0, rows_per_cta, 0); });
+  int rc = launch_ok("colstats");
+  if (rc) return rc;
+  reduce_parts2_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, sum, C, sumsq, accumulate);
+  return launch_ok("colstats_reduce");
+}
+
+// BatchNorm (training) finalize: from sum/sumsq over M rows -> mean, invstd, scale, shift; running stats (momentum, unbiased var)
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ w,
+                                   const float* __restrict__ b, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_o, float* __restrict__ invstd_o, float* __restrict__ scale_o,
+                                   float* __restrict__ shift_o, long long M, int C, float momentum, float eps, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    mean = sum[c] / (float)M;
+    var = fmaxf(sumsq[c] / (float)M - mean * mean, 0.f);
+    if (running_mean) {
+      const float unb = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float is = rsqrtf(var + eps);
+  const float sc = (w ? w[c] : 1.f) * is;
+  if (mean_o) mean_o[c] = mean;
+  if (invstd_o) invstd_o[c] = is;
+  scale_o[c] = sc;
+  shift_o[c] = (b ? b[c] : 0.f) - mean * sc;
+}
+extern "C" int ga_bn_finalize(const float* sum, const float* sumsq, const float* w, const float* b, float* running_mean,
+                              float* running_var, float* mean, float* invstd, float* scale, float* shift, long long M, int C,
+                              float momentum, float eps, int training, ga_stream_t s) {
+  GA_REQUIRE(scale && shift && C > 0, GA_ERR_SHAPE, "ga_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(sum, sumsq, w, b, running_mean, running_var, mean, invstd, scale, shift, M, C, momentum, eps, training);
+  return launch_ok("bn_finalize");
+}
+
+// y = act( x*scale + shift  (+ x2*scale2 + shift2) )
+template <typename T>
+__global__ void affine_act_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                  const T* __restrict__ x2, const float* __restrict__ scale2, const float* __restrict__ shift2,
+                                  T* __restrict__ y, long long M, int C, long long ldx, long long ldx2, long long ldy, int act) {
+  const int C4 = C >> 2;
+  const long long total = M * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long r = i / C4;
+    float4 v = ld4(x + r * ldx + c);
+    float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+    v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+    if (x2) {
+      float4 u = ld4(x2 + r * ldx2 + c);
+      if (scale2) {
+        float4 s2 = *reinterpret_cast<const float4*>(scale2 + c), h2 = *reinterpret_cast<const float4*>(shift2 + c);
+        u.x = u.x * s2.x + h2.x; u.y = u.y * s2.y + h2.y; u.z = u.z * s2.z + h2.z; u.w = u.w * s2.w + h2.w;
+      }
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    if (act == GA_ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    else if (act == GA_ACT_GELU) { v.x = gelu_f(v.x); v.y = gelu_f(v.y); v.z = gelu_f(v.z); v.w = gelu_f(v.w); }
+    st4(y + r * ldy + c, v);
+  }
+}
+extern "C" int ga_affine_act(const void* x, const float* scale, const float* shift, const void* x2, const float* scale2,
+                             const float* shift2, void* y, long long M, int C, long long ldx, long long ldx2, long long ldy,
+                             int act, int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && y && scale && shift && (C & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0 && (ldx2 & 3) == 0, GA_ERR_ALIGN,
+             "ga_affine_act: C/ld must be multiples of 4 (C=%d)", C);
+  const long long total = M * (C >> 2);
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, { affine_act_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, scale, shift, (const T*)x2, scale2, shift2, (T*)y, M, C, ldx, ldx2, ldy, act); });
+  return launch_ok("affine_act");
+}
+
+// BN backward, pass 1: c1[c] = sum d, c2[c] = sum d*xhat  (d = dy masked by relu(y))
+extern "C" int ga_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean, const float* invstd, float* c1,
+                                float* c2, float* partial, long long M, int C, long long lddy, long long ldx, long long ldy,
+                                int relu, int dtype, ga_stream_t s) {
+  GA_REQUIRE(dy && x && mean && invstd && partial && (C & 3) == 0 && (ldx & 3) == 0 && (lddy & 3) == 0, GA_ERR_ALIGN,
+             "ga_bn_bwd_reduce: bad arguments");
+  GA_REQUIRE(!relu || (y && (ldy & 3) == 0), GA_ERR_SHAPE, "ga_bn_bwd_reduce: relu mask needs y");
+  const int parts = ga_colstats_parts(M, C);
+  const int rows_per_cta = (int)((M + parts - 1) / parts);
+  dim3 grid((C + 127) / 128, parts);
+  DISPATCH_T(dtype, { colstats_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)dy, (const T*)y, mean, invstd, partial, M, C, ldx, lddy, ldy, rows_per_cta, relu); });
+  int rc = launch_ok("bn_bwd_reduce");
+  if (rc) return rc;
+  reduce_parts2_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, c1, C, c2, 0);
+  return launch_ok("bn_bwd_reduce2");
+}
+
+// BN backward, pass 2: dx = scale*(d - c1/M - xhat*c2/M)   (training) ; eval: dx = scale*d
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ scale, const float* __restrict__ c1, const float* __restrict__ c2,
+                                    T* __restrict__ dx, long long M, int C, long long lddy, long long ldx, long long ldy,
+                                    long long lddx, int relu, float invM) {
+  const int C4 = C >> 2;
+  const long long total = M * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long r = i / C4;
+    float4 d = ld4(dy + r * lddy + c);
+    if (relu) {
+      float4 yy = ld4(y + r * ldy + c);
+      d.x = yy.x > 0.f ? d.x : 0.f; d.y = yy.y > 0.f ? d.y : 0.f; d.z = yy.z > 0.f ? d.z : 0.f; d.w = yy.w > 0.f ? d.w : 0.f;
+    }
+    float4 sc = *reinterpret_cast<const float4*>(scale + c);
+    float4 o;
+    if (c1) {
+      float4 v = ld4(x + r * ldx + c);
+      float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+      float4 a = *reinterpret_cast<const float4*>(c1 + c), b = *reinterpret_cast<const float4*>(c2 + c);
+      o.x = sc.x * (d.x - a.x * invM - (v.x - mu.x) * is.x * b.x * invM);
+      o.y = sc.y * (d.y - a.y * invM - (v.y - mu.y) * is.y * b.y * invM);
+      o.z = sc.z * (d.z - a.z * invM - (v.z - mu.z) * is.z * b.z * invM);
+      o.w = sc.w * (d.w - a.w * invM - (v.w - mu.w) * is.w * b.w * invM);
+    } else {
+      o = make_float4(sc.x * d.x, sc.y * d.y, sc.z * d.z, sc.w * d.w);
+    }
+    st4(dx + r * lddx + c, o);
+  }
+}
+extern "C" int ga_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* mean, const float* invstd,
+                               const float* scale, const float* c1, const float* c2, void* dx, long long M, int C,
+                               long long lddy, long long ldx, long long ldy, long long lddx, int relu, int dtype, ga_stream_t s) {
+  GA_REQUIRE(dy && dx && scale && (C & 3) == 0 && (lddy & 3) == 0 && (lddx & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0,
+             GA_ERR_ALIGN, "ga_bn_bwd_apply: bad arguments");
+  const long long total = M * (C >> 2);
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, { bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)x, (const T*)y, mean, invstd, scale, c1, c2, (T*)dx, M, C, lddy, ldx, ldy, lddx, relu, 1.f / (float)M); });
+  return launch_ok("bn_bwd_apply");
+}
+
+// ---------------------------------------------------------------------------------------------- small element-wise
+template <typename TS, typename TD>
+__global__ void copy_cols_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long M, int C, long long lds, long long ldd) {
+  const long long total = M * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C; const int c = (int)(i - r * C);
+    st_f(dst + r * ldd + c, ld_f(src + r * lds + c));
+  }
+}
+extern "C" int ga_copy_cols(const void* src, void* dst, long long M, int C, long long lds, long long ldd, int src_dtype,
+                            int dst_dtype, ga_stream_t s) {
+  const long long total = M * C;
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)s;
+  if (src_dtype == GA_F32 && dst_dtype == GA_F32) copy_cols_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, M, C, lds, ldd);
+  else if (src_dtype == GA_F32) copy_cols_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)src, (bf16*)dst, M, C, lds, ldd);
+  else if (dst_dtype == GA_F32) copy_cols_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)src, (float*)dst, M, C, lds, ldd);
+  else copy_cols_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, M, C, lds, ldd);
+  return launch_ok("copy_cols");
+}
+
+// dst[r,c] = src[r,c] * rowscale[r] * colscale[c]
+template <typename TD>
+__global__ void scale_matrix_kernel(const float* __restrict__ src, const float* __restrict__ rs, const float* __restrict__ cs,
+                                    TD* __restrict__ dst, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    float v = src[i];
+    if (rs) v *= rs[r];
+    if (cs) v *= cs[c];
+    st_f(dst + i, v);
+  }
+}
+extern "C" int ga_scale_matrix(const float* src, const float* rowscale, const float* colscale, void* dst, int rows, int cols,
+                               int dst_dtype, ga_stream_t s) {
+  const long long total = (long long)rows * cols;
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+  if (dst_dtype == GA_BF16) scale_matrix_kernel<bf16><<<grid, 256, 0, (cudaStream_t)s>>>(src, rowscale, colscale, (bf16*)dst, rows, cols);
+  else scale_matrix_kernel<float><<<grid, 256, 0, (cudaStream_t)s>>>(src, rowscale, colscale, (float*)dst, rows, cols);
+  return launch_ok("scale_matrix");
+}
+extern "C" int ga_cast_bf16(const float* src, void* dst, long long n, ga_stream_t s) {
+  if (n == 0) return GA_OK;
+  GA_REQUIRE(n < (1LL << 31), GA_ERR_SHAPE, "ga_cast_bf16: too large");
+  return ga_scale_matrix(src, nullptr, nullptr, dst, 1, (int)n, GA_BF16, s);
+}
+
+// y[r, c] = x[r, c] * rowscale[r / rows_per_scale]   (drop-path on a gradient)
+template <typename T>
+__global__ void scale_rows_kernel(const T* __restrict__ x, const float* __restrict__ rs, T* __restrict__ y, long long M, int C,
+                                  int rows_per_scale) {
+  const int C4 = C >> 2;
+  const long long total = M * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C4;
+    const float sc = rs[r / rows_per_scale];
+    float4 v = ld4(x + i * 4);
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    st4(y + i * 4, v);
+  }
+}
+extern "C" int ga_scale_rows(const void* x, const float* rowscale, void* y, long long M, int C, int rows_per_scale, int dtype,
+                             ga_stream_t s) {
+  GA_REQUIRE(x && y && rowscale && (C & 3) == 0, GA_ERR_ALIGN, "ga_scale_rows: bad arguments");
+  const long long total = M * (C >> 2);
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, { scale_rows_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, rowscale, (T*)y, M, C, rows_per_scale); });
+  return launch_ok("scale_rows");
+}
+
+// Linear gradient finalisation with folded scales (see header).  One CTA per output row n (dW, dg) + column pass.
+__global__ void __launch_bounds__(256) linear_grad_rows_kernel(const float* __restrict__ G, const float* __restrict__ s,
+                                                               const float* __restrict__ W, const float* __restrict__ bias,
+                                                               const float* __restrict__ g, const float* __restrict__ w,
+                                                               const float* __restrict__ b_in, float* __restrict__ dW,
+                                                               float* __restrict__ dbias, float* __restrict__ dg, int N, int K) {
+  __shared__ float red[32];
+  const int n = blockIdx.x;
+  const float gn = g ? g[n] : 1.f;
+  const float sn = (b_in && s) ? s[n] : 0.f;
+  float dot = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float Gv = G[(size_t)n * K + k];
+    const float wk = w ? w[k] : 1.f;
+    // the layer saw in' = in*w + b_in, so dOut^T in' = G*w + s (x) b_in
+    if (dW) dW[(size_t)n * K + k] += gn * (Gv * wk + (b_in ? sn * b_in[k] : 0.f));
+    if (dg) dot += W[(size_t)n * K + k] * wk * Gv;
+  }
+  if (dg) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) dg[n] += dot + (bias ? bias[n] * s[n] : 0.f);
+  }
+  if (dbias && threadIdx.x == 0) dbias[n] += gn * s[n];
+}
+// dw[k] += sum_n W[n,k]*g[n]*G[n,k] ; db_in[k] += sum_n W[n,k]*g[n]*s[n]
+__global__ void __launch_bounds__(256) linear_grad_cols_kernel(const float* __restrict__ G, const float* __restrict__ s,
+                                                               const float* __restrict__ W, const float* __restrict__ g,
+                                                               float* __restrict__ dw, float* __restrict__ db_in, int N, int K) {
+  const int k = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int wid = threadIdx.x >> 5;
+  __shared__ float sh[2][8][32];
+  float a = 0.f, b = 0.f;
+  if (k < K) {
+    for (int n = wid; n < N; n += 8) {
+      const float wv = W[(size_t)n * K + k] * (g ? g[n] : 1.f);
+      a += wv * G[(size_t)n * K + k];
+      b += wv * s[n];
+    }
+  }
+  sh[0][wid][threadIdx.x & 31] = a; sh[1][wid][threadIdx.x & 31] = b;
+  __syncthreads();
+  if (wid == 0 && k < K) {
+    float ta = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ta += sh[0][i][threadIdx.x]; tb += sh[1][i][threadIdx.x]; }
+    if (dw) dw[k] += ta;
+    if (db_in) db_in[k] += tb;
+  }
+}
+extern "C" int ga_linear_grad_finalize(const float* G, const float* s, const float* W, const float* bias, const float* g,
+                                       const float* w, const float* b_in, float* dW, float* dbias, float* dg, float* dw,
+                                       float* db_in, int N, int K, ga_stream_t st) {
+  GA_REQUIRE(G && N > 0 && K > 0, GA_ERR_SHAPE, "ga_linear_grad_finalize: bad arguments");
+  GA_REQUIRE((!dg && !dw && !db_in) || W, GA_ERR_SHAPE, "ga_linear_grad_finalize: scale gradients need W");
+  GA_REQUIRE((!dbias && !db_in && !(dg && bias)) || s, GA_ERR_SHAPE, "ga_linear_grad_finalize: bias gradients need s");
+  if (dW || dg || dbias) {
+    linear_grad_rows_kernel<<<N, 256, 0, (cudaStream_t)st>>>(G, s, W, bias, g, w, b_in, dW, dbias, dg, N, K);
+    int rc = launch_ok("linear_grad_rows");
+    if (rc) return rc;
+  }
+  if (dw || db_in) {
+    linear_grad_cols_kernel<<<(K + 31) / 32, 256, 0, (cudaStream_t)st>>>(G, s, W, g, dw, db_in, N, K);
+    return launch_ok("linear_grad_cols");
+  }
+  return GA_OK;
+}
+
+// dz = dy * act'(.)  : GELU'(z) from the saved pre-activation, or the ReLU mask from the saved output
+template <typename T>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ zy, T* __restrict__ dz, long long M, int C,
+                               long long lddy, long long ldz, long long lddz, int act) {
+  const int C4 = C >> 2;
+  const long long total = M * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long r = i / C4;
+    float4 d = ld4(dy + r * lddy + c), z = ld4(zy + r * ldz + c);
+    if (act == GA_ACT_GELU) { d.x *= gelu_grad_f(z.x); d.y *= gelu_grad_f(z.y); d.z *= gelu_grad_f(z.z); d.w *= gelu_grad_f(z.w); }
+    else { d.x = z.x > 0.f ? d.x : 0.f; d.y = z.y > 0.f ? d.y : 0.f; d.z = z.z > 0.f ? d.z : 0.f; d.w = z.w > 0.f ? d.w : 0.f; }
+    st4(dz + r * lddz + c, d);
+  }
+}
+extern "C" int ga_act_bwd(const void* dy, const void* zy, void* dz, long long M, int C, long long lddy, long long ldz,
+                          long long lddz, int act, int dtype, ga_stream_t s) {
+  GA_REQUIRE(dy && zy && dz && (C & 3) == 0 && (lddy & 3) == 0 && (ldz & 3) == 0 && (lddz & 3) == 0, GA_ERR_ALIGN,
+             "ga_act_bwd: C/ld must be multiples of 4 (C=%d)", C);
+  const long long total = M * (C >> 2);
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, { act_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)zy, (T*)dz, M, C, lddy, ldz, lddz, act); });
+  return launch_ok("act_bwd");
+}

@@ -1,0 +1,484 @@
+// GA / MAP tail kernels: multi-scale aggregation (K3), SE gate (K3), Gram upper-triangle + L2 normalise (K4),
+// attention pooling with a handful of query rows (K5).  Warp-shuffle reductions; HBM/L2-bound.
+#include "common.cuh"
+
+#define DISPATCH_T(dtype, ...)                         \
+  if ((dtype) == GA_BF16) { typedef bf16 T; __VA_ARGS__; } \
+  else { typedef float T; __VA_ARGS__; }
+static inline int launch_ok(const char* n) { ga_count_launch(); return ga_check_launch(n); }
+
+// ---------------------------------------------------------------------------------------------- aggregation
+// PyTorch bilinear (align_corners=False, scale 2): src = 0.5*(dst+0.5)-0.5 clamped at 0
+__device__ __forceinline__ void bil_src(int o, int n_in, int* i0, int* i1, float* l) {
+  float s = 0.5f * ((float)o + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  int a = (int)s;
+  if (a > n_in - 1) a = n_in - 1;
+  *i0 = a;
+  *i1 = a + 1 < n_in ? a + 1 : n_in - 1;
+  *l = s - (float)a;
+}
+
+template <typename T>
+__global__ void aggregate_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int Hs, int Ws, int C, int Ho, int Wo,
+                                 long long ldd, int coff, int mode) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * Ho * Wo * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    long long p = i / C4;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float4 a = make_float4(0, 0, 0, 0);
+    if (mode == 0) {
+      const int f = Hs / Ho;
+      for (int dy = 0; dy < f; ++dy)
+        for (int dx = 0; dx < f; ++dx) {
+          float4 v = ld4(src + (((long long)b * Hs + oy * f + dy) * Ws + ox * f + dx) * C + c);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+      const float inv = 1.f / (float)(f * f);
+      a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+    } else if (mode == 1) {
+      a = ld4(src + (((long long)b * Hs + oy) * Ws + ox) * C + c);
+    } else {
+      int y0, y1, x0, x1; float ly, lx;
+      bil_src(oy, Hs, &y0, &y1, &ly);
+      bil_src(ox, Ws, &x0, &x1, &lx);
+      const T* base = src + (long long)b * Hs * Ws * C + c;
+      float4 v00 = ld4(base + ((long long)y0 * Ws + x0) * C), v01 = ld4(base + ((long long)y0 * Ws + x1) * C);
+      float4 v10 = ld4(base + ((long long)y1 * Ws + x0) * C), v11 = ld4(base + ((long long)y1 * Ws + x1) * C);
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+      a.x = w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+      a.y = w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+      a.z = w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
+      a.w = w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
+    }
+    st4(dst + (((long long)b * Ho + oy) * Wo + ox) * ldd + coff + c, a);
+  }
+}
+
+// adjoint, gather form: dsrc (contiguous [B,Hs,Ws,C]) from ddst slice
+template <typename T>
+__global__ void aggregate_bwd_kernel(T* __restrict__ dsrc, const T* __restrict__ ddst, int B, int Hs, int Ws, int C, int Ho,
+                                     int Wo, long long ldd, int coff, int mode) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * Hs * Ws * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    long long p = i / C4;
+    const int x = (int)(p % Ws); p /= Ws;
+    const int y = (int)(p % Hs);
+    const int b = (int)(p / Hs);
+    float4 a = make_float4(0, 0, 0, 0);
+    const T* dbase = ddst + (long long)b * Ho * Wo * ldd + coff + c;
+    if (mode == 0) {
+      const int f = Hs / Ho;
+      a = ld4(dbase + ((long long)(y / f) * Wo + x / f) * ldd);
+      const float inv = 1.f / (float)(f * f);
+      a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+    } else if (mode == 1) {
+      a = ld4(dbase + ((long long)y * Wo + x) * ldd);
+    } else {
+      const int oy_lo = max(0, 2 * y - 2), oy_hi = min(Ho - 1, 2 * y + 2);
+      const int ox_lo = max(0, 2 * x - 2), ox_hi = min(Wo - 1, 2 * x + 2);
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        int y0, y1; float ly;
+        bil_src(oy, Hs, &y0, &y1, &ly);
+        float wy = 0.f;
+        if (y0 == y) wy += 1.f - ly;
+        if (y1 == y) wy += ly;
+        if (wy == 0.f) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          int x0, x1; float lx;
+          bil_src(ox, Ws, &x0, &x1, &lx);
+          float wx = 0.f;
+          if (x0 == x) wx += 1.f - lx;
+          if (x1 == x) wx += lx;
+          if (wx == 0.f) continue;
+          float4 v = ld4(dbase + ((long long)oy * Wo + ox) * ldd);
+          const float w = wy * wx;
+          a.x += w * v.x; a.y += w * v.y; a.z += w * v.z; a.w += w * v.w;
+        }
+      }
+    }
+    st4(dsrc + i * 4, a);
+  }
+}
+
+extern "C" int ga_aggregate(const void* src, void* dst, int B, int Hs, int Ws, int C, int Ho, int Wo, long long ldd, int coff,
+                            int mode, int inverse, int dtype, ga_stream_t s) {
+  GA_REQUIRE(src && dst && (C & 3) == 0 && (ldd & 3) == 0 && (coff & 3) == 0, GA_ERR_ALIGN, "ga_aggregate: C/ldd/coff must be multiples of 4");
+  GA_REQUIRE(mode != 0 || (Hs % Ho == 0 && Ws % Wo == 0 && Hs / Ho == Ws / Wo), GA_ERR_SHAPE, "ga_aggregate: pool factor must be integral");
+  GA_REQUIRE(mode != 1 || (Hs == Ho && Ws == Wo), GA_ERR_SHAPE, "ga_aggregate: copy needs equal sizes");
+  GA_REQUIRE(mode != 2 || (Ho == 2 * Hs && Wo == 2 * Ws), GA_ERR_SHAPE, "ga_aggregate: bilinear is x2 only");
+  const long long total = (long long)B * (inverse ? Hs * Ws : Ho * Wo) * (C >> 2);
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, {
+    if (!inverse) aggregate_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)src, (T*)dst, B, Hs, Ws, C, Ho, Wo, ldd, coff, mode);
+    else aggregate_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((T*)const_cast<void*>(src), (const T*)dst, B, Hs, Ws, C, Ho, Wo, ldd, coff, mode);
+  });
+  return launch_ok("aggregate");
+}
+
+// ---------------------------------------------------------------------------------------------- SE gate
+// one CTA per image.  smem: pooled[C] | hidden[R] | gate[C] | part[8][C]
+template <typename T>
+__global__ void __launch_bounds__(256) se_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                     const float* __restrict__ w2, const float* __restrict__ b2, T* __restrict__ y,
+                                                     float* __restrict__ pooled_o, float* __restrict__ hidden_o,
+                                                     float* __restrict__ gate_o, int HW, int C, int R, long long ldx, long long ldy) {
+  extern __shared__ float sm[];
+  float* pooled = sm; float* hidden = pooled + C; float* gate = hidden + R; float* part = gate + C;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const T* xb = x + (long long)b * HW * ldx;
+  // column means: warp w strides rows, lanes stride channels
+  for (int c = lane; c < C; c += 32) {
+    float a = 0.f;
+    for (int p = wid; p < HW; p += 8) a += ld_f(xb + (long long)p * ldx + c);
+    part[wid * C + c] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += part[k * C + c];
+    a /= (float)HW;
+    pooled[c] = a;
+    pooled_o[(long long)b * C + c] = a;
+  }
+  __syncthreads();
+  for (int r = wid; r < R; r += 8) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += w1[(long long)r * C + c] * pooled[c];
+    a = warp_sum(a);
+    if (lane == 0) { a = fmaxf(a + b1[r], 0.f); hidden[r] = a; hidden_o[(long long)b * R + r] = a; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b2[c];
+    for (int r = 0; r < R; ++r) a += w2[(long long)c * R + r] * hidden[r];
+    a = 1.f / (1.f + __expf(-a));
+    gate[c] = a;
+    gate_o[(long long)b * C + c] = a;
+  }
+  __syncthreads();
+  T* yb = y + (long long)b * HW * ldy;
+  const int C4 = C >> 2;
+  for (int i = threadIdx.x; i < HW * C4; i += blockDim.x) {
+    const int p = i / C4, c = (i - p * C4) * 4;
+    float4 v = ld4(xb + (long long)p * ldx + c);
+    v.x *= gate[c]; v.y *= gate[c + 1]; v.z *= gate[c + 2]; v.w *= gate[c + 3];
+    st4(yb + (long long)p * ldy + c, v);
+  }
+}
+extern "C" int ga_se_fwd(const void* x, const float* w1, const float* b1, const float* w2, const float* b2, void* y,
+                         float* pooled, float* hidden, float* gate, int B, int HW, int C, int R, long long ldx, long long ldy,
+                         int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && y && w1 && w2 && b1 && b2 && pooled && hidden && gate && (C & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0,
+             GA_ERR_ALIGN, "ga_se_fwd: bad arguments");
+  if (B == 0) return GA_OK;
+  const size_t smem = (size_t)(2 * C + R + 8 * C) * sizeof(float);
+  DISPATCH_T(dtype, { se_fwd_kernel<T><<<B, 256, smem, (cudaStream_t)s>>>((const T*)x, w1, b1, w2, b2, (T*)y, pooled, hidden, gate, HW, C, R, ldx, ldy); });
+  return launch_ok("se_fwd");
+}
+
+// backward, one CTA per image: dx = dy*gate + dpooled/HW ; dpre2[b,:], dh[b,:] -> ws for the (tiny) weight-gradient GEMMs
+template <typename T>
+__global__ void __launch_bounds__(256) se_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ w1,
+                                                     const float* __restrict__ w2, const float* __restrict__ hidden_i,
+                                                     const float* __restrict__ gate_i, T* __restrict__ dx, float* __restrict__ dpre2_o,
+                                                     float* __restrict__ dh_o, int HW, int C, int R, long long lddy, long long ldx,
+                                                     long long lddx) {
+  extern __shared__ float sm[];
+  float* dpre2 = sm; float* dh = dpre2 + C; float* dpool = dh + R; float* gate = dpool + C; float* part = gate + C;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const T* xb = x + (long long)b * HW * ldx;
+  const T* dyb = dy + (long long)b * HW * lddy;
+  for (int c = lane; c < C; c += 32) {
+    float a = 0.f;
+    for (int p = wid; p < HW; p += 8) a += ld_f(dyb + (long long)p * lddy + c) * ld_f(xb + (long long)p * ldx + c);
+    part[wid * C + c] = a;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += part[k * C + c];
+    const float g = gate_i[(long long)b * C + c];
+    gate[c] = g;
+    a *= g * (1.f - g);
+    dpre2[c] = a;
+    dpre2_o[(long long)b * C + c] = a;
+  }
+  __syncthreads();
+  for (int r = wid; r < R; r += 8) {
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += w2[(long long)c * R + r] * dpre2[c];
+    a = warp_sum(a);
+    if (lane == 0) { a = hidden_i[(long long)b * R + r] > 0.f ? a : 0.f; dh[r] = a; dh_o[(long long)b * R + r] = a; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int r = 0; r < R; ++r) a += w1[(long long)r * C + c] * dh[r];
+    dpool[c] = a / (float)HW;
+  }
+  __syncthreads();
+  T* dxb = dx + (long long)b * HW * lddx;
+  const int C4 = C >> 2;
+  for (int i = threadIdx.x; i < HW * C4; i += blockDim.x) {
+    const int p = i / C4, c = (i - p * C4) * 4;
+    float4 v = ld4(dyb + (long long)p * lddy + c);
+    v.x = v.x * gate[c] + dpool[c]; v.y = v.y * gate[c + 1] + dpool[c + 1];
+    v.z = v.z * gate[c + 2] + dpool[c + 2]; v.w = v.w * gate[c + 3] + dpool[c + 3];
+    st4(dxb + (long long)p * lddx + c, v);
+  }
+}
+extern "C" int ga_se_bwd(const void* dy, const void* x, const float* w1, const float* w2, const float* hidden, const float* gate,
+                         void* dx, float* dpre2, float* dh, int B, int HW, int C, int R, long long lddy, long long ldx,
+                         long long lddx, int dtype, ga_stream_t s) {
+  GA_REQUIRE(dy && x && w1 && w2 && hidden && gate && dx && dpre2 && dh && (C & 3) == 0 && (ldx & 3) == 0 && (lddy & 3) == 0 &&
+                 (lddx & 3) == 0, GA_ERR_ALIGN, "ga_se_bwd: bad arguments");
+  if (B == 0) return GA_OK;
+  const size_t smem = (size_t)(4 * C + R + 8 * C) * sizeof(float);
+  DISPATCH_T(dtype, { se_bwd_kernel<T><<<B, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w1, w2, hidden, gate, (T*)dx, dpre2, dh, HW, C, R, lddy, ldx, lddx); });
+  return launch_ok("se_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------- Gram -> triu -> L2 normalise
+// G [B,C,C] fp32 (from the batched GEMM).  out[b, (t/glen)*gld + t%glen] = G[i,j]/max(||triu||,1e-12) for the row-major
+// i<=j enumeration t (ga_convnext.py:424-430).  One CTA per image.
+__device__ __forceinline__ int triu_row_start(int i, int C) { return i * C - (i * (i - 1)) / 2; }
+
+template <typename TO>
+__global__ void __launch_bounds__(512) gram_triu_fwd_kernel(const float* __restrict__ G, TO* __restrict__ out, float* __restrict__ norm_o,
+                                                            int C, int glen, int gld, long long out_bs) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* Gb = G + (long long)b * C * C;
+  float ss = 0.f;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int i = idx / C, j = idx - i * C;
+    if (j >= i) { const float v = Gb[idx]; ss += v * v; }
+  }
+  ss = block_sum(ss, red);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  if (threadIdx.x == 0) norm_o[b] = nrm;
+  const float inv = 1.f / nrm;
+  TO* ob = out + (long long)b * out_bs;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int i = idx / C, j = idx - i * C;
+    if (j >= i) {
+      const int t = triu_row_start(i, C) + (j - i);
+      st_f(ob + (long long)(t / glen) * gld + t % glen, Gb[idx] * inv);
+    }
+  }
+}
+extern "C" int ga_gram_triu_fwd(const float* G, void* out, float* norm, int B, int C, int glen, int gld, long long out_bs,
+                                int out_dtype, ga_stream_t s) {
+  GA_REQUIRE(G && out && norm && C > 0 && glen > 0 && gld >= glen, GA_ERR_SHAPE, "ga_gram_triu_fwd: bad arguments");
+  if (B == 0) return GA_OK;
+  if (out_dtype == GA_BF16) gram_triu_fwd_kernel<bf16><<<B, 512, 0, (cudaStream_t)s>>>(G, (bf16*)out, norm, C, glen, gld, out_bs);
+  else gram_triu_fwd_kernel<float><<<B, 512, 0, (cudaStream_t)s>>>(G, (float*)out, norm, C, glen, gld, out_bs);
+  return launch_ok("gram_triu_fwd");
+}
+
+// backward through normalise + gather: dt = (dout - out*(out.dout))/norm; S = dG + dG^T (symmetric, diag doubled), dtype TS
+template <typename TI, typename TS>
+__global__ void __launch_bounds__(512) gram_triu_bwd_kernel(const TI* __restrict__ dout, const TI* __restrict__ out, const float* __restrict__ norm,
+                                                            TS* __restrict__ S, int C, int glen, int gld, long long out_bs) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const TI* ob = out + (long long)b * out_bs;
+  const TI* db = dout + (long long)b * out_bs;
+  const int tri = C * (C + 1) / 2;
+  float dot = 0.f;
+  for (int t = threadIdx.x; t < tri; t += blockDim.x) {
+    const long long o = (long long)(t / glen) * gld + t % glen;
+    dot += ld_f(ob + o) * ld_f(db + o);
+  }
+  dot = block_sum(dot, red);
+  const float inv = 1.f / norm[b];
+  TS* Sb = S + (long long)b * C * C;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int i = idx / C, j = idx - i * C;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    const int t = triu_row_start(lo, C) + (hi - lo);
+    const long long o = (long long)(t / glen) * gld + t % glen;
+    float v = (ld_f(db + o) - ld_f(ob + o) * dot) * inv;
+    if (i == j) v *= 2.f;
+    st_f(Sb + idx, v);
+  }
+}
+extern "C" int ga_gram_triu_bwd(const void* dout, const void* out, const float* norm, void* S, int B, int C, int glen, int gld,
+                                long long out_bs, int io_dtype, int s_dtype, ga_stream_t s) {
+  GA_REQUIRE(dout && out && norm && S, GA_ERR_SHAPE, "ga_gram_triu_bwd: bad arguments");
+  if (B == 0) return GA_OK;
+  cudaStream_t st = (cudaStream_t)s;
+  if (io_dtype == GA_BF16 && s_dtype == GA_BF16) gram_triu_bwd_kernel<bf16, bf16><<<B, 512, 0, st>>>((const bf16*)dout, (const bf16*)out, norm, (bf16*)S, C, glen, gld, out_bs);
+  else if (io_dtype == GA_BF16) gram_triu_bwd_kernel<bf16, float><<<B, 512, 0, st>>>((const bf16*)dout, (const bf16*)out, norm, (float*)S, C, glen, gld, out_bs);
+  else if (s_dtype == GA_BF16) gram_triu_bwd_kernel<float, bf16><<<B, 512, 0, st>>>((const float*)dout, (const float*)out, norm, (bf16*)S, C, glen, gld, out_bs);
+  else gram_triu_bwd_kernel<float, float><<<B, 512, 0, st>>>((const float*)dout, (const float*)out, norm, (float*)S, C, glen, gld, out_bs);
+  return launch_ok("gram_triu_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------- attention pooling
+// Q query rows (the class / gram tokens, which are also keys) + N spatial keys.  One warp per (image, head):
+// lanes stride over keys; softmax by warp shuffles.  scores use q as given (caller pre-scales).
+// kvc [B,Q,2E] fp32: k = [..., :E], v = [..., E:];   kvt rows [B*N, ldt] (T): k at col 0, v at col E
+template <typename T, int HD_MAX>
+__global__ void __launch_bounds__(256) attnpool_fwd_kernel(const float* __restrict__ q, const float* __restrict__ kvc, const T* __restrict__ kvt,
+                                                           float* __restrict__ out, float* __restrict__ attn, int B, int Q, int N, int H,
+                                                           int E, long long ldt) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= B * H) return;
+  const int b = gw / H, h = gw - b * H, lane = threadIdx.x & 31;
+  const int hd = E / H, NK = Q + N;
+  for (int qi = 0; qi < Q; ++qi) {
+    float qv[HD_MAX];
+#pragma unroll
+    for (int d = 0; d < HD_MAX; ++d) qv[d] = d < hd ? q[((long long)b * Q + qi) * E + h * hd + d] : 0.f;
+    float* arow = attn + (((long long)b * H + h) * Q + qi) * NK;
+    float mx = -INFINITY;
+    for (int n = lane; n < NK; n += 32) {
+      float sc = 0.f;
+      if (n < Q) {
+        const float* kp = kvc + ((long long)b * Q + n) * 2 * E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) sc += qv[d] * kp[d];
+      } else {
+        const T* kp = kvt + ((long long)b * N + (n - Q)) * ldt + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) sc += qv[d] * ld_f(kp + d);
+      }
+      arow[n] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < NK; n += 32) { const float e = __expf(arow[n] - mx); arow[n] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    float ov[HD_MAX];
+#pragma unroll
+    for (int d = 0; d < HD_MAX; ++d) ov[d] = 0.f;
+    for (int n = lane; n < NK; n += 32) {
+      const float a = arow[n] * inv;
+      arow[n] = a;
+      if (n < Q) {
+        const float* vp = kvc + ((long long)b * Q + n) * 2 * E + E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) ov[d] += a * vp[d];
+      } else {
+        const T* vp = kvt + ((long long)b * N + (n - Q)) * ldt + E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) ov[d] += a * ld_f(vp + d);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < HD_MAX; ++d) {
+      const float v = warp_sum(ov[d]);
+      if (lane == 0 && d < hd) out[((long long)b * Q + qi) * E + h * hd + d] = v;
+    }
+  }
+}
+extern "C" int ga_attnpool_fwd(const float* q, const float* kv_cls, const void* kv_tok, float* out, float* attn, int B, int Q, int N,
+                               int H, int E, long long ldt, int dtype, ga_stream_t s) {
+  GA_REQUIRE(q && kv_cls && kv_tok && out && attn && H > 0 && E % H == 0, GA_ERR_SHAPE, "ga_attnpool_fwd: bad arguments");
+  GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_fwd: head_dim %d > 32", E / H);
+  if (B == 0) return GA_OK;
+  const int grid = (B * H + 7) / 8;
+  DISPATCH_T(dtype, { attnpool_fwd_kernel<T, 32><<<grid, 256, 0, (cudaStream_t)s>>>(q, kv_cls, (const T*)kv_tok, out, attn, B, Q, N, H, E, ldt); });
+  return launch_ok("attnpool_fwd");
+}
+
+// backward: one warp per (image, head).  dkv_tok written (=), dkv_cls / dq written (=).
+template <typename T, int HD_MAX>
+__global__ void __launch_bounds__(256) attnpool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ q, const float* __restrict__ kvc,
+                                                           const T* __restrict__ kvt, const float* __restrict__ attn, float* __restrict__ dq,
+                                                           float* __restrict__ dkvc, T* __restrict__ dkvt, int B, int Q, int N, int H, int E,
+                                                           long long ldt, long long lddt) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= B * H) return;
+  const int b = gw / H, h = gw - b * H, lane = threadIdx.x & 31;
+  const int hd = E / H, NK = Q + N;
+  for (int qi = 0; qi < Q; ++qi) {
+    const float* arow = attn + (((long long)b * H + h) * Q + qi) * NK;
+    float dov[HD_MAX], qv[HD_MAX];
+#pragma unroll
+    for (int d = 0; d < HD_MAX; ++d) {
+      dov[d] = d < hd ? dout[((long long)b * Q + qi) * E + h * hd + d] : 0.f;
+      qv[d] = d < hd ? q[((long long)b * Q + qi) * E + h * hd + d] : 0.f;
+    }
+    float rowdot = 0.f;
+    for (int n = lane; n < NK; n += 32) {
+      float da = 0.f;
+      if (n < Q) {
+        const float* vp = kvc + ((long long)b * Q + n) * 2 * E + E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) da += dov[d] * vp[d];
+      } else {
+        const T* vp = kvt + ((long long)b * N + (n - Q)) * ldt + E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) da += dov[d] * ld_f(vp + d);
+      }
+      rowdot += arow[n] * da;
+    }
+    rowdot = warp_sum(rowdot);
+    float dqv[HD_MAX];
+#pragma unroll
+    for (int d = 0; d < HD_MAX; ++d) dqv[d] = 0.f;
+    for (int n = lane; n < NK; n += 32) {
+      const float a = arow[n];
+      float da = 0.f;
+      float kk[HD_MAX];
+      if (n < Q) {
+        const float* kp = kvc + ((long long)b * Q + n) * 2 * E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) { kk[d] = kp[d]; da += dov[d] * kp[E + d]; }
+      } else {
+        const T* kp = kvt + ((long long)b * N + (n - Q)) * ldt + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) { kk[d] = ld_f(kp + d); da += dov[d] * ld_f(kp + E + d); }
+      }
+      const float ds = a * (da - rowdot);
+      // dk[n] += ds*q ; dv[n] += a*dout ; dq += ds*k
+      if (n < Q) {
+        float* gp = dkvc + ((long long)b * Q + n) * 2 * E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) {
+          const float pk = qi == 0 ? 0.f : gp[d], pv = qi == 0 ? 0.f : gp[E + d];
+          gp[d] = pk + ds * qv[d]; gp[E + d] = pv + a * dov[d];
+        }
+      } else {
+        T* gp = dkvt + ((long long)b * N + (n - Q)) * lddt + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) {
+          const float pk = qi == 0 ? 0.f : ld_f(gp + d), pv = qi == 0 ? 0.f : ld_f(gp + E + d);
+          st_f(gp + d, pk + ds * qv[d]); st_f(gp + E + d, pv + a * dov[d]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < HD_MAX; ++d) if (d < hd) dqv[d] += ds * kk[d];
+    }
+#pragma unroll
+    for (int d = 0; d < HD_MAX; ++d) {
+      const float v = warp_sum(dqv[d]);
+      if (lane == 0 && d < hd) dq[((long long)b * Q + qi) * E + h * hd + d] = v;
+    }
+  }
+}
+extern "C" int ga_attnpool_bwd(const float* dout, const float* q, const float* kv_cls, const void* kv_tok, const float* attn,
+                               float* dq, float* dkv_cls, void* dkv_tok, int B, int Q, int N, int H, int E, long long ldt,
+                               long long lddt, int dtype, ga_stream_t s) {
+  GA_REQUIRE(dout && q && kv_cls && kv_tok && attn && dq && dkv_cls && dkv_tok && H > 0 && E % H == 0, GA_ERR_SHAPE,
+             "ga_attnpool_bwd: bad arguments");
+  GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_bwd: head_dim %d > 32", E / H);
+  if (B == 0) return GA_OK;
+  const int grid = (B * H + 7) / 8;
+  DISPATCH_T(dtype, { attnpool_bwd_kernel<T, 32><<<grid, 256, 0, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt); });
+  return launch_ok("attnpool_bwd");
+}

@@ -1,0 +1,412 @@
+"""GA-ConvNeXt on sm_100a kernels: drop-in for `GA/ga_convnext.py` (same factories, attribute names, state_dict).
+
+The module tree below only *holds* parameters (so `state_dict()`, `load_state_dict(strict=True)`, `deepcopy`,
+`.cuda()`, DDP and optimizer factories see exactly the reference layout, 407 keys for tiny_688); the arithmetic
+is done by `ops.*` on NHWC row matrices through libga_sm100.so.  fp32 inputs run the fp32 kernels; under
+`torch.autocast(..., dtype=torch.bfloat16)` (or `model.compute_dtype = torch.bfloat16`) activations are bf16 with
+fp32 accumulation.  There is no PyTorch/CPU fallback: calling forward on CPU tensors raises.
+
+Reference lines are cited per method; construction order mirrors ga_convnext.py:335-432 so that
+`torch.manual_seed(s); create_model(name)` yields bit-identical initial weights.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .lib import ACT_GELU
+from .registry import build_model_with_cfg, register_model
+
+__all__ = ['GA_ConvNeXt']
+
+IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+
+
+def _cfg(url='', **kwargs):
+    return {'url': url, 'num_classes': 1000, 'input_size': (3, 224, 224), 'pool_size': (7, 7), 'crop_pct': 0.875,
+            'interpolation': 'bicubic', 'mean': IMAGENET_DEFAULT_MEAN, 'std': IMAGENET_DEFAULT_STD,
+            'first_conv': 'stem.0', 'classifier': 'head.fc', **kwargs}
+
+
+default_cfgs = dict(ga_convnext_tiny=_cfg(), ga_convnext_small=_cfg(), ga_convnext_base=_cfg())
+
+
+def _params(mod: nn.Module) -> dict:
+    """Flat {relative name: tensor} of a holder module (parameters and buffers)."""
+    d = dict(mod.named_parameters())
+    d.update(dict(mod.named_buffers()))
+    return d
+
+
+def _path_scale(p: float, training: bool, batch: int, device) -> Optional[torch.Tensor]:
+    """timm DropPath: per-sample bernoulli(keep)/keep multiplier on the residual branch (None = identity)."""
+    if p == 0. or not training:
+        return None
+    keep = 1.0 - p
+    m = torch.empty(batch, dtype=torch.float32, device=device).bernoulli_(keep)
+    if keep > 0.0:
+        m.div_(keep)
+    return m
+
+
+class LayerNorm2d(nn.LayerNorm):
+    """Parameter holder for the channel LayerNorm of stem / downsample (ga_convnext.py:51-67), eps 1e-6."""
+
+    def __init__(self, normalized_shape, eps=1e-6):
+        super().__init__(normalized_shape, eps=eps)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class ConvNeXtBlock(nn.Module):
+    """ga_convnext.py:70-112.  One fused autograd node: K1 + two tcgen05 GEMMs (see ops.ConvNeXtBlockFn)."""
+
+    def __init__(self, dim, drop_path=0., ls_init_value=1e-6, mlp_ratio=4):
+        super().__init__()
+        self.conv_dw = nn.Conv2d(dim, dim, kernel_size=7, padding=3, groups=dim)
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim, int(mlp_ratio * dim))
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(dim)) if ls_init_value > 0 else None
+        self.drop_prob = float(drop_path)
+
+    def run(self, x, geom):
+        p = _params(self)
+        if self.gamma is None:
+            p['gamma'] = torch.ones_like(p['norm.weight'])
+        ps = _path_scale(self.drop_prob, self.training, geom[0], x.device)
+        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled())
+
+
+class ConvNeXtStage(nn.Module):
+    """ga_convnext.py:115-150: optional LN2d + 2x2/2 conv, block sequence, taps for deep stages."""
+
+    def __init__(self, in_chs, out_chs, stride=2, depth=2, dp_rates=None, ls_init_value=1.0, stage3_naggre=2):
+        super().__init__()
+        self.stage3_naggre = stage3_naggre
+        self.stride = stride
+        if in_chs != out_chs or stride > 1:
+            self.downsample = nn.Sequential(LayerNorm2d(in_chs), nn.Conv2d(in_chs, out_chs, kernel_size=stride, stride=stride))
+        else:
+            self.downsample = nn.Identity()
+        dp_rates = dp_rates or [0.] * depth
+        self.blocks = nn.Sequential(*[ConvNeXtBlock(out_chs, drop_path=dp_rates[j], ls_init_value=ls_init_value)
+                                      for j in range(depth)])
+
+    def run(self, x, geom):
+        Bn, H, W = geom
+        if not isinstance(self.downsample, nn.Identity):
+            ln, conv = self.downsample[0], self.downsample[1]
+            k = self.stride
+            cin, cout = conv.in_channels, conv.out_channels
+            x = ops.layernorm(x, ln.weight, ln.bias, ln.eps)
+            if k > 1:
+                x = ops.patchify(x, (Bn, H, W, cin), k)
+                H, W = H // k, W // k
+            x = ops.linear(x, conv.weight.permute(0, 2, 3, 1).reshape(cout, k * k * cin), conv.bias)
+        geom = (Bn, H, W)
+        taps: List[torch.Tensor] = []
+        n = len(self.blocks)
+        for i, blk in enumerate(self.blocks):
+            x = blk.run(x, geom)
+            if n > 5 and (i + 1) % (n // (self.stage3_naggre + 1)) == 0 and len(taps) < self.stage3_naggre:
+                taps.append(x)
+        return x, geom, taps
+
+
+class _SE(nn.Module):
+    """timm SEModule parameter layout (fc1/fc2 1x1 convs); reduce width = make_divisible(C/4, 8, round_limit=0)."""
+
+    def __init__(self, channels, rd_ratio=0.25):
+        super().__init__()
+        rd = max(8, int(channels * rd_ratio + 4) // 8 * 8)
+        self.fc1 = nn.Conv2d(channels, rd, kernel_size=1, bias=True)
+        self.fc2 = nn.Conv2d(rd, channels, kernel_size=1, bias=True)
+
+
+class Bottleneck(nn.Module):
+    """ga_convnext.py:251-318: 1x1+BN+ReLU, 3x3+BN+ReLU, SE, 1x1+BN, DropPath, + (1x1+BN shortcut), ReLU."""
+
+    def __init__(self, inplanes, planes, outplanes, drop_path=0.):
+        super().__init__()
+        self.downsample = nn.Sequential(nn.Conv2d(inplanes, outplanes, kernel_size=1, stride=1), nn.BatchNorm2d(outplanes))
+        width = planes
+        self.conv1 = nn.Conv2d(inplanes, width, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = nn.Conv2d(width, width, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.se = _SE(width)
+        self.conv3 = nn.Conv2d(width, outplanes, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(outplanes)
+        self.drop_prob = float(drop_path or 0.)
+
+    def run(self, x, geom):
+        Bn, H, W = geom
+        tr = self.training
+        cin, width, cout = self.conv1.in_channels, self.conv1.out_channels, self.conv3.out_channels
+        y = ops.linear(x, self.conv1.weight.reshape(width, cin))
+        y = ops.batchnorm(y, _params(self.bn1), tr, relu=True)
+        col = ops.im2col3(y, geom)
+        y = ops.linear(col, self.conv2.weight.permute(0, 2, 3, 1).reshape(width, 9 * width))
+        y = ops.batchnorm(y, _params(self.bn2), tr, relu=True)
+        y = ops.se_gate(y, self.se.fc1.weight, self.se.fc1.bias, self.se.fc2.weight, self.se.fc2.bias, Bn, H * W)
+        y = ops.linear(y, self.conv3.weight.reshape(cout, width))
+        sc = ops.linear(x, self.downsample[0].weight.reshape(cout, cin), self.downsample[0].bias)
+        ps = _path_scale(self.drop_prob, tr, Bn, x.device)
+        if ps is None:
+            return ops.batchnorm(y, _params(self.bn3), tr, relu=True, xb=sc, bnb=_params(self.downsample[1]))
+        y = ops.batchnorm(y, _params(self.bn3), tr)
+        y = ops.scale_rows(y, ps, H * W)
+        return ops.batchnorm(sc, _params(self.downsample[1]), tr, relu=True, xb=y)
+
+
+class ClassAttn(nn.Module):
+    """ga_convnext.py:153-187 parameter holder (q from the class token only; k, v from all tokens)."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, dim_embed=128):
+        super().__init__()
+        self.dim_embed, self.num_heads = dim_embed, num_heads
+        self.scale = (dim_embed // num_heads) ** -0.5
+        self.q = nn.Linear(dim, dim_embed, bias=qkv_bias)
+        self.k = nn.Linear(dim, dim_embed, bias=qkv_bias)
+        self.v = nn.Linear(dim, dim_embed, bias=qkv_bias)
+        self.proj = nn.Linear(dim_embed, dim)
+
+
+class GroupConvMlp(nn.Module):
+    """ga_convnext.py:190-222 parameter holder: grouped 1x1 -> act -> channel_shuffle -> grouped 1x1."""
+
+    def __init__(self, in_features, hidden_features, groups):
+        super().__init__()
+        self.groups = groups
+        self.fc1 = nn.Conv2d(in_features, hidden_features, kernel_size=1, bias=True, groups=groups)
+        self.fc2 = nn.Conv2d(hidden_features, in_features, kernel_size=1, bias=True, groups=groups)
+
+    def run(self, t):
+        """t [B, C] fp32 token.  The shuffle is a strided view of the hidden activation (no copy)."""
+        Bn, Cc = t.shape
+        g = self.groups
+        hid = self.fc1.out_channels
+        a3 = t.view(Bn, g, Cc // g).transpose(0, 1)
+        h = ops.grouped_linear(a3, self.fc1.weight.view(g, hid // g, Cc // g), self.fc1.bias, act=ACT_GELU)
+        # channel_shuffle: shuffled[a*(hid/g) + b] = h[b*g + a]  (ga_convnext.py:557-566)
+        a3 = h.view(Bn, hid // g, g).permute(2, 0, 1)
+        return ops.grouped_linear(a3, self.fc2.weight.view(g, Cc // g, hid // g), self.fc2.bias)
+
+
+class LayerScaleBlockClassAttn(nn.Module):
+    """ga_convnext.py:225-248 parameter holder; evaluated branch-batched in GA_ConvNeXt._heads."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4., mlp_block_groups=2, init_values=1e-4, dim_embed=128):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = ClassAttn(dim, num_heads=num_heads, dim_embed=dim_embed)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = GroupConvMlp(dim, int(dim * mlp_ratio), mlp_block_groups)
+        self.gamma_1 = nn.Parameter(init_values * torch.ones(dim))
+        self.gamma_2 = nn.Parameter(init_values * torch.ones(dim))
+
+
+def _init_weights(module):
+    """ga_convnext.py:508-519: trunc_normal(std .02) on every Conv2d / Linear weight, zero bias."""
+    if isinstance(module, (nn.Conv2d, nn.Linear)):
+        nn.init.trunc_normal_(module.weight, std=.02, a=-2., b=2.)
+        if module.bias is not None:
+            nn.init.constant_(module.bias, 0)
+
+
+def _apply_children_first(fn, module):
+    """timm.named_apply(depth_first=True, include_root=False) traversal order."""
+    for child in module.children():
+        _apply_children_first(fn, child)
+        fn(child)
+
+
+class GA_ConvNeXt(nn.Module):
+    """ga_convnext.py:320-505."""
+
+    def __init__(self, in_chans=3, num_classes=1000, output_stride=32, patch_size=4, depths=(3, 3, 9, 3, 1),
+                 dims=(96, 192, 384, 768, 768), ls_init_value=1e-6, conv_mlp=False, head_init_scale=1., norm_layer=None,
+                 drop_rate=0., drop_path_rate=0., branches=5, gram_embedding_gropus=8, dim_embed=128, stage3_naggre=2,
+                 gram_dim=192, gram_layer=True, **unused):
+        super().__init__()
+        assert output_stride == 32 and in_chans == 3 and not conv_mlp and norm_layer is None and gram_layer
+        depths, dims = tuple(depths), tuple(dims)
+        self.num_classes, self.drop_rate = num_classes, drop_rate
+        self.patch_size, self.branches, self.gram_dim = patch_size, branches, gram_dim
+        self.embed_groups, self.naggre, self.dims = gram_embedding_gropus, stage3_naggre, dims
+        self.compute_dtype = None   # None: follow autocast; else torch.float32 / torch.bfloat16
+        self.default_cfg = self.pretrained_cfg = default_cfgs['ga_convnext_tiny']
+
+        self.stem = nn.Sequential(nn.Conv2d(in_chans, dims[0], kernel_size=patch_size, stride=patch_size), LayerNorm2d(dims[0]))
+        dp_rates = [x.tolist() for x in torch.linspace(0, drop_path_rate, sum(depths)).split(depths)]
+        stages, prev = [], dims[0]
+        for i in range(len(dims)):
+            if i == 4:
+                prev = sum(dims[:-1]) + dims[2] * stage3_naggre
+                stages.append(Bottleneck(prev, dims[i] // 4, dims[i], drop_path=drop_path_rate))
+            else:
+                stages.append(ConvNeXtStage(prev, dims[i], stride=2 if i > 0 else 1, depth=depths[i], dp_rates=dp_rates[i],
+                                            ls_init_value=ls_init_value, stage3_naggre=stage3_naggre))
+            prev = dims[i]
+        self.stages = nn.Sequential(*stages)
+        self.num_features = prev
+
+        self.gram_contraction, self.gram_layer = nn.ModuleList(), nn.ModuleList()
+        self.gram_embedding, self.ga, self.fc = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        tri = (gram_dim + 1) * gram_dim // 2
+        for _ in range(branches):
+            self.gram_contraction.append(nn.Sequential(nn.Conv2d(dims[-1], gram_dim, kernel_size=1), nn.BatchNorm2d(gram_dim)))
+            self.gram_layer.append(ConvNeXtStage(gram_dim, gram_dim, stride=1, depth=1, dp_rates=dp_rates[-1],
+                                                 ls_init_value=ls_init_value))
+            self.gram_embedding.append(nn.Sequential(nn.Conv2d(tri, dims[-1], kernel_size=1, groups=gram_embedding_gropus),
+                                                     nn.BatchNorm2d(dims[-1])))
+            self.ga.append(LayerScaleBlockClassAttn(dims[-1], num_heads=8, mlp_block_groups=4, dim_embed=dim_embed))
+            self.fc.append(nn.Linear(dims[-1], num_classes))
+        _apply_children_first(_init_weights, self)
+
+    # -- reference API surface kept for callers -------------------------------------------------------------
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return set()
+
+    def get_classifier(self):
+        return self.fc
+
+    # -- execution ------------------------------------------------------------------------------------------------
+    def _dtype(self, x):
+        if self.compute_dtype is not None:
+            return self.compute_dtype
+        if torch.is_autocast_enabled():
+            dt = torch.get_autocast_gpu_dtype()
+            if dt == torch.float16:
+                warnings.warn('fp16 autocast requested: the sm_100a kernels compute in bf16 (fp32 accumulate) instead', stacklevel=3)
+            return torch.bfloat16
+        return torch.float32
+
+    def forward_features(self, x):
+        """stem -> 4 stages -> aggregation -> Bottleneck (ga_convnext.py:469-485); returns ([B*14*14, C] rows, geom)."""
+        if not x.is_cuda:
+            raise ops.L.GaError('GA_ConvNeXt runs on CUDA (sm_100a) tensors only: there is no CPU path')
+        T = self._dtype(x)
+        Bn, _, H, W = x.shape
+        k = self.patch_size
+        stem_conv, stem_ln = self.stem[0], self.stem[1]
+        with torch.autocast('cuda', enabled=False):
+            rows = ops.stem_patchify(x.float(), k, T)
+            y = ops.linear(rows, stem_conv.weight.permute(0, 2, 3, 1).reshape(stem_conv.out_channels, -1), stem_conv.bias)
+            y = ops.layernorm(y, stem_ln.weight, stem_ln.bias, stem_ln.eps)
+            geom = (Bn, H // k, W // k)
+            feats, taps = [], []
+            for i in range(4):
+                y, geom, t = self.stages[i].run(y, geom)
+                feats.append((y, geom))
+                taps += [(tt, geom) for tt in t]
+            (x0, g0), (x1, g1), (x2, g2), (x3, g3) = feats
+            Ho, Wo = g2[1], g2[2]     # the reference pools to 14 = H/16 at 224 (ga_convnext.py:397); generalised to H/16
+            items = [(g0[1], g0[2], x0.shape[1], 0), (g1[1], g1[2], x1.shape[1], 0)]
+            items += [(g[1], g[2], t.shape[1], 1) for t, g in taps]
+            items += [(g2[1], g2[2], x2.shape[1], 1), (g3[1], g3[2], x3.shape[1], 2)]
+            cat = ops.aggregate((Bn, Ho, Wo, items), [x0, x1, *[t for t, _ in taps], x2, x3])
+            f = self.stages[4].run(cat, (Bn, Ho, Wo))
+        return f, (Bn, Ho, Wo)
+
+    def _heads(self, f, geom):
+        """The `branches` GA heads (ga_convnext.py:491-504).  Token-side work is batched over branches: one shared
+        normalisation of the 196 tokens (norm1's affine folded into k/v), one k/v projection GEMM of width
+        branches*2E and one attention-pooling pass; class-token work ([B, C] rows) stays fp32."""
+        Bn, H, W = geom
+        HW = H * W
+        nb = self.branches
+        tr = self.training
+        Cc = f.shape[1]
+        E = self.ga[0].attn.dim_embed
+        heads = self.ga[0].attn.num_heads
+        fhat = ops.layernorm(f, None, None, self.ga[0].norm1.eps)
+        wkv = torch.cat([torch.cat((g.attn.k.weight, g.attn.v.weight), 0) * g.norm1.weight[None, :] for g in self.ga], 0)
+        bkv = torch.cat([torch.cat((g.attn.k.weight, g.attn.v.weight), 0) @ g.norm1.bias for g in self.ga], 0)
+        kv_tok = ops.linear(fhat, wkv, bkv)                                        # [B*HW, nb*2E]
+        cls, qs, kvcs = [], [], []
+        for k in range(nb):
+            conv, bn = self.gram_contraction[k][0], self.gram_contraction[k][1]
+            g = ops.linear(f, conv.weight.reshape(self.gram_dim, Cc), conv.bias)
+            g = ops.batchnorm(g, _params(bn), tr)
+            g, _, _ = self.gram_layer[k].run(g, geom)
+            gv = ops.gram_vector(g, Bn, HW, float(H))                              # [B, tri] fp32
+            emb, ebn = self.gram_embedding[k][0], self.gram_embedding[k][1]
+            G = self.embed_groups
+            a3 = gv.view(Bn, G, -1).transpose(0, 1)
+            c = ops.grouped_linear(a3, emb.weight.view(G, Cc // G, -1), emb.bias)  # [B, C] fp32
+            c = ops.batchnorm(c, _params(ebn), tr)
+            blk = self.ga[k]
+            cn = ops.layernorm(c, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+            qs.append(ops.linear(cn, blk.attn.q.weight * blk.attn.scale))
+            kvcs.append(ops.linear(cn, torch.cat((blk.attn.k.weight, blk.attn.v.weight), 0)))
+            cls.append(c)
+        q = torch.stack(qs).view(nb, Bn, 1, E)
+        kvc = torch.stack(kvcs).view(nb, Bn, 1, 2 * E)
+        o = ops.attnpool(q, kvc, kv_tok, HW, heads)                                # [nb, B, 1, E]
+        outs = []
+        for k in range(nb):
+            blk = self.ga[k]
+            c = cls[k] + blk.gamma_1 * ops.linear(o[k, :, 0], blk.attn.proj.weight, blk.attn.proj.bias)
+            h = ops.layernorm(c, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+            c = c + blk.gamma_2 * blk.mlp.run(h)
+            outs.append(ops.linear(c, self.fc[k].weight, self.fc[k].bias))
+        return outs
+
+    def forward(self, x):
+        f, geom = self.forward_features(x)
+        with torch.autocast('cuda', enabled=False):
+            return self._heads(f, geom)
+
+
+def _create_convnext(variant, pretrained=False, **kwargs):
+    return build_model_with_cfg(GA_ConvNeXt, variant, pretrained, **kwargs)
+
+
+@register_model
+def ga_convnext_tiny_688(pretrained=False, **kwargs):
+    args = dict(depths=[3, 3, 9, 3, 1], dims=[96, 192, 384, 688, 688], gram_embedding_gropus=8, **kwargs)
+    return _create_convnext('ga_convnext_tiny', pretrained=pretrained, dim_embed=168, stage3_naggre=2, gram_dim=192, **args)
+
+
+@register_model
+def ga_convnext_tiny_768(pretrained=False, **kwargs):
+    args = dict(depths=[3, 3, 9, 3, 1], dims=[96, 192, 384, 768, 768], gram_embedding_gropus=8, **kwargs)
+    return _create_convnext('ga_convnext_tiny', pretrained=pretrained, dim_embed=192, stage3_naggre=2, gram_dim=192, **args)
+
+
+@register_model
+def ga_convnext_small_688(pretrained=False, **kwargs):
+    args = dict(depths=[3, 3, 27, 3, 1], dims=[96, 192, 384, 688, 688], gram_embedding_gropus=8, **kwargs)
+    return _create_convnext('ga_convnext_small', pretrained=pretrained, dim_embed=168, stage3_naggre=4, gram_dim=192, **args)
+
+
+@register_model
+def ga_convnext_small_768(pretrained=False, **kwargs):
+    args = dict(depths=[3, 3, 27, 3, 1], dims=[96, 192, 384, 768, 768], gram_embedding_gropus=8, **kwargs)
+    return _create_convnext('ga_convnext_small', pretrained=pretrained, dim_embed=192, stage3_naggre=4, gram_dim=192, **args)
+
+
+@register_model
+def ga_convnext_base_976(pretrained=False, **kwargs):
+    args = dict(depths=[3, 3, 27, 3, 1], dims=[128, 256, 512, 976, 976], gram_embedding_gropus=8, dim_embed=240,
+                stage3_naggre=4, gram_dim=192, **kwargs)
+    return _create_convnext('ga_convnext_base', pretrained=pretrained, **args)
+
+
+@register_model
+def ga_convnext_base_1024(pretrained=False, **kwargs):
+    args = dict(depths=[3, 3, 27, 3, 1], dims=[128, 256, 512, 1024, 1024], gram_embedding_gropus=8, dim_embed=256,
+                stage3_naggre=4, gram_dim=192, **kwargs)
+    return _create_convnext('ga_convnext_base', pretrained=pretrained, **args)

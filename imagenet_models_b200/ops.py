@@ -1,0 +1,725 @@
+"""Host-side operators over libga_sm100.so: raw kernel wrappers + torch.autograd.Function glue.
+
+Activations are NHWC row matrices [rows, C] (row stride padded to 8 elements when C is not a multiple of 8, so
+TMA can address them) in fp32 or bf16; parameters stay fp32 (the autograd leaves) and are cast / folded into
+operand dtype per call.  Every backward here is hand written and calls the same C ABI -- autograd is only the tape.
+There is no CPU path: every function raises on CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from .lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32
+
+Function = torch.autograd.Function
+
+
+def _L():
+    return L.load()
+
+
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def alloc_rows(rows: int, cols: int, dtype, device) -> torch.Tensor:
+    """[rows, cols] matrix whose row stride is a multiple of 8 elements (16-byte pitch for bf16 TMA)."""
+    ld = pad8(cols)
+    if ld == cols:
+        return torch.empty(rows, cols, dtype=dtype, device=device)
+    return torch.empty(rows, ld, dtype=dtype, device=device)[:, :cols]
+
+
+def rowmat(t: torch.Tensor) -> torch.Tensor:
+    """Accept a 2-D tensor with unit column stride, else make it so."""
+    assert t.dim() == 2
+    return t if t.stride(1) == 1 else t.contiguous()
+
+
+_ws_cache = {}
+
+
+def workspace(n_floats: int, device, tag: str) -> torch.Tensor:
+    """Reusable fp32 scratch (stream-ordered use only; one buffer per tag)."""
+    key = (tag, str(device))
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < n_floats:
+        t = torch.empty(max(int(n_floats), 1 << 16), dtype=torch.float32, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+# ------------------------------------------------------------------------------------------------- raw kernels
+def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None, rowscale=None, rows_per_scale=1,
+         residual=None, zin=None, zmode=ACT_NONE, alpha=1.0, accumulate=False, out_dtype=None, backend=L.BACKEND_AUTO,
+         splits=0):
+    """D[b,m,n] = epi(alpha * sum_k A[b,m,k] * B[b,n,k]);  A:[M,K]|[b,M,K], B:[N,K]|[b,N,K], arbitrary strides.
+
+    A batch stride of 0 (expanded tensor) broadcasts that operand.  `out` may be any strided [.., M, N] view.
+    """
+    batched = A.dim() == 3 or B.dim() == 3
+    A3 = A if A.dim() == 3 else A.unsqueeze(0)
+    B3 = B if B.dim() == 3 else B.unsqueeze(0)
+    nb = max(A3.shape[0], B3.shape[0])
+    M, K = A3.shape[1], A3.shape[2]
+    N = B3.shape[1]
+    assert K == B3.shape[2], (A3.shape, B3.shape)
+    assert A3.dtype == B3.dtype, (A3.dtype, B3.dtype)
+    dev = A.device
+    if not (A.is_cuda and B.is_cuda):
+        raise L.GaError('ga_gemm needs CUDA tensors: there is no CPU path')
+    if out is None:
+        odt = out_dtype or A.dtype
+        out = torch.empty(nb, M, N, dtype=odt, device=dev) if batched else alloc_rows(M, N, odt, dev)
+    D3 = out if out.dim() == 3 else out.unsqueeze(0)
+    assert tuple(D3.shape) == (nb, M, N), (D3.shape, (nb, M, N))
+
+    def bs(t):
+        return t.stride(0) if (t.shape[0] > 1 and nb > 1) else 0
+
+    g = L.GaGemm()
+    g.A, g.a_rs, g.a_cs, g.a_bs = A3.data_ptr(), A3.stride(1), A3.stride(2), bs(A3)
+    g.B, g.b_rs, g.b_cs, g.b_bs = B3.data_ptr(), B3.stride(1), B3.stride(2), bs(B3)
+    g.D, g.ldd, g.d_bs, g.d_cs = D3.data_ptr(), D3.stride(1), bs(D3), D3.stride(2)
+    g.M, g.N, g.K, g.batch = M, N, K, nb
+    g.in_dtype, g.out_dtype = L.dt(A3), L.dt(D3)
+    g.accumulate, g.alpha = int(accumulate), alpha
+    Z = None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.stride(-1) == 1
+        g.bias = bias.data_ptr()
+        g.bias_bs = bias.stride(0) if (bias.dim() == 2 and nb > 1) else 0
+    g.act = act
+    if save_z is not False and save_z is not None:
+        if isinstance(save_z, torch.Tensor):       # caller-provided view with D's shape and strides
+            Z = save_z if save_z.dim() == 3 else save_z.unsqueeze(0)
+            assert Z.stride() == D3.stride() and Z.dtype == D3.dtype
+        else:
+            assert out.is_contiguous() or out.dim() == 2
+            Z = torch.empty_strided(out.shape, out.stride(), dtype=out.dtype, device=dev)
+        g.Z = Z.data_ptr()
+    if colscale is not None:
+        assert colscale.dtype == torch.float32
+        g.colscale = colscale.data_ptr()
+        g.colscale_bs = colscale.stride(0) if (colscale.dim() == 2 and nb > 1) else 0
+    if rowscale is not None:
+        assert rowscale.dtype == torch.float32
+        g.rowscale, g.rows_per_scale = rowscale.data_ptr(), rows_per_scale
+    if residual is not None:
+        R3 = residual if residual.dim() == 3 else residual.unsqueeze(0)
+        assert R3.dtype == D3.dtype and R3.stride(-1) == 1
+        g.R, g.ldr, g.r_bs = R3.data_ptr(), R3.stride(1), bs(R3)
+    if zin is not None:
+        Z3 = zin if zin.dim() == 3 else zin.unsqueeze(0)
+        assert Z3.dtype == D3.dtype and Z3.stride(-1) == 1
+        g.Zin, g.ldz, g.z_bs, g.zmode = Z3.data_ptr(), Z3.stride(1), bs(Z3), zmode
+    g.backend, g.splits = backend, splits
+    L.check(_L().ga_gemm(C.byref(g), L.stream()), 'ga_gemm')
+    return (out, Z) if (save_z is not False and save_z is not None) else out
+
+
+def cast_like(w: torch.Tensor, like_dtype) -> torch.Tensor:
+    """fp32 parameter -> operand dtype (bf16 shadow made by the cast kernel; fp32 passes through)."""
+    if like_dtype == torch.float32:
+        return w
+    w = w if w.is_contiguous() else w.contiguous()
+    o = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    L.check(_L().ga_cast_bf16(L.ptr(w), L.ptr(o), L.ll(w.numel()), L.stream()), 'ga_cast_bf16')
+    return o
+
+
+def scale_matrix(w, rowscale=None, colscale=None, dtype=torch.float32):
+    assert w.is_contiguous() and w.dim() == 2 and w.dtype == torch.float32
+    o = torch.empty(w.shape, dtype=dtype, device=w.device)
+    L.check(_L().ga_scale_matrix(L.ptr(w), L.ptr(rowscale), L.ptr(colscale), L.ptr(o), w.shape[0], w.shape[1],
+                                 BF16 if dtype == torch.bfloat16 else F32, L.stream()), 'ga_scale_matrix')
+    return o
+
+
+def colsum(x: torch.Tensor, sumsq: bool = False):
+    """fp32 column sums (and sums of squares) of a row matrix."""
+    M, Cc = x.shape
+    ld = x.stride(0)
+    if Cc % 4 or ld % 4 or x.stride(1) != 1:   # odd widths: ones-vector GEMM on the generic kernel
+        ones = torch.ones(1, M, dtype=x.dtype, device=x.device)
+        s = gemm(x.t(), ones, out_dtype=torch.float32).reshape(Cc)
+        assert not sumsq
+        return s
+    s = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    q = torch.empty(Cc, dtype=torch.float32, device=x.device) if sumsq else None
+    parts = _L().ga_colstats_parts(L.ll(M), Cc)
+    ws = workspace(parts * 2 * Cc, x.device, 'colstats')
+    L.check(_L().ga_colstats(L.ptr(x), L.ptr(s), L.ptr(q), L.ptr(ws), L.ll(M), Cc, L.ll(ld), 0, L.dt(x), L.stream()),
+            'ga_colstats')
+    return (s, q) if sumsq else s
+
+
+def convert(x: torch.Tensor, dtype) -> torch.Tensor:
+    """Row-matrix dtype conversion through the copy kernel (keeps torch casts off the path)."""
+    if x.dtype == dtype:
+        return x
+    x = rowmat(x)
+    o = alloc_rows(x.shape[0], x.shape[1], dtype, x.device)
+    L.check(_L().ga_copy_cols(L.ptr(x), L.ptr(o), L.ll(x.shape[0]), x.shape[1], L.ll(x.stride(0)), L.ll(o.stride(0)),
+                              L.dt(x), L.dt(o), L.stream()), 'ga_copy_cols')
+    return o
+
+
+def act_bwd(dy, zy, act):
+    dy, zy = rowmat(dy), rowmat(zy)
+    M, N = dy.shape
+    dz = alloc_rows(M, N, dy.dtype, dy.device)
+    if N % 4 == 0:
+        L.check(_L().ga_act_bwd(L.ptr(dy), L.ptr(zy), L.ptr(dz), L.ll(M), N, L.ll(dy.stride(0)), L.ll(zy.stride(0)),
+                                L.ll(dz.stride(0)), act, L.dt(dy), L.stream()), 'ga_act_bwd')
+        return dz
+    raise L.GaError('act_bwd: width must be a multiple of 4')
+
+
+# ------------------------------------------------------------------------------------------------- grouped linear
+class GemmFn(Function):
+    """out[m, g*N + n] = act( sum_k A[g,m,k] * W[g,n,k] + bias[g*N + n] )
+
+    A: [G,M,K] (any strides, may be an expanded / permuted view); W: [G,N,K] fp32 parameter view (contiguous);
+    bias: [G*N] fp32.  Covers nn.Linear, 1x1 / k=s convs on patch rows and grouped 1x1 convs.
+    """
+
+    @staticmethod
+    def forward(ctx, A, W, bias, act, out_dtype):
+        G, M, K = A.shape
+        N = W.shape[1]
+        Wc = cast_like(W, A.dtype)
+        odt = out_dtype or A.dtype
+        out = alloc_rows(M, G * N, odt, A.device)
+        ld = out.stride(0)
+        D3 = out.as_strided((G, M, N), (N, ld, 1), out.storage_offset())
+        b2 = bias.view(G, N) if bias is not None else None
+        z = None
+        if act == ACT_GELU:
+            # the pre-activation is saved through the epilogue into a base with the same row layout as `out`
+            z = alloc_rows(M, G * N, odt, A.device)
+            Z3 = z.as_strided((G, M, N), (N, z.stride(0), 1), z.storage_offset())
+            gemm(A, Wc, D3, bias=b2, act=act, save_z=Z3)
+        else:
+            gemm(A, Wc, D3, bias=b2, act=act)
+        ctx.save_for_backward(A, W, z if z is not None else (out if act == ACT_RELU else None))
+        ctx.act, ctx.has_bias = act, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        A, W, zy = ctx.saved_tensors
+        G, M, K = A.shape
+        N = W.shape[1]
+        dout = rowmat(dout)
+        if dout.dtype != A.dtype:
+            dout = convert(dout, A.dtype)
+        if ctx.act != ACT_NONE:
+            dout = act_bwd(dout, zy, ctx.act)
+        ld = dout.stride(0)
+        dD3 = dout.as_strided((G, M, N), (N, ld, 1), dout.storage_offset())
+        dA = dW = db = None
+        if ctx.needs_input_grad[0]:
+            Wc = cast_like(W, A.dtype)
+            dA = torch.empty(G, M, K, dtype=A.dtype, device=A.device) if (G > 1 or K % 8) else alloc_rows(M, K, A.dtype, A.device).unsqueeze(0)
+            gemm(dD3, Wc.transpose(1, 2), dA)              # dA[g,m,k] = sum_n dD[g,m,n] W[g,n,k]
+        if ctx.needs_input_grad[1]:
+            dW = torch.zeros(G, N, K, dtype=torch.float32, device=A.device)
+            gemm(dD3.transpose(1, 2), A.transpose(1, 2), dW, accumulate=True)   # dW[g,n,k] = sum_m dD[g,m,n] A[g,m,k]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dout)
+        return dA, dW, db, None, None
+
+
+def linear(x2, W, bias=None, act=ACT_NONE, out_dtype=None):
+    """y = act(x W^T + b) on a row matrix x2 [M,K]; W [N,K] fp32."""
+    x2 = rowmat(x2)
+    return GemmFn.apply(x2.unsqueeze(0), W.unsqueeze(0), bias, act, out_dtype)
+
+
+def grouped_linear(A3, W3, bias=None, act=ACT_NONE, out_dtype=None):
+    return GemmFn.apply(A3, W3, bias, act, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------- ConvNeXt block
+class ConvNeXtBlockFn(Function):
+    """dw7x7 -> LN -> fc1 -> GELU -> fc2 -> *gamma -> drop-path -> +x  on NHWC rows  (ga_convnext.py:98-112).
+
+    Kernels: K1 (dwconv+LN -> xhat), GEMM(fc1', bias+GELU, saves z), GEMM(fc2, bias, *gamma, *path, +x).
+    LayerNorm's affine is folded into fc1 (W1' = W1 diag(ln_w), b1' = b1 + W1 ln_b); its gradients are recovered
+    from the fc1 weight-gradient tile (ga_linear_grad_finalize), likewise the layer-scale gradient from fc2's.
+    """
+
+    @staticmethod
+    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, path_scale, geom, train):
+        Bn, H, W_ = geom
+        M, Cc = x.shape
+        assert x.is_contiguous() and M == Bn * H * W_
+        dev, T = x.device, x.dtype
+        lib = _L()
+        w49c = dw_w.reshape(Cc, 49).t().contiguous()
+        xhat = torch.empty(M, Cc, dtype=T, device=dev)
+        rstd = torch.empty(M, dtype=torch.float32, device=dev)
+        L.check(lib.ga_dwconv7_ln_fwd(L.ptr(x), L.ptr(w49c), L.ptr(dw_b), None, None, L.ptr(xhat), L.ptr(rstd), Bn, H, W_, Cc,
+                                      L.f(1e-6), L.dt(x), L.stream()), 'ga_dwconv7_ln_fwd')
+        w1f = scale_matrix(w1, None, ln_w, T)
+        b1f = gemm(ln_b.unsqueeze(0), w1, bias=b1, out_dtype=torch.float32).reshape(-1)
+        if train:
+            a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU, save_z=True)
+        else:
+            a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU), None
+        w2c = cast_like(w2, T)
+        y = gemm(a, w2c, bias=b2, colscale=gamma, rowscale=path_scale, rows_per_scale=H * W_, residual=x)
+        if train:
+            ctx.save_for_backward(x, xhat, rstd, z, a, w49c, ln_w, ln_b, w1, w1f, b1, w2, b2, gamma, path_scale)
+            ctx.geom = geom
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, xhat, rstd, z, a, w49c, ln_w, ln_b, w1, w1f, b1, w2, b2, gamma, path_scale = ctx.saved_tensors
+        Bn, H, W_ = ctx.geom
+        M, Cc = x.shape
+        Hd = w1.shape[0]
+        dev, T = x.device, x.dtype
+        lib = _L()
+        dy = dy.contiguous()
+        dys = dy
+        if path_scale is not None:
+            dys = torch.empty_like(dy)
+            L.check(lib.ga_scale_rows(L.ptr(dy), L.ptr(path_scale), L.ptr(dys), L.ll(M), Cc, H * W_, L.dt(dy), L.stream()),
+                    'ga_scale_rows')
+        # one zeroed slab for every parameter gradient of the block
+        sizes = [49 * Cc, Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, Cc, Cc, Cc * Hd, Hd * Cc]
+        slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, o = [], 0
+        for n in sizes:
+            views.append(slab[o:o + n])
+            o += n
+        d49, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgam, G2, G1 = views
+        # fc2: G2 = dys^T a ; dW2 = gamma*G2 ; db2 = gamma*s2 ; dgamma = rowdot(W2, G2) + b2*s2
+        s2 = colsum(dys)
+        gemm(dys.t(), a.t(), G2.view(Cc, Hd), accumulate=True)
+        L.check(lib.ga_linear_grad_finalize(L.ptr(G2), L.ptr(s2), L.ptr(w2), L.ptr(b2), L.ptr(gamma), None, None, L.ptr(dw2),
+                                            L.ptr(db2), L.ptr(dgam), None, None, Cc, Hd, L.stream()), 'linear_grad_finalize')
+        # dz = (dys . (gamma*W2)) * gelu'(z)
+        w2s = scale_matrix(w2, gamma, None, T)
+        dz = gemm(dys, w2s.t(), zin=z, zmode=ACT_GELU)
+        # fc1: G1 = dz^T xhat ; dW1 = G1*ln_w ; db1 = s1 ; dln_w = coldot(W1, G1) ; dln_b = W1^T s1
+        s1 = colsum(dz)
+        gemm(dz.t(), xhat.t(), G1.view(Hd, Cc), accumulate=True)
+        L.check(lib.ga_linear_grad_finalize(L.ptr(G1), L.ptr(s1), L.ptr(w1), None, None, L.ptr(ln_w), L.ptr(ln_b), L.ptr(dw1), L.ptr(db1),
+                                            None, L.ptr(dlnw), L.ptr(dlnb), Hd, Cc, L.stream()), 'linear_grad_finalize')
+        dxhat = gemm(dz, w1f.t())
+        del dz
+        dconv = torch.empty(M, Cc, dtype=T, device=dev)
+        L.check(lib.ga_ln_bwd_rows(L.ptr(dxhat), L.ptr(xhat), L.ptr(rstd), L.ptr(dconv), L.ll(M), Cc, L.dt(x), L.stream()),
+                'ga_ln_bwd_rows')
+        dx = torch.empty(M, Cc, dtype=T, device=dev)
+        parts = lib.ga_dwconv7_bwd_parts(Bn, H, W_, Cc)
+        ws = workspace(parts * 50 * Cc, dev, 'dwconv')
+        L.check(lib.ga_dwconv7_bwd(L.ptr(dconv), L.ptr(x), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(d49), L.ptr(ddwb), L.ptr(ws),
+                                   Bn, H, W_, Cc, L.dt(x), L.stream()), 'ga_dwconv7_bwd')
+        d_dw_w = d49.view(49, Cc).t().reshape(Cc, 1, 7, 7)
+        return (dx, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None)
+
+
+def convnext_block(x, p, geom, path_scale=None, train=True):
+    """p: dict with conv_dw.weight/bias, norm.weight/bias, mlp.fc1/fc2.weight/bias, gamma (reference key names)."""
+    return ConvNeXtBlockFn.apply(x, p['conv_dw.weight'], p['conv_dw.bias'], p['norm.weight'], p['norm.bias'],
+                                 p['mlp.fc1.weight'], p['mlp.fc1.bias'], p['mlp.fc2.weight'], p['mlp.fc2.bias'], p['gamma'],
+                                 path_scale, geom, train)
+
+
+# ------------------------------------------------------------------------------------------------- LayerNorm rows
+class LayerNormFn(Function):
+    """Row LayerNorm with optional affine (LayerNorm2d on NHWC rows, nn.LayerNorm)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        x = rowmat(x)
+        M, Cc = x.shape
+        y = alloc_rows(M, Cc, x.dtype, x.device)
+        mean = torch.empty(M, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+        L.check(_L().ga_layernorm_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(mean), L.ptr(rstd), L.ll(M), Cc,
+                                      L.ll(x.stride(0)), L.ll(y.stride(0)), L.f(eps), L.dt(x), L.stream()), 'ga_layernorm_fwd')
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        M, Cc = x.shape
+        dy = rowmat(dy)
+        if dy.dtype != x.dtype:
+            dy = convert(dy, x.dtype)
+        dx = alloc_rows(M, Cc, x.dtype, x.device)
+        dw = db = ws = None
+        if w is not None:
+            dwb = torch.zeros(2 * Cc, dtype=torch.float32, device=x.device)
+            dw, db = dwb[:Cc], dwb[Cc:]
+            ws = workspace(_L().ga_layernorm_bwd_parts(L.ll(M), Cc) * 2 * Cc, x.device, 'ln')
+        L.check(_L().ga_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(dw), L.ptr(db),
+                                      L.ptr(ws), L.ll(M), Cc, L.ll(dy.stride(0)), L.ll(x.stride(0)), L.ll(dx.stride(0)),
+                                      L.dt(x), L.stream()), 'ga_layernorm_bwd')
+        return dx, dw, db, None
+
+
+def layernorm(x, w, b, eps):
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+# ------------------------------------------------------------------------------------------------- patch gathers
+class PatchifyFn(Function):
+    @staticmethod
+    def forward(ctx, x, geom, k):
+        Bn, H, W_, Cc = geom
+        x = x.contiguous()
+        y = torch.empty(Bn * (H // k) * (W_ // k), k * k * Cc, dtype=x.dtype, device=x.device)
+        L.check(_L().ga_patchify(L.ptr(x), L.ptr(y), Bn, H, W_, Cc, k, 0, L.dt(x), L.stream()), 'ga_patchify')
+        ctx.geom, ctx.k = geom, k
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        Bn, H, W_, Cc = ctx.geom
+        dy = dy.contiguous()
+        dx = torch.empty(Bn * H * W_, Cc, dtype=dy.dtype, device=dy.device)
+        L.check(_L().ga_patchify(L.ptr(dy), L.ptr(dx), Bn, H, W_, Cc, ctx.k, 1, L.dt(dy), L.stream()), 'ga_patchify')
+        return dx, None, None
+
+
+def patchify(x, geom, k):
+    return PatchifyFn.apply(x, geom, k)
+
+
+def stem_patchify(img: torch.Tensor, k: int, dtype) -> torch.Tensor:
+    """NCHW fp32 image batch -> patch rows (no gradient: the image is a leaf)."""
+    Bn, Cin, H, W_ = img.shape
+    assert Cin == 3 and img.dtype == torch.float32
+    y = torch.empty(Bn * (H // k) * (W_ // k), k * k * 3, dtype=dtype, device=img.device)
+    sb, sc, sy, sx = img.stride()
+    L.check(_L().ga_stem_patchify(L.ptr(img), L.ptr(y), Bn, H, W_, k, L.ll(sb), L.ll(sc), L.ll(sy), L.ll(sx),
+                                  BF16 if dtype == torch.bfloat16 else F32, L.stream()), 'ga_stem_patchify')
+    return y
+
+
+class Im2col3Fn(Function):
+    @staticmethod
+    def forward(ctx, x, geom):
+        Bn, H, W_ = geom
+        x = rowmat(x)
+        Cc = x.shape[1]
+        y = alloc_rows(x.shape[0], 9 * Cc, x.dtype, x.device)
+        L.check(_L().ga_im2col3(L.ptr(x), L.ptr(y), Bn, H, W_, Cc, L.ll(x.stride(0)), L.ll(y.stride(0)), 0, L.dt(x), L.stream()),
+                'ga_im2col3')
+        ctx.geom, ctx.Cc = geom, Cc
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        Bn, H, W_ = ctx.geom
+        dy = rowmat(dy)
+        dx = alloc_rows(dy.shape[0], ctx.Cc, dy.dtype, dy.device)
+        L.check(_L().ga_im2col3(L.ptr(dy), L.ptr(dx), Bn, H, W_, ctx.Cc, L.ll(dy.stride(0)), L.ll(dx.stride(0)), 1, L.dt(dy),
+                                L.stream()), 'ga_im2col3')
+        return dx, None
+
+
+def im2col3(x, geom):
+    return Im2col3Fn.apply(x, geom)
+
+
+# ------------------------------------------------------------------------------------------------- BatchNorm
+def _bn_stats(x, w, b, rm, rv, training, momentum, eps):
+    M, Cc = x.shape
+    dev = x.device
+    st = torch.empty(4, Cc, dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
+    s = q = None
+    if training:
+        s, q = colsum(x, sumsq=True)
+    L.check(_L().ga_bn_finalize(L.ptr(s), L.ptr(q), L.ptr(w), L.ptr(b), L.ptr(rm), L.ptr(rv), L.ptr(st[0]), L.ptr(st[1]),
+                                L.ptr(st[2]), L.ptr(st[3]), L.ll(M), Cc, L.f(momentum), L.f(eps), int(training), L.stream()),
+            'ga_bn_finalize')
+    return st
+
+
+class BatchNormFn(Function):
+    """y = act(BN(x)) (+ optional second BN branch: y = act(BN_a(xa) + BN_b(xb)), the Bottleneck merge)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, rm, rv, xb, wb, bb, rmb, rvb, training, momentum, eps, relu):
+        x = rowmat(x)
+        M, Cc = x.shape
+        assert Cc % 4 == 0
+        st = _bn_stats(x, w, b, rm, rv, training, momentum, eps)
+        stb = None
+        y = alloc_rows(M, Cc, x.dtype, x.device)
+        if xb is not None:
+            xb = rowmat(xb)
+            if wb is not None:                     # second BN branch; else xb is a plain residual
+                stb = _bn_stats(xb, wb, bb, rmb, rvb, training, momentum, eps)
+        L.check(_L().ga_affine_act(L.ptr(x), L.ptr(st[2]), L.ptr(st[3]), L.ptr(xb), L.ptr(stb[2]) if stb is not None else None,
+                                   L.ptr(stb[3]) if stb is not None else None, L.ptr(y), L.ll(M), Cc, L.ll(x.stride(0)),
+                                   L.ll(xb.stride(0)) if xb is not None else L.ll(0), L.ll(y.stride(0)),
+                                   ACT_RELU if relu else ACT_NONE, L.dt(x), L.stream()), 'ga_affine_act')
+        ctx.save_for_backward(x, st, xb, stb, y if relu else None)
+        ctx.training, ctx.relu = training, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, st, xb, stb, y = ctx.saved_tensors
+        dy = rowmat(dy)
+        if dy.dtype != x.dtype:
+            dy = convert(dy, x.dtype)
+        outs = []
+        for xi, sti in ((x, st), (xb, stb)):
+            if xi is None:
+                outs += [None, None, None]
+                continue
+            if sti is None:                        # plain residual input: gradient is the (ReLU-masked) dy
+                outs += [act_bwd(dy, y, ACT_RELU) if ctx.relu else dy, None, None]
+                continue
+            M, Cc = xi.shape
+            cc = torch.empty(2, Cc, dtype=torch.float32, device=xi.device)
+            parts = _L().ga_colstats_parts(L.ll(M), Cc)
+            ws = workspace(parts * 2 * Cc, xi.device, 'colstats')
+            L.check(_L().ga_bn_bwd_reduce(L.ptr(dy), L.ptr(xi), L.ptr(y), L.ptr(sti[0]), L.ptr(sti[1]), L.ptr(cc[0]), L.ptr(cc[1]),
+                                          L.ptr(ws), L.ll(M), Cc, L.ll(dy.stride(0)), L.ll(xi.stride(0)),
+                                          L.ll(y.stride(0)) if y is not None else L.ll(0), int(ctx.relu), L.dt(xi), L.stream()),
+                    'ga_bn_bwd_reduce')
+            dx = alloc_rows(M, Cc, xi.dtype, xi.device)
+            L.check(_L().ga_bn_bwd_apply(L.ptr(dy), L.ptr(xi), L.ptr(y), L.ptr(sti[0]), L.ptr(sti[1]), L.ptr(sti[2]),
+                                         L.ptr(cc[0]) if ctx.training else None, L.ptr(cc[1]) if ctx.training else None, L.ptr(dx),
+                                         L.ll(M), Cc, L.ll(dy.stride(0)), L.ll(xi.stride(0)),
+                                         L.ll(y.stride(0)) if y is not None else L.ll(0), L.ll(dx.stride(0)), int(ctx.relu),
+                                         L.dt(xi), L.stream()), 'ga_bn_bwd_apply')
+            outs += [dx, cc[1], cc[0]]
+        dxa, dwa, dba, dxb, dwb, dbb = outs
+        return dxa, dwa, dba, None, None, dxb, dwb, dbb, None, None, None, None, None, None
+
+
+class ScaleRowsFn(Function):
+    """y[r,:] = x[r,:] * scale[r // rows_per_scale]  (DropPath on a residual branch)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, rows_per_scale):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        L.check(_L().ga_scale_rows(L.ptr(x), L.ptr(scale), L.ptr(y), L.ll(x.shape[0]), x.shape[1], rows_per_scale, L.dt(x),
+                                   L.stream()), 'ga_scale_rows')
+        ctx.save_for_backward(scale)
+        ctx.rps = rows_per_scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        L.check(_L().ga_scale_rows(L.ptr(dy), L.ptr(scale), L.ptr(dx), L.ll(dy.shape[0]), dy.shape[1], ctx.rps, L.dt(dy),
+                                   L.stream()), 'ga_scale_rows')
+        return dx, None, None
+
+
+def scale_rows(x, scale, rows_per_scale):
+    return ScaleRowsFn.apply(x, scale, rows_per_scale)
+
+
+def batchnorm(x, bn, training, relu=False, xb=None, bnb=None):
+    """bn / bnb: dicts with weight, bias, running_mean, running_var, num_batches_tracked (reference key names)."""
+    if training:
+        bn['num_batches_tracked'].add_(1)
+        if bnb is not None:
+            bnb['num_batches_tracked'].add_(1)
+    return BatchNormFn.apply(x, bn['weight'], bn['bias'], bn['running_mean'], bn['running_var'], xb,
+                             bnb['weight'] if bnb else None, bnb['bias'] if bnb else None,
+                             bnb['running_mean'] if bnb else None, bnb['running_var'] if bnb else None,
+                             training, 0.1, 1e-5, relu)
+
+
+# ------------------------------------------------------------------------------------------------- aggregation
+class AggregateFn(Function):
+    """Multi-scale concat (ga_convnext.py:479-483): each source is resampled straight into its channel slice."""
+
+    @staticmethod
+    def forward(ctx, spec, *srcs):
+        # spec: (B, Ho, Wo, [(Hs, Ws, C, mode), ...])
+        Bn, Ho, Wo, items = spec
+        total = sum(it[2] for it in items)
+        T, dev = srcs[0].dtype, srcs[0].device
+        dst = torch.empty(Bn * Ho * Wo, total, dtype=T, device=dev)
+        off = 0
+        for (Hs, Ws, Cc, mode), s in zip(items, srcs):
+            s = s.contiguous()
+            L.check(_L().ga_aggregate(L.ptr(s), L.ptr(dst), Bn, Hs, Ws, Cc, Ho, Wo, L.ll(total), off, mode, 0, L.dt(dst), L.stream()),
+                    'ga_aggregate')
+            off += Cc
+        ctx.spec = spec
+        return dst
+
+    @staticmethod
+    def backward(ctx, ddst):
+        Bn, Ho, Wo, items = ctx.spec
+        ddst = ddst.contiguous()
+        total = ddst.shape[1]
+        grads, off = [], 0
+        for (Hs, Ws, Cc, mode) in items:
+            d = torch.empty(Bn * Hs * Ws, Cc, dtype=ddst.dtype, device=ddst.device)
+            L.check(_L().ga_aggregate(L.ptr(d), L.ptr(ddst), Bn, Hs, Ws, Cc, Ho, Wo, L.ll(total), off, mode, 1, L.dt(ddst),
+                                      L.stream()), 'ga_aggregate')
+            grads.append(d)
+            off += Cc
+        return (None, *grads)
+
+
+def aggregate(spec, srcs):
+    return AggregateFn.apply(spec, *srcs)
+
+
+# ------------------------------------------------------------------------------------------------- SE gate
+class SEFn(Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, Bn, HW):
+        x = rowmat(x)
+        Cc, R = x.shape[1], w1.shape[0]
+        dev = x.device
+        y = alloc_rows(x.shape[0], Cc, x.dtype, dev)
+        pooled = torch.empty(Bn, Cc, dtype=torch.float32, device=dev)
+        hidden = torch.empty(Bn, R, dtype=torch.float32, device=dev)
+        gate = torch.empty(Bn, Cc, dtype=torch.float32, device=dev)
+        w1m, w2m = w1.reshape(R, Cc), w2.reshape(Cc, R)
+        L.check(_L().ga_se_fwd(L.ptr(x), L.ptr(w1m), L.ptr(b1), L.ptr(w2m), L.ptr(b2), L.ptr(y), L.ptr(pooled), L.ptr(hidden),
+                               L.ptr(gate), Bn, HW, Cc, R, L.ll(x.stride(0)), L.ll(y.stride(0)), L.dt(x), L.stream()), 'ga_se_fwd')
+        ctx.save_for_backward(x, w1m, w2m, pooled, hidden, gate)
+        ctx.dims = (Bn, HW, Cc, R, w1.shape, w2.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1m, w2m, pooled, hidden, gate = ctx.saved_tensors
+        Bn, HW, Cc, R, w1s, w2s = ctx.dims
+        dy = rowmat(dy)
+        dev = x.device
+        dx = alloc_rows(x.shape[0], Cc, x.dtype, dev)
+        dpre2 = torch.empty(Bn, Cc, dtype=torch.float32, device=dev)
+        dh = torch.empty(Bn, R, dtype=torch.float32, device=dev)
+        L.check(_L().ga_se_bwd(L.ptr(dy), L.ptr(x), L.ptr(w1m), L.ptr(w2m), L.ptr(hidden), L.ptr(gate), L.ptr(dx), L.ptr(dpre2),
+                               L.ptr(dh), Bn, HW, Cc, R, L.ll(dy.stride(0)), L.ll(x.stride(0)), L.ll(dx.stride(0)), L.dt(x),
+                               L.stream()), 'ga_se_bwd')
+        dw2 = gemm(dpre2.t(), hidden.t())      # [C,R] = sum_b dpre2[b,c] hidden[b,r]
+        dw1 = gemm(dh.t(), pooled.t())         # [R,C]
+        return dx, dw1.reshape(w1s), colsum(dh), dw2.reshape(w2s), colsum(dpre2), None, None
+
+
+def se_gate(x, w1, b1, w2, b2, Bn, HW):
+    return SEFn.apply(x, w1, b1, w2, b2, Bn, HW)
+
+
+# ------------------------------------------------------------------------------------------------- Gram vector
+class GramFn(Function):
+    """get_gram (ga_convnext.py:452-467): x/div -> X X^T / HW -> row-major upper triangle -> L2 normalise -> fp32."""
+
+    @staticmethod
+    def forward(ctx, x, Bn, HW, div):
+        x = x.contiguous()
+        Cc = x.shape[1]
+        dev = x.device
+        X3 = x.view(Bn, HW, Cc).transpose(1, 2)            # [B, C, HW]: (m=i, k=p)
+        alpha = 1.0 / (div * div * HW)
+        G = torch.empty(Bn, Cc, Cc, dtype=torch.float32, device=dev)
+        gemm(X3, X3, G, alpha=alpha)
+        tri = Cc * (Cc + 1) // 2
+        out = torch.empty(Bn, tri, dtype=torch.float32, device=dev)
+        norm = torch.empty(Bn, dtype=torch.float32, device=dev)
+        L.check(_L().ga_gram_triu_fwd(L.ptr(G), L.ptr(out), L.ptr(norm), Bn, Cc, tri, tri, L.ll(tri), F32, L.stream()),
+                'ga_gram_triu_fwd')
+        ctx.save_for_backward(x, out, norm)
+        ctx.dims = (Bn, HW, Cc, alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, out, norm = ctx.saved_tensors
+        Bn, HW, Cc, alpha = ctx.dims
+        dout = dout.contiguous().float()
+        tri = out.shape[1]
+        S = torch.empty(Bn, Cc, Cc, dtype=x.dtype, device=x.device)
+        L.check(_L().ga_gram_triu_bwd(L.ptr(dout), L.ptr(out), L.ptr(norm), L.ptr(S), Bn, Cc, tri, tri, L.ll(tri), F32, L.dt(S),
+                                      L.stream()), 'ga_gram_triu_bwd')
+        dx = torch.empty(Bn * HW, Cc, dtype=x.dtype, device=x.device)
+        gemm(x.view(Bn, HW, Cc), S, dx.view(Bn, HW, Cc), alpha=alpha)   # dX = alpha * X (dG + dG^T)
+        return dx, None, None, None
+
+
+def gram_vector(x, Bn, HW, div):
+    return GramFn.apply(x, Bn, HW, div)
+
+
+# ------------------------------------------------------------------------------------------------- attention pooling
+class AttnPoolFn(Function):
+    """Class attention for nb branches at once: q [nb,B,Q,E] fp32 (pre-scaled), kv_cls [nb,B,Q,2E] fp32,
+    kv_tok [B*N, nb*2E] (branch k owns columns [k*2E, (k+1)*2E)).  -> out [nb,B,Q,E] fp32."""
+
+    @staticmethod
+    def forward(ctx, q, kv_cls, kv_tok, N, H):
+        nb, Bn, Q, E = q.shape
+        q, kv_cls, kv_tok = q.contiguous(), kv_cls.contiguous(), rowmat(kv_tok)
+        dev = q.device
+        out = torch.empty(nb, Bn, Q, E, dtype=torch.float32, device=dev)
+        attn = torch.empty(nb, Bn, H, Q, Q + N, dtype=torch.float32, device=dev)
+        for k in range(nb):
+            L.check(_L().ga_attnpool_fwd(L.ptr(q[k]), L.ptr(kv_cls[k]), L.ptr(kv_tok[:, k * 2 * E:]), L.ptr(out[k]), L.ptr(attn[k]),
+                                         Bn, Q, N, H, E, L.ll(kv_tok.stride(0)), L.dt(kv_tok), L.stream()), 'ga_attnpool_fwd')
+        ctx.save_for_backward(q, kv_cls, kv_tok, attn)
+        ctx.dims = (N, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv_cls, kv_tok, attn = ctx.saved_tensors
+        N, H = ctx.dims
+        nb, Bn, Q, E = q.shape
+        dout = dout.contiguous()
+        dq = torch.empty_like(q)
+        dkvc = torch.empty_like(kv_cls)
+        dkvt = alloc_rows(kv_tok.shape[0], kv_tok.shape[1], kv_tok.dtype, kv_tok.device)
+        for k in range(nb):
+            L.check(_L().ga_attnpool_bwd(L.ptr(dout[k]), L.ptr(q[k]), L.ptr(kv_cls[k]), L.ptr(kv_tok[:, k * 2 * E:]), L.ptr(attn[k]),
+                                         L.ptr(dq[k]), L.ptr(dkvc[k]), L.ptr(dkvt[:, k * 2 * E:]), Bn, Q, N, H, E,
+                                         L.ll(kv_tok.stride(0)), L.ll(dkvt.stride(0)), L.dt(kv_tok), L.stream()), 'ga_attnpool_bwd')
+        return dq, dkvc, dkvt, None, None
+
+
+def attnpool(q, kv_cls, kv_tok, N, H):
+    return AttnPoolFn.apply(q, kv_cls, kv_tok, N, H)
+
+
+# ------------------------------------------------------------------------------------------------- loss
+class GALossFn(Function):
+    """sum_k CE(out_k, y) + lam * sum_k KL_mean(logsm(out_k) || logsm(mean out).detach())  (GA/train.py:735-745)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, lam):
+        nb, Bn, ncls = logits.shape
+        logits = logits.contiguous().float()
+        loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        dl = torch.empty_like(logits)
+        L.check(_L().ga_loss_fwd_bwd(L.ptr(logits), L.ptr(target), L.ptr(loss), L.ptr(dl), nb, Bn, ncls, L.f(lam), L.f(1.0),
+                                     L.stream()), 'ga_loss_fwd_bwd')
+        ctx.save_for_backward(dl)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None
+
+
+def ga_loss(logits, target, lam):
+    return GALossFn.apply(logits, target, lam)

@@ -1,0 +1,385 @@
+"""GPU: every kernel of libga_sm100.so through the C ABI against a plain PyTorch fp32 restatement of the same op.
+
+Tolerances: fp32 path 1e-5 relative (L2), bf16 path 2e-2 relative (north_star).  Shapes include the awkward widths
+of ga_convnext_tiny_688 (688, 172, 168, 2128) and ragged tails.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from imagenet_models_b200 import lib as L  # noqa: E402
+from imagenet_models_b200 import ops  # noqa: E402
+
+DEV = 'cuda'
+torch.backends.cuda.matmul.allow_tf32 = False
+torch.backends.cudnn.allow_tf32 = False
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def tol(dtype):
+    return 1e-5 if dtype == torch.float32 else 1.2e-2
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 384, 96), (300, 200, 200), (1000, 96, 384), (77, 688, 172), (513, 172, 2128),
+                                   (64, 1000, 688), (130, 64, 48)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gemm_plain(M, N, K, dtype):
+    A, B = rnd(M, K, dtype=dtype, seed=1), rnd(N, K, dtype=dtype, seed=2)
+    D = ops.gemm(A, B)
+    ref = A.float() @ B.float().t()
+    assert rel(D.float(), ref) < tol(dtype)
+    if dtype == torch.bfloat16 and K % 8 == 0:
+        assert L.load().ga_gemm_last_backend() == L.BACKEND_TCGEN05
+
+
+@pytest.mark.parametrize('a_mn,b_mn', [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (384, 96, 1000), (200, 344, 304), (96, 384, 4096)])
+def test_gemm_tc_majors(a_mn, b_mn, M, N, K):
+    """MN-major operands (weight-gradient / data-gradient GEMMs read activations and weights in place)."""
+    dtype = torch.bfloat16
+    A = rnd(K, M, dtype=dtype, seed=3).t() if a_mn else rnd(M, K, dtype=dtype, seed=3)
+    B = rnd(K, N, dtype=dtype, seed=4).t() if b_mn else rnd(N, K, dtype=dtype, seed=4)
+    D = ops.gemm(A, B, out_dtype=torch.float32)
+    assert L.load().ga_gemm_last_backend() == L.BACKEND_TCGEN05
+    ref = A.float() @ B.float().t()
+    assert rel(D, ref) < 1e-2 * 0.2   # fp32 output of bf16 products: only accumulation-order error
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gemm_epilogues(dtype):
+    M, N, K = 392, 384, 96
+    A, B = rnd(M, K, dtype=dtype, seed=5), rnd(N, K, dtype=dtype, seed=6, scale=0.2)
+    bias, gam = rnd(N, seed=7), rnd(N, seed=8)
+    R = rnd(M, N, dtype=dtype, seed=9)
+    rs = torch.tensor([1.25, 0.0], device=DEV)
+    y, z = ops.gemm(A, B, bias=bias, act=L.ACT_GELU, save_z=True)
+    zr = A.float() @ B.float().t() + bias
+    assert rel(z.float(), zr) < tol(dtype) and rel(y.float(), F.gelu(zr)) < tol(dtype)
+    y2 = ops.gemm(A, B, bias=bias, colscale=gam, rowscale=rs, rows_per_scale=196, residual=R)
+    ref2 = zr * gam * rs.repeat_interleave(196)[:, None] + R.float()
+    assert rel(y2.float(), ref2) < tol(dtype)
+    # dgrad epilogue: acc * gelu'(Zin)
+    zin = rnd(M, N, dtype=dtype, seed=10)
+    y3 = ops.gemm(A, B, zin=zin, zmode=L.ACT_GELU)
+    zz = zin.float().requires_grad_(True)
+    F.gelu(zz).sum().backward()
+    assert rel(y3.float(), (A.float() @ B.float().t()) * zz.grad) < tol(dtype)
+    y4 = ops.gemm(A, B, bias=bias, act=L.ACT_RELU)
+    assert rel(y4.float(), F.relu(zr)) < tol(dtype)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gemm_wgrad_splitk_accumulate(dtype):
+    T_, N, K = 5000, 384, 96      # dW[n,k] = sum_t dY[t,n] X[t,k]
+    dY, X = rnd(T_, N, dtype=dtype, seed=11), rnd(T_, K, dtype=dtype, seed=12)
+    dW = torch.zeros(N, K, device=DEV)
+    ops.gemm(dY.t(), X.t(), dW, accumulate=True)
+    ref = dY.float().t() @ X.float()
+    assert rel(dW, ref) < (1e-5 if dtype == torch.float32 else 2e-3)
+    ops.gemm(dY.t(), X.t(), dW, accumulate=True)     # accumulates on top
+    assert rel(dW, 2 * ref) < (1e-5 if dtype == torch.float32 else 2e-3)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gemm_batched_and_strided(dtype):
+    # Gram: per-image X^T X from NHWC rows
+    Bn, HW, Cc = 3, 196, 192
+    x = rnd(Bn * HW, Cc, dtype=dtype, seed=13)
+    X3 = x.view(Bn, HW, Cc).transpose(1, 2)
+    G = torch.empty(Bn, Cc, Cc, device=DEV)
+    ops.gemm(X3, X3, G, alpha=0.5)
+    ref = 0.5 * torch.bmm(X3.float(), X3.float().transpose(1, 2))
+    assert rel(G, ref) < (1e-5 if dtype == torch.float32 else 2e-3)
+    # grouped 1x1 conv with a channel-shuffled (strided-K) operand and an interleaved output
+    Bm, Gp, Kc, Nc = 16, 4, 688, 172
+    h = rnd(Bm, Gp * Kc, dtype=dtype, seed=14)
+    W = rnd(Gp, Nc, Kc, dtype=dtype, seed=15, scale=0.1)
+    A3 = h.view(Bm, Kc, Gp).permute(2, 0, 1)
+    out = torch.empty(Bm, Gp * Nc, dtype=dtype, device=DEV)
+    D3 = out.as_strided((Gp, Bm, Nc), (Nc, Gp * Nc, 1))
+    ops.gemm(A3, W, D3)
+    ref = torch.einsum('gmk,gnk->mgn', A3.float(), W.float()).reshape(Bm, Gp * Nc)
+    assert rel(out.float(), ref) < tol(dtype)
+
+
+def test_gemm_rejects_cpu():
+    with pytest.raises(L.GaError):
+        ops.gemm(torch.zeros(4, 4), torch.zeros(4, 4).cuda())
+
+
+# ------------------------------------------------------------------------------------------------- K1 dwconv + LN
+@pytest.mark.parametrize('Bn,H,Cc', [(2, 56, 96), (2, 28, 192), (3, 14, 384), (2, 7, 688), (2, 14, 192), (1, 9, 32), (2, 14, 128)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_dwconv_ln_fwd_bwd(Bn, H, Cc, dtype):
+    x = rnd(Bn * H * H, Cc, dtype=dtype, seed=20)
+    w = rnd(Cc, 1, 7, 7, seed=21, scale=0.15)
+    b = rnd(Cc, seed=22, scale=0.1)
+    w49c = w.reshape(Cc, 49).t().contiguous()
+    xhat = torch.empty_like(x)
+    rstd = torch.empty(Bn * H * H, device=DEV)
+    lib = L.load()
+    L.check(lib.ga_dwconv7_ln_fwd(L.ptr(x), L.ptr(w49c), L.ptr(b), None, None, L.ptr(xhat), L.ptr(rstd), Bn, H, H, Cc, L.f(1e-6),
+                                  L.dt(x), L.stream()), 'fwd')
+    xr = x.float().view(Bn, H, H, Cc).permute(0, 3, 1, 2)
+    conv = F.conv2d(xr, w, b, padding=3, groups=Cc).permute(0, 2, 3, 1).reshape(-1, Cc)
+    ref = F.layer_norm(conv, (Cc,), None, None, 1e-6)
+    assert rel(xhat.float(), ref) < tol(dtype)
+    var = conv.var(dim=1, unbiased=False)
+    assert rel(rstd, torch.rsqrt(var + 1e-6)) < (1e-5 if dtype == torch.float32 else 1e-2)
+    # backward pieces: dgrad (+residual) and wgrad
+    dconv = rnd(Bn * H * H, Cc, dtype=dtype, seed=23)
+    dres = rnd(Bn * H * H, Cc, dtype=dtype, seed=24)
+    dx = torch.empty_like(x)
+    d49 = torch.zeros(49, Cc, device=DEV)
+    db = torch.zeros(Cc, device=DEV)
+    ws = torch.empty(lib.ga_dwconv7_bwd_parts(Bn, H, H, Cc) * 50 * Cc, device=DEV)
+    L.check(lib.ga_dwconv7_bwd(L.ptr(dconv), L.ptr(x), L.ptr(dres), L.ptr(w49c), L.ptr(dx), L.ptr(d49), L.ptr(db), L.ptr(ws), Bn, H,
+                               H, Cc, L.dt(x), L.stream()), 'bwd')
+    xg = xr.clone().requires_grad_(True)
+    wg = w.clone().requires_grad_(True)
+    bg = b.clone().requires_grad_(True)
+    out = F.conv2d(xg, wg, bg, padding=3, groups=Cc)
+    out.backward(dconv.float().view(Bn, H, H, Cc).permute(0, 3, 1, 2))
+    dx_ref = xg.grad.permute(0, 2, 3, 1).reshape(-1, Cc) + dres.float()
+    assert rel(dx.float(), dx_ref) < tol(dtype)
+    assert rel(d49, wg.grad.reshape(Cc, 49).t()) < (2e-5 if dtype == torch.float32 else 5e-3)
+    assert rel(db, bg.grad) < (2e-5 if dtype == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize('cname', ['c32_h9', 'c96_h14', 'c192_h14', 'c688_h7'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_convnext_block_vs_golden(cname, dtype, golden_dir):
+    """Whole ConvNeXtBlock fwd+bwd through the autograd Function against the REFERENCE's outputs (tests/golden)."""
+    import os
+    from oracle import cases
+    g = torch.load(os.path.join(golden_dir, 'ga_convnext_modules.pt'))[cname]
+    Cc, H, Bn = cases.BLOCK_CASES[cname]
+    P = {k: v.to(DEV).requires_grad_(True) for k, v in cases.block_state(Cc).items()}
+    x, dy = cases.block_inputs(Cc, H, Bn)
+    xr = x.to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc).to(dtype).contiguous().requires_grad_(True)
+    y = ops.convnext_block(xr, P, (Bn, H, H), None, True)
+    y.backward(dy.to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc).to(dtype))
+    t = 2e-5 if dtype == torch.float32 else 2e-2
+    yref = g['y'].to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc)
+    dxref = g['dx'].to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc)
+    assert rel(y.float(), yref) < t
+    assert rel(xr.grad.float(), dxref) < t
+    for k, d in g['grads'].items():
+        assert cases.digest_close(P[k].grad, d, t * (1 if dtype == torch.float32 else 1.5), 1e-5), k
+
+
+# ------------------------------------------------------------------------------------------------- rows / columns
+@pytest.mark.parametrize('M,Cc', [(1000, 96), (333, 688), (50, 2048), (64, 1536)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_layernorm_fwd_bwd(M, Cc, dtype):
+    x = rnd(M, Cc, dtype=dtype, seed=30).requires_grad_(True)
+    w = (rnd(Cc, seed=31) * 0.2 + 1).requires_grad_(True)
+    b = rnd(Cc, seed=32).requires_grad_(True)
+    dy = rnd(M, Cc, dtype=dtype, seed=33)
+    y = ops.layernorm(x, w, b, 1e-6)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (Cc,), wr, br, 1e-6)
+    yr.backward(dy.float())
+    t = tol(dtype)
+    assert rel(y.float(), yr) < t and rel(x.grad.float(), xr.grad) < t
+    assert rel(w.grad, wr.grad) < (2e-5 if dtype == torch.float32 else 5e-3)
+    assert rel(b.grad, br.grad) < (2e-5 if dtype == torch.float32 else 5e-3)
+
+
+@pytest.mark.parametrize('relu', [False, True])
+@pytest.mark.parametrize('training', [True, False])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_batchnorm(relu, training, dtype):
+    M, Cc = 784, 172
+    xp = ops.alloc_rows(M, Cc, dtype, DEV)
+    xp.copy_(rnd(M, Cc, dtype=dtype, seed=40) * 1.5 + 0.3)
+    x = xp.detach().requires_grad_(True)
+    bn = {'weight': (rnd(Cc, seed=41) * 0.2 + 1).requires_grad_(True), 'bias': rnd(Cc, seed=42).requires_grad_(True),
+          'running_mean': rnd(Cc, seed=43) * 0.1, 'running_var': rnd(Cc, seed=44).abs() + 0.5,
+          'num_batches_tracked': torch.zeros((), dtype=torch.long, device=DEV)}
+    rm0, rv0 = bn['running_mean'].clone(), bn['running_var'].clone()
+    dy = rnd(M, Cc, dtype=dtype, seed=45)
+    y = ops.batchnorm(x, bn, training, relu=relu)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    wr, br = bn['weight'].detach().clone().requires_grad_(True), bn['bias'].detach().clone().requires_grad_(True)
+    rm, rv = rm0.clone(), rv0.clone()
+    yr = F.batch_norm(xr, rm, rv, wr, br, training, 0.1, 1e-5)
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(dy.float())
+    t = tol(dtype)
+    assert rel(y.float(), yr) < t
+    assert rel(x.grad.float(), xr.grad) < (t if dtype == torch.float32 else 3e-2)
+    assert rel(bn['weight'].grad, wr.grad) < (5e-5 if dtype == torch.float32 else 1e-2)
+    assert rel(bn['bias'].grad, br.grad) < (5e-5 if dtype == torch.float32 else 1e-2)
+    if training:
+        assert rel(bn['running_mean'], rm) < (1e-5 if dtype == torch.float32 else 1e-2)
+        assert rel(bn['running_var'], rv) < (1e-5 if dtype == torch.float32 else 1e-2)
+        assert int(bn['num_batches_tracked']) == 1
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_patchify_im2col_aggregate(dtype):
+    Bn, H, Cc = 2, 28, 96
+    x = rnd(Bn * H * H, Cc, dtype=dtype, seed=50).requires_grad_(True)
+    p = ops.patchify(x, (Bn, H, H, Cc), 2)
+    xr = x.detach().float().view(Bn, H, H, Cc).permute(0, 3, 1, 2)
+    ref = F.unfold(xr, 2, stride=2).view(Bn, Cc, 4, -1).permute(0, 3, 2, 1).reshape(-1, 4 * Cc)
+    assert torch.equal(p.float(), ref)
+    p.backward(p.detach())
+    assert torch.equal(x.grad, x.detach())      # a permutation: adjoint == inverse
+    # stem patchify from NCHW and channels_last storage
+    img = rnd(2, 3, 32, 32, seed=51)
+    ref = F.unfold(img, 4, stride=4).view(2, 3, 16, -1).permute(0, 3, 2, 1).reshape(-1, 48)
+    for im in (img, img.contiguous(memory_format=torch.channels_last)):
+        assert rel(ops.stem_patchify(im, 4, dtype).float(), ref) < (1e-7 if dtype == torch.float32 else 4e-3)
+    # 3x3 im2col and its adjoint
+    H2, C2 = 14, 172
+    xs = ops.alloc_rows(Bn * H2 * H2, C2, dtype, DEV)
+    xs.copy_(rnd(Bn * H2 * H2, C2, dtype=dtype, seed=52))
+    xs = xs.detach().requires_grad_(True)
+    col = ops.im2col3(xs, (Bn, H2, H2))
+    xr = xs.detach().float().view(Bn, H2, H2, C2).permute(0, 3, 1, 2).requires_grad_(True)
+    cref = F.unfold(xr, 3, padding=1).view(Bn, C2, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * C2)
+    assert torch.equal(col.float(), cref.detach())
+    dcol = rnd(*col.shape, dtype=dtype, seed=53)
+    col.backward(dcol)
+    cref.backward(dcol.float())
+    assert rel(xs.grad.float(), xr.grad.permute(0, 2, 3, 1).reshape(-1, C2)) < tol(dtype)
+    # aggregation: pool 56->14, pool 28->14, copy, bilinear 7->14
+    Bn = 2
+    srcs = [rnd(Bn * 56 * 56, 96, dtype=dtype, seed=54), rnd(Bn * 28 * 28, 192, dtype=dtype, seed=55),
+            rnd(Bn * 14 * 14, 384, dtype=dtype, seed=56), rnd(Bn * 7 * 7, 688, dtype=dtype, seed=57)]
+    srcs = [s.requires_grad_(True) for s in srcs]
+    spec = (Bn, 14, 14, [(56, 56, 96, 0), (28, 28, 192, 0), (14, 14, 384, 1), (7, 7, 688, 2)])
+    cat = ops.aggregate(spec, srcs)
+    refs = [s.detach().float().view(Bn, hw, hw, c).permute(0, 3, 1, 2).requires_grad_(True)
+            for s, (hw, _, c, _) in zip(srcs, spec[3])]
+    rcat = torch.cat((F.adaptive_avg_pool2d(refs[0], 14), F.adaptive_avg_pool2d(refs[1], 14), refs[2],
+                      F.interpolate(refs[3], scale_factor=2, mode='bilinear')), 1)
+    assert rel(cat.float(), rcat.permute(0, 2, 3, 1).reshape(-1, 1360)) < tol(dtype)
+    dc = rnd(*cat.shape, dtype=dtype, seed=58)
+    cat.backward(dc)
+    rcat.backward(dc.float().view(Bn, 14, 14, 1360).permute(0, 3, 1, 2))
+    for s, r in zip(srcs, refs):
+        assert rel(s.grad.float(), r.grad.permute(0, 2, 3, 1).reshape(s.shape)) < tol(dtype)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_se_gate(dtype):
+    Bn, HW, Cc, R = 3, 196, 172, 40
+    xp = ops.alloc_rows(Bn * HW, Cc, dtype, DEV)
+    xp.copy_(rnd(Bn * HW, Cc, dtype=dtype, seed=60))
+    x = xp.detach().requires_grad_(True)
+    ps = [rnd(R, Cc, 1, 1, seed=61, scale=0.1), rnd(R, seed=62, scale=0.1), rnd(Cc, R, 1, 1, seed=63, scale=0.2), rnd(Cc, seed=64, scale=0.1)]
+    ps = [p.requires_grad_(True) for p in ps]
+    y = ops.se_gate(x, *ps, Bn, HW)
+    dy = rnd(Bn * HW, Cc, dtype=dtype, seed=65)
+    y.backward(dy)
+    xr = x.detach().float().view(Bn, HW, Cc).permute(0, 2, 1).reshape(Bn, Cc, 14, 14).requires_grad_(True)
+    pr = [p.detach().clone().requires_grad_(True) for p in ps]
+    s = xr.mean((2, 3), keepdim=True)
+    s = F.conv2d(F.relu(F.conv2d(s, pr[0], pr[1])), pr[2], pr[3])
+    yr = xr * torch.sigmoid(s)
+    yr.backward(dy.float().view(Bn, 14, 14, Cc).permute(0, 3, 1, 2))
+    t = tol(dtype)
+    assert rel(y.float(), yr.permute(0, 2, 3, 1).reshape(-1, Cc)) < t
+    assert rel(x.grad.float(), xr.grad.permute(0, 2, 3, 1).reshape(-1, Cc)) < t
+    for a, b in zip(ps, pr):
+        assert rel(a.grad, b.grad) < (5e-5 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize('cname', ['c192_h14', 'c24_h5'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_gram_vector(cname, dtype, golden_dir):
+    import os
+    from oracle import cases
+    from oracle import ga_convnext_oracle as O
+    Cc, H, Bn = cases.GRAM_CASES[cname]
+    x = cases.gram_input(Cc, H, Bn)
+    gold = torch.load(os.path.join(golden_dir, 'ga_convnext_modules.pt'))[f'{cname}/train0'].reshape(Bn, -1)
+    xr = x.to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc).to(dtype).contiguous().requires_grad_(True)
+    out = ops.gram_vector(xr, Bn, H * H, float(H))
+    assert out.dtype == torch.float32
+    assert rel(out.cpu(), gold) < (1e-5 if dtype == torch.float32 else 6e-3)
+    dout = rnd(*out.shape, seed=70)
+    out.backward(dout)
+    xo = x.clone().requires_grad_(True)
+    O.gram_vector(xo, False).reshape(Bn, -1).backward(dout.cpu())
+    assert rel(xr.grad.float().cpu(), xo.grad.permute(0, 2, 3, 1).reshape(-1, Cc)) < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize('Q,N,H,E', [(1, 196, 8, 168), (3, 196, 12, 384), (1, 10, 8, 32)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_attnpool(Q, N, H, E, dtype):
+    nb, Bn = 2, 3
+    q = rnd(nb, Bn, Q, E, seed=80, scale=0.3).requires_grad_(True)
+    kvc = rnd(nb, Bn, Q, 2 * E, seed=81).requires_grad_(True)
+    kvt = rnd(Bn * N, nb * 2 * E, dtype=dtype, seed=82).requires_grad_(True)
+    out = ops.attnpool(q, kvc, kvt, N, H)
+    dout = rnd(*out.shape, seed=83)
+    out.backward(dout)
+    qr, kr, tr = q.detach().clone().requires_grad_(True), kvc.detach().clone().requires_grad_(True), kvt.detach().float().requires_grad_(True)
+    hd = E // H
+    outs = []
+    for k in range(nb):
+        t = tr[:, k * 2 * E:(k + 1) * 2 * E].view(Bn, N, 2 * E)
+        kk = torch.cat((kr[k][..., :E], t[..., :E]), 1).view(Bn, Q + N, H, hd).permute(0, 2, 1, 3)
+        vv = torch.cat((kr[k][..., E:], t[..., E:]), 1).view(Bn, Q + N, H, hd).permute(0, 2, 1, 3)
+        qq = qr[k].view(Bn, Q, H, hd).permute(0, 2, 1, 3)
+        a = torch.softmax(qq @ kk.transpose(-1, -2), -1)
+        outs.append((a @ vv).permute(0, 2, 1, 3).reshape(Bn, Q, E))
+    ref = torch.stack(outs)
+    ref.backward(dout)
+    t = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel(out, ref) < t
+    assert rel(q.grad, qr.grad) < t and rel(kvc.grad, kr.grad) < t
+    assert rel(kvt.grad.float(), tr.grad) < (t if dtype == torch.float32 else 2e-2)
+
+
+def test_loss_and_adamw():
+    from oracle import ga_convnext_oracle as O
+    nb, Bn, ncls = 5, 6, 1000
+    lg = rnd(nb, Bn, ncls, seed=90, scale=2.0).requires_grad_(True)
+    y = torch.randint(0, ncls, (Bn,), device=DEV)
+    loss = ops.ga_loss(lg, y, -0.8)
+    loss.backward()
+    lr = lg.detach().cpu().clone().requires_grad_(True)
+    lref = O.ga_loss([lr[k] for k in range(nb)], y.cpu(), -0.8)
+    lref.backward()
+    assert abs(loss.item() - lref.item()) < 1e-4 * abs(lref.item())
+    assert rel(lg.grad.cpu(), lr.grad) < 1e-5
+    # fused AdamW + EMA vs torch.optim.AdamW + lerp
+    n = 4096 * 3 + 8
+    p = rnd(n, seed=91)
+    g = rnd(n, seed=92)
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    m, v, ema = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), p.clone()
+    ema_r = p.clone()
+    p16 = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    lib = L.load()
+    for step in range(1, 4):
+        pr.grad = g.clone() * step
+        opt.step()
+        ema_r.mul_(0.99).add_(pr.detach(), alpha=0.01)
+        L.check(lib.ga_adamw_ema(L.ptr(p), L.ptr(g * step), L.ptr(m), L.ptr(v), L.ptr(ema), L.ptr(p16), None, 12, L.ll(n), L.f(1e-3),
+                                 L.f(0.9), L.f(0.999), L.f(1e-8), L.f(0.05), L.f(1 - 0.9 ** step), L.f(1 - 0.999 ** step), L.f(0.99),
+                                 L.f(1.0), L.stream()), 'adamw')
+    assert rel(p, pr.detach()) < 1e-6 and rel(ema, ema_r) < 1e-6
+    assert rel(p16.float(), p) < 4e-3
