@@ -1,0 +1,244 @@
+#!/usr/bin/env python3
+"""Headline benchmark: GA-ConvNeXt-T (ga_convnext_tiny_688) training step, bf16, batch 256 per GPU, 224x224 synthetic.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                      (the reference's CPU path = oracle port, on the host cores)
+
+One step = forward (5 branch logits) + GA loss (CE + lam*KL) + backward + gradient all-reduce (N>1) + fused AdamW + EMA.
+`value` times steps with the batch already resident in HBM; `e2e` times the same steps fed from pinned host memory
+(uint8 images -> H2D -> normalise, as timm's PrefetchLoader does) with the loss read back every step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = 'ga_convnext_tiny_688'
+TRAIN_GFLOP_PER_IMG = 32.73      # BASELINE.md section 4 (3 x 10.909 forward)
+TRAIN_MB_PER_IMG = 268.0         # GEMM-boundary-fusion convention, bf16
+GA_LAM = -0.8
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d['hbm_gbs'], d.get('bf16_tflops_sustained', d['bf16_tflops']), 'measured'
+    return 6650.0, 1400.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        busy = sorted(float(r[0]) for r in rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in rows)]
+        return {'sm_mhz': statistics.median(busy), 'sm_max_mhz': float(rows[0][1]), 'power_w_max': max(float(r[2]) for r in rows),
+                'samples': len(rows), 'reasons': reasons}
+
+
+def cpu_reference_step_rate(batch, steps, warmup, threads=None):
+    """The reference's CPU path (fp32, all host threads): oracle port of GA_ConvNeXt fwd + GA loss + bwd.  img/s."""
+    import torch
+    from oracle import ga_convnext_oracle as O
+    torch.set_num_threads(threads or os.cpu_count())
+    spec = O.SPECS[MODEL]
+    P = O.make_state(spec, 7)
+    leaves = {k: (v.requires_grad_(True) if v.is_floating_point() and 'running' not in k else v) for k, v in P.items()}
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(batch, 3, 224, 224, generator=g)
+    y = torch.randint(0, 1000, (batch,), generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        for v in leaves.values():
+            v.grad = None
+        out = O.forward(leaves, spec, x, training=True)
+        O.ga_loss(out, y, GA_LAM).backward()
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times[warmup:])
+    return batch / t, t, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = 8
+    rate, t, threads = cpu_reference_step_rate(batch, args.steps, args.warmup)
+    line = {
+        'impl': 'reference', 'metric': 'train images/sec (whole job)', 'value': rate, 'unit': 'img/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{MODEL} fwd+loss+bwd, fp32, 224x224, CPU', 'sample': f'batch {batch} per step (bounded sample of the batch-256 step)'},
+        'cpu_baseline': {'value': rate, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
+                         'sample': f'{args.steps} steps of batch {batch}, oracle port of the reference modules (timm absent: cannot import the reference on this box)'},
+        'e2e': {'value': rate, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='per-GPU batch')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from imagenet_models_b200 import lib as L
+    from imagenet_models_b200 import ops
+    from imagenet_models_b200.optim import FusedAdamWEma, GradBuckets
+    from imagenet_models_b200.registry import create_model
+    import imagenet_models_b200.ga_convnext  # noqa: F401
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', init_method='env://')
+    dev = torch.device('cuda', local)
+    L.load()
+
+    torch.manual_seed(42 + rank)                       # random_seed(seed, rank), GA/train.py:402
+    model = create_model(MODEL).to(dev).train()
+    opt = FusedAdamWEma(model, lr=1e-3, weight_decay=0.05, ema_decay=0.9998)
+    buckets = GradBuckets(opt.state) if world > 1 else None
+    B = args.batch
+    x_dev = torch.randn(B, 3, 224, 224, device=dev)
+    y_dev = torch.randint(0, 1000, (B,), device=dev)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1) * 255
+    std = torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1) * 255
+    x_host = torch.randint(0, 256, (B, 3, 224, 224), dtype=torch.uint8).pin_memory()
+    y_host = torch.randint(0, 1000, (B,)).pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(x, y):
+        opt.zero_grad()
+        if buckets:
+            buckets.prepare()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            out = model(x)
+        loss = ops.ga_loss(torch.stack(out), y, GA_LAM)
+        loss.backward()
+        scale = buckets.finish() if buckets else 1.0
+        opt.step(grad_scale=scale)
+        return loss
+
+    def step_e2e():
+        x = x_host.to(dev, non_blocking=True).float().sub_(mean).div_(std)
+        y = y_host.to(dev, non_blocking=True)
+        loss = step(x, y)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return loss_host.item()
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev, y_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = L.launch_count()
+    ms = timed(lambda: step(x_dev, y_dev), args.steps)
+    launches = L.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+        e2e = {'value': world * B * args.steps / (ms_e2e / 1e3), 'unit': 'img/s', 'ms_per_step': ms_e2e / args.steps,
+               'h2d_bytes_per_step': x_host.numel() + y_host.numel() * 8, 'd2h_bytes_per_step': 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms / args.steps
+    img_s = world * B * args.steps / (ms / 1e3)
+    hbm, tf, src = peaks()
+    per_gpu = img_s / world
+    frac_hbm = per_gpu * TRAIN_MB_PER_IMG / 1e3 / hbm
+    frac_tensor = per_gpu * TRAIN_GFLOP_PER_IMG / 1e3 / tf
+    line = {
+        'metric': 'train images/sec (whole job)', 'value': img_s, 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': f'{MODEL} training step (fwd + GA loss + bwd + all-reduce + fused AdamW + EMA), bf16 autocast, '
+                               f'batch {B}/GPU, 224x224', 'global_batch': B * world, 'parallelism': f'dp{world}',
+                   'l2': 'activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed'},
+        'gpu_launches': launches, 'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'achieved': per_gpu * TRAIN_MB_PER_IMG / 1e3, 'peak': hbm, 'unit': 'GB/s', 'frac': frac_hbm,
+                     'traffic': None, 'peak_source': src,
+                     'note': 'whole-step algorithmic bytes (268 MB/img, BASELINE.md section 4) / step time; tensor fraction = '
+                             f'{frac_tensor:.3f} of {tf} TFLOP/s'},
+    }
+    if e2e:
+        line['e2e'] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        rate, t, threads = cpu_reference_step_rate(8, 3, 1)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
+                                'sample': '3 fwd+loss+bwd steps of batch 8 (fp32) after 1 warm-up, oracle port of the reference modules'}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -88,11 +88,11 @@ __device__ __forceinline__ void load_halo(T* tile, uint64_t* bar, const CUtensor
 // MODE 1: dgrad    y = corr(x = dconv, flipped taps) + res
 constexpr int max_threads_for(int tw, int cpt) { return tw * cpt >= 28 ? 512 : (tw * cpt >= 14 ? 768 : 1024); }
 
-template <typename T, int TW, int CPT, int MODE>
+template <typename T, typename TO, int TW, int CPT, int MODE>
 __global__ void __launch_bounds__(max_threads_for(TW, CPT)) dwconv7_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ w49c,
                                                        const float* __restrict__ bias, const float* __restrict__ ln_w,
-                                                       const float* __restrict__ ln_b, const T* __restrict__ res,
-                                                       T* __restrict__ y, float* __restrict__ rstd_out, float eps, Geo g) {
+                                                       const float* __restrict__ ln_b, const TO* __restrict__ res,
+                                                       TO* __restrict__ y, float* __restrict__ rstd_out, float eps, Geo g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint64_t* bar = (uint64_t*)sm;
@@ -166,11 +166,11 @@ __global__ void __launch_bounds__(max_threads_for(TW, CPT)) dwconv7_kernel(const
           for (int j = 0; j < CPT; ++j) v[j] = acc[i][j];
           if (res) {
             float r[CPT];
-            LdC<CPT, T>::ld(res + off, r);
+            LdC<CPT, TO>::ld(res + off, r);
 #pragma unroll
             for (int j = 0; j < CPT; ++j) v[j] += r[j];
           }
-          StC<CPT, T>::st(y + off, v);
+          StC<CPT, TO>::st(y + off, v);
         }
       }
     }
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(max_threads_for(TW, CPT)) dwconv7_kernel(const
         float v[CPT];
 #pragma unroll
         for (int j = 0; j < CPT; ++j) v[j] = (acc[i][j] - mean[i]) * r * lw[j] + lb[j];
-        StC<CPT, T>::st(y + (((size_t)b * g.H + oy) * g.W + ox) * g.C + c, v);
+        StC<CPT, TO>::st(y + (((size_t)b * g.H + oy) * g.W + ox) * g.C + c, v);
       }
     }
   }
@@ -381,15 +381,15 @@ static int plan(int B, int H, int W, int C, int dtype, bool wgrad, Plan* p) {
   return GA_OK;
 }
 
-template <typename T, int MODE>
+template <typename T, typename TO, int MODE>
 static int launch_conv(const Plan& p, const CUtensorMap& tm, const float* w, const float* bias, const float* ln_w,
                        const float* ln_b, const void* res, void* y, float* rstd, float eps, cudaStream_t st) {
   dim3 grid(p.g.tiles_x * p.g.tiles_y, p.g.B);
 #define GA_DW_LAUNCH(TW_, CPT_)                                                                                         \
   if (p.tw == TW_ && p.cpt == CPT_) {                                                                                   \
-    auto k = dwconv7_kernel<T, TW_, CPT_, MODE>;                                                                        \
+    auto k = dwconv7_kernel<T, TO, TW_, CPT_, MODE>;                                                                    \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                                   \
-    k<<<grid, p.threads, p.smem, st>>>(tm, w, bias, ln_w, ln_b, (const T*)res, (T*)y, rstd, eps, p.g);                   \
+    k<<<grid, p.threads, p.smem, st>>>(tm, w, bias, ln_w, ln_b, (const TO*)res, (TO*)y, rstd, eps, p.g);                 \
     ga_count_launch();                                                                                                  \
     return ga_check_launch("dwconv7");                                                                                  \
   }
@@ -411,14 +411,15 @@ extern "C" int ga_dwconv7_ln_fwd(const void* x, const float* w49c, const float* 
   CUtensorMap tm;
   rc = dw::make_x_map(x, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
   if (rc) return rc;
-  if (dtype == GA_BF16) return dw::launch_conv<bf16, 0>(p, tm, w49c, bias, ln_w, ln_b, nullptr, y, rstd, eps, (cudaStream_t)s);
-  return dw::launch_conv<float, 0>(p, tm, w49c, bias, ln_w, ln_b, nullptr, y, rstd, eps, (cudaStream_t)s);
+  if (dtype == GA_BF16) return dw::launch_conv<bf16, bf16, 0>(p, tm, w49c, bias, ln_w, ln_b, nullptr, y, rstd, eps, (cudaStream_t)s);
+  return dw::launch_conv<float, float, 0>(p, tm, w49c, bias, ln_w, ln_b, nullptr, y, rstd, eps, (cudaStream_t)s);
 }
 
 extern "C" int ga_dwconv7_bwd_parts(int B, int H, int W, int C) { return 32; }
 
 extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, float* dw49c,
-                              float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype, ga_stream_t s) {
+                              float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype, int res_dtype,
+                              ga_stream_t s) {
   cudaStream_t st = (cudaStream_t)s;
   GA_REQUIRE(dconv && w49c && B > 0, GA_ERR_SHAPE, "ga_dwconv7_bwd: bad arguments");
   int rc;
@@ -429,8 +430,10 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
     CUtensorMap tm;
     rc = dw::make_x_map(dconv, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
     if (rc) return rc;
-    if (dtype == GA_BF16) rc = dw::launch_conv<bf16, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, nullptr, 0.f, st);
-    else rc = dw::launch_conv<float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, nullptr, 0.f, st);
+    GA_REQUIRE(dtype == GA_BF16 || res_dtype == GA_F32, GA_ERR_UNSUPPORTED, "ga_dwconv7_bwd: fp32 gradients need an fp32 residual stream");
+    if (dtype == GA_BF16 && res_dtype == GA_BF16) rc = dw::launch_conv<bf16, bf16, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, nullptr, 0.f, st);
+    else if (dtype == GA_BF16) rc = dw::launch_conv<bf16, float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, nullptr, 0.f, st);
+    else rc = dw::launch_conv<float, float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, nullptr, 0.f, st);
     if (rc) return rc;
   }
   if (dw49c || dbias) {

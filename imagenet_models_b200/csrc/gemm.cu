@@ -24,6 +24,7 @@ struct EpiArgs {
   const float* rowscale; int rows_per_scale;
   const void* R; long long ldr, r_bs;
   const void* Zin; long long ldz, z_bs; int zmode;
+  int z_shadow;  // Z receives a bf16 copy of the final value instead of the pre-activation
   int M, N;
 };
 
@@ -43,7 +44,7 @@ __device__ __forceinline__ void epi_store1(const EpiArgs& e, int b, int m, int n
     v *= (e.zmode == GA_ACT_GELU) ? gelu_grad_f(z) : (z > 0.f ? 1.f : 0.f);
   } else {
     if (e.bias) v += e.bias[(long long)b * e.bias_bs + n];
-    if (e.Z) { if (e.out_f32) ((float*)e.Z)[off] = v; else ((bf16*)e.Z)[off] = __float2bfloat16_rn(v); }
+    if (e.Z && !e.z_shadow) { if (e.out_f32) ((float*)e.Z)[off] = v; else ((bf16*)e.Z)[off] = __float2bfloat16_rn(v); }
     v = epi_act(v, e.act);
     if (e.colscale) v *= e.colscale[(long long)b * e.colscale_bs + n];
     if (e.rowscale) v *= e.rowscale[m / e.rows_per_scale];
@@ -52,6 +53,7 @@ __device__ __forceinline__ void epi_store1(const EpiArgs& e, int b, int m, int n
       v += e.out_f32 ? ((const float*)e.R)[ro] : __bfloat162float(((const bf16*)e.R)[ro]);
     }
   }
+  if (e.Z && e.z_shadow) ((bf16*)e.Z)[off] = __float2bfloat16_rn(v);
   if (e.accumulate) atomicAdd(((float*)e.D) + off, v);
   else if (e.out_f32) ((float*)e.D)[off] = v;
   else ((bf16*)e.D)[off] = __float2bfloat16_rn(v);
@@ -72,7 +74,7 @@ __device__ __forceinline__ void epi_store4(const EpiArgs& e, int b, int m, int n
       float4 bb = *reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bs + n);
       v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
     }
-    if (e.Z) {
+    if (e.Z && !e.z_shadow) {
       float4 zv = make_float4(v[0], v[1], v[2], v[3]);
       if (e.out_f32) st4((float*)e.Z + off, zv); else st4((bf16*)e.Z + off, zv);
     }
@@ -93,6 +95,7 @@ __device__ __forceinline__ void epi_store4(const EpiArgs& e, int b, int m, int n
       v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
     }
   }
+  if (e.Z && e.z_shadow) st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
   if (e.accumulate) {
     float* d = (float*)e.D + off;
 #pragma unroll
@@ -513,7 +516,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
   e.colscale = g->colscale; e.colscale_bs = g->colscale_bs;
   e.rowscale = g->rowscale; e.rows_per_scale = g->rows_per_scale > 0 ? g->rows_per_scale : 1;
   e.R = g->R; e.ldr = g->ldr; e.r_bs = g->r_bs;
-  e.Zin = g->Zin; e.ldz = g->ldz; e.z_bs = g->z_bs; e.zmode = g->zmode;
+  e.Zin = g->Zin; e.ldz = g->ldz; e.z_bs = g->z_bs; e.zmode = g->zmode; e.z_shadow = g->z_shadow;
   e.M = g->M; e.N = g->N;
 
   bool a_mn = false, b_mn = false;

@@ -79,12 +79,13 @@ class ConvNeXtBlock(nn.Module):
         self.gamma = nn.Parameter(ls_init_value * torch.ones(dim)) if ls_init_value > 0 else None
         self.drop_prob = float(drop_path)
 
-    def run(self, x, geom):
+    def run(self, x, xs, geom, T):
+        """x: residual stream (fp32 under bf16 compute, as in the autocast reference); xs: its bf16 shadow or None."""
         p = _params(self)
         if self.gamma is None:
             p['gamma'] = torch.ones_like(p['norm.weight'])
         ps = _path_scale(self.drop_prob, self.training, geom[0], x.device)
-        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled())
+        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T)
 
 
 class ConvNeXtStage(nn.Module):
@@ -102,25 +103,28 @@ class ConvNeXtStage(nn.Module):
         self.blocks = nn.Sequential(*[ConvNeXtBlock(out_chs, drop_path=dp_rates[j], ls_init_value=ls_init_value)
                                       for j in range(depth)])
 
-    def run(self, x, geom):
+    def run(self, x, xs, geom, T, RT):
+        """x / xs: residual stream (dtype RT) and its compute-dtype (T) shadow (None when RT == T).
+        Returns (x, xs, geom, taps); taps hold the compute-dtype view of the tapped activations."""
         Bn, H, W = geom
         if not isinstance(self.downsample, nn.Identity):
             ln, conv = self.downsample[0], self.downsample[1]
             k = self.stride
             cin, cout = conv.in_channels, conv.out_channels
-            x = ops.layernorm(x, ln.weight, ln.bias, ln.eps)
+            h = ops.layernorm(xs if xs is not None else x, ln.weight, ln.bias, ln.eps)
             if k > 1:
-                x = ops.patchify(x, (Bn, H, W, cin), k)
+                h = ops.patchify(h, (Bn, H, W, cin), k)
                 H, W = H // k, W // k
-            x = ops.linear(x, conv.weight.permute(0, 2, 3, 1).reshape(cout, k * k * cin), conv.bias)
+            x = ops.linear(h, conv.weight.permute(0, 2, 3, 1).reshape(cout, k * k * cin), conv.bias, out_dtype=RT)
+            xs = ops.to_dtype(x, T) if RT != T else None
         geom = (Bn, H, W)
         taps: List[torch.Tensor] = []
         n = len(self.blocks)
         for i, blk in enumerate(self.blocks):
-            x = blk.run(x, geom)
+            x, xs = blk.run(x, xs, geom, T)
             if n > 5 and (i + 1) % (n // (self.stage3_naggre + 1)) == 0 and len(taps) < self.stage3_naggre:
-                taps.append(x)
-        return x, geom, taps
+                taps.append(xs if xs is not None else x)
+        return x, xs, geom, taps
 
 
 class _SE(nn.Module):
@@ -302,14 +306,17 @@ class GA_ConvNeXt(nn.Module):
         k = self.patch_size
         stem_conv, stem_ln = self.stem[0], self.stem[1]
         with torch.autocast('cuda', enabled=False):
+            RT = torch.float32                         # residual stream stays fp32 (autocast semantics of the reference)
             rows = ops.stem_patchify(x.float(), k, T)
-            y = ops.linear(rows, stem_conv.weight.permute(0, 2, 3, 1).reshape(stem_conv.out_channels, -1), stem_conv.bias)
+            y = ops.linear(rows, stem_conv.weight.permute(0, 2, 3, 1).reshape(stem_conv.out_channels, -1), stem_conv.bias,
+                           out_dtype=RT)
             y = ops.layernorm(y, stem_ln.weight, stem_ln.bias, stem_ln.eps)
+            ys = ops.to_dtype(y, T) if RT != T else None
             geom = (Bn, H // k, W // k)
             feats, taps = [], []
             for i in range(4):
-                y, geom, t = self.stages[i].run(y, geom)
-                feats.append((y, geom))
+                y, ys, geom, t = self.stages[i].run(y, ys, geom, T, RT)
+                feats.append((ys if ys is not None else y, geom))
                 taps += [(tt, geom) for tt in t]
             (x0, g0), (x1, g1), (x2, g2), (x3, g3) = feats
             Ho, Wo = g2[1], g2[2]     # the reference pools to 14 = H/16 at 224 (ga_convnext.py:397); generalised to H/16
@@ -340,7 +347,7 @@ class GA_ConvNeXt(nn.Module):
             conv, bn = self.gram_contraction[k][0], self.gram_contraction[k][1]
             g = ops.linear(f, conv.weight.reshape(self.gram_dim, Cc), conv.bias)
             g = ops.batchnorm(g, _params(bn), tr)
-            g, _, _ = self.gram_layer[k].run(g, geom)
+            g, _, _, _ = self.gram_layer[k].run(g, None, geom, g.dtype, g.dtype)
             gv = ops.gram_vector(g, Bn, HW, float(H))                              # [B, tri] fp32
             emb, ebn = self.gram_embedding[k][0], self.gram_embedding[k][1]
             G = self.embed_groups

@@ -36,7 +36,7 @@ class GaGemm(C.Structure):
         ('rowscale', C.c_void_p), ('rows_per_scale', C.c_int),
         ('R', C.c_void_p), ('ldr', C.c_longlong), ('r_bs', C.c_longlong),
         ('Zin', C.c_void_p), ('ldz', C.c_longlong), ('z_bs', C.c_longlong), ('zmode', C.c_int),
-        ('backend', C.c_int), ('splits', C.c_int),
+        ('backend', C.c_int), ('splits', C.c_int), ('z_shadow', C.c_int),
     ]
 
 

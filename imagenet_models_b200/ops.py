@@ -55,7 +55,7 @@ def workspace(n_floats: int, device, tag: str) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------- raw kernels
 def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None, rowscale=None, rows_per_scale=1,
          residual=None, zin=None, zmode=ACT_NONE, alpha=1.0, accumulate=False, out_dtype=None, backend=L.BACKEND_AUTO,
-         splits=0):
+         splits=0, shadow=None):
     """D[b,m,n] = epi(alpha * sum_k A[b,m,k] * B[b,n,k]);  A:[M,K]|[b,M,K], B:[N,K]|[b,N,K], arbitrary strides.
 
     A batch stride of 0 (expanded tensor) broadcasts that operand.  `out` may be any strided [.., M, N] view.
@@ -116,6 +116,9 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
         Z3 = zin if zin.dim() == 3 else zin.unsqueeze(0)
         assert Z3.dtype == D3.dtype and Z3.stride(-1) == 1
         g.Zin, g.ldz, g.z_bs, g.zmode = Z3.data_ptr(), Z3.stride(1), bs(Z3), zmode
+    if shadow is not None:                       # bf16 copy of the final value, same row layout as D
+        assert save_z is False and shadow.dtype == torch.bfloat16 and shadow.stride() == out.stride()
+        g.Z, g.z_shadow = shadow.data_ptr(), 1
     g.backend, g.splits = backend, splits
     L.check(_L().ga_gemm(C.byref(g), L.stream()), 'ga_gemm')
     return (out, Z) if (save_z is not False and save_z is not None) else out
@@ -126,6 +129,12 @@ def cast_like(w: torch.Tensor, like_dtype) -> torch.Tensor:
     if like_dtype == torch.float32:
         return w
     w = w if w.is_contiguous() else w.contiguous()
+    K = w.shape[-1]
+    if K % 8:      # pad the row pitch to 16 bytes so TMA can address the operand (K=172, 1548 in the Bottleneck)
+        o = torch.empty(*w.shape[:-1], pad8(K), dtype=torch.bfloat16, device=w.device)
+        L.check(_L().ga_copy_cols(L.ptr(w), L.ptr(o), L.ll(w.numel() // K), K, L.ll(K), L.ll(pad8(K)), F32, BF16, L.stream()),
+                'ga_copy_cols')
+        return o[..., :K]
     o = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
     L.check(_L().ga_cast_bf16(L.ptr(w), L.ptr(o), L.ll(w.numel()), L.stream()), 'ga_cast_bf16')
     return o
@@ -251,20 +260,27 @@ class ConvNeXtBlockFn(Function):
     Kernels: K1 (dwconv+LN -> xhat), GEMM(fc1', bias+GELU, saves z), GEMM(fc2, bias, *gamma, *path, +x).
     LayerNorm's affine is folded into fc1 (W1' = W1 diag(ln_w), b1' = b1 + W1 ln_b); its gradients are recovered
     from the fc1 weight-gradient tile (ga_linear_grad_finalize), likewise the layer-scale gradient from fc2's.
+
+    Residual stream: `x` may be fp32 while the block computes in bf16 (what torch.autocast does in the reference:
+    `x.mul(gamma)` promotes to fp32, so the stream never rounds to bf16).  `xs` is then the bf16 shadow of x that the
+    conv reads; the fc2 epilogue emits the next shadow.  With x already in the compute dtype, xs is None.
     """
 
     @staticmethod
-    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, path_scale, geom, train):
+    def forward(ctx, x, xs, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, path_scale, geom, train, T):
         Bn, H, W_ = geom
         M, Cc = x.shape
         assert x.is_contiguous() and M == Bn * H * W_
-        dev, T = x.device, x.dtype
+        mixed = x.dtype != T
+        src = xs if mixed else x
+        assert src is not None and src.dtype == T and src.is_contiguous()
+        dev = x.device
         lib = _L()
         w49c = dw_w.reshape(Cc, 49).t().contiguous()
         xhat = torch.empty(M, Cc, dtype=T, device=dev)
         rstd = torch.empty(M, dtype=torch.float32, device=dev)
-        L.check(lib.ga_dwconv7_ln_fwd(L.ptr(x), L.ptr(w49c), L.ptr(dw_b), None, None, L.ptr(xhat), L.ptr(rstd), Bn, H, W_, Cc,
-                                      L.f(1e-6), L.dt(x), L.stream()), 'ga_dwconv7_ln_fwd')
+        L.check(lib.ga_dwconv7_ln_fwd(L.ptr(src), L.ptr(w49c), L.ptr(dw_b), None, None, L.ptr(xhat), L.ptr(rstd), Bn, H, W_, Cc,
+                                      L.f(1e-6), L.dt(src), L.stream()), 'ga_dwconv7_ln_fwd')
         w1f = scale_matrix(w1, None, ln_w, T)
         b1f = gemm(ln_b.unsqueeze(0), w1, bias=b1, out_dtype=torch.float32).reshape(-1)
         if train:
@@ -272,26 +288,34 @@ class ConvNeXtBlockFn(Function):
         else:
             a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU), None
         w2c = cast_like(w2, T)
-        y = gemm(a, w2c, bias=b2, colscale=gamma, rowscale=path_scale, rows_per_scale=H * W_, residual=x)
+        y = torch.empty(M, Cc, dtype=x.dtype, device=dev)
+        ys = torch.empty(M, Cc, dtype=T, device=dev) if mixed else None
+        gemm(a, w2c, y, bias=b2, colscale=gamma, rowscale=path_scale, rows_per_scale=H * W_, residual=x, shadow=ys)
         if train:
-            ctx.save_for_backward(x, xhat, rstd, z, a, w49c, ln_w, ln_b, w1, w1f, b1, w2, b2, gamma, path_scale)
-            ctx.geom = geom
-        return y
+            ctx.save_for_backward(src, xhat, rstd, z, a, w49c, ln_w, ln_b, w1, w1f, b1, w2, b2, gamma, path_scale)
+            ctx.geom, ctx.T, ctx.RT = geom, T, x.dtype
+        return y, ys
 
     @staticmethod
-    def backward(ctx, dy):
-        x, xhat, rstd, z, a, w49c, ln_w, ln_b, w1, w1f, b1, w2, b2, gamma, path_scale = ctx.saved_tensors
+    def backward(ctx, dy, dys_in):
+        src, xhat, rstd, z, a, w49c, ln_w, ln_b, w1, w1f, b1, w2, b2, gamma, path_scale = ctx.saved_tensors
         Bn, H, W_ = ctx.geom
-        M, Cc = x.shape
+        T, RT = ctx.T, ctx.RT
+        M, Cc = src.shape
         Hd = w1.shape[0]
-        dev, T = x.device, x.dtype
+        dev = src.device
         lib = _L()
+        if dy is None:
+            dy = torch.zeros(M, Cc, dtype=RT, device=dev)
         dy = dy.contiguous()
-        dys = dy
+        if dys_in is not None:                      # gradient that arrived through the bf16 shadow (stage boundaries)
+            dy = dy + dys_in.to(RT)
+        dys = convert(dy, T) if RT != T else dy     # bf16 operand copy of the stream gradient
         if path_scale is not None:
-            dys = torch.empty_like(dy)
-            L.check(lib.ga_scale_rows(L.ptr(dy), L.ptr(path_scale), L.ptr(dys), L.ll(M), Cc, H * W_, L.dt(dy), L.stream()),
+            t = torch.empty_like(dys)
+            L.check(lib.ga_scale_rows(L.ptr(dys), L.ptr(path_scale), L.ptr(t), L.ll(M), Cc, H * W_, L.dt(dys), L.stream()),
                     'ga_scale_rows')
+            dys = t
         # one zeroed slab for every parameter gradient of the block
         sizes = [49 * Cc, Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, Cc, Cc, Cc * Hd, Hd * Cc]
         slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
@@ -308,30 +332,49 @@ class ConvNeXtBlockFn(Function):
         # dz = (dys . (gamma*W2)) * gelu'(z)
         w2s = scale_matrix(w2, gamma, None, T)
         dz = gemm(dys, w2s.t(), zin=z, zmode=ACT_GELU)
-        # fc1: G1 = dz^T xhat ; dW1 = G1*ln_w ; db1 = s1 ; dln_w = coldot(W1, G1) ; dln_b = W1^T s1
+        # fc1: G1 = dz^T xhat ; dW1 = G1*ln_w + s1 (x) ln_b ; db1 = s1 ; dln_w = coldot(W1, G1) ; dln_b = W1^T s1
         s1 = colsum(dz)
         gemm(dz.t(), xhat.t(), G1.view(Hd, Cc), accumulate=True)
-        L.check(lib.ga_linear_grad_finalize(L.ptr(G1), L.ptr(s1), L.ptr(w1), None, None, L.ptr(ln_w), L.ptr(ln_b), L.ptr(dw1), L.ptr(db1),
-                                            None, L.ptr(dlnw), L.ptr(dlnb), Hd, Cc, L.stream()), 'linear_grad_finalize')
+        L.check(lib.ga_linear_grad_finalize(L.ptr(G1), L.ptr(s1), L.ptr(w1), None, None, L.ptr(ln_w), L.ptr(ln_b), L.ptr(dw1),
+                                            L.ptr(db1), None, L.ptr(dlnw), L.ptr(dlnb), Hd, Cc, L.stream()), 'linear_grad_finalize')
         dxhat = gemm(dz, w1f.t())
         del dz
         dconv = torch.empty(M, Cc, dtype=T, device=dev)
-        L.check(lib.ga_ln_bwd_rows(L.ptr(dxhat), L.ptr(xhat), L.ptr(rstd), L.ptr(dconv), L.ll(M), Cc, L.dt(x), L.stream()),
+        L.check(lib.ga_ln_bwd_rows(L.ptr(dxhat), L.ptr(xhat), L.ptr(rstd), L.ptr(dconv), L.ll(M), Cc, L.dt(dconv), L.stream()),
                 'ga_ln_bwd_rows')
-        dx = torch.empty(M, Cc, dtype=T, device=dev)
+        dx = torch.empty(M, Cc, dtype=RT, device=dev)
         parts = lib.ga_dwconv7_bwd_parts(Bn, H, W_, Cc)
         ws = workspace(parts * 50 * Cc, dev, 'dwconv')
-        L.check(lib.ga_dwconv7_bwd(L.ptr(dconv), L.ptr(x), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(d49), L.ptr(ddwb), L.ptr(ws),
-                                   Bn, H, W_, Cc, L.dt(x), L.stream()), 'ga_dwconv7_bwd')
+        L.check(lib.ga_dwconv7_bwd(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(d49), L.ptr(ddwb), L.ptr(ws),
+                                   Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream()), 'ga_dwconv7_bwd')
         d_dw_w = d49.view(49, Cc).t().reshape(Cc, 1, 7, 7)
-        return (dx, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None)
+        return (dx, None, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None, None)
 
 
-def convnext_block(x, p, geom, path_scale=None, train=True):
-    """p: dict with conv_dw.weight/bias, norm.weight/bias, mlp.fc1/fc2.weight/bias, gamma (reference key names)."""
-    return ConvNeXtBlockFn.apply(x, p['conv_dw.weight'], p['conv_dw.bias'], p['norm.weight'], p['norm.bias'],
+def convnext_block(x, p, geom, path_scale=None, train=True, xs=None, T=None):
+    """p: dict with conv_dw.weight/bias, norm.weight/bias, mlp.fc1/fc2.weight/bias, gamma (reference key names).
+    Returns (y, ys): the residual stream and its compute-dtype shadow (None when they coincide)."""
+    T = T or (xs.dtype if xs is not None else x.dtype)
+    return ConvNeXtBlockFn.apply(x, xs, p['conv_dw.weight'], p['conv_dw.bias'], p['norm.weight'], p['norm.bias'],
                                  p['mlp.fc1.weight'], p['mlp.fc1.bias'], p['mlp.fc2.weight'], p['mlp.fc2.bias'], p['gamma'],
-                                 path_scale, geom, train)
+                                 path_scale, geom, train, T)
+
+
+class ConvertFn(Function):
+    """dtype change of a row matrix through the copy kernel (bf16 shadow of an fp32 stream, and back for its gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        return convert(x, dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return convert(rowmat(dy), ctx.src_dtype), None
+
+
+def to_dtype(x, dtype):
+    return x if x.dtype == dtype else ConvertFn.apply(x, dtype)
 
 
 # ------------------------------------------------------------------------------------------------- LayerNorm rows

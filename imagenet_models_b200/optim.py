@@ -1,0 +1,192 @@
+"""Flat-buffer training state: fused AdamW + EMA step (K7) and bucketed gradient all-reduce.
+
+Reference behaviour being replaced (GA/train.py:466,499,505-515,758-761):
+  * `create_optimizer_v2(model, opt='adamw', lr, weight_decay, filter_bias_and_bn=True)` -> torch AdamW over 365 tensors,
+    no decay on 1-D parameters / biases;
+  * `ModelEmaV2(model, decay)` -> python loop `ema = d*ema + (1-d)*model` over all 407 state_dict entries;
+  * `DistributedDataParallel` -> bucketed NCCL all-reduce(avg) of gradients overlapped with backward.
+Here every parameter (and its gradient, Adam moments and EMA copy) is a view into ONE flat fp32 buffer, so the
+optimizer + EMA is a single kernel launch and gradient buckets are contiguous slices handed to NCCL as they fill.
+"""
+from __future__ import annotations
+
+import copy
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import lib as L
+
+SEG_SHIFT = 4           # weight-decay flags are per 16-element segment; tensors are padded to that
+SEG = 1 << SEG_SHIFT
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class FlatState:
+    """Re-homes a module's parameters into one flat fp32 buffer (+ flat grad)."""
+
+    def __init__(self, model: nn.Module):
+        params = [p for p in model.parameters() if p.requires_grad]
+        assert params and all(p.dtype == torch.float32 for p in params), 'fp32 parameters expected'
+        dev = params[0].device
+        self.names = [n for n, p in model.named_parameters() if p.requires_grad]
+        self.params = params
+        self.offsets, off = [], 0
+        for p in params:
+            self.offsets.append(off)
+            off += _round_up(p.numel(), SEG)
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(params, self.offsets):
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+        # float buffers (BatchNorm running statistics) re-homed the same way, for a one-launch EMA of non-parameter state
+        self.bufflat = _flatten_buffers(model, dev)
+
+    def decay_flags(self, no_decay_1d: bool = True) -> torch.Tensor:
+        """timm filter_bias_and_bn: 1-D tensors and biases get no weight decay."""
+        flags = torch.zeros(self.numel >> SEG_SHIFT, dtype=torch.uint8)
+        for name, p, o in zip(self.names, self.params, self.offsets):
+            decay = not (no_decay_1d and (p.ndim <= 1 or name.endswith('.bias')))
+            if decay:
+                flags[o >> SEG_SHIFT:(o + _round_up(p.numel(), SEG)) >> SEG_SHIFT] = 1
+        return flags.to(self.flat.device)
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, o in zip(self.params, self.offsets):     # autograd may have replaced .grad; re-attach the view
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+def _flatten_buffers(model: nn.Module, dev) -> torch.Tensor:
+    bufs = [b for b in model.buffers() if b.is_floating_point()]
+    offs, off = [], 0
+    for b in bufs:
+        offs.append(off)
+        off += _round_up(b.numel(), 4)
+    flat = torch.zeros(max(off, 4), dtype=torch.float32, device=dev)
+    for b, o in zip(bufs, offs):
+        flat[o:o + b.numel()].copy_(b.data.reshape(-1))
+        b.data = flat[o:o + b.numel()].view(b.shape)
+    return flat
+
+
+class FusedAdamWEma:
+    """torch.optim.AdamW semantics + timm ModelEmaV2, one kernel over the flat state (ga_adamw_ema)."""
+
+    def __init__(self, model: nn.Module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05, ema_decay: Optional[float] = None,
+                 filter_bias_and_bn=True):
+        self.model = model
+        self.state = FlatState(model)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(self.state.flat)
+        self.v = torch.zeros_like(self.state.flat)
+        self.flags = self.state.decay_flags(filter_bias_and_bn) if weight_decay else None
+        self.step_count = 0
+        self.ema_decay = ema_decay
+        self.ema_flat = self.ema_model = None
+        if ema_decay is not None:
+            self.ema_flat = self.state.flat.clone()
+            self.ema_model = copy.deepcopy(model).eval()          # same layout -> same offsets
+            for p in self.ema_model.parameters():
+                p.requires_grad_(False)
+            ema_params = [p for p in self.ema_model.parameters()]
+            for p, o in zip(ema_params, self.state.offsets):
+                p.data = self.ema_flat[o:o + p.numel()].view(p.shape)
+            self.ema_bufflat = _flatten_buffers(self.ema_model, self.ema_flat.device)
+        self.param_groups = [{'lr': lr}]                          # what the reference's logging / schedulers read
+
+    def zero_grad(self, set_to_none=False):
+        self.state.zero_grad()
+
+    def step(self, grad_scale: float = 1.0):
+        self.step_count += 1
+        t = self.step_count
+        b1, b2 = self.betas
+        lr = self.param_groups[0]['lr']
+        lib = L.load()
+        L.check(lib.ga_adamw_ema(L.ptr(self.state.flat), L.ptr(self.state.grad), L.ptr(self.m), L.ptr(self.v),
+                                 L.ptr(self.ema_flat), None, L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel), L.f(lr), L.f(b1),
+                                 L.f(b2), L.f(self.eps), L.f(self.wd), L.f(1 - b1 ** t), L.f(1 - b2 ** t),
+                                 L.f(self.ema_decay if self.ema_decay is not None else 0.0), L.f(grad_scale), L.stream()),
+                'ga_adamw_ema')
+        if self.ema_model is not None:
+            L.check(lib.ga_ema_lerp(L.ptr(self.ema_bufflat), L.ptr(self.state.bufflat), L.ll(self.ema_bufflat.numel()),
+                                    L.f(self.ema_decay), L.stream()), 'ga_ema_lerp')
+
+
+class GradBuckets:
+    """Overlapped data-parallel gradient all-reduce (mean) over contiguous slices of the flat gradient.
+
+    Parameters are bucketed in reverse registration order (the order backward produces them); a post-accumulate
+    hook counts a bucket down and launches its all-reduce on a side stream as soon as it is complete.
+    """
+
+    def __init__(self, state: FlatState, process_group=None, bucket_mb: float = 25.0, overlap: bool = True):
+        self.state, self.pg, self.overlap = state, process_group, overlap
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        cap = int(bucket_mb * (1 << 20) / 4)
+        self.buckets: List[dict] = []
+        cur = None
+        for idx in reversed(range(len(state.params))):
+            o, n = state.offsets[idx], _round_up(state.params[idx].numel(), SEG)
+            if cur is None or cur['hi'] - o > cap:
+                cur = {'lo': o, 'hi': o + n, 'members': [], 'pending': 0, 'work': None}
+                self.buckets.append(cur)
+            cur['lo'] = o
+            cur['members'].append(idx)
+        self.bucket_of = {}
+        for b in self.buckets:
+            for idx in b['members']:
+                self.bucket_of[idx] = b
+        self.enabled = True
+        self._cuda = state.flat.is_cuda
+        self.side = torch.cuda.Stream() if (self._cuda and overlap) else None
+        if self.world > 1:
+            for idx, p in enumerate(state.params):
+                p.register_post_accumulate_grad_hook(self._make_hook(idx))
+
+    def _make_hook(self, idx):
+        def hook(param):
+            if not self.enabled:
+                return
+            b = self.bucket_of[idx]
+            b['pending'] -= 1
+            if b['pending'] == 0:
+                self._launch(b)
+        return hook
+
+    def prepare(self):
+        for b in self.buckets:
+            b['pending'], b['work'] = len(b['members']), None
+
+    def _launch(self, b):
+        buf = self.state.grad[b['lo']:b['hi']]
+        if self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                b['work'] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        else:
+            b['work'] = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
+    def finish(self) -> float:
+        """Wait for every bucket; returns the 1/world factor to fold into the optimizer's grad_scale."""
+        if self.world == 1:
+            return 1.0
+        for b in self.buckets:
+            if b['work'] is None:           # parameter without gradient this step: reduce the (zero) slice anyway
+                self._launch(b)
+        for b in self.buckets:
+            b['work'].wait()
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        return 1.0 / self.world

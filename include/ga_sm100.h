@@ -60,6 +60,7 @@ typedef struct GaGemm {
   const void* Zin; long long ldz, z_bs; int zmode; /* GA_ACT_GELU: *gelu'(Zin); GA_ACT_RELU: *(Zin>0) */
   int backend;    /* GA_BACKEND_* */
   int splits;     /* split-K factor for accumulate mode; 0 = auto */
+  int z_shadow;   /* 1: Z receives a bf16 copy of the FINAL value (bf16 shadow of an fp32 residual stream) */
 } GaGemm;
 int ga_gemm(const GaGemm* p, ga_stream_t s);
 
@@ -76,7 +77,7 @@ int ga_ln_bwd_rows(const void* dxhat, const void* xhat, const float* rstd, void*
 int ga_dwconv7_bwd_parts(int B, int H, int W, int C);
 int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx,
                    float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype,
-                   ga_stream_t s);
+                   int res_dtype /* dtype of dres and dx: the residual-stream gradient */, ga_stream_t s);
 
 /* ---- row LayerNorm over the last dim (LayerNorm2d on NHWC rows, nn.LayerNorm)  (ga_convnext.py:51-67,233,237) */
 int ga_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,

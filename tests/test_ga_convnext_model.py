@@ -124,8 +124,11 @@ def test_train_step_vs_reference(gmodel, dtype, tol):
     m = _build(name, dtype).train()
     x, y = cases.ga_inputs(B)
     out = m(x.cuda())
+    # train-mode BatchNorm (batch of 2) amplifies bf16 rounding: the reference's own bf16 autocast is 5-6e-2 away from
+    # its fp32 result on this fixture (recorded by make_golden.py), so the bf16 bound is max(2e-2, that self error)
+    ltol = tol if dtype == torch.float32 else max(tol, g['ref_bf16_self_err']['train'])
     for a, b in zip(out, g['train_logits']):
-        assert rel(a.detach().cpu(), b) < tol, rel(a.detach().cpu(), b)
+        assert rel(a.detach().cpu(), b) < ltol, rel(a.detach().cpu(), b)
     loss = ops.ga_loss(torch.stack(out), y.cuda(), cases.GA_LAM)
     assert abs(loss.item() - g['loss'].item()) < (1e-4 if dtype == torch.float32 else 3e-2) * abs(g['loss'].item())
     loss.backward()

@@ -146,7 +146,7 @@ def test_dwconv_ln_fwd_bwd(Bn, H, Cc, dtype):
     db = torch.zeros(Cc, device=DEV)
     ws = torch.empty(lib.ga_dwconv7_bwd_parts(Bn, H, H, Cc) * 50 * Cc, device=DEV)
     L.check(lib.ga_dwconv7_bwd(L.ptr(dconv), L.ptr(x), L.ptr(dres), L.ptr(w49c), L.ptr(dx), L.ptr(d49), L.ptr(db), L.ptr(ws), Bn, H,
-                               H, Cc, L.dt(x), L.stream()), 'bwd')
+                               H, Cc, L.dt(x), L.dt(x), L.stream()), 'bwd')
     xg = xr.clone().requires_grad_(True)
     wg = w.clone().requires_grad_(True)
     bg = b.clone().requires_grad_(True)
@@ -169,7 +169,7 @@ def test_convnext_block_vs_golden(cname, dtype, golden_dir):
     P = {k: v.to(DEV).requires_grad_(True) for k, v in cases.block_state(Cc).items()}
     x, dy = cases.block_inputs(Cc, H, Bn)
     xr = x.to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc).to(dtype).contiguous().requires_grad_(True)
-    y = ops.convnext_block(xr, P, (Bn, H, H), None, True)
+    y, _ = ops.convnext_block(xr, P, (Bn, H, H), None, True)
     y.backward(dy.to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc).to(dtype))
     t = 2e-5 if dtype == torch.float32 else 2e-2
     yref = g['y'].to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc)
