@@ -94,10 +94,32 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-// ---- activations (exact erf GELU, as nn.GELU() default) ------------------------------------------
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// ---- activations: nn.GELU() (erf form).  erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32 round-off).
+// The GELU epilogues are issue-bound, so the form below is the shortest instruction sequence found: with
+//   h(x) = 0.5 * erfc(|x|/sqrt2) = 0.5 * poly(t) * t * exp(-x^2/2),  t = 1/(1 + p|x|/sqrt2)
+//   gelu(x)  = relu(x) - |x| * h            (x>=0: x(1-h);  x<0: x*h)
+//   gelu'(x) = Phi(x) + x * phi(x),  Phi = x>=0 ? 1-h : h,  phi = exp(-x^2/2)/sqrt(2 pi)
+// = 2 MUFU (rcp, ex2) + 12 FMA-pipe instructions for gelu.  exp(-x^2/2) is shared by h and phi.
+__device__ __forceinline__ float gelu_h(float x, float* ex_out) {
+  const float u = fabsf(x);
+  float t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, u, 1.f)));        // p/sqrt2 = 0.3275911/1.41421356
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"((u * u) * -0.72134752f));           // exp(-x^2/2) = 2^(-x^2 * 0.5*log2 e)
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);                                   // 0.5 * A-S coefficients
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  *ex_out = ex;
+  return (poly * t) * ex;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float ex;
+  const float h = gelu_h(x, &ex);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
-  float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float ex;
+  const float h = gelu_h(x, &ex);
+  const float cdf = x >= 0.f ? 1.f - h : h;
+  return fmaf(x * 0.39894228040143268f, ex, cdf);
 }

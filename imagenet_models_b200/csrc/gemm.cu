@@ -59,41 +59,41 @@ __device__ __forceinline__ void epi_store1(const EpiArgs& e, int b, int m, int n
   else ((bf16*)e.D)[off] = __float2bfloat16_rn(v);
 }
 
-// four consecutive columns n..n+3 (requires N%4==0, ld%4==0, 16B-aligned bases): coalesced vector path
-__device__ __forceinline__ void epi_store4(const EpiArgs& e, int b, int m, int n, float4 acc) {
+// four consecutive columns n..n+3 (requires N%4==0, ld%4==0, 16B-aligned bases): coalesced vector path.
+// `pre` holds the already-loaded per-element operand: Zin values when e.Zin is set, else the residual R values.
+__device__ __forceinline__ void epi_store4p(const EpiArgs& e, int b, int m, int n, float4 acc, float4 pre) {
   float v[4] = {acc.x * e.alpha, acc.y * e.alpha, acc.z * e.alpha, acc.w * e.alpha};
-  long long off = (long long)b * e.d_bs + (long long)m * e.ldd + n;
+  const long long off = (long long)b * e.d_bs + (long long)m * e.ldd + n;
   if (e.Zin) {
-    long long zo = (long long)b * e.z_bs + (long long)m * e.ldz + n;
-    float4 z = e.out_f32 ? ld4((const float*)e.Zin + zo) : ld4((const bf16*)e.Zin + zo);
-    float zz[4] = {z.x, z.y, z.z, z.w};
+    const float zz[4] = {pre.x, pre.y, pre.z, pre.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] *= (e.zmode == GA_ACT_GELU) ? gelu_grad_f(zz[i]) : (zz[i] > 0.f ? 1.f : 0.f);
   } else {
     if (e.bias) {
-      float4 bb = *reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bs + n);
+      const float4 bb = *reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bs + n);
       v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
     }
     if (e.Z && !e.z_shadow) {
-      float4 zv = make_float4(v[0], v[1], v[2], v[3]);
+      const float4 zv = make_float4(v[0], v[1], v[2], v[3]);
       if (e.out_f32) st4((float*)e.Z + off, zv); else st4((bf16*)e.Z + off, zv);
     }
+    if (e.act == GA_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = epi_act(v[i], e.act);
+      for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+    } else if (e.act == GA_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
     if (e.colscale) {
-      float4 cs = *reinterpret_cast<const float4*>(e.colscale + (long long)b * e.colscale_bs + n);
+      const float4 cs = *reinterpret_cast<const float4*>(e.colscale + (long long)b * e.colscale_bs + n);
       v[0] *= cs.x; v[1] *= cs.y; v[2] *= cs.z; v[3] *= cs.w;
     }
     if (e.rowscale) {
-      float rs = e.rowscale[m / e.rows_per_scale];
+      const float rs = e.rowscale[m / e.rows_per_scale];
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] *= rs;
     }
-    if (e.R) {
-      long long ro = (long long)b * e.r_bs + (long long)m * e.ldr + n;
-      float4 r = e.out_f32 ? ld4((const float*)e.R + ro) : ld4((const bf16*)e.R + ro);
-      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
-    }
+    if (e.R) { v[0] += pre.x; v[1] += pre.y; v[2] += pre.z; v[3] += pre.w; }
   }
   if (e.Z && e.z_shadow) st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
   if (e.accumulate) {
@@ -101,9 +101,21 @@ __device__ __forceinline__ void epi_store4(const EpiArgs& e, int b, int m, int n
 #pragma unroll
     for (int i = 0; i < 4; ++i) atomicAdd(d + i, v[i]);
   } else {
-    float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    const float4 o = make_float4(v[0], v[1], v[2], v[3]);
     if (e.out_f32) st4((float*)e.D + off, o); else st4((bf16*)e.D + off, o);
   }
+}
+
+__device__ __forceinline__ void epi_store4(const EpiArgs& e, int b, int m, int n, float4 acc) {
+  float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (e.Zin) {
+    const long long zo = (long long)b * e.z_bs + (long long)m * e.ldz + n;
+    pre = e.out_f32 ? ld4((const float*)e.Zin + zo) : ld4((const bf16*)e.Zin + zo);
+  } else if (e.R) {
+    const long long ro = (long long)b * e.r_bs + (long long)m * e.ldr + n;
+    pre = e.out_f32 ? ld4((const float*)e.R + ro) : ld4((const bf16*)e.R + ro);
+  }
+  epi_store4p(e, b, m, n, acc, pre);
 }
 
 // ------------------------------------------------------------------------------------------------ SIMT kernel
@@ -402,6 +414,274 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
   if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
+// ------------------------------------------------------------------------------------------------ persistent kernel
+// One CTA per SM walks tiles (n fastest, so the CTAs running concurrently share A rows in L2).  576 threads:
+//   warp 0  TMA producer   : smem ring of `stages` {A,B} k-blocks that keeps running across tile boundaries
+//   warp 1  MMA issuer     : tcgen05.mma into one of TWO TMEM accumulators (2*BN columns), so the MMAs of tile i+1
+//                            overlap the epilogue of tile i
+//   warps 2..17 epilogue   : warp e owns TMEM lane quadrant (warp id % 4) and a BN/4 column slice; TMEM -> regs -> smem
+//                            transpose -> coalesced global stores.  The epilogue is specialised at compile time (EPI_*):
+//                            with GELU in it the kernel is issue-bound, so the hot loop carries no runtime flags, column
+//                            operands (bias, gamma) are loaded once per chunk and row operands (residual, Zin) are
+//                            prefetched four rows ahead.
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// control-warp wait: back off between polls so the spinning thread does not steal issue slots from the epilogue warps
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (;;) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(40);
+  }
+}
+
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_C = 32;                 // columns per epilogue chunk (one tcgen05.ld.32x32b.x32)
+constexpr int ST_LD = EPI_C + 4;          // staging row pitch (floats): conflict-free float4 writes and reads
+
+enum { EPI_GENERIC = 0, EPI_BIAS_GELU_Z = 1, EPI_BIAS_GELU = 2, EPI_RES_F32_SHADOW = 3, EPI_ZIN_GELU = 4, EPI_PLAIN_BF16 = 5,
+       EPI_ACCUM = 6 };
+
+// one 32-row x 32-column chunk held in this warp's staging buffer -> global memory
+template <int EPI, bool FULL>
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st, int lane, int batch, int m_base, int n) {
+  // lane -> 4 columns (lane & 7) * 4 of rows (lane >> 3) + 4 * it, it = 0..7
+  const int cl = (lane & 7) * 4;
+  const int r0 = lane >> 3;
+  if (EPI == EPI_GENERIC) {
+    const bool vec_ok = ((e.N & 3) == 0) && ((e.ldd & 3) == 0) && (!e.R || (e.ldr & 3) == 0) && (!e.Zin || (e.ldz & 3) == 0) &&
+                        (!e.bias || ((e.bias_bs & 3) == 0)) && (!e.colscale || ((e.colscale_bs & 3) == 0));
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int rl = r0 + 4 * it;
+      const int m = m_base + rl;
+      if (m < e.M && n < e.N) {
+        const float4 acc = *reinterpret_cast<const float4*>(st + rl * ST_LD + cl);
+        if (vec_ok) {
+          epi_store4(e, batch, m, n, acc);
+        } else {
+          const float a_[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < e.N) epi_store1(e, batch, m, n + j, a_[j]);
+        }
+      }
+    }
+    return;
+  }
+  if (n >= e.N) return;
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (EPI == EPI_BIAS_GELU_Z || EPI == EPI_BIAS_GELU || EPI == EPI_RES_F32_SHADOW || EPI == EPI_PLAIN_BF16) {
+    if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + (long long)batch * e.bias_bs + n);
+  }
+  if (EPI == EPI_RES_F32_SHADOW) {
+    if (e.colscale) cs4 = *reinterpret_cast<const float4*>(e.colscale + (long long)batch * e.colscale_bs + n);
+  }
+  const long long dbase = (long long)batch * e.d_bs + n;
+#pragma unroll
+  for (int g4 = 0; g4 < 2; ++g4) {
+    float4 pre[4];
+    if (EPI == EPI_RES_F32_SHADOW || EPI == EPI_ZIN_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m_base + r0 + 4 * (g4 * 4 + j);
+        pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FULL || m < e.M) {
+          if (EPI == EPI_RES_F32_SHADOW) pre[j] = ld4((const float*)e.R + (long long)batch * e.r_bs + (long long)m * e.ldr + n);
+          else pre[j] = ld4((const bf16*)e.Zin + (long long)batch * e.z_bs + (long long)m * e.ldz + n);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rl = r0 + 4 * (g4 * 4 + j);
+      const int m = m_base + rl;
+      if (!FULL && m >= e.M) continue;
+      const float4 acc = *reinterpret_cast<const float4*>(st + rl * ST_LD + cl);
+      const long long off = dbase + (long long)m * e.ldd;
+      float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      if (EPI == EPI_BIAS_GELU_Z || EPI == EPI_BIAS_GELU) {
+        v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
+        if (EPI == EPI_BIAS_GELU_Z) st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+        st4((bf16*)e.D + off, make_float4(v[0], v[1], v[2], v[3]));
+      } else if (EPI == EPI_RES_F32_SHADOW) {
+        float rs = 1.f;
+        if (e.rowscale) rs = e.rowscale[m / e.rows_per_scale];
+        v[0] = fmaf((v[0] + bias4.x) * cs4.x, rs, pre[j].x); v[1] = fmaf((v[1] + bias4.y) * cs4.y, rs, pre[j].y);
+        v[2] = fmaf((v[2] + bias4.z) * cs4.z, rs, pre[j].z); v[3] = fmaf((v[3] + bias4.w) * cs4.w, rs, pre[j].w);
+        const float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        st4((float*)e.D + off, o);
+        if (e.Z) st4((bf16*)e.Z + off, o);
+      } else if (EPI == EPI_ZIN_GELU) {
+        const float zz[4] = {pre[j].x, pre[j].y, pre[j].z, pre[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] *= gelu_grad_f(zz[i]);
+        st4((bf16*)e.D + off, make_float4(v[0], v[1], v[2], v[3]));
+      } else if (EPI == EPI_PLAIN_BF16) {
+        st4((bf16*)e.D + off, make_float4(v[0] + bias4.x, v[1] + bias4.y, v[2] + bias4.z, v[3] + bias4.w));
+      } else if (EPI == EPI_ACCUM) {
+        atomicAdd(reinterpret_cast<float4*>((float*)e.D + off), make_float4(v[0] * e.alpha, v[1] * e.alpha, v[2] * e.alpha, v[3] * e.alpha));
+      }
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                          const __grid_constant__ CUtensorMap tmB, Params p,
+                                                                          EpiArgs e, int mt, int nt, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int SLICE = BN / 4;                // columns per epilogue warp
+  uint8_t* stage_base = smem;
+  float* staging = (float*)(smem + (size_t)p.stages * STAGE_BYTES);            // EPI_WARPS x 32 x ST_LD floats
+  uint64_t* full_bar = (uint64_t*)((uint8_t*)staging + EPI_WARPS * 32 * ST_LD * 4);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full = empty_bar + 8;         // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_t = t % nt, m_t = (t / nt) % mt, z = t / (nt * mt);
+        const int batch = z / p.splits, split = z % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        int kb1 = kb0 + p.kb_per_split;
+        if (kb1 > p.kb_total) kb1 = p.kb_total;
+        const int m0 = m_t * BM, n0 = n_t * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* sa = stage_base + (size_t)s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_3d(sa, &tmA, &full_bar[s], k0, m0, batch);
+          } else {
+            tma_load_3d(sa, &tmA, &full_bar[s], m0, k0, batch);
+            tma_load_3d(sa + 64 * BK * 2, &tmA, &full_bar[s], m0 + 64, k0, batch);
+          }
+          if (!B_MN) {
+            tma_load_3d(sb, &tmB, &full_bar[s], k0, n0, batch);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 64 * BK * 2, &tmB, &full_bar[s], n0 + 64 * j, k0, batch);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const int z = t / (nt * mt);
+        const int split = z % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        int kb1 = kb0 + p.kb_per_split;
+        if (kb1 > p.kb_total) kb1 = p.kb_total;
+        const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+        mbar_wait_backoff(&tmem_empty[buf], bph ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait_backoff(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          const uint64_t adesc = make_desc(sa, p.lbo_a, p.sbo_a);
+          const uint64_t bdesc = make_desc(sb, p.lbo_b, p.sbo_b);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ka = A_MN ? (uint64_t)((k * 16 * 128) >> 4) : (uint64_t)((k * 32) >> 4);
+            const uint64_t kb_ = B_MN ? (uint64_t)((k * 16 * 128) >> 4) : (uint64_t)((k * 32) >> 4);
+            umma_bf16(tacc, adesc + ka, bdesc + kb_, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int q = warp & 3;                   // TMEM lane quadrant accessible to this warp (warp id % 4)
+    const int slice = ew >> 2;                // which quarter of the BN columns
+    float* st = staging + (size_t)ew * 32 * ST_LD;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const int n_t = t % nt, m_t = (t / nt) % mt, z = t / (nt * mt);
+      const int batch = z / p.splits;
+      const int m0 = m_t * BM, n0 = n_t * BN;
+      const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      mbar_wait_backoff(&tmem_full[buf], bph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < SLICE / EPI_C; ++c) {
+        const int col0 = slice * SLICE + c * EPI_C;
+        const bool live = (n0 + col0 < e.N);
+        const bool last = (c == SLICE / EPI_C - 1);
+        if (live) {
+          uint32_t r[32];
+          tmem_ld32(tacc + (uint32_t)col0, r);
+          float* row = st + lane * ST_LD;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(row + 4 * i) =
+                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                            __uint_as_float(r[4 * i + 3]));
+        }
+        if (last) {                           // all TMEM reads of this tile are done: hand the accumulator back
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+        if (!live) continue;
+        __syncwarp();
+        if (m0 + q * 32 + 32 <= e.M) epilogue_chunk<EPI, true>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4);
+        else epilogue_chunk<EPI, false>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4);
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
 // ---- host: tensor maps (shared cache in runtime.cu) -------------------------------------------------------
 // 3-D bf16 tensor map: dims {d0 (contiguous), d1, d2}, strides in elements, box {b0, b1, 1}, SWIZZLE_128B
 static int get_map(const void* ptr, long long d0, long long d1, long long d2, long long s1, long long s2, int b0, int b1,
@@ -479,6 +759,61 @@ static int launch(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   return ga_check_launch("gemm_tc");
 }
 
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  int rc;
+  if (!A_MN) rc = get_map(g->A, g->K, g->M, g->batch, g->a_rs, g->a_bs, BK, BM, &ma);
+  else rc = get_map(g->A, g->M, g->K, g->batch, g->a_cs, g->a_bs, 64, BK, &ma);
+  if (rc) return rc;
+  if (!B_MN) rc = get_map(g->B, g->K, g->N, g->batch, g->b_rs, g->b_bs, BK, BN, &mb);
+  else rc = get_map(g->B, g->N, g->K, g->batch, g->b_cs, g->b_bs, 64, BK, &mb);
+  if (rc) return rc;
+  Params p;
+  p.M = g->M; p.N = g->N; p.K = g->K;
+  p.kb_total = (g->K + BK - 1) / BK;
+  const int mt = (g->M + BM - 1) / BM, nt = (g->N + BN - 1) / BN;
+  const int sms = ga_num_sms();
+  int splits = 1;
+  if (g->accumulate) {
+    splits = g->splits;
+    if (splits <= 0) {
+      const long long tiles = (long long)mt * nt * g->batch;
+      splits = (int)((2LL * sms + tiles - 1) / tiles);
+      int maxs = p.kb_total / 4; if (maxs < 1) maxs = 1;
+      if (splits > maxs) splits = maxs;
+      if (splits < 1) splits = 1;
+    }
+    if (splits > p.kb_total) splits = p.kb_total;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.splits = splits;
+  constexpr int STAGE_BYTES = (BM + BN) * BK * 2;
+  constexpr size_t FIXED = 1024 + (size_t)EPI_WARPS * 32 * ST_LD * 4 + 256;
+  int stages = (int)((225 * 1024 - FIXED) / STAGE_BYTES);
+  static int stages_env = -1;
+  if (stages_env < 0) { const char* sv = getenv("GA_GEMM_STAGES"); stages_env = sv ? atoi(sv) : 0; }
+  if (stages_env > 0 && stages_env < stages) stages = stages_env;
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  p.idesc = make_idesc(BM, BN, A_MN, B_MN);
+  p.lbo_a = A_MN ? 64 * BK * 2 : 16; p.sbo_a = 1024;
+  p.lbo_b = B_MN ? 64 * BK * 2 : 16; p.sbo_b = 1024;
+  const size_t smem = FIXED + (size_t)stages * STAGE_BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_tc2_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_done = true;
+  }
+  const long long total = (long long)mt * nt * g->batch * splits;
+  GA_REQUIRE(total < (1LL << 31), GA_ERR_SHAPE, "ga_gemm: too many tiles");
+  const int grid = (int)(total < sms ? total : sms);
+  gemm_tc2_kernel<BN, A_MN, B_MN, EPI><<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ma, mb, p, e, mt, nt, (int)total);
+  ga_count_launch();
+  return ga_check_launch("gemm_tc2");
+}
+
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------ entry point
@@ -527,10 +862,51 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
     GA_REQUIRE(use_tc, GA_ERR_ALIGN, "ga_gemm: operands not eligible for the tcgen05 path (bf16, 16B-aligned, unit stride)");
   if (use_tc) {
     g_last_backend = GA_BACKEND_TCGEN05;
+    static int v1_env = -1;
+    if (v1_env < 0) { const char* sv = getenv("GA_GEMM_V1"); v1_env = (sv && atoi(sv)) ? 1 : 0; }
     const bool wide = g->N > 64;
-#define GA_TC_CASE(AM, BM_)                                                        \
-  if (a_mn == AM && b_mn == BM_)                                                    \
-    return wide ? tc::launch<128, AM, BM_>(g, e, st) : tc::launch<64, AM, BM_>(g, e, st);
+    const bool wide256 = (g->N >= 512) || (g->N % 256 == 0);
+    // compile-time specialised epilogues for the ConvNeXt-block GEMMs (vector path: widths and pitches multiples of 4)
+    const bool v4 = ((g->N & 3) == 0) && ((g->ldd & 3) == 0) && e.d_cs == 1 && g->alpha == 1.0f;
+    const bool bf_out = (g->out_dtype == GA_BF16);
+    const bool b4 = !g->bias || (((uintptr_t)g->bias & 15) == 0 && (g->bias_bs & 3) == 0);
+    int epi = tc::EPI_GENERIC;
+    if (v4 && b4 && !v1_env && wide) {
+      const bool plain = !g->Z && !g->colscale && !g->rowscale && !g->R && !g->Zin && !g->accumulate;
+      if (!a_mn && !b_mn && bf_out && g->act == GA_ACT_GELU && !g->colscale && !g->rowscale && !g->R && !g->Zin && !g->accumulate && !g->z_shadow)
+        epi = g->Z ? tc::EPI_BIAS_GELU_Z : tc::EPI_BIAS_GELU;
+      else if (!a_mn && !b_mn && !bf_out && g->act == GA_ACT_NONE && g->R && (g->ldr & 3) == 0 && !g->Zin && !g->accumulate &&
+               (!g->Z || g->z_shadow) && (!g->colscale || (((uintptr_t)g->colscale & 15) == 0 && (g->colscale_bs & 3) == 0)))
+        epi = tc::EPI_RES_F32_SHADOW;
+      else if (!a_mn && b_mn && bf_out && g->Zin && g->zmode == GA_ACT_GELU && (g->ldz & 3) == 0 && !g->bias && !g->Z && !g->colscale &&
+               !g->rowscale && !g->R && !g->accumulate)
+        epi = tc::EPI_ZIN_GELU;
+      else if (!a_mn && bf_out && g->act == GA_ACT_NONE && plain)
+        epi = tc::EPI_PLAIN_BF16;
+    }
+    if (((g->N & 3) == 0) && ((g->ldd & 3) == 0) && e.d_cs == 1 && !v1_env && wide && a_mn && b_mn && g->accumulate &&
+        ((uintptr_t)g->D & 15) == 0 && (g->d_bs & 3) == 0)
+      epi = tc::EPI_ACCUM;
+#define GA_TC2(BN_, AM, BM_, EP) return tc::launch2<BN_, AM, BM_, EP>(g, e, st)
+#define GA_TC_BN(AM, BM_, EP) { if (wide256) GA_TC2(256, AM, BM_, EP); else GA_TC2(128, AM, BM_, EP); }
+    if (wide && !v1_env) {
+      switch (epi) {
+        case tc::EPI_BIAS_GELU_Z: GA_TC_BN(false, false, tc::EPI_BIAS_GELU_Z)
+        case tc::EPI_BIAS_GELU: GA_TC_BN(false, false, tc::EPI_BIAS_GELU)
+        case tc::EPI_RES_F32_SHADOW: GA_TC_BN(false, false, tc::EPI_RES_F32_SHADOW)
+        case tc::EPI_ZIN_GELU: GA_TC_BN(false, true, tc::EPI_ZIN_GELU)
+        case tc::EPI_ACCUM: GA_TC_BN(true, true, tc::EPI_ACCUM)
+        case tc::EPI_PLAIN_BF16:
+          if (b_mn) GA_TC_BN(false, true, tc::EPI_PLAIN_BF16) else GA_TC_BN(false, false, tc::EPI_PLAIN_BF16)
+        default: break;
+      }
+    }
+#define GA_TC_CASE(AM, BM_)                                                                      \
+  if (a_mn == AM && b_mn == BM_) {                                                                \
+    if (!wide) return tc::launch<64, AM, BM_>(g, e, st);                                          \
+    if (v1_env) return tc::launch<128, AM, BM_>(g, e, st);                                        \
+    GA_TC_BN(AM, BM_, tc::EPI_GENERIC)                                                            \
+  }
     GA_TC_CASE(false, false)
     GA_TC_CASE(false, true)
     GA_TC_CASE(true, false)

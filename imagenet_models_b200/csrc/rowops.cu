@@ -149,7 +149,7 @@ __global__ void reduce_parts2_kernel(const float* __restrict__ partial, int npar
 
 static inline int row_parts(long long M) {
   long long p = (M + 63) / 64;  // >= 64 rows per CTA
-  const long long cap = 2LL * 148;
+  const long long cap = 8LL * 148;
   if (p > cap) p = cap;
   if (p < 1) p = 1;
   return (int)p;
@@ -165,7 +165,12 @@ extern "C" int ga_layernorm_bwd(const void* dy, const void* x, const float* w, c
   if (M == 0) return GA_OK;
   const bool want_param = (dw || db);
   GA_REQUIRE(!want_param || partial, GA_ERR_SHAPE, "ga_layernorm_bwd: parameter gradients need the partial workspace");
-  const int parts = row_parts(M);
+  int parts = row_parts(M);
+  if (!want_param) {                      // no partial buffers needed: one warp-row per slot, many CTAs in flight
+    long long p = (M + 15) / 16;
+    if (p > 32LL * 148) p = 32LL * 148;
+    parts = (int)(p < 1 ? 1 : p);
+  }
   const int rows_per_cta = (int)((M + parts - 1) / parts);
   const size_t smem = want_param ? (size_t)2 * C * sizeof(float) : 0;
   const int x_is_hat = (mean == nullptr);
@@ -308,7 +313,19 @@ __global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, 
   if (c < C) {
     float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
     if (MODE == 1) { mu = *reinterpret_cast<const float4*>(mean + c); is = *reinterpret_cast<const float4*>(invstd + c); }
-    for (long long r = r0 + wid; r < r0 + rows_per_cta && r < M; r += 8) {
+    long long rend = r0 + rows_per_cta;
+    if (rend > M) rend = M;
+    long long r = r0 + wid;
+    if (MODE == 0) {
+      for (; r + 24 < rend; r += 32) {     // four independent row loads in flight
+        float4 v0 = ld4(x + r * ldx + c), v1 = ld4(x + (r + 8) * ldx + c), v2 = ld4(x + (r + 16) * ldx + c), v3 = ld4(x + (r + 24) * ldx + c);
+        a.x += (v0.x + v1.x) + (v2.x + v3.x); a.y += (v0.y + v1.y) + (v2.y + v3.y);
+        a.z += (v0.z + v1.z) + (v2.z + v3.z); a.w += (v0.w + v1.w) + (v2.w + v3.w);
+        q.x += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x); q.y += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+        q.z += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z); q.w += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+      }
+    }
+    for (; r < rend; r += 8) {
       float4 v = ld4(x + r * ldx + c);
       if (MODE == 0) {
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
@@ -336,7 +353,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, 
 
 extern "C" int ga_colstats_parts(long long M, int C) {
   const int strips = (C + 127) / 128;
-  long long p = (2LL * 148 + strips - 1) / strips;
+  long long p = (8LL * 148 + strips - 1) / strips;
   const long long maxp = (M + 63) / 64;
   if (p > maxp) p = maxp;
   if (p < 1) p = 1;

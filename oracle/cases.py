@@ -102,3 +102,11 @@ def digest_close(t, dig, rtol, atol=3e-4):
     ok_sample = err <= rtol * sample.double().norm().item() + atol
     ok_norm = abs(flat.double().norm().item() - norm) <= rtol * norm + atol
     return ok_sample and ok_norm
+
+
+def digest_rel_err(t, dig):
+    """Relative L2 error of a tensor against the sampled entries of a digest made by digest()."""
+    norm, sample, stride = dig
+    flat = t.detach().reshape(-1).float().cpu()
+    mine = flat[::stride][:sample.numel()]
+    return (mine.double() - sample.double()).norm().item() / max(sample.double().norm().item(), 1e-30)

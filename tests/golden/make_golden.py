@@ -101,6 +101,20 @@ def golden_ga_model():
                 o16 = m2(x)
             base = r_eval if mode == 'eval' else [t.detach() for t in r_train]
             self_err[mode] = max(rel(a.float(), b) for a, b in zip(o16, base))
+        # per-parameter deviation of the reference's bf16-autocast GRADIENTS from its fp32 gradients (train mode)
+        m3 = timm.create_model(name)
+        m3.load_state_dict(P, strict=True)
+        m3.train()
+        with torch.autocast('cpu', dtype=torch.bfloat16):
+            o3 = m3(x)
+            l3 = sum(F.cross_entropy(o.float(), y) for o in o3)
+            mean3 = sum(o.detach().float() for o in o3) / len(o3)
+            for o in o3:
+                l3 = l3 + F.kl_div(F.log_softmax(o.float(), -1), F.log_softmax(mean3, -1), reduction='mean', log_target=True) * cases.GA_LAM
+        l3.backward()
+        self_err['grads'] = {k: rel(p.grad.float(), r_grads[k]) for k, p in m3.named_parameters()}
+        big = sorted(self_err['grads'].values())
+        print(f'   reference bf16-autocast gradient self error: median {big[len(big)//2]:.2e}, max {big[-1]:.2e}')
         print(f'{name} B={B}: oracle==reference  (loss {loss.item():.6f}, worst grad rel {worst:.2e}, '
               f"reference bf16-autocast self error eval {self_err['eval']:.2e} train {self_err['train']:.2e})")
         out[f'{name}/B{B}'] = dict(ref_bf16_self_err=self_err,
