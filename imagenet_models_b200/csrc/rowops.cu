@@ -88,7 +88,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) { dwv[i] = make_float4(0, 0, 0, 0); dbv[i] = make_float4(0, 0, 0, 0); }
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
-  for (long long row = r0 + wid; row < r0 + rows_per_cta && row < M; row += nw) {
+  long long row_end = r0 + rows_per_cta;
+  if (row_end > M) row_end = M;
+  // prefetch hint for the row after next keeps two rows of loads in flight per warp
+  for (long long row = r0 + wid; row < row_end; row += nw) {
+    if (row + nw < row_end) {
+      const int c0 = lane * 4;
+      if (c0 < C) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + (row + nw) * lddy + c0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (row + nw) * ldx + c0));
+      }
+    }
     const float mu = x_is_hat ? 0.f : mean[row];
     const float rs = rstd[row];
     float4 g[MAXV], xh[MAXV];
@@ -137,14 +147,29 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
 }
 
 // out0[j] += sum_p partial[p][j] (j < n0), out1[j-n0] += ... (j >= n0)
-__global__ void reduce_parts2_kernel(const float* __restrict__ partial, int nparts, int n, float* __restrict__ out0, int n0,
-                                     float* __restrict__ out1, int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+// block = 32 columns x 8 part-slices (256 threads); launch with grid ((n + 31) / 32)
+__global__ void __launch_bounds__(256) reduce_parts2_kernel(const float* __restrict__ partial, int nparts, int n,
+                                                            float* __restrict__ out0, int n0, float* __restrict__ out1,
+                                                            int accumulate) {
+  __shared__ float sh[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n + j];
-  float* o = (j < n0) ? (out0 ? out0 + j : nullptr) : (out1 ? out1 + (j - n0) : nullptr);
-  if (o) *o = accumulate ? (*o + s) : s;
+  if (j < n) {
+    int p = slice;
+    for (; p + 24 < nparts; p += 32)
+      s += (partial[(size_t)p * n + j] + partial[(size_t)(p + 8) * n + j]) + (partial[(size_t)(p + 16) * n + j] + partial[(size_t)(p + 24) * n + j]);
+    for (; p < nparts; p += 8) s += partial[(size_t)p * n + j];
+  }
+  sh[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && j < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][lane];
+    float* o = (j < n0) ? (out0 ? out0 + j : nullptr) : (out1 ? out1 + (j - n0) : nullptr);
+    if (o) *o = accumulate ? (*o + t) : t;
+  }
 }
 
 static inline int row_parts(long long M) {
@@ -181,13 +206,85 @@ extern "C" int ga_layernorm_bwd(const void* dy, const void* x, const float* w, c
   });
   int rc = launch_ok("layernorm_bwd");
   if (rc || !want_param) return rc;
-  reduce_parts2_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, dw, C, db, 1);
+  reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, dw, C, db, 1);
   return launch_ok("layernorm_bwd_reduce");
+}
+
+// LN backward with xhat saved and no parameters: the hot form inside the ConvNeXt block.  VPL float4 vectors per lane
+// cover C <= 128*VPL channels; ROWS rows are loaded before any reduction so each warp keeps 2*ROWS*VPL 128-bit loads in flight.
+template <typename T, int VPL, int ROWS>
+__global__ void __launch_bounds__(256) ln_bwd_hat_kernel(const T* __restrict__ dxhat, const T* __restrict__ xhat,
+                                                         const float* __restrict__ rstd, T* __restrict__ dconv, long long M, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float invC = 1.f / (float)C;
+  for (long long row0 = gw * ROWS; row0 < M; row0 += nwarps * ROWS) {
+    float4 g[ROWS][VPL], xh[ROWS][VPL];
+    float s1[ROWS], s2[ROWS], rs[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r;
+      rs[r] = row < M ? rstd[row] : 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int c = (v * 32 + lane) * 4;
+        if (row < M && c < C) { g[r][v] = ld4(dxhat + row * C + c); xh[r][v] = ld4(xhat + row * C + c); }
+        else { g[r][v] = make_float4(0, 0, 0, 0); xh[r][v] = g[r][v]; }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        a += (g[r][v].x + g[r][v].y) + (g[r][v].z + g[r][v].w);
+        b += (g[r][v].x * xh[r][v].x + g[r][v].y * xh[r][v].y) + (g[r][v].z * xh[r][v].z + g[r][v].w * xh[r][v].w);
+      }
+      s1[r] = a; s2[r] = b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+        s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = row0 + r;
+      if (row >= M) continue;
+      const float m1 = s1[r] * invC, m2 = s2[r] * invC;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int c = (v * 32 + lane) * 4;
+        if (c < C) {
+          float4 o = make_float4(rs[r] * (g[r][v].x - m1 - xh[r][v].x * m2), rs[r] * (g[r][v].y - m1 - xh[r][v].y * m2),
+                                 rs[r] * (g[r][v].z - m1 - xh[r][v].z * m2), rs[r] * (g[r][v].w - m1 - xh[r][v].w * m2));
+          st4(dconv + row * C + c, o);
+        }
+      }
+    }
+  }
 }
 
 extern "C" int ga_ln_bwd_rows(const void* dxhat, const void* xhat, const float* rstd, void* dconv, long long M, int C, int dtype,
                               ga_stream_t s) {
-  return ga_layernorm_bwd(dxhat, xhat, nullptr, nullptr, rstd, dconv, nullptr, nullptr, nullptr, M, C, C, C, C, dtype, s);
+  if (C > 512 || (C & 3))
+    return ga_layernorm_bwd(dxhat, xhat, nullptr, nullptr, rstd, dconv, nullptr, nullptr, nullptr, M, C, C, C, C, dtype, s);
+  GA_REQUIRE(dxhat && xhat && rstd && dconv, GA_ERR_SHAPE, "ga_ln_bwd_rows: null argument");
+  if (M == 0) return GA_OK;
+  const int rows = C <= 128 ? 4 : (C <= 256 ? 2 : 1);
+  long long blocks = (M + 8LL * rows - 1) / (8LL * rows);
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  cudaStream_t st = (cudaStream_t)s;
+  DISPATCH_T(dtype, {
+    if (C <= 128) ln_bwd_hat_kernel<T, 1, 4><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, M, C);
+    else if (C <= 256) ln_bwd_hat_kernel<T, 2, 2><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, M, C);
+    else ln_bwd_hat_kernel<T, 4, 1><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, M, C);
+  });
+  return launch_ok("ln_bwd_hat");
 }
 
 // ---------------------------------------------------------------------------------------------- patch gathers
@@ -369,7 +466,7 @@ extern "C" int ga_colstats(const void* x, float* sum, float* sumsq, float* parti
   DISPATCH_T(dtype, { colstats_kernel<T, 0><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, partial, M, C, ldx, 0, 0, rows_per_cta, 0); });
   int rc = launch_ok("colstats");
   if (rc) return rc;
-  reduce_parts2_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, sum, C, sumsq, accumulate);
+  reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, sum, C, sumsq, accumulate);
   return launch_ok("colstats_reduce");
 }
 
@@ -459,7 +556,7 @@ extern "C" int ga_bn_bwd_reduce(const void* dy, const void* x, const void* y, co
   DISPATCH_T(dtype, { colstats_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)dy, (const T*)y, mean, invstd, partial, M, C, ldx, lddy, ldy, rows_per_cta, relu); });
   int rc = launch_ok("bn_bwd_reduce");
   if (rc) return rc;
-  reduce_parts2_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, c1, C, c2, 0);
+  reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, c1, C, c2, 0);
   return launch_ok("bn_bwd_reduce2");
 }
 
@@ -517,10 +614,29 @@ __global__ void copy_cols_kernel(const TS* __restrict__ src, TD* __restrict__ ds
     st_f(dst + r * ldd + c, ld_f(src + r * lds + c));
   }
 }
+template <typename TS, typename TD>
+__global__ void copy_cols4_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long M, int C4, long long lds, long long ldd) {
+  const long long total = M * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C4; const int c = (int)(i - r * C4) * 4;
+    st4(dst + r * ldd + c, ld4(src + r * lds + c));
+  }
+}
 extern "C" int ga_copy_cols(const void* src, void* dst, long long M, int C, long long lds, long long ldd, int src_dtype,
                             int dst_dtype, ga_stream_t s) {
   const long long total = M * C;
   if (total == 0) return GA_OK;
+  if ((C & 3) == 0 && (lds & 3) == 0 && (ldd & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    const long long t4 = total >> 2;
+    const int grid4 = (int)((t4 + 255) / 256 > 148 * 16 ? 148 * 16 : (t4 + 255) / 256);
+    cudaStream_t st4s = (cudaStream_t)s;
+    const int C4 = C >> 2;
+    if (src_dtype == GA_F32 && dst_dtype == GA_F32) copy_cols4_kernel<float, float><<<grid4, 256, 0, st4s>>>((const float*)src, (float*)dst, M, C4, lds, ldd);
+    else if (src_dtype == GA_F32) copy_cols4_kernel<float, bf16><<<grid4, 256, 0, st4s>>>((const float*)src, (bf16*)dst, M, C4, lds, ldd);
+    else if (dst_dtype == GA_F32) copy_cols4_kernel<bf16, float><<<grid4, 256, 0, st4s>>>((const bf16*)src, (float*)dst, M, C4, lds, ldd);
+    else copy_cols4_kernel<bf16, bf16><<<grid4, 256, 0, st4s>>>((const bf16*)src, (bf16*)dst, M, C4, lds, ldd);
+    return launch_ok("copy_cols4");
+  }
   const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
   cudaStream_t st = (cudaStream_t)s;
   if (src_dtype == GA_F32 && dst_dtype == GA_F32) copy_cols_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, M, C, lds, ldd);
@@ -614,8 +730,11 @@ __global__ void __launch_bounds__(256) linear_grad_cols_kernel(const float* __re
   const int wid = threadIdx.x >> 5;
   __shared__ float sh[2][8][32];
   float a = 0.f, b = 0.f;
+  const int rows_per = (N + gridDim.y - 1) / gridDim.y;
+  const int n_begin = blockIdx.y * rows_per;
+  const int n_end = min(N, n_begin + rows_per);
   if (k < K) {
-    for (int n = wid; n < N; n += 8) {
+    for (int n = n_begin + wid; n < n_end; n += 8) {
       const float wv = W[(size_t)n * K + k] * (g ? g[n] : 1.f);
       a += wv * G[(size_t)n * K + k];
       b += wv * s[n];
@@ -627,8 +746,8 @@ __global__ void __launch_bounds__(256) linear_grad_cols_kernel(const float* __re
     float ta = 0.f, tb = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ta += sh[0][i][threadIdx.x]; tb += sh[1][i][threadIdx.x]; }
-    if (dw) dw[k] += ta;
-    if (db_in) db_in[k] += tb;
+    if (dw) atomicAdd(dw + k, ta);
+    if (db_in) atomicAdd(db_in + k, tb);
   }
 }
 extern "C" int ga_linear_grad_finalize(const float* G, const float* s, const float* W, const float* bias, const float* g,
@@ -643,7 +762,11 @@ extern "C" int ga_linear_grad_finalize(const float* G, const float* s, const flo
     if (rc) return rc;
   }
   if (dw || db_in) {
-    linear_grad_cols_kernel<<<(K + 31) / 32, 256, 0, (cudaStream_t)st>>>(G, s, W, g, dw, db_in, N, K);
+    const int kb = (K + 31) / 32;
+    int ny = (2 * 148 + kb - 1) / kb;
+    if (ny > (N + 63) / 64) ny = (N + 63) / 64;
+    if (ny < 1) ny = 1;
+    linear_grad_cols_kernel<<<dim3(kb, ny), 256, 0, (cudaStream_t)st>>>(G, s, W, g, dw, db_in, N, K);
     return launch_ok("linear_grad_cols");
   }
   return GA_OK;

@@ -336,6 +336,7 @@ class GA_ConvNeXt(nn.Module):
         nb = self.branches
         tr = self.training
         Cc = f.shape[1]
+        T = f.dtype
         E = self.ga[0].attn.dim_embed
         heads = self.ga[0].attn.num_heads
         fhat = ops.layernorm(f, None, None, self.ga[0].norm1.eps)
@@ -348,16 +349,18 @@ class GA_ConvNeXt(nn.Module):
             g = ops.linear(f, conv.weight.reshape(self.gram_dim, Cc), conv.bias)
             g = ops.batchnorm(g, _params(bn), tr)
             g, _, _, _ = self.gram_layer[k].run(g, None, geom, g.dtype, g.dtype)
-            gv = ops.gram_vector(g, Bn, HW, float(H))                              # [B, tri] fp32
             emb, ebn = self.gram_embedding[k][0], self.gram_embedding[k][1]
             G = self.embed_groups
-            a3 = gv.view(Bn, G, -1).transpose(0, 1)
-            c = ops.grouped_linear(a3, emb.weight.view(G, Cc // G, -1), emb.bias)  # [B, C] fp32
+            glen = emb.weight.shape[1]
+            gv = ops.gram_vector(g, Bn, HW, float(H), T, G)                        # [B, G*pad8(glen)] in T (fp32: unpadded)
+            a3 = gv.view(Bn, G, -1)[:, :, :glen].transpose(0, 1)
+            c = ops.grouped_linear(a3, emb.weight.view(G, Cc // G, glen), emb.bias, out_dtype=torch.float32)  # [B, C] fp32
             c = ops.batchnorm(c, _params(ebn), tr)
             blk = self.ga[k]
             cn = ops.layernorm(c, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
-            qs.append(ops.linear(cn, blk.attn.q.weight * blk.attn.scale))
-            kvcs.append(ops.linear(cn, torch.cat((blk.attn.k.weight, blk.attn.v.weight), 0)))
+            cn_t = ops.to_dtype(cn, T)       # like autocast: fp32 LayerNorm output, bf16 operands for the Linear
+            qs.append(ops.linear(cn_t, blk.attn.q.weight * blk.attn.scale, out_dtype=torch.float32))
+            kvcs.append(ops.linear(cn_t, torch.cat((blk.attn.k.weight, blk.attn.v.weight), 0), out_dtype=torch.float32))
             cls.append(c)
         q = torch.stack(qs).view(nb, Bn, 1, E)
         kvc = torch.stack(kvcs).view(nb, Bn, 1, 2 * E)
@@ -365,10 +368,11 @@ class GA_ConvNeXt(nn.Module):
         outs = []
         for k in range(nb):
             blk = self.ga[k]
-            c = cls[k] + blk.gamma_1 * ops.linear(o[k, :, 0], blk.attn.proj.weight, blk.attn.proj.bias)
+            c = cls[k] + blk.gamma_1 * ops.linear(ops.to_dtype(o[k, :, 0], T), blk.attn.proj.weight, blk.attn.proj.bias,
+                                                  out_dtype=torch.float32)
             h = ops.layernorm(c, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
             c = c + blk.gamma_2 * blk.mlp.run(h)
-            outs.append(ops.linear(c, self.fc[k].weight, self.fc[k].bias))
+            outs.append(ops.linear(ops.to_dtype(c, T), self.fc[k].weight, self.fc[k].bias, out_dtype=torch.float32))
         return outs
 
     def forward(self, x):

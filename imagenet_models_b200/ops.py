@@ -309,7 +309,7 @@ class ConvNeXtBlockFn(Function):
             dy = torch.zeros(M, Cc, dtype=RT, device=dev)
         dy = dy.contiguous()
         if dys_in is not None:                      # gradient that arrived through the bf16 shadow (stage boundaries)
-            dy = dy + dys_in.to(RT)
+            dy = dy + dys_in                        # type promotion keeps the sum in the stream dtype
         dys = convert(dy, T) if RT != T else dy     # bf16 operand copy of the stream gradient
         if path_scale is not None:
             t = torch.empty_like(dys)
@@ -666,10 +666,13 @@ def se_gate(x, w1, b1, w2, b2, Bn, HW):
 
 # ------------------------------------------------------------------------------------------------- Gram vector
 class GramFn(Function):
-    """get_gram (ga_convnext.py:452-467): x/div -> X X^T / HW -> row-major upper triangle -> L2 normalise -> fp32."""
+    """get_gram (ga_convnext.py:452-467): x/div -> X X^T / HW -> row-major upper triangle -> L2 normalise.
+
+    The vector is emitted in `out_dtype` with each of `groups` equal slices padded to a 16-byte multiple (the layout
+    the grouped 1x1 gram_embedding conv reads through TMA); fp32 output is unpadded like the reference's."""
 
     @staticmethod
-    def forward(ctx, x, Bn, HW, div):
+    def forward(ctx, x, Bn, HW, div, out_dtype, groups):
         x = x.contiguous()
         Cc = x.shape[1]
         dev = x.device
@@ -678,30 +681,34 @@ class GramFn(Function):
         G = torch.empty(Bn, Cc, Cc, dtype=torch.float32, device=dev)
         gemm(X3, X3, G, alpha=alpha)
         tri = Cc * (Cc + 1) // 2
-        out = torch.empty(Bn, tri, dtype=torch.float32, device=dev)
+        assert tri % groups == 0
+        glen = tri // groups
+        gld = pad8(glen) if out_dtype == torch.bfloat16 else glen
+        out = torch.empty(Bn, groups * gld, dtype=out_dtype, device=dev)
         norm = torch.empty(Bn, dtype=torch.float32, device=dev)
-        L.check(_L().ga_gram_triu_fwd(L.ptr(G), L.ptr(out), L.ptr(norm), Bn, Cc, tri, tri, L.ll(tri), F32, L.stream()),
-                'ga_gram_triu_fwd')
+        L.check(_L().ga_gram_triu_fwd(L.ptr(G), L.ptr(out), L.ptr(norm), Bn, Cc, glen, gld, L.ll(groups * gld), L.dt(out),
+                                      L.stream()), 'ga_gram_triu_fwd')
         ctx.save_for_backward(x, out, norm)
-        ctx.dims = (Bn, HW, Cc, alpha)
+        ctx.dims = (Bn, HW, Cc, alpha, glen, gld)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, out, norm = ctx.saved_tensors
-        Bn, HW, Cc, alpha = ctx.dims
-        dout = dout.contiguous().float()
-        tri = out.shape[1]
+        Bn, HW, Cc, alpha, glen, gld = ctx.dims
+        dout = dout.contiguous()
+        if dout.dtype != out.dtype:
+            dout = dout.to(out.dtype)
         S = torch.empty(Bn, Cc, Cc, dtype=x.dtype, device=x.device)
-        L.check(_L().ga_gram_triu_bwd(L.ptr(dout), L.ptr(out), L.ptr(norm), L.ptr(S), Bn, Cc, tri, tri, L.ll(tri), F32, L.dt(S),
-                                      L.stream()), 'ga_gram_triu_bwd')
+        L.check(_L().ga_gram_triu_bwd(L.ptr(dout), L.ptr(out), L.ptr(norm), L.ptr(S), Bn, Cc, glen, gld, L.ll(out.shape[1]),
+                                      L.dt(out), L.dt(S), L.stream()), 'ga_gram_triu_bwd')
         dx = torch.empty(Bn * HW, Cc, dtype=x.dtype, device=x.device)
         gemm(x.view(Bn, HW, Cc), S, dx.view(Bn, HW, Cc), alpha=alpha)   # dX = alpha * X (dG + dG^T)
-        return dx, None, None, None
+        return dx, None, None, None, None, None
 
 
-def gram_vector(x, Bn, HW, div):
-    return GramFn.apply(x, Bn, HW, div)
+def gram_vector(x, Bn, HW, div, out_dtype=torch.float32, groups=1):
+    return GramFn.apply(x, Bn, HW, div, out_dtype, groups)
 
 
 # ------------------------------------------------------------------------------------------------- attention pooling

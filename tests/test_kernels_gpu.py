@@ -314,7 +314,7 @@ def test_gram_vector(cname, dtype, golden_dir):
     x = cases.gram_input(Cc, H, Bn)
     gold = torch.load(os.path.join(golden_dir, 'ga_convnext_modules.pt'))[f'{cname}/train0'].reshape(Bn, -1)
     xr = x.to(DEV).permute(0, 2, 3, 1).reshape(-1, Cc).to(dtype).contiguous().requires_grad_(True)
-    out = ops.gram_vector(xr, Bn, H * H, float(H))
+    out = ops.gram_vector(xr, Bn, H * H, float(H))      # fp32, unpadded (the reference's layout)
     assert out.dtype == torch.float32
     assert rel(out.cpu(), gold) < (1e-5 if dtype == torch.float32 else 6e-3)
     dout = rnd(*out.shape, seed=70)
