@@ -3,15 +3,21 @@
 // (ga_convnext.py:92-93,100,105-106; map_convnext.py:18-19,29-31) and their autograd.
 //
 // Layout: x is NHWC.  One CTA owns a TH x TW pixel tile for ALL channels (LayerNorm needs the whole row).
-// The (TH+6) x (TW+6) x C input halo is staged in shared memory by TMA (4-D tensor map, out-of-bounds = zero
-// = the conv padding), one elected thread, one mbarrier.  Thread (row, channel-group) slides a 7-tap window
-// along its output row keeping TW x CPT fp32 accumulators in registers; LayerNorm statistics are reduced with
-// warp shuffles + one small smem exchange (two rounds: mean, then centred variance).
+//  * The (TH+6) x (TW+6) x C input halo is staged in shared memory by TMA (4-D tensor map; out-of-bounds = zero =
+//    the conv padding): one elected thread, one mbarrier.  Two CTAs are resident per SM, so one CTA's halo load
+//    overlaps the other's FMA phase.
+//  * Thread (row, channel PAIR) slides the 7-tap window along its output row: the halo row streams through one
+//    LDS at a time (32-bit shared-window addresses, no generic pointers) and every tap is ONE packed FFMA2
+//    (fma.rn.f32x2, two channels per issue slot) into TW fp32x2 accumulators held in registers.
+//  * LayerNorm statistics: per-thread pair sums -> shared memory -> one warp per pixel (two rounds: mean, then
+//    centred variance), independent of how rows map onto warps (no idle lanes at C=96).
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 
 namespace dw {
+
+typedef unsigned long long u64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -32,44 +38,57 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-          smem_u32(dst)),
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
+// packed fp32x2 arithmetic (Blackwell FFMA2: two FMAs per issue slot)
+__device__ __forceinline__ u64 pack2(float lo, float hi) { return ((u64)__float_as_uint(hi) << 32) | (u64)__float_as_uint(lo); }
+__device__ __forceinline__ float lo2(u64 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2(u64 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// two consecutive channels from shared memory (32-bit shared-window address) as packed fp32x2
+template <typename T> __device__ __forceinline__ u64 lds_pair(uint32_t a);
+template <> __device__ __forceinline__ u64 lds_pair<float>(uint32_t a) {
+  u64 v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+  return v;
+}
+template <> __device__ __forceinline__ u64 lds_pair<bf16>(uint32_t a) {
+  uint32_t u;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(a));
+  return ((u64)(u & 0xffff0000u) << 32) | (u64)(u << 16);
+}
+template <typename T> __device__ __forceinline__ u64 ldg_pair(const T* p);
+template <> __device__ __forceinline__ u64 ldg_pair<float>(const float* p) { return *reinterpret_cast<const u64*>(p); }
+template <> __device__ __forceinline__ u64 ldg_pair<bf16>(const bf16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return ((u64)(u & 0xffff0000u) << 32) | (u64)(u << 16);
+}
+template <typename T> __device__ __forceinline__ void stg_pair(T* p, float lo, float hi);
+template <> __device__ __forceinline__ void stg_pair<float>(float* p, float lo, float hi) { *reinterpret_cast<float2*>(p) = make_float2(lo, hi); }
+template <> __device__ __forceinline__ void stg_pair<bf16>(bf16* p, float lo, float hi) { *reinterpret_cast<uint32_t*>(p) = pack_bf16(lo, hi); }
+
 struct Geo {
   int B, H, W, C;
-  int TH;            // output rows per CTA
+  int TH;            // output rows per CTA tile
+  int TR;            // rows computed per pass (threads = TR * P); the CTA makes ceil(TH/TR) passes over its halo
   int tiles_x, tiles_y;
   int cbox, nbox;    // channel box of the TMA load and number of boxes (nbox*cbox >= C)
   int box_stride;    // elements between consecutive channel boxes in smem (128-byte aligned)
-  int cgpad;         // channel groups per row padded to a multiple of 32 (threads per output row)
+  int P;             // channel pairs (C/2)
 };
-
-// smem element (halo row hy, halo col hx, channel c)
-template <typename T, int TW>
-__device__ __forceinline__ const T* halo_ptr(const T* tile, const Geo& g, int hy, int hx, int c) {
-  const int box = c / g.cbox, cc = c - box * g.cbox;
-  return tile + (size_t)box * g.box_stride + ((size_t)hy * (TW + 6) + hx) * g.cbox + cc;
-}
-
-template <int CPT, typename T> struct LdC;
-template <> struct LdC<1, float> { static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = p[0]; } };
-template <> struct LdC<2, float> { static __device__ __forceinline__ void ld(const float* p, float* v) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; } };
-template <> struct LdC<1, bf16> { static __device__ __forceinline__ void ld(const bf16* p, float* v) { v[0] = __bfloat162float(p[0]); } };
-template <> struct LdC<2, bf16> { static __device__ __forceinline__ void ld(const bf16* p, float* v) { uint32_t u = *reinterpret_cast<const uint32_t*>(p); v[0] = bf16lo(u); v[1] = bf16hi(u); } };
-template <int CPT, typename T> struct StC;
-template <> struct StC<1, float> { static __device__ __forceinline__ void st(float* p, const float* v) { p[0] = v[0]; } };
-template <> struct StC<2, float> { static __device__ __forceinline__ void st(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); } };
-template <> struct StC<1, bf16> { static __device__ __forceinline__ void st(bf16* p, const float* v) { p[0] = __float2bfloat16_rn(v[0]); } };
-template <> struct StC<2, bf16> { static __device__ __forceinline__ void st(bf16* p, const float* v) { *reinterpret_cast<uint32_t*>(p) = pack_bf16(v[0], v[1]); } };
 
 // stage the halo tile: one thread arms the barrier and issues one 4-D box per channel box
 template <typename T, int TW>
-__device__ __forceinline__ void load_halo(T* tile, uint64_t* bar, const CUtensorMap* map, const Geo& g, int b, int y0, int x0) {
+__device__ __forceinline__ void load_halo(uint32_t tile_s, uint64_t* bar, const CUtensorMap* map, const Geo& g, int b, int y0, int x0) {
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -79,77 +98,86 @@ __device__ __forceinline__ void load_halo(T* tile, uint64_t* bar, const CUtensor
     const uint32_t box_bytes = (uint32_t)((g.TH + 6) * (TW + 6) * g.cbox * sizeof(T));
     mbar_expect_tx(bar, box_bytes * g.nbox);
     for (int j = 0; j < g.nbox; ++j)
-      tma_load_4d(tile + (size_t)j * g.box_stride, map, bar, j * g.cbox, x0 - 3, y0 - 3, b);
+      tma_load_4d(tile_s + (uint32_t)((size_t)j * g.box_stride * sizeof(T)), map, bar, j * g.cbox, x0 - 3, y0 - 3, b);
   }
   mbar_wait(bar, 0);
 }
 
+// sum over the P channel pairs of every pixel: part[pixel][pair] -> stat[pixel]; one warp per pixel
+__device__ __forceinline__ void reduce_pixels(const float* part, float* stat, int npix, int P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int p = warp; p < npix; p += nw) {
+    float s = 0.f;
+    for (int k = lane; k < P; k += 32) s += part[p * P + k];
+    s = warp_sum(s);
+    if (lane == 0) stat[p] = s;
+  }
+}
+
 // MODE 0: forward  y = LN(conv(x) + bias)  (xhat, optional affine), rstd saved
 // MODE 1: dgrad    y = corr(x = dconv, flipped taps) + res
-constexpr int max_threads_for(int tw, int cpt) { return tw * cpt >= 28 ? 512 : (tw * cpt >= 14 ? 768 : 1024); }
-
-template <typename T, typename TO, int TW, int CPT, int MODE>
-__global__ void __launch_bounds__(max_threads_for(TW, CPT)) dwconv7_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ w49c,
-                                                       const float* __restrict__ bias, const float* __restrict__ ln_w,
-                                                       const float* __restrict__ ln_b, const TO* __restrict__ res,
-                                                       TO* __restrict__ y, float* __restrict__ rstd_out, float eps, Geo g) {
-  extern __shared__ uint8_t smem_raw[];
+template <typename T, typename TO, int TW, int MODE>
+__global__ void __launch_bounds__(512, 2) dwconv7_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ w49c,
+                                                         const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                         const float* __restrict__ ln_b, const TO* __restrict__ res,
+                                                         TO* __restrict__ y, float* __restrict__ rstd_out, float eps, Geo g) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint64_t* bar = (uint64_t*)sm;
-  T* tile = (T*)(sm + 128);
+  const uint32_t tile_s = smem_u32(sm + 128);
   const size_t tile_bytes = (size_t)g.nbox * g.box_stride * sizeof(T);
-  float* red = (float*)(sm + 128 + ((tile_bytes + 15) & ~(size_t)15));   // [TH][TW][nwarps_per_row]
-  const int wpr = g.cgpad / 32;                                     // warps per output row
-  float* stat = red + g.TH * TW * wpr;                              // [TH][TW] (mean, then rstd)
+  float* part = (float*)(sm + 128 + tile_bytes);                   // [TR*TW][P]
+  float* stat = part + (size_t)g.TR * TW * g.P;                    // [2][TR*TW]
 
   const int tile_id = blockIdx.x;
   const int tx = tile_id % g.tiles_x, ty = tile_id / g.tiles_x;
   const int b = blockIdx.y;
   const int x0 = tx * TW, y0 = ty * g.TH;
 
-  load_halo<T, TW>(tile, bar, &tm, g, b, y0, x0);
+  load_halo<T, TW>(tile_s, bar, &tm, g, b, y0, x0);
 
-  const int row = threadIdx.x / g.cgpad;         // output row inside the tile
-  const int cg = threadIdx.x - row * g.cgpad;    // channel group
-  const int c = cg * CPT;
-  const bool active = (c < g.C);
-  const int lane = threadIdx.x & 31, wrow = cg >> 5;
+  const int trow = threadIdx.x / g.P;            // row slot of this thread inside a pass
+  const int pr = threadIdx.x - trow * g.P;       // channel pair
+  const int c = pr * 2;
+#pragma unroll 1
+  for (int r0 = 0; r0 < g.TH; r0 += g.TR) {
+  const int row = r0 + trow;                     // output row inside the tile
+  const bool active = (trow < g.TR) && (row < g.TH);
 
-  float acc[TW][CPT];
+  u64 acc[TW];
+  {
+    u64 init = 0ull;
+    if (MODE == 0 && bias && active) init = *reinterpret_cast<const u64*>(bias + c);
 #pragma unroll
-  for (int i = 0; i < TW; ++i)
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
-
+    for (int i = 0; i < TW; ++i) acc[i] = init;
+  }
   if (active) {
-    if (MODE == 0 && bias) {
-      float bv[CPT];
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) bv[j] = bias[c + j];
-#pragma unroll
-      for (int i = 0; i < TW; ++i)
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) acc[i][j] = bv[j];
-    }
+    const int box = c / g.cbox, cc = c - box * g.cbox;
+    const uint32_t cbs = (uint32_t)(g.cbox * sizeof(T));
+    uint32_t rowaddr = tile_s + (uint32_t)(((size_t)box * g.box_stride + (size_t)row * (TW + 6) * g.cbox + cc) * sizeof(T));
+    const uint32_t row_pitch = (uint32_t)(TW + 6) * cbs;
+    // taps walk forward (conv) or backward (data gradient = correlation with the flipped kernel)
+    const float* wk = w49c + c + (MODE == 0 ? 0 : 48 * g.C);
+    const int wstep = (MODE == 0) ? g.C : -g.C;
 #pragma unroll 1
     for (int ky = 0; ky < 7; ++ky) {
-      float wv[7][CPT];
+      u64 wv[7];
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const int tap = (MODE == 0) ? (ky * 7 + kx) : ((6 - ky) * 7 + (6 - kx));
+      for (int kx = 0; kx < 7; ++kx) wv[kx] = __ldg(reinterpret_cast<const u64*>(wk + kx * wstep));
+      wk += 7 * wstep;
+      uint32_t a = rowaddr;
+      rowaddr += row_pitch;
+      // stream the TW+6 inputs of this halo row: one packed value live at a time, 7 FFMA2 each
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) wv[kx][j] = __ldg(w49c + (size_t)tap * g.C + c + j);
+      for (int jx = 0; jx < TW + 6; ++jx) {
+        const u64 in = lds_pair<T>(a);
+        a += cbs;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const int i = jx - kx;
+          if (i >= 0 && i < TW) acc[i] = ffma2(in, wv[kx], acc[i]);
+        }
       }
-      const T* rowp = halo_ptr<T, TW>(tile, g, row + ky, 0, c);
-      float in[TW + 6][CPT];
-#pragma unroll
-      for (int i = 0; i < TW + 6; ++i) LdC<CPT, T>::ld(rowp + (size_t)i * g.cbox, in[i]);
-#pragma unroll
-      for (int i = 0; i < TW; ++i)
-#pragma unroll
-        for (int kx = 0; kx < 7; ++kx)
-#pragma unroll
-          for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(in[i + kx][j], wv[kx][j], acc[i][j]);
     }
   }
 
@@ -161,152 +189,143 @@ __global__ void __launch_bounds__(max_threads_for(TW, CPT)) dwconv7_kernel(const
         const int ox = x0 + i;
         if (ox < g.W) {
           const size_t off = (((size_t)b * g.H + oy) * g.W + ox) * g.C + c;
-          float v[CPT];
-#pragma unroll
-          for (int j = 0; j < CPT; ++j) v[j] = acc[i][j];
-          if (res) {
-            float r[CPT];
-            LdC<CPT, TO>::ld(res + off, r);
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) v[j] += r[j];
-          }
-          StC<CPT, TO>::st(y + off, v);
+          float v0 = lo2(acc[i]), v1 = hi2(acc[i]);
+          if (res) { const u64 r = ldg_pair<TO>(res + off); v0 += lo2(r); v1 += hi2(r); }
+          stg_pair<TO>(y + off, v0, v1);
         }
       }
     }
-    return;
+    continue;
   }
 
   // ---- LayerNorm over channels (per pixel): round 1 mean, round 2 centred variance
   const float invC = 1.f / (float)g.C;
+  const int npix = g.TR * TW;
+  if (active) {
 #pragma unroll
-  for (int i = 0; i < TW; ++i) {
-    float s = 0.f;
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) s += acc[i][j];
-    }
-    s = warp_sum(s);
-    if (lane == 0) red[(row * TW + i) * wpr + wrow] = s;
+    for (int i = 0; i < TW; ++i) part[(trow * TW + i) * g.P + pr] = lo2(acc[i]) + hi2(acc[i]);
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < g.TH * TW; p += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < wpr; ++k) s += red[p * wpr + k];
-    stat[p] = s * invC;
-  }
+  reduce_pixels(part, stat, npix, g.P);
   __syncthreads();
   float mean[TW];
+  if (active) {
 #pragma unroll
-  for (int i = 0; i < TW; ++i) {
-    mean[i] = stat[row * TW + i];
-    float s = 0.f;
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < CPT; ++j) { float d = acc[i][j] - mean[i]; s += d * d; }
+    for (int i = 0; i < TW; ++i) {
+      mean[i] = stat[trow * TW + i] * invC;
+      const float d0 = lo2(acc[i]) - mean[i], d1 = hi2(acc[i]) - mean[i];
+      part[(trow * TW + i) * g.P + pr] = d0 * d0 + d1 * d1;
     }
-    s = warp_sum(s);
-    if (lane == 0) red[(row * TW + i) * wpr + wrow] = s;
   }
   __syncthreads();
-  for (int p = threadIdx.x; p < g.TH * TW; p += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < wpr; ++k) s += red[p * wpr + k];
-    const float r = rsqrtf(s * invC + eps);
-    stat[p] = r;
-    const int py = y0 + p / TW, px = x0 + p % TW;
-    if (rstd_out && py < g.H && px < g.W) rstd_out[((size_t)b * g.H + py) * g.W + px] = r;
+  reduce_pixels(part, stat + npix, npix, g.P);
+  __syncthreads();
+  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+    const float r = rsqrtf(stat[npix + p] * invC + eps);
+    stat[npix + p] = r;
+    const int py = y0 + r0 + p / TW, px = x0 + p % TW;
+    if (rstd_out && r0 + p / TW < g.TH && py < g.H && px < g.W) rstd_out[((size_t)b * g.H + py) * g.W + px] = r;
   }
   __syncthreads();
   if (active && oy < g.H) {
-    float lw[CPT], lb[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) { lw[j] = ln_w ? ln_w[c + j] : 1.f; lb[j] = ln_w ? ln_b[c + j] : 0.f; }
+    float lw0 = 1.f, lw1 = 1.f, lb0 = 0.f, lb1 = 0.f;
+    if (ln_w) { lw0 = ln_w[c]; lw1 = ln_w[c + 1]; lb0 = ln_b[c]; lb1 = ln_b[c + 1]; }
 #pragma unroll
     for (int i = 0; i < TW; ++i) {
       const int ox = x0 + i;
       if (ox < g.W) {
-        const float r = stat[row * TW + i];
-        float v[CPT];
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) v[j] = (acc[i][j] - mean[i]) * r * lw[j] + lb[j];
-        StC<CPT, TO>::st(y + (((size_t)b * g.H + oy) * g.W + ox) * g.C + c, v);
+        const float r = stat[npix + trow * TW + i];
+        stg_pair<TO>(y + (((size_t)b * g.H + oy) * g.W + ox) * g.C + c, (lo2(acc[i]) - mean[i]) * r * lw0 + lb0,
+                     (hi2(acc[i]) - mean[i]) * r * lw1 + lb1);
       }
     }
   }
+  __syncthreads();                       // `part` / `stat` are reused by the next pass
+  }  // pass over row groups
 }
 
 // weight gradient: dw[tap][c] += sum_pixels dconv(p, c) * x(p + tap - 3, c);  dbias[c] += sum dconv(p, c)
-// One CTA per tile; thread (row, channel) keeps 49 accumulators; rows are folded through smem, then one
-// atomicAdd per (tap, channel) per CTA into partial slot (blockIdx % nparts).
+// Thread (row, channel pair): for each ky the halo row streams through, 7 packed accumulators; rows are folded through
+// shared memory once per ky, then one atomicAdd per (tap, channel) per CTA into partial slot (blockIdx % nparts).
 template <typename T, int TW>
-__global__ void __launch_bounds__(max_threads_for(TW, 1)) dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const T* __restrict__ dconv,
-                                                             float* __restrict__ partial, int nparts, Geo g) {
-  extern __shared__ uint8_t smem_raw[];
+__global__ void __launch_bounds__(512, 2) dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const T* __restrict__ dconv,
+                                                               float* __restrict__ partial, int nparts, Geo g) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint64_t* bar = (uint64_t*)sm;
-  T* tile = (T*)(sm + 128);
+  const uint32_t tile_s = smem_u32(sm + 128);
   const size_t tile_bytes = (size_t)g.nbox * g.box_stride * sizeof(T);
-  float* fold = (float*)(sm + 128 + ((tile_bytes + 15) & ~(size_t)15));   // [7][TH][cgpad]
+  u64* fold = (u64*)(sm + 128 + tile_bytes);                       // [7][TR][P] packed pairs
 
   const int tile_id = blockIdx.x;
   const int tx = tile_id % g.tiles_x, ty = tile_id / g.tiles_x;
   const int b = blockIdx.y;
   const int x0 = tx * TW, y0 = ty * g.TH;
-  load_halo<T, TW>(tile, bar, &tmx, g, b, y0, x0);
+  load_halo<T, TW>(tile_s, bar, &tmx, g, b, y0, x0);
 
-  const int row = threadIdx.x / g.cgpad;
-  const int c = threadIdx.x - row * g.cgpad;
-  const bool active = (c < g.C);
-  const int oy = y0 + row;
-
-  float d[TW];
-  float dsum = 0.f;
-#pragma unroll
-  for (int i = 0; i < TW; ++i) {
-    const int ox = x0 + i;
-    d[i] = (active && oy < g.H && ox < g.W) ? ld_f(dconv + (((size_t)b * g.H + oy) * g.W + ox) * g.C + c) : 0.f;
-    dsum += d[i];
-  }
+  const int trow = threadIdx.x / g.P;
+  const int pr = threadIdx.x - trow * g.P;
+  const int c = pr * 2;
   float* slot = partial + (size_t)((blockIdx.x + blockIdx.y * gridDim.x) % nparts) * 50 * g.C;
+  const int box = c / g.cbox, cc = c - box * g.cbox;
+  const uint32_t cbs = (uint32_t)(g.cbox * sizeof(T));
+  const uint32_t row_pitch = (uint32_t)(TW + 6) * cbs;
+  const uint32_t base = tile_s + (uint32_t)(((size_t)box * g.box_stride + cc) * sizeof(T));
+  float ds0 = 0.f, ds1 = 0.f;
 #pragma unroll 1
   for (int ky = 0; ky < 7; ++ky) {
-    float a[7];
+    u64 a7[7];
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx) a[kx] = 0.f;
-    if (active) {
-      const T* rowp = halo_ptr<T, TW>(tile, g, row + ky, 0, c);
-      float in[TW + 6];
+    for (int kx = 0; kx < 7; ++kx) a7[kx] = 0ull;
+    // every row group of the tile accumulates into the same 7 packed registers: one fold per ky, not per pass
+#pragma unroll 1
+    for (int r0 = 0; r0 < g.TH; r0 += g.TR) {
+      const int row = r0 + trow;
+      const int oy = y0 + row;
+      if (!((trow < g.TR) && (row < g.TH) && oy < g.H)) continue;
+      u64 d[TW];
 #pragma unroll
-      for (int i = 0; i < TW + 6; ++i) in[i] = ld_f(rowp + (size_t)i * g.cbox);
-#pragma unroll
-      for (int i = 0; i < TW; ++i)
-#pragma unroll
-        for (int kx = 0; kx < 7; ++kx) a[kx] = fmaf(d[i], in[i + kx], a[kx]);
-    }
-    __syncthreads();  // previous round's fold buffer fully consumed
-#pragma unroll
-    for (int kx = 0; kx < 7; ++kx) fold[(kx * g.TH + row) * g.cgpad + c] = a[kx];
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 7 * g.cgpad; idx += blockDim.x) {
-      const int kx = idx / g.cgpad, cc = idx - kx * g.cgpad;
-      if (cc < g.C) {
-        float s = 0.f;
-        for (int r = 0; r < g.TH; ++r) s += fold[(kx * g.TH + r) * g.cgpad + cc];
-        atomicAdd(slot + (size_t)(ky * 7 + kx) * g.C + cc, s);
+      for (int i = 0; i < TW; ++i) {
+        const int ox = x0 + i;
+        d[i] = (ox < g.W) ? ldg_pair<T>(dconv + (((size_t)b * g.H + oy) * g.W + ox) * g.C + c) : 0ull;
+        if (ky == 0) { ds0 += lo2(d[i]); ds1 += hi2(d[i]); }
       }
+      uint32_t a = base + (uint32_t)(row + ky) * row_pitch;
+#pragma unroll
+      for (int jx = 0; jx < TW + 6; ++jx) {
+        const u64 in = lds_pair<T>(a);
+        a += cbs;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const int i = jx - kx;
+          if (i >= 0 && i < TW) a7[kx] = ffma2(d[i], in, a7[kx]);
+        }
+      }
+    }
+    __syncthreads();  // previous round's fold buffer fully consumed (first round: nothing pending)
+    if (trow < g.TR) {
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) fold[(kx * g.TR + trow) * g.P + pr] = a7[kx];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 7 * g.P; idx += blockDim.x) {
+      const int kx = idx / g.P, pp = idx - kx * g.P;
+      float s0 = 0.f, s1 = 0.f;
+      for (int r = 0; r < g.TR; ++r) { const u64 v = fold[(kx * g.TR + r) * g.P + pp]; s0 += lo2(v); s1 += hi2(v); }
+      float* dst = slot + (size_t)(ky * 7 + kx) * g.C + pp * 2;
+      atomicAdd(dst, s0);
+      atomicAdd(dst + 1, s1);
     }
   }
   // bias gradient
   __syncthreads();
-  fold[row * g.cgpad + c] = dsum;
+  if (trow < g.TR) fold[trow * g.P + pr] = pack2(ds0, ds1);
   __syncthreads();
-  for (int cc = threadIdx.x; cc < g.cgpad; cc += blockDim.x) {
-    if (cc < g.C) {
-      float s = 0.f;
-      for (int r = 0; r < g.TH; ++r) s += fold[r * g.cgpad + cc];
-      atomicAdd(slot + (size_t)49 * g.C + cc, s);
-    }
+  for (int pp = threadIdx.x; pp < g.P; pp += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = 0; r < g.TR; ++r) { const u64 v = fold[r * g.P + pp]; s0 += lo2(v); s1 += hi2(v); }
+    atomicAdd(slot + (size_t)49 * g.C + pp * 2, s0);
+    atomicAdd(slot + (size_t)49 * g.C + pp * 2 + 1, s1);
   }
 }
 
@@ -330,54 +349,63 @@ static int make_x_map(const void* x, int B, int H, int W, int C, int dtype, int 
   return ga_tensor_map(out, dtype, 4, x, dims, strides, box, 0);
 }
 
-struct Plan { Geo g; int tw, cpt, threads; size_t smem; };
+struct Plan { Geo g; int tw, threads; size_t smem; };
 
-// choose tile width, channels per thread and rows per CTA
+// choose tile width and rows per CTA: <=512 threads, <=110 KB shared memory (two CTAs per SM)
 static int plan(int B, int H, int W, int C, int dtype, bool wgrad, Plan* p) {
   const int es = dtype == GA_BF16 ? 2 : 4;
-  GA_REQUIRE(C >= 8 && (C * es) % 16 == 0, GA_ERR_ALIGN, "dwconv7: C=%d rows must be 16-byte multiples", C);
-  int cpt = 1;
-  if (!wgrad && C % 2 == 0) {
-    const int pad2 = ((C / 2 + 31) / 32) * 64, pad1 = ((C + 31) / 32) * 32;  // padded channel slots
-    if (pad2 <= pad1) cpt = 2;
-  }
-  const char* ev = getenv("GA_DW_CPT");
-  if (ev && !wgrad) { int v = atoi(ev); if ((v == 1 || v == 2) && C % v == 0) cpt = v; }
-  const int cgpad = ((C / cpt + 31) / 32) * 32;
-  GA_REQUIRE(cgpad <= 1024, GA_ERR_UNSUPPORTED, "dwconv7: C=%d too wide for one CTA row", C);
+  GA_REQUIRE(C >= 8 && (C * es) % 16 == 0 && (C & 1) == 0, GA_ERR_ALIGN, "dwconv7: C=%d must be even with 16-byte rows", C);
+  const int P = C / 2;
+  GA_REQUIRE(P <= 512, GA_ERR_UNSUPPORTED, "dwconv7: C=%d too wide for one CTA row", C);
   int tw = (W % 14 == 0) ? 14 : ((W % 7 == 0) ? 7 : (W >= 12 ? 14 : (W >= 6 ? 7 : 4)));
-  if (cpt == 2 && tw == 14 && dtype == GA_F32) tw = 7;
   const char* et = getenv("GA_DW_TW");
   if (et) { int v = atoi(et); if (v == 4 || v == 7 || v == 14) tw = v; }
-  while (cgpad > max_threads_for(tw, cpt) && tw > 4) tw = (tw == 14) ? 7 : 4;
-  GA_REQUIRE(cgpad <= max_threads_for(tw, cpt), GA_ERR_UNSUPPORTED, "dwconv7: C=%d does not fit a CTA", C);
   const int align = 16 / es;                 // channel boxes: <=256 elements, 16-byte multiples
   const int nbox = (C + 255) / 256;
   const int cbox = (((C + nbox - 1) / nbox) + align - 1) / align * align;
+  int tr = 512 / P;
+  if (tr < 1) tr = 1;
+  if (tr > H) tr = H;
   int th = 1, box_stride = 0;
   size_t smem = 0;
-  const size_t limit = 200 * 1024;
-  for (;;) {
-    th = max_threads_for(tw, cpt) / cgpad;
-    if (th > H) th = H;
-    const char* eh = getenv("GA_DW_TH");
-    if (eh) { int v = atoi(eh); if (v >= 1 && v * cgpad <= max_threads_for(tw, cpt)) th = v; }
-    for (;; --th) {
-      const size_t box_bytes = (((size_t)(th + 6) * (tw + 6) * cbox * es) + 127) & ~(size_t)127;
-      box_stride = (int)(box_bytes / es);
-      const size_t tile = (size_t)nbox * box_bytes;
-      const size_t extra = wgrad ? (size_t)7 * th * cgpad * 4 : (size_t)th * tw * (cgpad / 32 + 1) * 4;
-      smem = 128 + 128 + tile + extra + 64;
-      if (smem <= limit || th == 1) break;
+  auto fit = [&](int tw_, size_t limit) {          // largest tile height (<= 14 rows) whose halo + scratch fit `limit`
+    int best = 0;
+    for (int t = 1; t <= 14 && t <= H; ++t) {
+      const int trr = tr < t ? tr : t;
+      const size_t box_bytes = (((size_t)(t + 6) * (tw_ + 6) * cbox * es) + 127) & ~(size_t)127;
+      const size_t extra = wgrad ? (size_t)7 * trr * P * 8 : ((size_t)trr * tw_ * P + 2 * (size_t)trr * tw_) * 4;
+      if (128 + 128 + (size_t)nbox * box_bytes + extra + 64 <= limit) best = t;
     }
-    if (smem <= 227 * 1024 || tw == 4) break;
-    tw = (tw == 14) ? 7 : 4;   // narrower tile when even one row does not fit (wide C in fp32)
+    return best;
+  };
+  // prefer two resident CTAs per SM (110 KB each); fall back to one big CTA when that leaves fewer than 3 rows per tile
+  size_t limit = 110 * 1024;
+  th = fit(tw, limit);
+  if (th < 3 && th < H) {
+    int th7 = (tw == 14) ? fit(7, limit) : 0;
+    if (th7 >= 3) { tw = 7; th = th7; }
+    else { limit = 225 * 1024; th = fit(tw, limit); if (th < 1 && tw == 14) { tw = 7; th = fit(7, limit); } if (th < 1) { tw = 4; th = fit(4, limit); } }
+  }
+  {
+    const char* eh = getenv("GA_DW_TH");
+    if (eh) { int v = atoi(eh); if (v >= 1 && v <= 14) th = v; }
+  }
+  GA_REQUIRE(th >= 1, GA_ERR_UNSUPPORTED, "dwconv7: tile does not fit shared memory (C=%d W=%d)", C, W);
+  // balance the passes: e.g. 7 rows with 5 row slots -> 2 passes of 4 rows
+  if (tr > th) tr = th;
+  {
+    const int passes = (th + tr - 1) / tr;
+    tr = (th + passes - 1) / passes;
+    const size_t box_bytes = (((size_t)(th + 6) * (tw + 6) * cbox * es) + 127) & ~(size_t)127;
+    box_stride = (int)(box_bytes / es);
+    const size_t extra = wgrad ? (size_t)7 * tr * P * 8 : ((size_t)tr * tw * P + 2 * (size_t)tr * tw) * 4;
+    smem = 128 + 128 + (size_t)nbox * box_bytes + extra + 64;
   }
   GA_REQUIRE(smem <= 227 * 1024, GA_ERR_UNSUPPORTED, "dwconv7: tile does not fit shared memory (C=%d W=%d)", C, W);
-  p->g.B = B; p->g.H = H; p->g.W = W; p->g.C = C; p->g.TH = th;
+  p->g.B = B; p->g.H = H; p->g.W = W; p->g.C = C; p->g.TH = th; p->g.TR = tr;
   p->g.tiles_x = (W + tw - 1) / tw; p->g.tiles_y = (H + th - 1) / th;
-  p->g.cbox = cbox; p->g.nbox = nbox; p->g.cgpad = cgpad; p->g.box_stride = box_stride;
-  p->tw = tw; p->cpt = cpt; p->threads = th * cgpad; p->smem = smem;
+  p->g.cbox = cbox; p->g.nbox = nbox; p->g.box_stride = box_stride; p->g.P = P;
+  p->tw = tw; p->threads = ((tr * P + 31) / 32) * 32; p->smem = smem;
   return GA_OK;
 }
 
@@ -385,17 +413,18 @@ template <typename T, typename TO, int MODE>
 static int launch_conv(const Plan& p, const CUtensorMap& tm, const float* w, const float* bias, const float* ln_w,
                        const float* ln_b, const void* res, void* y, float* rstd, float eps, cudaStream_t st) {
   dim3 grid(p.g.tiles_x * p.g.tiles_y, p.g.B);
-#define GA_DW_LAUNCH(TW_, CPT_)                                                                                         \
-  if (p.tw == TW_ && p.cpt == CPT_) {                                                                                   \
-    auto k = dwconv7_kernel<T, TO, TW_, CPT_, MODE>;                                                                    \
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                                   \
+#define GA_DW_LAUNCH(TW_)                                                                                               \
+  if (p.tw == TW_) {                                                                                                    \
+    auto k = dwconv7_kernel<T, TO, TW_, MODE>;                                                                          \
+    static bool attr = false;                                                                                           \
+    if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }       \
     k<<<grid, p.threads, p.smem, st>>>(tm, w, bias, ln_w, ln_b, (const TO*)res, (TO*)y, rstd, eps, p.g);                 \
     ga_count_launch();                                                                                                  \
     return ga_check_launch("dwconv7");                                                                                  \
   }
-  GA_DW_LAUNCH(14, 1) GA_DW_LAUNCH(14, 2) GA_DW_LAUNCH(7, 1) GA_DW_LAUNCH(7, 2) GA_DW_LAUNCH(4, 1) GA_DW_LAUNCH(4, 2)
+  GA_DW_LAUNCH(14) GA_DW_LAUNCH(7) GA_DW_LAUNCH(4)
 #undef GA_DW_LAUNCH
-  ga_set_error("dwconv7: no kernel for tw=%d cpt=%d", p.tw, p.cpt);
+  ga_set_error("dwconv7: no kernel for tw=%d", p.tw);
   return GA_ERR_UNSUPPORTED;
 }
 
@@ -404,7 +433,8 @@ static int launch_conv(const Plan& p, const CUtensorMap& tm, const float* w, con
 extern "C" int ga_dwconv7_ln_fwd(const void* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
                                  void* y, float* rstd, int B, int H, int W, int C, float eps, int dtype, ga_stream_t s) {
   GA_REQUIRE(x && w49c && y && B > 0 && H > 0 && W > 0, GA_ERR_SHAPE, "ga_dwconv7_ln_fwd: bad arguments");
-  GA_REQUIRE(((uintptr_t)x & 15) == 0, GA_ERR_ALIGN, "ga_dwconv7_ln_fwd: x must be 16-byte aligned");
+  GA_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w49c & 7) == 0 && ((uintptr_t)bias & 7) == 0, GA_ERR_ALIGN,
+             "ga_dwconv7_ln_fwd: x must be 16-byte, weights 8-byte aligned");
   dw::Plan p;
   int rc = dw::plan(B, H, W, C, dtype, false, &p);
   if (rc) return rc;
@@ -422,6 +452,7 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
                               ga_stream_t s) {
   cudaStream_t st = (cudaStream_t)s;
   GA_REQUIRE(dconv && w49c && B > 0, GA_ERR_SHAPE, "ga_dwconv7_bwd: bad arguments");
+  GA_REQUIRE(((uintptr_t)dconv & 15) == 0 && ((uintptr_t)w49c & 7) == 0, GA_ERR_ALIGN, "ga_dwconv7_bwd: misaligned operands");
   int rc;
   if (dx) {
     dw::Plan p;
@@ -438,6 +469,7 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
   }
   if (dw49c || dbias) {
     GA_REQUIRE(x && dw_partial, GA_ERR_SHAPE, "ga_dwconv7_bwd: weight gradient needs x and a partial workspace");
+    GA_REQUIRE(((uintptr_t)x & 15) == 0, GA_ERR_ALIGN, "ga_dwconv7_bwd: x must be 16-byte aligned");
     dw::Plan p;
     rc = dw::plan(B, H, W, C, dtype, true, &p);
     if (rc) return rc;
@@ -450,7 +482,8 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
 #define GA_DWW_LAUNCH(T_, TW_)                                                                      \
   {                                                                                                 \
     auto k = dw::dwconv7_wgrad_kernel<T_, TW_>;                                                     \
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);               \
+    static bool attr = false;                                                                       \
+    if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; } \
     k<<<grid, p.threads, p.smem, st>>>(tm, (const T_*)dconv, dw_partial, nparts, p.g);              \
   }
     if (dtype == GA_BF16) {
