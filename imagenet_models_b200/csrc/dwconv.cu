@@ -116,8 +116,8 @@ __device__ __forceinline__ void reduce_pixels(const float* part, float* stat, in
 
 // MODE 0: forward  y = LN(conv(x) + bias)  (xhat, optional affine), rstd saved
 // MODE 1: dgrad    y = corr(x = dconv, flipped taps) + res
-template <typename T, typename TO, int TW, int MODE>
-__global__ void __launch_bounds__(512, 2) dwconv7_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ w49c,
+template <typename T, typename TO, int TW, int MODE, bool BIG>
+__global__ void __launch_bounds__(BIG ? 512 : (MODE == 0 ? 384 : 448), BIG ? 1 : 2) dwconv7_kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ w49c,
                                                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                          const float* __restrict__ ln_b, const TO* __restrict__ res,
                                                          TO* __restrict__ y, float* __restrict__ rstd_out, float eps, Geo g) {
@@ -184,15 +184,14 @@ __global__ void __launch_bounds__(512, 2) dwconv7_kernel(const __grid_constant__
   const int oy = y0 + row;
   if (MODE == 1) {
     if (active && oy < g.H) {
+      const size_t off0 = (((size_t)b * g.H + oy) * g.W + x0) * g.C + c;
+      u64 r[TW];
+      // all TW residual loads are issued back to back (one latency per row, not one per pixel), then add + store
+#pragma unroll
+      for (int i = 0; i < TW; ++i) r[i] = (res && x0 + i < g.W) ? ldg_pair<TO>(res + off0 + (size_t)i * g.C) : 0ull;
 #pragma unroll
       for (int i = 0; i < TW; ++i) {
-        const int ox = x0 + i;
-        if (ox < g.W) {
-          const size_t off = (((size_t)b * g.H + oy) * g.W + ox) * g.C + c;
-          float v0 = lo2(acc[i]), v1 = hi2(acc[i]);
-          if (res) { const u64 r = ldg_pair<TO>(res + off); v0 += lo2(r); v1 += hi2(r); }
-          stg_pair<TO>(y + off, v0, v1);
-        }
+        if (x0 + i < g.W) stg_pair<TO>(y + off0 + (size_t)i * g.C, lo2(acc[i]) + lo2(r[i]), hi2(acc[i]) + hi2(r[i]));
       }
     }
     continue;
@@ -247,21 +246,37 @@ __global__ void __launch_bounds__(512, 2) dwconv7_kernel(const __grid_constant__
 // weight gradient: dw[tap][c] += sum_pixels dconv(p, c) * x(p + tap - 3, c);  dbias[c] += sum dconv(p, c)
 // Thread (row, channel pair): for each ky the halo row streams through, 7 packed accumulators; rows are folded through
 // shared memory once per ky, then one atomicAdd per (tap, channel) per CTA into partial slot (blockIdx % nparts).
-template <typename T, int TW>
-__global__ void __launch_bounds__(512, 2) dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap tmx, const T* __restrict__ dconv,
+template <typename T, int TW, bool BIG>
+__global__ void __launch_bounds__(BIG ? 512 : 448, BIG ? 1 : 2) dwconv7_wgrad_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                               const __grid_constant__ CUtensorMap tmd, int dbox_stride,
                                                                float* __restrict__ partial, int nparts, Geo g) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   uint64_t* bar = (uint64_t*)sm;
   const uint32_t tile_s = smem_u32(sm + 128);
   const size_t tile_bytes = (size_t)g.nbox * g.box_stride * sizeof(T);
-  u64* fold = (u64*)(sm + 128 + tile_bytes);                       // [7][TR][P] packed pairs
+  const uint32_t dtile_s = tile_s + (uint32_t)tile_bytes;          // dconv tile [box][TH][TW][cbox], no halo
+  const size_t dtile_bytes = (size_t)g.nbox * dbox_stride * sizeof(T);
+  u64* fold = (u64*)(sm + 128 + tile_bytes + dtile_bytes);         // [7][TR][P] packed pairs
 
   const int tile_id = blockIdx.x;
   const int tx = tile_id % g.tiles_x, ty = tile_id / g.tiles_x;
   const int b = blockIdx.y;
   const int x0 = tx * TW, y0 = ty * g.TH;
-  load_halo<T, TW>(tile_s, bar, &tmx, g, b, y0, x0);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t hb = (uint32_t)((g.TH + 6) * (TW + 6) * g.cbox * sizeof(T)), db = (uint32_t)(g.TH * TW * g.cbox * sizeof(T));
+    mbar_expect_tx(bar, (hb + db) * g.nbox);
+    for (int j = 0; j < g.nbox; ++j) {
+      tma_load_4d(tile_s + (uint32_t)((size_t)j * g.box_stride * sizeof(T)), &tmx, bar, j * g.cbox, x0 - 3, y0 - 3, b);
+      tma_load_4d(dtile_s + (uint32_t)((size_t)j * dbox_stride * sizeof(T)), &tmd, bar, j * g.cbox, x0, y0, b);
+    }
+  }
+  mbar_wait(bar, 0);
 
   const int trow = threadIdx.x / g.P;
   const int pr = threadIdx.x - trow * g.P;
@@ -271,6 +286,7 @@ __global__ void __launch_bounds__(512, 2) dwconv7_wgrad_kernel(const __grid_cons
   const uint32_t cbs = (uint32_t)(g.cbox * sizeof(T));
   const uint32_t row_pitch = (uint32_t)(TW + 6) * cbs;
   const uint32_t base = tile_s + (uint32_t)(((size_t)box * g.box_stride + cc) * sizeof(T));
+  const uint32_t dbase = dtile_s + (uint32_t)(((size_t)box * dbox_stride + cc) * sizeof(T));
   float ds0 = 0.f, ds1 = 0.f;
 #pragma unroll 1
   for (int ky = 0; ky < 7; ++ky) {
@@ -284,11 +300,14 @@ __global__ void __launch_bounds__(512, 2) dwconv7_wgrad_kernel(const __grid_cons
       const int oy = y0 + row;
       if (!((trow < g.TR) && (row < g.TH) && oy < g.H)) continue;
       u64 d[TW];
+      {
+        uint32_t da = dbase + (uint32_t)(row * TW) * cbs;      // out-of-image pixels were zero-filled by TMA
 #pragma unroll
-      for (int i = 0; i < TW; ++i) {
-        const int ox = x0 + i;
-        d[i] = (ox < g.W) ? ldg_pair<T>(dconv + (((size_t)b * g.H + oy) * g.W + ox) * g.C + c) : 0ull;
-        if (ky == 0) { ds0 += lo2(d[i]); ds1 += hi2(d[i]); }
+        for (int i = 0; i < TW; ++i) {
+          d[i] = lds_pair<T>(da);
+          da += cbs;
+          if (ky == 0) { ds0 += lo2(d[i]); ds1 += hi2(d[i]); }
+        }
       }
       uint32_t a = base + (uint32_t)(row + ky) * row_pitch;
 #pragma unroll
@@ -341,29 +360,31 @@ __global__ void reduce_parts_kernel(const float* __restrict__ partial, int npart
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
-static int make_x_map(const void* x, int B, int H, int W, int C, int dtype, int cbox, int tw, int th, CUtensorMap* out) {
+static int make_x_map(const void* x, int B, int H, int W, int C, int dtype, int cbox, int tw, int th, CUtensorMap* out,
+                      int halo = 6) {
   const uint64_t es = dtype == GA_BF16 ? 2 : 4;
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)C * es, (uint64_t)W * C * es, (uint64_t)H * W * C * es};
-  uint32_t box[4] = {(uint32_t)cbox, (uint32_t)(tw + 6), (uint32_t)(th + 6), 1};
+  uint32_t box[4] = {(uint32_t)cbox, (uint32_t)(tw + halo), (uint32_t)(th + halo), 1};
   return ga_tensor_map(out, dtype, 4, x, dims, strides, box, 0);
 }
 
-struct Plan { Geo g; int tw, threads; size_t smem; };
+struct Plan { Geo g; int tw, threads, dbox_stride; size_t smem; };
 
 // choose tile width and rows per CTA: <=512 threads, <=110 KB shared memory (two CTAs per SM)
-static int plan(int B, int H, int W, int C, int dtype, bool wgrad, Plan* p) {
+static int plan(int B, int H, int W, int C, int dtype, bool wgrad, Plan* p, int max_threads = 512) {
   const int es = dtype == GA_BF16 ? 2 : 4;
   GA_REQUIRE(C >= 8 && (C * es) % 16 == 0 && (C & 1) == 0, GA_ERR_ALIGN, "dwconv7: C=%d must be even with 16-byte rows", C);
   const int P = C / 2;
   GA_REQUIRE(P <= 512, GA_ERR_UNSUPPORTED, "dwconv7: C=%d too wide for one CTA row", C);
+  if (P > max_threads) max_threads = 512;   // C up to 1024: one row per pass, registers spill a little
   int tw = (W % 14 == 0) ? 14 : ((W % 7 == 0) ? 7 : (W >= 12 ? 14 : (W >= 6 ? 7 : 4)));
   const char* et = getenv("GA_DW_TW");
   if (et) { int v = atoi(et); if (v == 4 || v == 7 || v == 14) tw = v; }
   const int align = 16 / es;                 // channel boxes: <=256 elements, 16-byte multiples
   const int nbox = (C + 255) / 256;
   const int cbox = (((C + nbox - 1) / nbox) + align - 1) / align * align;
-  int tr = 512 / P;
+  int tr = max_threads / P;
   if (tr < 1) tr = 1;
   if (tr > H) tr = H;
   int th = 1, box_stride = 0;
@@ -373,7 +394,8 @@ static int plan(int B, int H, int W, int C, int dtype, bool wgrad, Plan* p) {
     for (int t = 1; t <= 14 && t <= H; ++t) {
       const int trr = tr < t ? tr : t;
       const size_t box_bytes = (((size_t)(t + 6) * (tw_ + 6) * cbox * es) + 127) & ~(size_t)127;
-      const size_t extra = wgrad ? (size_t)7 * trr * P * 8 : ((size_t)trr * tw_ * P + 2 * (size_t)trr * tw_) * 4;
+      const size_t dbox = wgrad ? ((((size_t)t * tw_ * cbox * es) + 127) & ~(size_t)127) : 0;
+      const size_t extra = wgrad ? (size_t)7 * trr * P * 8 + (size_t)nbox * dbox : ((size_t)trr * tw_ * P + 2 * (size_t)trr * tw_) * 4;
       if (128 + 128 + (size_t)nbox * box_bytes + extra + 64 <= limit) best = t;
     }
     return best;
@@ -398,7 +420,9 @@ static int plan(int B, int H, int W, int C, int dtype, bool wgrad, Plan* p) {
     tr = (th + passes - 1) / passes;
     const size_t box_bytes = (((size_t)(th + 6) * (tw + 6) * cbox * es) + 127) & ~(size_t)127;
     box_stride = (int)(box_bytes / es);
-    const size_t extra = wgrad ? (size_t)7 * tr * P * 8 : ((size_t)tr * tw * P + 2 * (size_t)tr * tw) * 4;
+    const size_t dbox = wgrad ? ((((size_t)th * tw * cbox * es) + 127) & ~(size_t)127) : 0;
+    p->dbox_stride = (int)(dbox / es);
+    const size_t extra = wgrad ? (size_t)7 * tr * P * 8 + (size_t)nbox * dbox : ((size_t)tr * tw * P + 2 * (size_t)tr * tw) * 4;
     smem = 128 + 128 + (size_t)nbox * box_bytes + extra + 64;
   }
   GA_REQUIRE(smem <= 227 * 1024, GA_ERR_UNSUPPORTED, "dwconv7: tile does not fit shared memory (C=%d W=%d)", C, W);
@@ -415,9 +439,8 @@ static int launch_conv(const Plan& p, const CUtensorMap& tm, const float* w, con
   dim3 grid(p.g.tiles_x * p.g.tiles_y, p.g.B);
 #define GA_DW_LAUNCH(TW_)                                                                                               \
   if (p.tw == TW_) {                                                                                                    \
-    auto k = dwconv7_kernel<T, TO, TW_, MODE>;                                                                          \
-    static bool attr = false;                                                                                           \
-    if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }       \
+    auto k = p.threads > 448 ? dwconv7_kernel<T, TO, TW_, MODE, true> : dwconv7_kernel<T, TO, TW_, MODE, false>;         \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                                   \
     k<<<grid, p.threads, p.smem, st>>>(tm, w, bias, ln_w, ln_b, (const TO*)res, (TO*)y, rstd, eps, p.g);                 \
     ga_count_launch();                                                                                                  \
     return ga_check_launch("dwconv7");                                                                                  \
@@ -436,7 +459,7 @@ extern "C" int ga_dwconv7_ln_fwd(const void* x, const float* w49c, const float* 
   GA_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w49c & 7) == 0 && ((uintptr_t)bias & 7) == 0, GA_ERR_ALIGN,
              "ga_dwconv7_ln_fwd: x must be 16-byte, weights 8-byte aligned");
   dw::Plan p;
-  int rc = dw::plan(B, H, W, C, dtype, false, &p);
+  int rc = dw::plan(B, H, W, C, dtype, false, &p, 384);
   if (rc) return rc;
   CUtensorMap tm;
   rc = dw::make_x_map(x, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
@@ -456,7 +479,7 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
   int rc;
   if (dx) {
     dw::Plan p;
-    rc = dw::plan(B, H, W, C, dtype, false, &p);
+    rc = dw::plan(B, H, W, C, dtype, false, &p, 448);
     if (rc) return rc;
     CUtensorMap tm;
     rc = dw::make_x_map(dconv, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
@@ -471,20 +494,22 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
     GA_REQUIRE(x && dw_partial, GA_ERR_SHAPE, "ga_dwconv7_bwd: weight gradient needs x and a partial workspace");
     GA_REQUIRE(((uintptr_t)x & 15) == 0, GA_ERR_ALIGN, "ga_dwconv7_bwd: x must be 16-byte aligned");
     dw::Plan p;
-    rc = dw::plan(B, H, W, C, dtype, true, &p);
+    rc = dw::plan(B, H, W, C, dtype, true, &p, 448);
     if (rc) return rc;
     CUtensorMap tm;
     rc = dw::make_x_map(x, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
+    if (rc) return rc;
+    CUtensorMap tmd;
+    rc = dw::make_x_map(dconv, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tmd, 0);
     if (rc) return rc;
     const int nparts = ga_dwconv7_bwd_parts(B, H, W, C);
     cudaMemsetAsync(dw_partial, 0, (size_t)nparts * 50 * C * sizeof(float), st);
     dim3 grid(p.g.tiles_x * p.g.tiles_y, B);
 #define GA_DWW_LAUNCH(T_, TW_)                                                                      \
   {                                                                                                 \
-    auto k = dw::dwconv7_wgrad_kernel<T_, TW_>;                                                     \
-    static bool attr = false;                                                                       \
-    if (!attr) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; } \
-    k<<<grid, p.threads, p.smem, st>>>(tm, (const T_*)dconv, dw_partial, nparts, p.g);              \
+    auto k = p.threads > 448 ? dw::dwconv7_wgrad_kernel<T_, TW_, true> : dw::dwconv7_wgrad_kernel<T_, TW_, false>; \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);               \
+    k<<<grid, p.threads, p.smem, st>>>(tm, tmd, p.dbox_stride, dw_partial, nparts, p.g);             \
   }
     if (dtype == GA_BF16) {
       if (p.tw == 14) GA_DWW_LAUNCH(bf16, 14) else if (p.tw == 7) GA_DWW_LAUNCH(bf16, 7) else GA_DWW_LAUNCH(bf16, 4)
