@@ -7,6 +7,8 @@
 One step = forward (5 branch logits) + GA loss (CE + lam*KL) + backward + gradient all-reduce (N>1) + fused AdamW + EMA.
 `value` times steps with the batch already resident in HBM; `e2e` times the same steps fed from pinned host memory
 (uint8 images -> H2D -> normalise, as timm's PrefetchLoader does) with the loss read back every step.
+`roofline` is the dominant kernel call site (largest share of the timed region among the tcgen05 GEMM launches):
+algorithmic bytes / CUDA-event time measured on the launching stream inside the timed region.
 """
 import argparse
 import json
@@ -24,6 +26,8 @@ MODEL = 'ga_convnext_tiny_688'
 TRAIN_GFLOP_PER_IMG = 32.73      # BASELINE.md section 4 (3 x 10.909 forward)
 TRAIN_MB_PER_IMG = 268.0         # GEMM-boundary-fusion convention, bf16
 GA_LAM = -0.8
+# dram__bytes_read+write per launch from profiles/r01_ncu_fc1_gelu.txt (ncu --set full) for the stage-0 fc1+GELU GEMM
+NCU_TRAFFIC = {(802816, 384, 96, 'gelu+z'): 1333.1e6}
 
 
 def peaks():
@@ -103,9 +107,11 @@ def run_reference(args):
         'impl': 'reference', 'metric': 'train images/sec (whole job)', 'value': rate, 'unit': 'img/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{MODEL} fwd+loss+bwd, fp32, 224x224, CPU', 'sample': f'batch {batch} per step (bounded sample of the batch-256 step)'},
+        'config': {'workload': f'{MODEL} training step (fwd + GA loss + bwd), fp32, 224x224, host CPU',
+                   'sample': f'batch {batch} per step: a bounded sample of the batch-256 step'},
         'cpu_baseline': {'value': rate, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{args.steps} steps of batch {batch}, oracle port of the reference modules (timm absent: cannot import the reference on this box)'},
+                         'sample': f'{args.steps} steps of batch {batch}; oracle port of the reference modules (timm is absent, so the '
+                                   f'reference itself cannot be imported on this box)'},
         'e2e': {'value': rate, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
@@ -128,7 +134,7 @@ def main():
     import torch.distributed as dist
     from imagenet_models_b200 import lib as L
     from imagenet_models_b200 import ops
-    from imagenet_models_b200.optim import FusedAdamWEma, GradBuckets
+    from imagenet_models_b200.engine import TrainEngine
     from imagenet_models_b200.registry import create_model
     import imagenet_models_b200.ga_convnext  # noqa: F401
 
@@ -143,8 +149,10 @@ def main():
 
     torch.manual_seed(42 + rank)                       # random_seed(seed, rank), GA/train.py:402
     model = create_model(MODEL).to(dev).train()
-    opt = FusedAdamWEma(model, lr=1e-3, weight_decay=0.05, ema_decay=0.9998)
-    buckets = GradBuckets(opt.state) if world > 1 else None
+    if world > 1:
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, 0)
+    engine = TrainEngine(model, lr=1e-3, weight_decay=0.05, ema_decay=0.9998, ga_lam=GA_LAM, amp_dtype=torch.bfloat16)
     B = args.batch
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, 1000, (B,), device=dev)
@@ -154,22 +162,14 @@ def main():
     y_host = torch.randint(0, 1000, (B,)).pin_memory()
     loss_host = torch.zeros(1).pin_memory()
 
-    def step(x, y):
-        opt.zero_grad()
-        if buckets:
-            buckets.prepare()
-        with torch.autocast('cuda', dtype=torch.bfloat16):
-            out = model(x)
-        loss = ops.ga_loss(torch.stack(out), y, GA_LAM)
-        loss.backward()
-        scale = buckets.finish() if buckets else 1.0
-        opt.step(grad_scale=scale)
-        return loss
+    def step_resident():
+        engine.step(x_dev, y_dev)
 
     def step_e2e():
+        # timm PrefetchLoader semantics: uint8 batch over PCIe, normalise on the device, then the step; loss read back
         x = x_host.to(dev, non_blocking=True).float().sub_(mean).div_(std)
         y = y_host.to(dev, non_blocking=True)
-        loss = step(x, y)
+        loss = engine.step(x, y)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return loss_host.item()
@@ -189,14 +189,18 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(max(args.warmup, 3)):
-        step(x_dev, y_dev)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        ops.TIMER = ops.GemmTimer()                    # CUDA events around every ga_gemm launch of the timed region
     n0 = L.launch_count()
-    ms = timed(lambda: step(x_dev, y_dev), args.steps)
+    ms = timed(step_resident, args.steps)
     launches = L.launch_count() - n0
+    gemm_times = ops.TIMER.summary() if rank == 0 else {}
+    ops.TIMER = None
     clocks = sampler.stop() if rank == 0 else None
     e2e = None
     if not args.no_e2e:
@@ -214,27 +218,35 @@ def main():
     img_s = world * B * args.steps / (ms / 1e3)
     hbm, tf, src = peaks()
     per_gpu = img_s / world
-    frac_hbm = per_gpu * TRAIN_MB_PER_IMG / 1e3 / hbm
-    frac_tensor = per_gpu * TRAIN_GFLOP_PER_IMG / 1e3 / tf
+    # dominant kernel call site: the GEMM shape with the largest total time inside the timed region
+    key, (n_launch, t_ms) = max(gemm_times.items(), key=lambda kv: kv[1][1])
+    nb, M, N, K, dt, kind, byts = key
+    avg_us = t_ms / n_launch * 1e3
+    achieved = byts / (avg_us * 1e-6) / 1e9
+    gemm_total_ms = sum(v[1] for v in gemm_times.values()) / args.steps
     line = {
         'metric': 'train images/sec (whole job)', 'value': img_s, 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': f'{MODEL} training step (fwd + GA loss + bwd + all-reduce + fused AdamW + EMA), bf16 autocast, '
-                               f'batch {B}/GPU, 224x224', 'global_batch': B * world, 'parallelism': f'dp{world}',
-                   'l2': 'activations per step (>10 GB) exceed the 126 MB L2; no explicit flush needed'},
+        'config': {'workload': f'{MODEL} training step (fwd + GA loss + bwd + all-reduce + fused AdamW + EMA), bf16 autocast '
+                               f'(fp32 residual stream), batch {B}/GPU, 224x224', 'global_batch': B * world,
+                   'parallelism': f'dp{world}', 'l2': 'activations per step (>10 GB) exceed the 126 MB L2; no explicit flush'},
         'gpu_launches': launches, 'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'achieved': per_gpu * TRAIN_MB_PER_IMG / 1e3, 'peak': hbm, 'unit': 'GB/s', 'frac': frac_hbm,
-                     'traffic': None, 'peak_source': src,
-                     'note': 'whole-step algorithmic bytes (268 MB/img, BASELINE.md section 4) / step time; tensor fraction = '
-                             f'{frac_tensor:.3f} of {tf} TFLOP/s'},
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
+                     'traffic': NCU_TRAFFIC.get((M, N, K, kind)), 'peak_source': src,
+                     'kernel': f'tc::gemm_tc2_kernel (tcgen05 persistent GEMM), call site M={M} N={N} K={K} {dt} epilogue {kind}',
+                     'algorithmic_bytes_per_launch': byts, 'avg_launch_us': avg_us, 'launches_timed': n_launch,
+                     'share_of_step': (t_ms / args.steps) / ms_step, 'all_gemm_share_of_step': gemm_total_ms / ms_step},
+        'step_roofline': {'hbm_frac': per_gpu * TRAIN_MB_PER_IMG / 1e3 / hbm, 'tensor_frac': per_gpu * TRAIN_GFLOP_PER_IMG / 1e3 / tf,
+                          'note': '268 MB/img and 32.73 GFLOP/img (BASELINE.md section 4) x img/s/GPU over the measured peaks'},
     }
     if e2e:
         line['e2e'] = e2e
     if not args.no_cpu_baseline and world == 1:
         rate, t, threads = cpu_reference_step_rate(8, 3, 1)
         line['cpu_baseline'] = {'value': rate, 'unit': 'img/s', 'cores': threads, 'kind': 'port',
-                                'sample': '3 fwd+loss+bwd steps of batch 8 (fp32) after 1 warm-up, oracle port of the reference modules'}
+                                'sample': '3 training steps (fwd + GA loss + bwd) of batch 8, fp32, after 1 warm-up; oracle port of '
+                                          'the reference modules on all host threads'}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

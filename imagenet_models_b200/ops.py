@@ -53,6 +53,25 @@ def workspace(n_floats: int, device, tag: str) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------- raw kernels
+class GemmTimer:
+    """Optional CUDA-event instrumentation of every ga_gemm launch (bench.py's live per-kernel roofline).
+    Events are recorded on the launching stream around the single kernel launch; read with summary() after a sync."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        agg = {}
+        for key, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            n, t = agg.get(key, (0, 0.0))
+            agg[key] = (n + 1, t + ms)
+        return agg
+
+
+TIMER = None      # set to a GemmTimer() to time GEMM launches
+
+
 def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None, rowscale=None, rows_per_scale=1,
          residual=None, zin=None, zmode=ACT_NONE, alpha=1.0, accumulate=False, out_dtype=None, backend=L.BACKEND_AUTO,
          splits=0, shadow=None):
@@ -120,6 +139,19 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
         assert save_z is False and shadow.dtype == torch.bfloat16 and shadow.stride() == out.stride()
         g.Z, g.z_shadow = shadow.data_ptr(), 1
     g.backend, g.splits = backend, splits
+    if TIMER is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(_L().ga_gemm(C.byref(g), L.stream()), 'ga_gemm')
+        e1.record()
+        kind = ('gelu' if act == ACT_GELU else 'relu' if act == ACT_RELU else 'lin') + ('+z' if save_z is not False and save_z is not None else '') + \
+            ('+res' if residual is not None else '') + ('+zin' if zin is not None else '') + ('+acc' if accumulate else '') + \
+            ('+shadow' if shadow is not None else '')
+        byts = nb * (M * K + N * K) * A3.element_size() + nb * M * N * D3.element_size() * (2 if (save_z is not False and save_z is not None) else 1) + \
+            (nb * M * N * D3.element_size() if residual is not None else 0) + (nb * M * N * D3.element_size() if zin is not None else 0) + \
+            (nb * M * N * 2 if shadow is not None else 0)
+        TIMER.records.append(((nb, M, N, K, str(A3.dtype).split('.')[-1], kind, byts), e0, e1))
+        return (out, Z) if (save_z is not False and save_z is not None) else out
     L.check(_L().ga_gemm(C.byref(g), L.stream()), 'ga_gemm')
     return (out, Z) if (save_z is not False and save_z is not None) else out
 
