@@ -16,6 +16,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import imagenet_models_b200.ga_convnext  # noqa: F401,E402
+import imagenet_models_b200.map_convnext  # noqa: F401,E402
 from imagenet_models_b200.engine import evaluate_batch  # noqa: E402
 from imagenet_models_b200.registry import create_model  # noqa: E402
 

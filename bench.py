@@ -124,6 +124,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256, help='per-GPU batch')
+    ap.add_argument('--model', default=MODEL, help='headline: ga_convnext_tiny_688; also map_convnext_tiny (config 4, use --batch 512)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -137,6 +138,7 @@ def main():
     from imagenet_models_b200.engine import TrainEngine
     from imagenet_models_b200.registry import create_model
     import imagenet_models_b200.ga_convnext  # noqa: F401
+    import imagenet_models_b200.map_convnext  # noqa: F401
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -148,7 +150,8 @@ def main():
     L.load()
 
     torch.manual_seed(42 + rank)                       # random_seed(seed, rank), GA/train.py:402
-    model = create_model(MODEL).to(dev).train()
+    model = create_model(args.model).to(dev).train()
+    gf_img, mb_img = (TRAIN_GFLOP_PER_IMG, TRAIN_MB_PER_IMG) if args.model == MODEL else ({'map_convnext_tiny': 30.4}.get(args.model), None)
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
@@ -228,7 +231,7 @@ def main():
         'metric': 'train images/sec (whole job)', 'value': img_s, 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': f'{MODEL} training step (fwd + GA loss + bwd + all-reduce + fused AdamW + EMA), bf16 autocast '
+        'config': {'workload': f'{args.model} training step (fwd + GA loss + bwd + all-reduce + fused AdamW + EMA), bf16 autocast '
                                f'(fp32 residual stream), batch {B}/GPU, 224x224', 'global_batch': B * world,
                    'parallelism': f'dp{world}', 'l2': 'activations per step (>10 GB) exceed the 126 MB L2; no explicit flush'},
         'gpu_launches': launches, 'clocks': clocks,
@@ -237,7 +240,7 @@ def main():
                      'kernel': f'tc::gemm_tc2_kernel (tcgen05 persistent GEMM), call site M={M} N={N} K={K} {dt} epilogue {kind}',
                      'algorithmic_bytes_per_launch': byts, 'avg_launch_us': avg_us, 'launches_timed': n_launch,
                      'share_of_step': (t_ms / args.steps) / ms_step, 'all_gemm_share_of_step': gemm_total_ms / ms_step},
-        'step_roofline': {'hbm_frac': per_gpu * TRAIN_MB_PER_IMG / 1e3 / hbm, 'tensor_frac': per_gpu * TRAIN_GFLOP_PER_IMG / 1e3 / tf,
+        'step_roofline': {'hbm_frac': per_gpu * mb_img / 1e3 / hbm if mb_img else None, 'tensor_frac': per_gpu * gf_img / 1e3 / tf if gf_img else None,
                           'note': '268 MB/img and 32.73 GFLOP/img (BASELINE.md section 4) x img/s/GPU over the measured peaks'},
     }
     if e2e:

@@ -84,6 +84,7 @@ struct Geo {
   int cbox, nbox;    // channel box of the TMA load and number of boxes (nbox*cbox >= C)
   int box_stride;    // elements between consecutive channel boxes in smem (128-byte aligned)
   int P;             // channel pairs (C/2)
+  int c0, Cfull;     // weight-gradient channel slice: this launch covers channels [c0, c0 + C) of Cfull
 };
 
 // stage the halo tile: one thread arms the barrier and issues one 4-D box per channel box
@@ -272,8 +273,8 @@ __global__ void __launch_bounds__(BIG ? 512 : 448, BIG ? 1 : 2) dwconv7_wgrad_ke
     const uint32_t hb = (uint32_t)((g.TH + 6) * (TW + 6) * g.cbox * sizeof(T)), db = (uint32_t)(g.TH * TW * g.cbox * sizeof(T));
     mbar_expect_tx(bar, (hb + db) * g.nbox);
     for (int j = 0; j < g.nbox; ++j) {
-      tma_load_4d(tile_s + (uint32_t)((size_t)j * g.box_stride * sizeof(T)), &tmx, bar, j * g.cbox, x0 - 3, y0 - 3, b);
-      tma_load_4d(dtile_s + (uint32_t)((size_t)j * dbox_stride * sizeof(T)), &tmd, bar, j * g.cbox, x0, y0, b);
+      tma_load_4d(tile_s + (uint32_t)((size_t)j * g.box_stride * sizeof(T)), &tmx, bar, g.c0 + j * g.cbox, x0 - 3, y0 - 3, b);
+      tma_load_4d(dtile_s + (uint32_t)((size_t)j * dbox_stride * sizeof(T)), &tmd, bar, g.c0 + j * g.cbox, x0, y0, b);
     }
   }
   mbar_wait(bar, 0);
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(BIG ? 512 : 448, BIG ? 1 : 2) dwconv7_wgrad_ke
   const int trow = threadIdx.x / g.P;
   const int pr = threadIdx.x - trow * g.P;
   const int c = pr * 2;
-  float* slot = partial + (size_t)((blockIdx.x + blockIdx.y * gridDim.x) % nparts) * 50 * g.C;
+  float* slot = partial + (size_t)((blockIdx.x + blockIdx.y * gridDim.x) % nparts) * 50 * g.Cfull + g.c0;
   const int box = c / g.cbox, cc = c - box * g.cbox;
   const uint32_t cbs = (uint32_t)(g.cbox * sizeof(T));
   const uint32_t row_pitch = (uint32_t)(TW + 6) * cbs;
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(BIG ? 512 : 448, BIG ? 1 : 2) dwconv7_wgrad_ke
       const int kx = idx / g.P, pp = idx - kx * g.P;
       float s0 = 0.f, s1 = 0.f;
       for (int r = 0; r < g.TR; ++r) { const u64 v = fold[(kx * g.TR + r) * g.P + pp]; s0 += lo2(v); s1 += hi2(v); }
-      float* dst = slot + (size_t)(ky * 7 + kx) * g.C + pp * 2;
+      float* dst = slot + (size_t)(ky * 7 + kx) * g.Cfull + pp * 2;
       atomicAdd(dst, s0);
       atomicAdd(dst + 1, s1);
     }
@@ -343,8 +344,8 @@ __global__ void __launch_bounds__(BIG ? 512 : 448, BIG ? 1 : 2) dwconv7_wgrad_ke
   for (int pp = threadIdx.x; pp < g.P; pp += blockDim.x) {
     float s0 = 0.f, s1 = 0.f;
     for (int r = 0; r < g.TR; ++r) { const u64 v = fold[r * g.P + pp]; s0 += lo2(v); s1 += hi2(v); }
-    atomicAdd(slot + (size_t)49 * g.C + pp * 2, s0);
-    atomicAdd(slot + (size_t)49 * g.C + pp * 2 + 1, s1);
+    atomicAdd(slot + (size_t)49 * g.Cfull + pp * 2, s0);
+    atomicAdd(slot + (size_t)49 * g.Cfull + pp * 2 + 1, s1);
   }
 }
 
@@ -428,7 +429,7 @@ static int plan(int B, int H, int W, int C, int dtype, bool wgrad, Plan* p, int 
   GA_REQUIRE(smem <= 227 * 1024, GA_ERR_UNSUPPORTED, "dwconv7: tile does not fit shared memory (C=%d W=%d)", C, W);
   p->g.B = B; p->g.H = H; p->g.W = W; p->g.C = C; p->g.TH = th; p->g.TR = tr;
   p->g.tiles_x = (W + tw - 1) / tw; p->g.tiles_y = (H + th - 1) / th;
-  p->g.cbox = cbox; p->g.nbox = nbox; p->g.box_stride = box_stride; p->g.P = P;
+  p->g.cbox = cbox; p->g.nbox = nbox; p->g.box_stride = box_stride; p->g.P = P; p->g.c0 = 0; p->g.Cfull = C;
   p->tw = tw; p->threads = ((tr * P + 31) / 32) * 32; p->smem = smem;
   return GA_OK;
 }
@@ -493,33 +494,42 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
   if (dw49c || dbias) {
     GA_REQUIRE(x && dw_partial, GA_ERR_SHAPE, "ga_dwconv7_bwd: weight gradient needs x and a partial workspace");
     GA_REQUIRE(((uintptr_t)x & 15) == 0, GA_ERR_ALIGN, "ga_dwconv7_bwd: x must be 16-byte aligned");
+    // wide C in fp32 does not fit one CTA's shared memory: cover the channels in equal slices (multiples of 8)
+    int nslice = 1;
     dw::Plan p;
-    rc = dw::plan(B, H, W, C, dtype, true, &p, 448);
-    if (rc) return rc;
-    CUtensorMap tm;
-    rc = dw::make_x_map(x, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
-    if (rc) return rc;
-    CUtensorMap tmd;
-    rc = dw::make_x_map(dconv, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tmd, 0);
-    if (rc) return rc;
+    for (;; ++nslice) {
+      if (C % nslice || (C / nslice) % 8) { GA_REQUIRE(nslice < 16, GA_ERR_UNSUPPORTED, "dwconv7 wgrad: cannot slice C=%d", C); continue; }
+      rc = dw::plan(B, H, W, C / nslice, dtype, true, &p, 448);
+      if (rc == GA_OK) break;
+      GA_REQUIRE(nslice < 16, GA_ERR_UNSUPPORTED, "dwconv7 wgrad: C=%d does not fit shared memory", C);
+    }
     const int nparts = ga_dwconv7_bwd_parts(B, H, W, C);
     cudaMemsetAsync(dw_partial, 0, (size_t)nparts * 50 * C * sizeof(float), st);
+    CUtensorMap tm, tmd;
+    rc = dw::make_x_map(x, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
+    if (rc) return rc;
+    rc = dw::make_x_map(dconv, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tmd, 0);
+    if (rc) return rc;
     dim3 grid(p.g.tiles_x * p.g.tiles_y, B);
+    p.g.Cfull = C;
 #define GA_DWW_LAUNCH(T_, TW_)                                                                      \
   {                                                                                                 \
     auto k = p.threads > 448 ? dw::dwconv7_wgrad_kernel<T_, TW_, true> : dw::dwconv7_wgrad_kernel<T_, TW_, false>; \
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);               \
     k<<<grid, p.threads, p.smem, st>>>(tm, tmd, p.dbox_stride, dw_partial, nparts, p.g);             \
   }
-    if (dtype == GA_BF16) {
-      if (p.tw == 14) GA_DWW_LAUNCH(bf16, 14) else if (p.tw == 7) GA_DWW_LAUNCH(bf16, 7) else GA_DWW_LAUNCH(bf16, 4)
-    } else {
-      if (p.tw == 14) GA_DWW_LAUNCH(float, 14) else if (p.tw == 7) GA_DWW_LAUNCH(float, 7) else GA_DWW_LAUNCH(float, 4)
+    for (int sl = 0; sl < nslice; ++sl) {
+      p.g.c0 = sl * (C / nslice);
+      if (dtype == GA_BF16) {
+        if (p.tw == 14) GA_DWW_LAUNCH(bf16, 14) else if (p.tw == 7) GA_DWW_LAUNCH(bf16, 7) else GA_DWW_LAUNCH(bf16, 4)
+      } else {
+        if (p.tw == 14) GA_DWW_LAUNCH(float, 14) else if (p.tw == 7) GA_DWW_LAUNCH(float, 7) else GA_DWW_LAUNCH(float, 4)
+      }
+      ga_count_launch();
+      rc = ga_check_launch("dwconv7_wgrad");
+      if (rc) return rc;
     }
 #undef GA_DWW_LAUNCH
-    ga_count_launch();
-    rc = ga_check_launch("dwconv7_wgrad");
-    if (rc) return rc;
     const int n = 50 * C;
     dw::reduce_parts_kernel<<<(n + 255) / 256, 256, 0, st>>>(dw_partial, nparts, n, dw49c, 49 * C, dbias);
     ga_count_launch();

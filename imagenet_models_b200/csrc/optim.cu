@@ -76,18 +76,38 @@ extern "C" int ga_ema_lerp(float* ema, const float* src, long long n, float deca
   return launch_ok("ema_lerp");
 }
 
-// ---------------------------------------------------------------------------------------------- GA loss
+// ---------------------------------------------------------------------------------------------- GA / MAP loss
 // logits [nb][B][ncls] fp32.  loss = sum_k mean_b CE(out_k[b], y_b) + lam * sum_k mean_{b,c} KL term
 //   KL_mean(logp_k || logq) with log_target: mean over B*ncls of  q*(logq - logp_k),  q = softmax(mean_k out) (detached)
-// One CTA per sample: nb+1 log-softmaxes kept in smem; writes dlogits and atomically adds the sample's loss.
-__global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
-                                                      float* __restrict__ loss, float* __restrict__ dlogits, int nb, int B, int ncls,
+// Optional aux logits (MAP's self-distillation heads, MAP/train.py:815-821):
+//   + sum_k (1/(B*ncls)) sum_{b,c} p_k (logp_k - logpaux_k),  p_k = softmax(out_k) detached
+// One CTA per sample: the log-softmaxes stay in smem; writes dlogits / daux and atomically adds the sample's loss.
+__device__ __forceinline__ void log_softmax_row(float* row, int ncls, float* red) {
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) mx = fmaxf(mx, row[c]);
+  mx = warp_max(mx);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  float se = 0.f;
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) se += expf(row[c] - mx);
+  se = block_sum(se, red);
+  const float lse = mx + logf(se);
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) row[c] -= lse;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ logits, const float* __restrict__ aux,
+                                                      const long long* __restrict__ target, float* __restrict__ loss,
+                                                      float* __restrict__ dlogits, float* __restrict__ daux, int nb, int B, int ncls,
                                                       float lam, float grad_scale) {
-  extern __shared__ float sm[];  // [(nb+1)][ncls] log-probs
+  extern __shared__ float sm[];  // [(nb+2)][ncls]: nb branch rows, the mean row, one aux row
   __shared__ float red[32];
   const int b = blockIdx.x;
   float* lq = sm + (size_t)nb * ncls;
-  // mean logits
+  float* la = lq + ncls;
   for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
     float a = 0.f;
     for (int k = 0; k < nb; ++k) {
@@ -98,24 +118,7 @@ __global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ 
     lq[c] = a / (float)nb;
   }
   __syncthreads();
-  // log-softmax of each of the nb+1 rows
-  for (int k = 0; k <= nb; ++k) {
-    float* row = sm + (size_t)k * ncls;
-    float mx = -INFINITY;
-    for (int c = threadIdx.x; c < ncls; c += blockDim.x) mx = fmaxf(mx, row[c]);
-    mx = warp_max(mx);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    mx = red[0];
-    for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
-    float se = 0.f;
-    for (int c = threadIdx.x; c < ncls; c += blockDim.x) se += expf(row[c] - mx);
-    se = block_sum(se, red);
-    const float lse = mx + logf(se);
-    for (int c = threadIdx.x; c < ncls; c += blockDim.x) row[c] -= lse;
-    __syncthreads();
-  }
+  for (int k = 0; k <= nb; ++k) log_softmax_row(sm + (size_t)k * ncls, ncls, red);
   const int y = (int)target[b];
   const float invB = 1.f / (float)B, inv_bc = 1.f / ((float)B * (float)ncls);
   float local = 0.f;
@@ -132,16 +135,27 @@ __global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ 
         dlogits[((size_t)k * B + b) * ncls + c] = (gce + gkl) * grad_scale;
       }
     }
+    if (aux) {
+      __syncthreads();
+      for (int c = threadIdx.x; c < ncls; c += blockDim.x) la[c] = aux[((size_t)k * B + b) * ncls + c];
+      __syncthreads();
+      log_softmax_row(la, ncls, red);
+      for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+        const float p = expf(lp[c]);
+        local += inv_bc * p * (lp[c] - la[c]);
+        if (daux) daux[((size_t)k * B + b) * ncls + c] = -inv_bc * (p - expf(la[c])) * grad_scale;
+      }
+    }
   }
   local = block_sum(local, red);
   if (threadIdx.x == 0) atomicAdd(loss, local);
 }
-extern "C" int ga_loss_fwd_bwd(const float* logits, const long long* target, float* loss, float* dlogits, int nb, int B, int ncls,
-                               float lam, float grad_scale, ga_stream_t s) {
+extern "C" int ga_loss_fwd_bwd(const float* logits, const float* aux, const long long* target, float* loss, float* dlogits,
+                               float* daux, int nb, int B, int ncls, float lam, float grad_scale, ga_stream_t s) {
   GA_REQUIRE(logits && target && loss && nb > 0 && B > 0 && ncls > 0, GA_ERR_SHAPE, "ga_loss_fwd_bwd: bad arguments");
-  const size_t smem = (size_t)(nb + 1) * ncls * sizeof(float);
-  GA_REQUIRE(smem <= 200 * 1024, GA_ERR_UNSUPPORTED, "ga_loss_fwd_bwd: (nb+1)*ncls too large for shared memory");
+  const size_t smem = (size_t)(nb + 2) * ncls * sizeof(float);
+  GA_REQUIRE(smem <= 200 * 1024, GA_ERR_UNSUPPORTED, "ga_loss_fwd_bwd: (nb+2)*ncls too large for shared memory");
   cudaFuncSetAttribute(ga_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ga_loss_kernel<<<B, 256, smem, (cudaStream_t)s>>>(logits, target, loss, dlogits, nb, B, ncls, lam, grad_scale);
+  ga_loss_kernel<<<B, 256, smem, (cudaStream_t)s>>>(logits, aux, target, loss, dlogits, daux, nb, B, ncls, lam, grad_scale);
   return launch_ok("ga_loss");
 }

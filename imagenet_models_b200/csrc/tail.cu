@@ -42,6 +42,20 @@ __global__ void aggregate_kernel(const T* __restrict__ src, T* __restrict__ dst,
       a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
     } else if (mode == 1) {
       a = ld4(src + (((long long)b * Hs + oy) * Ws + ox) * C + c);
+    } else if (mode == 3) {
+      // non-antialiased bilinear shrink by an even factor f: src = (dst+0.5)*f - 0.5 falls midway between pixels
+      // f*dst + f/2 - 1 and f*dst + f/2, so the result is the mean of that 2x2 block (map.py:328)
+      const int f = Hs / Ho, o = f / 2 - 1;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          float4 v = ld4(src + (((long long)b * Hs + oy * f + o + dy) * Ws + ox * f + o + dx) * C + c);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+      a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f;
+    } else if (mode == 4) {
+      // adaptive_avg_pool2d to a k-times larger map = replication (map.py:326)
+      const int k = Ho / Hs;
+      a = ld4(src + (((long long)b * Hs + oy / k) * Ws + ox / k) * C + c);
     } else {
       int y0, y1, x0, x1; float ly, lx;
       bil_src(oy, Hs, &y0, &y1, &ly);
@@ -80,6 +94,20 @@ __global__ void aggregate_bwd_kernel(T* __restrict__ dsrc, const T* __restrict__
       a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
     } else if (mode == 1) {
       a = ld4(dbase + ((long long)y * Wo + x) * ldd);
+    } else if (mode == 3) {
+      const int f = Hs / Ho, o = f / 2 - 1;
+      const int ry = y % f, rx = x % f;
+      if ((ry == o || ry == o + 1) && (rx == o || rx == o + 1)) {
+        a = ld4(dbase + ((long long)(y / f) * Wo + x / f) * ldd);
+        a.x *= 0.25f; a.y *= 0.25f; a.z *= 0.25f; a.w *= 0.25f;
+      }
+    } else if (mode == 4) {
+      const int k = Ho / Hs;
+      for (int dy = 0; dy < k; ++dy)
+        for (int dx = 0; dx < k; ++dx) {
+          float4 v = ld4(dbase + ((long long)(y * k + dy) * Wo + x * k + dx) * ldd);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
     } else {
       const int oy_lo = max(0, 2 * y - 2), oy_hi = min(Ho - 1, 2 * y + 2);
       const int ox_lo = max(0, 2 * x - 2), ox_hi = min(Wo - 1, 2 * x + 2);
@@ -113,6 +141,9 @@ extern "C" int ga_aggregate(const void* src, void* dst, int B, int Hs, int Ws, i
   GA_REQUIRE(mode != 0 || (Hs % Ho == 0 && Ws % Wo == 0 && Hs / Ho == Ws / Wo), GA_ERR_SHAPE, "ga_aggregate: pool factor must be integral");
   GA_REQUIRE(mode != 1 || (Hs == Ho && Ws == Wo), GA_ERR_SHAPE, "ga_aggregate: copy needs equal sizes");
   GA_REQUIRE(mode != 2 || (Ho == 2 * Hs && Wo == 2 * Ws), GA_ERR_SHAPE, "ga_aggregate: bilinear is x2 only");
+  GA_REQUIRE(mode != 3 || (Hs % Ho == 0 && Ws % Wo == 0 && Hs / Ho == Ws / Wo && ((Hs / Ho) & 1) == 0), GA_ERR_SHAPE,
+             "ga_aggregate: bilinear shrink needs an even integer factor");
+  GA_REQUIRE(mode != 4 || (Ho % Hs == 0 && Wo % Ws == 0 && Ho / Hs == Wo / Ws), GA_ERR_SHAPE, "ga_aggregate: replicate factor must be integral");
   const long long total = (long long)B * (inverse ? Hs * Ws : Ho * Wo) * (C >> 2);
   if (total == 0) return GA_OK;
   const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
@@ -253,9 +284,12 @@ extern "C" int ga_se_bwd(const void* dy, const void* x, const float* w1, const f
 // i<=j enumeration t (ga_convnext.py:424-430).  One CTA per image.
 __device__ __forceinline__ int triu_row_start(int i, int C) { return i * C - (i * (i - 1)) / 2; }
 
+// optional token interleave of the triu vector (GramToken, map.py:225-227): position t -> (t % nt) * (tri / nt) + t / nt
+__device__ __forceinline__ int triu_pos(int t, int tri, int nt) { return nt > 1 ? (t % nt) * (tri / nt) + t / nt : t; }
+
 template <typename TO>
 __global__ void __launch_bounds__(512) gram_triu_fwd_kernel(const float* __restrict__ G, TO* __restrict__ out, float* __restrict__ norm_o,
-                                                            int C, int glen, int gld, long long out_bs) {
+                                                            int C, int glen, int gld, long long out_bs, int nt) {
   __shared__ float red[32];
   const int b = blockIdx.x;
   const float* Gb = G + (long long)b * C * C;
@@ -272,24 +306,24 @@ __global__ void __launch_bounds__(512) gram_triu_fwd_kernel(const float* __restr
   for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
     const int i = idx / C, j = idx - i * C;
     if (j >= i) {
-      const int t = triu_row_start(i, C) + (j - i);
+      const int t = triu_pos(triu_row_start(i, C) + (j - i), C * (C + 1) / 2, nt);
       st_f(ob + (long long)(t / glen) * gld + t % glen, Gb[idx] * inv);
     }
   }
 }
 extern "C" int ga_gram_triu_fwd(const float* G, void* out, float* norm, int B, int C, int glen, int gld, long long out_bs,
-                                int out_dtype, ga_stream_t s) {
+                                int out_dtype, int interleave, ga_stream_t s) {
   GA_REQUIRE(G && out && norm && C > 0 && glen > 0 && gld >= glen, GA_ERR_SHAPE, "ga_gram_triu_fwd: bad arguments");
   if (B == 0) return GA_OK;
-  if (out_dtype == GA_BF16) gram_triu_fwd_kernel<bf16><<<B, 512, 0, (cudaStream_t)s>>>(G, (bf16*)out, norm, C, glen, gld, out_bs);
-  else gram_triu_fwd_kernel<float><<<B, 512, 0, (cudaStream_t)s>>>(G, (float*)out, norm, C, glen, gld, out_bs);
+  if (out_dtype == GA_BF16) gram_triu_fwd_kernel<bf16><<<B, 512, 0, (cudaStream_t)s>>>(G, (bf16*)out, norm, C, glen, gld, out_bs, interleave);
+  else gram_triu_fwd_kernel<float><<<B, 512, 0, (cudaStream_t)s>>>(G, (float*)out, norm, C, glen, gld, out_bs, interleave);
   return launch_ok("gram_triu_fwd");
 }
 
 // backward through normalise + gather: dt = (dout - out*(out.dout))/norm; S = dG + dG^T (symmetric, diag doubled), dtype TS
 template <typename TI, typename TS>
 __global__ void __launch_bounds__(512) gram_triu_bwd_kernel(const TI* __restrict__ dout, const TI* __restrict__ out, const float* __restrict__ norm,
-                                                            TS* __restrict__ S, int C, int glen, int gld, long long out_bs) {
+                                                            TS* __restrict__ S, int C, int glen, int gld, long long out_bs, int nt) {
   __shared__ float red[32];
   const int b = blockIdx.x;
   const TI* ob = out + (long long)b * out_bs;
@@ -306,7 +340,7 @@ __global__ void __launch_bounds__(512) gram_triu_bwd_kernel(const TI* __restrict
   for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
     const int i = idx / C, j = idx - i * C;
     const int lo = i < j ? i : j, hi = i < j ? j : i;
-    const int t = triu_row_start(lo, C) + (hi - lo);
+    const int t = triu_pos(triu_row_start(lo, C) + (hi - lo), tri, nt);
     const long long o = (long long)(t / glen) * gld + t % glen;
     float v = (ld_f(db + o) - ld_f(ob + o) * dot) * inv;
     if (i == j) v *= 2.f;
@@ -314,14 +348,14 @@ __global__ void __launch_bounds__(512) gram_triu_bwd_kernel(const TI* __restrict
   }
 }
 extern "C" int ga_gram_triu_bwd(const void* dout, const void* out, const float* norm, void* S, int B, int C, int glen, int gld,
-                                long long out_bs, int io_dtype, int s_dtype, ga_stream_t s) {
+                                long long out_bs, int io_dtype, int s_dtype, int interleave, ga_stream_t s) {
   GA_REQUIRE(dout && out && norm && S, GA_ERR_SHAPE, "ga_gram_triu_bwd: bad arguments");
   if (B == 0) return GA_OK;
   cudaStream_t st = (cudaStream_t)s;
-  if (io_dtype == GA_BF16 && s_dtype == GA_BF16) gram_triu_bwd_kernel<bf16, bf16><<<B, 512, 0, st>>>((const bf16*)dout, (const bf16*)out, norm, (bf16*)S, C, glen, gld, out_bs);
-  else if (io_dtype == GA_BF16) gram_triu_bwd_kernel<bf16, float><<<B, 512, 0, st>>>((const bf16*)dout, (const bf16*)out, norm, (float*)S, C, glen, gld, out_bs);
-  else if (s_dtype == GA_BF16) gram_triu_bwd_kernel<float, bf16><<<B, 512, 0, st>>>((const float*)dout, (const float*)out, norm, (bf16*)S, C, glen, gld, out_bs);
-  else gram_triu_bwd_kernel<float, float><<<B, 512, 0, st>>>((const float*)dout, (const float*)out, norm, (float*)S, C, glen, gld, out_bs);
+  if (io_dtype == GA_BF16 && s_dtype == GA_BF16) gram_triu_bwd_kernel<bf16, bf16><<<B, 512, 0, st>>>((const bf16*)dout, (const bf16*)out, norm, (bf16*)S, C, glen, gld, out_bs, interleave);
+  else if (io_dtype == GA_BF16) gram_triu_bwd_kernel<bf16, float><<<B, 512, 0, st>>>((const bf16*)dout, (const bf16*)out, norm, (float*)S, C, glen, gld, out_bs, interleave);
+  else if (s_dtype == GA_BF16) gram_triu_bwd_kernel<float, bf16><<<B, 512, 0, st>>>((const float*)dout, (const float*)out, norm, (bf16*)S, C, glen, gld, out_bs, interleave);
+  else gram_triu_bwd_kernel<float, float><<<B, 512, 0, st>>>((const float*)dout, (const float*)out, norm, (float*)S, C, glen, gld, out_bs, interleave);
   return launch_ok("gram_triu_bwd");
 }
 

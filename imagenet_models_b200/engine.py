@@ -48,7 +48,10 @@ class TrainEngine:
                 out = self.model(x)
         else:
             out = self.model(x)
-        loss = ops.ga_loss(torch.stack(out), y, self.ga_lam)
+        if isinstance(out[0], (list, tuple)):            # MAP train mode: [main, self-distillation] pairs per group
+            loss = ops.ga_loss(torch.stack([o[0] for o in out]), y, self.ga_lam, aux=torch.stack([o[1] for o in out]))
+        else:
+            loss = ops.ga_loss(torch.stack(out), y, self.ga_lam)
         (loss / self.accum if self.accum > 1 else loss).backward()
         if last:
             scale = self.buckets.finish() if self.buckets is not None else 1.0

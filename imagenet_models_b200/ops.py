@@ -52,6 +52,23 @@ def workspace(n_floats: int, device, tag: str) -> torch.Tensor:
     return t
 
 
+_const_cache = {}
+
+
+def _ones(n, device):
+    k = ('1', n, str(device))
+    if k not in _const_cache:
+        _const_cache[k] = torch.ones(n, dtype=torch.float32, device=device)
+    return _const_cache[k]
+
+
+def _zeros(n, device):
+    k = ('0', n, str(device))
+    if k not in _const_cache:
+        _const_cache[k] = torch.zeros(n, dtype=torch.float32, device=device)
+    return _const_cache[k]
+
+
 # ------------------------------------------------------------------------------------------------- raw kernels
 class GemmTimer:
     """Optional CUDA-event instrumentation of every ga_gemm launch (bench.py's live per-kernel roofline).
@@ -579,6 +596,34 @@ class BatchNormFn(Function):
         return dxa, dwa, dba, None, None, dxb, dwb, dbb, None, None, None, None, None, None
 
 
+class GeluFn(Function):
+    """Stand-alone erf-GELU on a row matrix (MAP's concat_conv: 1x1 conv -> BN -> GELU, map.py:281-288)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = rowmat(x)
+        M, Cc = x.shape
+        assert Cc % 4 == 0
+        y = alloc_rows(M, Cc, x.dtype, x.device)
+        L.check(_L().ga_affine_act(L.ptr(x), L.ptr(_ones(Cc, x.device)), L.ptr(_zeros(Cc, x.device)), None, None, None, L.ptr(y),
+                                   L.ll(M), Cc, L.ll(x.stride(0)), L.ll(0), L.ll(y.stride(0)), ACT_GELU, L.dt(x), L.stream()),
+                'ga_affine_act')
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = rowmat(dy)
+        if dy.dtype != x.dtype:
+            dy = convert(dy, x.dtype)
+        return act_bwd(dy, x, ACT_GELU)
+
+
+def gelu(x):
+    return GeluFn.apply(x)
+
+
 class ScaleRowsFn(Function):
     """y[r,:] = x[r,:] * scale[r // rows_per_scale]  (DropPath on a residual branch)."""
 
@@ -704,7 +749,7 @@ class GramFn(Function):
     the grouped 1x1 gram_embedding conv reads through TMA); fp32 output is unpadded like the reference's."""
 
     @staticmethod
-    def forward(ctx, x, Bn, HW, div, out_dtype, groups):
+    def forward(ctx, x, Bn, HW, div, out_dtype, groups, interleave=1):
         x = x.contiguous()
         Cc = x.shape[1]
         dev = x.device
@@ -719,28 +764,28 @@ class GramFn(Function):
         out = torch.empty(Bn, groups * gld, dtype=out_dtype, device=dev)
         norm = torch.empty(Bn, dtype=torch.float32, device=dev)
         L.check(_L().ga_gram_triu_fwd(L.ptr(G), L.ptr(out), L.ptr(norm), Bn, Cc, glen, gld, L.ll(groups * gld), L.dt(out),
-                                      L.stream()), 'ga_gram_triu_fwd')
+                                      interleave, L.stream()), 'ga_gram_triu_fwd')
         ctx.save_for_backward(x, out, norm)
-        ctx.dims = (Bn, HW, Cc, alpha, glen, gld)
+        ctx.dims = (Bn, HW, Cc, alpha, glen, gld, interleave)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, out, norm = ctx.saved_tensors
-        Bn, HW, Cc, alpha, glen, gld = ctx.dims
+        Bn, HW, Cc, alpha, glen, gld, interleave = ctx.dims
         dout = dout.contiguous()
         if dout.dtype != out.dtype:
             dout = dout.to(out.dtype)
         S = torch.empty(Bn, Cc, Cc, dtype=x.dtype, device=x.device)
         L.check(_L().ga_gram_triu_bwd(L.ptr(dout), L.ptr(out), L.ptr(norm), L.ptr(S), Bn, Cc, glen, gld, L.ll(out.shape[1]),
-                                      L.dt(out), L.dt(S), L.stream()), 'ga_gram_triu_bwd')
+                                      L.dt(out), L.dt(S), interleave, L.stream()), 'ga_gram_triu_bwd')
         dx = torch.empty(Bn * HW, Cc, dtype=x.dtype, device=x.device)
         gemm(x.view(Bn, HW, Cc), S, dx.view(Bn, HW, Cc), alpha=alpha)   # dX = alpha * X (dG + dG^T)
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
-def gram_vector(x, Bn, HW, div, out_dtype=torch.float32, groups=1):
-    return GramFn.apply(x, Bn, HW, div, out_dtype, groups)
+def gram_vector(x, Bn, HW, div, out_dtype=torch.float32, groups=1, interleave=1):
+    return GramFn.apply(x, Bn, HW, div, out_dtype, groups, interleave)
 
 
 # ------------------------------------------------------------------------------------------------- attention pooling
@@ -784,24 +829,30 @@ def attnpool(q, kv_cls, kv_tok, N, H):
 
 # ------------------------------------------------------------------------------------------------- loss
 class GALossFn(Function):
-    """sum_k CE(out_k, y) + lam * sum_k KL_mean(logsm(out_k) || logsm(mean out).detach())  (GA/train.py:735-745)."""
+    """sum_k CE(out_k, y) + lam * sum_k KL_mean(logsm(out_k) || logsm(mean out).detach())  (GA/train.py:735-745);
+    with aux logits also MAP's self-distillation term sum_k KL_sum(logsm(aux_k) || logsm(out_k).detach())/numel
+    (multi_group_loss, MAP/train.py:792-839)."""
 
     @staticmethod
-    def forward(ctx, logits, target, lam):
+    def forward(ctx, logits, aux, target, lam):
         nb, Bn, ncls = logits.shape
         logits = logits.contiguous().float()
         loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
         dl = torch.empty_like(logits)
-        L.check(_L().ga_loss_fwd_bwd(L.ptr(logits), L.ptr(target), L.ptr(loss), L.ptr(dl), nb, Bn, ncls, L.f(lam), L.f(1.0),
-                                     L.stream()), 'ga_loss_fwd_bwd')
-        ctx.save_for_backward(dl)
+        da = None
+        if aux is not None:
+            aux = aux.contiguous().float()
+            da = torch.empty_like(aux)
+        L.check(_L().ga_loss_fwd_bwd(L.ptr(logits), L.ptr(aux), L.ptr(target), L.ptr(loss), L.ptr(dl), L.ptr(da), nb, Bn, ncls,
+                                     L.f(lam), L.f(1.0), L.stream()), 'ga_loss_fwd_bwd')
+        ctx.save_for_backward(dl, da)
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        (dl,) = ctx.saved_tensors
-        return dl * g, None, None
+        dl, da = ctx.saved_tensors
+        return dl * g, (da * g if da is not None else None), None, None
 
 
-def ga_loss(logits, target, lam):
-    return GALossFn.apply(logits, target, lam)
+def ga_loss(logits, target, lam, aux=None):
+    return GALossFn.apply(logits, aux, target, lam)

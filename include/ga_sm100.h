@@ -124,7 +124,8 @@ int ga_bn_bwd_apply(const void* dy, const void* x, const void* y, const float* m
                     long long lddy, long long ldx, long long ldy, long long lddx, int relu, int dtype, ga_stream_t s);
 
 /* ---- K3: multi-scale aggregation and SE gate  (ga_convnext.py:479-483, :305; map.py:322-331) ------------------
- * mode 0: avg-pool by integer factor (56->14, 28->14); 1: copy; 2: bilinear x2 (align_corners=False).  Writes channel
+ * mode 0: avg-pool by integer factor (56->14, 28->14); 1: copy; 2: bilinear x2 (align_corners=False); 3: non-antialiased
+ * bilinear shrink by an even factor (MAP MultiScale, map.py:328); 4: replication (adaptive_avg_pool2d to a larger map).  Writes channel
  * slice [coff, coff+C) of dst [B,Ho,Wo,ldd].  inverse=1: adjoint, src (contiguous) receives the gradient of the slice. */
 int ga_aggregate(const void* src, void* dst, int B, int Hs, int Ws, int C, int Ho, int Wo, long long ldd, int coff,
                  int mode, int inverse, int dtype, ga_stream_t s);
@@ -141,10 +142,11 @@ int ga_se_bwd(const void* dy, const void* x, const float* w1, const float* w2, c
  * G [B,C,C] fp32 comes from ga_gemm (X^T X, alpha = 1/(div^2 HW)).  out[b, (t/glen)*gld + t%glen] = triu(G)_t / max(||triu||,1e-12)
  * with t the row-major i<=j enumeration; (glen, gld) let the caller pad each conv group to a 16-byte multiple. */
 int ga_gram_triu_fwd(const float* G, void* out, float* norm, int B, int C, int glen, int gld, long long out_bs,
-                     int out_dtype, ga_stream_t s);
+                     int out_dtype, int interleave /* n_tokens of map.GramToken's token interleave, map.py:225-227; 1 = none */,
+                     ga_stream_t s);
 /* backward through normalise + gather: S[b] = dG + dG^T (C x C, diagonal doubled); dX = alpha * X S is a ga_gemm */
 int ga_gram_triu_bwd(const void* dout, const void* out, const float* norm, void* S, int B, int C, int glen, int gld,
-                     long long out_bs, int io_dtype, int s_dtype, ga_stream_t s);
+                     long long out_bs, int io_dtype, int s_dtype, int interleave, ga_stream_t s);
 
 /* ---- K5: attention pooling: Q query tokens against Q+N keys  (ClassAttn ga_convnext.py:170-183; map.py:100-144)
  * q [B,Q,E] fp32 pre-scaled; kv_cls [B,Q,2E] fp32 (k | v of the query tokens); kv_tok rows [B*N, ldt] (k at col 0,
@@ -181,9 +183,11 @@ int ga_linear_grad_finalize(const float* G, const float* s, const float* W, cons
                             float* db_in, int N, int K, ga_stream_t st);
 
 /* ---- loss: sum_k CE(out_k, y) + lam * sum_k KL_mean(logsm(out_k) || logsm(mean_k out).detach())  (GA/train.py:735-745)
- * logits [nb][B][ncls] fp32; dlogits same shape (may be NULL), scaled by grad_scale; loss[0] += value */
-int ga_loss_fwd_bwd(const float* logits, const long long* target, float* loss, float* dlogits, int nb, int B,
-                    int ncls, float lam, float grad_scale, ga_stream_t s);
+ * plus, when aux != NULL (MAP's self-distillation heads, MAP/train.py:815-821, 833-837 with lam = dec_lam):
+ *   sum_k KL_sum(logsm(aux_k) || logsm(out_k).detach()) / numel.
+ * logits, aux: [nb][B][ncls] fp32; dlogits / daux same shape (may be NULL), scaled by grad_scale; loss[0] += value */
+int ga_loss_fwd_bwd(const float* logits, const float* aux, const long long* target, float* loss, float* dlogits,
+                    float* daux, int nb, int B, int ncls, float lam, float grad_scale, ga_stream_t s);
 
 /* ---- K7: fused multi-tensor AdamW + EMA over flat fp32 buffers  (GA/train.py:466,499,760-761; timm ModelEmaV2)
  * torch.optim.AdamW update of p from g (scaled by grad_scale) with state m, v; bias_c1 = 1-beta1^t, bias_c2 = 1-beta2^t.

@@ -11,6 +11,8 @@ import torch
 STATE_SEED = 7
 GA_LAM = -0.8          # --GA_lam used by the published recipe (GA/README.md:26)
 GA_MODEL_CASES = [('ga_convnext_tiny_688', 2)]
+MAP_MODEL_CASES = [('map_convnext_tiny', 2)]
+MAP_DEC_LAM = -0.8
 PARAM_COUNTS = {
     'ga_convnext_tiny_688': 47821324, 'ga_convnext_tiny_768': 54354584,
     'ga_convnext_small_688': 70116364, 'ga_convnext_small_768': 76726424,

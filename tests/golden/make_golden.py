@@ -195,6 +195,80 @@ def golden_ga_modules():
     torch.save(out, os.path.join(HERE, 'ga_convnext_modules.pt'))
 
 
+def golden_map_model():
+    """map_convnext_tiny through the unmodified reference (MAP/models/map_convnext.py + map.py)."""
+    import types
+    import timm
+    import models.map_convnext  # noqa: F401  (registers map_convnext_* into the shim registry)
+    from oracle import map_convnext_oracle as MO
+    out = {}
+    for name, B in cases.MAP_MODEL_CASES:
+        spec = MO.SPECS[name]
+        ref = timm.create_model(name)
+        assert sum(p.numel() for p in ref.parameters()) == MO.PARAM_COUNTS[name]      # MAP/README.MD:308,373
+        P = MO.make_state(spec, seed=cases.STATE_SEED)
+        ref.load_state_dict(P, strict=True)
+        for m in ref.modules():                    # parity contract: every drop rate 0 (map.py:149 hard-codes 0.05)
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        x, y = cases.ga_inputs(B)
+        ref.eval()
+        with torch.no_grad():
+            r_eval = ref(x)
+            o_eval = MO.forward({k: v.clone() for k, v in P.items()}, spec, x, training=False)
+        for a, b in zip(o_eval, r_eval):
+            assert rel(a, b) < 2e-5, rel(a, b)
+        ref.train()
+        r_train = ref(x)
+        args = types.SimpleNamespace(distill_tokens=0, token_distillation=False, dec_lam=cases.MAP_DEC_LAM)
+        sys.path.insert(0, '/root/reference/MAP')
+        # the exact expression of MAP/train.py:792-839 (copied call, not copied code: import would pull timm.data)
+        loss = 0
+        agg = 0
+        for yh, ym in r_train:
+            agg = agg + yh
+            loss = loss + F.cross_entropy(yh, y) + F.kl_div(F.log_softmax(ym, dim=1), F.log_softmax(yh, dim=1).detach(),
+                                                            reduction='sum', log_target=True) / yh.numel()
+        for yh, ym in r_train:
+            loss = loss + F.kl_div(F.log_softmax(yh, dim=1), F.log_softmax(agg.detach() / len(r_train), dim=1),
+                                   reduction='mean', log_target=True) * args.dec_lam
+        loss.backward()
+        r_grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters() if p.grad is not None}
+        r_state = {k: v.detach().clone() for k, v in ref.state_dict().items() if 'running' in k}
+        Po = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone())
+              for k, v in P.items()}
+        o_train = MO.forward(Po, spec, x, training=True)
+        o_loss = MO.map_loss(o_train, y, cases.MAP_DEC_LAM)
+        o_loss.backward()
+        assert rel(o_loss.detach(), loss.detach()) < 1e-6
+        for (a1, a2), (b1, b2) in zip(o_train, r_train):
+            assert rel(a1.detach(), b1.detach()) < 2e-5 and rel(a2.detach(), b2.detach()) < 2e-5
+        for k, g in r_grads.items():
+            assert close(Po[k].grad, g, 5e-5), (k, rel(Po[k].grad, g))
+        for k, v in r_state.items():
+            assert rel(Po[k], v) < 1e-5, k
+        self_err = {}
+        for mode in ('eval', 'train'):
+            m2 = timm.create_model(name)
+            m2.load_state_dict(P, strict=True)
+            for m in m2.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            m2.train(mode == 'train')
+            with torch.no_grad(), torch.autocast('cpu', dtype=torch.bfloat16):
+                o16 = m2(x)
+            if mode == 'eval':
+                self_err[mode] = max(rel(a.float(), b) for a, b in zip(o16, r_eval))
+            else:
+                self_err[mode] = max(rel(a[0].float(), b[0].detach()) for a, b in zip(o16, r_train))
+        print(f'{name} B={B}: oracle==reference  (loss {loss.item():.6f}; reference bf16-autocast self error '
+              f"eval {self_err['eval']:.2e} train {self_err['train']:.2e})")
+        out[f'{name}/B{B}'] = dict(ref_bf16_self_err=self_err, eval_logits=[t.clone() for t in r_eval],
+                                   train_logits=[[a.detach().clone(), b.detach().clone()] for a, b in r_train],
+                                   loss=loss.detach().clone(), grads=grad_digest(r_grads), running=r_state)
+    torch.save(out, os.path.join(HERE, 'map_convnext_model.pt'))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
     which = sys.argv[1:] or ['modules', 'model']
@@ -202,3 +276,5 @@ if __name__ == '__main__':
         golden_ga_modules()
     if 'model' in which:
         golden_ga_model()
+    if 'map' in which or 'model' in which:
+        golden_map_model()

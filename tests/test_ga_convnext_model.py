@@ -18,7 +18,7 @@ def rel(a, b):
 
 # ------------------------------------------------------------------------------------------------- CPU: structure
 def test_registry_names():
-    assert list_models() == sorted(cases.PARAM_COUNTS)      # the six factories of ga_convnext.py:572-613
+    assert set(cases.PARAM_COUNTS) <= set(list_models())    # the six factories of ga_convnext.py:572-613
     with pytest.raises(RuntimeError):
         create_model('ga_convnext_tiny')                    # README name is not a registered model
 

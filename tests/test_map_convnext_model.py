@@ -1,0 +1,127 @@
+"""MAP-ConvNeXt drop-in (MAP head + backbone): structure on CPU, whole-model parity against reference fixtures on GPU."""
+import os
+
+import pytest
+import torch
+
+import imagenet_models_b200.map_convnext  # noqa: F401
+from imagenet_models_b200 import lib as L
+from imagenet_models_b200.registry import create_model
+from oracle import cases
+from oracle import map_convnext_oracle as MO
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('name', ['map_convnext_tiny', 'map_convnext_small'])
+def test_state_dict_contract_and_readme_param_counts(name):
+    m = create_model(name, pretrained_cfg=None)
+    sd = m.state_dict()
+    want = MO.state_shapes(MO.SPECS[name])
+    assert sorted(sd.keys()) == sorted(want.keys())
+    for k, (shape, _) in want.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert sum(p.numel() for p in m.parameters()) == MO.PARAM_COUNTS[name]     # MAP/README.MD:308, :373
+    m.load_state_dict(MO.make_state(MO.SPECS[name], 3), strict=True)
+    if name == 'map_convnext_tiny':
+        assert len(sd) == 332
+    assert hasattr(m.head.heads[0].head, 'bias')                                # read by MAP/validate.py:236-237
+
+
+def test_oracle_eval_vs_reference_fixture(golden_dir):
+    g = torch.load(os.path.join(golden_dir, 'map_convnext_model.pt'))
+    name, B = cases.MAP_MODEL_CASES[0]
+    spec = MO.SPECS[name]
+    x, _ = cases.ga_inputs(B)
+    with torch.no_grad():
+        out = MO.forward(MO.make_state(spec, cases.STATE_SEED), spec, x, training=False)
+    for a, b in zip(out, g[f'{name}/B{B}']['eval_logits']):
+        assert rel(a, b) < 2e-5
+
+
+def test_init_matches_reference_bitwise():
+    if not os.path.isdir('/root/reference/MAP'):
+        pytest.skip('reference sources not present on this box')
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'oracle', 'timm_shim'))
+    sys.path.insert(0, '/root/reference/MAP')
+    import timm
+    import models.map_convnext  # noqa: F401
+    torch.manual_seed(5)
+    ref = timm.create_model('map_convnext_tiny')
+    torch.manual_seed(5)
+    mine = create_model('map_convnext_tiny')
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+
+
+@pytest.fixture(scope='module')
+def gmap(golden_dir):
+    return torch.load(os.path.join(golden_dir, 'map_convnext_model.pt'))
+
+
+def _build(name, dtype):
+    m = create_model(name).cuda()
+    m.load_state_dict({k: v.cuda() for k, v in MO.make_state(MO.SPECS[name], cases.STATE_SEED).items()}, strict=True)
+    m.compute_dtype = dtype
+    return m
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_eval_logits_vs_reference(gmap, dtype, tol):
+    name, B = cases.MAP_MODEL_CASES[0]
+    g = gmap[f'{name}/B{B}']
+    m = _build(name, dtype).eval()
+    x, _ = cases.ga_inputs(B)
+    with torch.no_grad():
+        out = m(x.cuda())
+    assert len(out) == 4
+    for a, b in zip(out, g['eval_logits']):
+        assert a.shape == (B, 1000) and a.dtype == torch.float32
+        assert rel(a.cpu(), b) < tol, rel(a.cpu(), b)
+        if dtype == torch.float32:
+            assert torch.equal(a.cpu().topk(5).indices, b.topk(5).indices)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 5e-5), (torch.bfloat16, 2e-2)])
+def test_train_step_vs_reference(gmap, dtype, tol):
+    """forward (pairs) + multi_group_loss (dec_lam=-0.8) + backward vs the reference's logits, loss, gradients, BN stats."""
+    from imagenet_models_b200 import ops
+    name, B = cases.MAP_MODEL_CASES[0]
+    g = gmap[f'{name}/B{B}']
+    m = _build(name, dtype).train()
+    x, y = cases.ga_inputs(B)
+    out = m(x.cuda())
+    ltol = tol if dtype == torch.float32 else max(tol, g['ref_bf16_self_err']['train'])
+    for (a1, a2), (b1, b2) in zip(out, g['train_logits']):
+        assert rel(a1.detach().cpu(), b1) < ltol and rel(a2.detach().cpu(), b2) < ltol
+    loss = ops.ga_loss(torch.stack([o[0] for o in out]), y.cuda(), cases.MAP_DEC_LAM, aux=torch.stack([o[1] for o in out]))
+    assert abs(loss.item() - g['loss'].item()) < (1e-4 if dtype == torch.float32 else 3e-2) * abs(g['loss'].item())
+    loss.backward()
+    bad = []
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        if dtype == torch.float32:
+            ok = cases.digest_close(p.grad, g['grads'][k], tol, 3e-4)
+        else:
+            ok = cases.digest_rel_err(p.grad, g['grads'][k]) <= 0.15 or g['grads'][k][0] < 2e-2
+        if not ok:
+            bad.append((k, g['grads'][k][0], p.grad.double().norm().item()))
+    assert not bad, bad[:10]
+    sd = m.state_dict()
+    for k, v in g['running'].items():
+        assert rel(sd[k].cpu(), v) < (1e-5 if dtype == torch.float32 else 1e-2), k
+
+
+def test_cpu_tensor_raises():
+    m = create_model('map_convnext_tiny')
+    with pytest.raises(L.GaError):
+        m(torch.zeros(1, 3, 224, 224))
