@@ -212,9 +212,12 @@ extern "C" int ga_layernorm_bwd(const void* dy, const void* x, const float* w, c
 
 // LN backward with xhat saved and no parameters: the hot form inside the ConvNeXt block.  VPL float4 vectors per lane
 // cover C <= 128*VPL channels; ROWS rows are loaded before any reduction so each warp keeps 2*ROWS*VPL 128-bit loads in flight.
-template <typename T, int VPL, int ROWS>
+// Optional residual: out = res + LN'(dxhat) in the residual dtype TO (the transformer-block form, where the stream gradient
+// bypasses the norm), plus an optional compute-dtype shadow of the sum.
+template <typename T, typename TO, int VPL, int ROWS>
 __global__ void __launch_bounds__(256) ln_bwd_hat_kernel(const T* __restrict__ dxhat, const T* __restrict__ xhat,
-                                                         const float* __restrict__ rstd, T* __restrict__ dconv, long long M, int C) {
+                                                         const float* __restrict__ rstd, TO* __restrict__ dconv,
+                                                         const TO* __restrict__ res, T* __restrict__ shadow, long long M, int C) {
   const int lane = threadIdx.x & 31;
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -262,7 +265,12 @@ __global__ void __launch_bounds__(256) ln_bwd_hat_kernel(const T* __restrict__ d
         if (c < C) {
           float4 o = make_float4(rs[r] * (g[r][v].x - m1 - xh[r][v].x * m2), rs[r] * (g[r][v].y - m1 - xh[r][v].y * m2),
                                  rs[r] * (g[r][v].z - m1 - xh[r][v].z * m2), rs[r] * (g[r][v].w - m1 - xh[r][v].w * m2));
+          if (res) {
+            const float4 rr = ld4(res + row * C + c);
+            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+          }
           st4(dconv + row * C + c, o);
+          if (shadow) st4(shadow + row * C + c, o);
         }
       }
     }
@@ -280,11 +288,34 @@ extern "C" int ga_ln_bwd_rows(const void* dxhat, const void* xhat, const float* 
   if (blocks > 148LL * 8) blocks = 148LL * 8;
   cudaStream_t st = (cudaStream_t)s;
   DISPATCH_T(dtype, {
-    if (C <= 128) ln_bwd_hat_kernel<T, 1, 4><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, M, C);
-    else if (C <= 256) ln_bwd_hat_kernel<T, 2, 2><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, M, C);
-    else ln_bwd_hat_kernel<T, 4, 1><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, M, C);
+    if (C <= 128) ln_bwd_hat_kernel<T, T, 1, 4><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, nullptr, nullptr, M, C);
+    else if (C <= 256) ln_bwd_hat_kernel<T, T, 2, 2><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, nullptr, nullptr, M, C);
+    else ln_bwd_hat_kernel<T, T, 4, 1><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (T*)dconv, nullptr, nullptr, M, C);
   });
   return launch_ok("ln_bwd_hat");
+}
+
+extern "C" int ga_ln_bwd_rows_res(const void* dxhat, const void* xhat, const float* rstd, const void* res, void* out, void* shadow,
+                                  long long M, int C, int dtype, int res_dtype, ga_stream_t s) {
+  GA_REQUIRE(dxhat && xhat && rstd && res && out, GA_ERR_SHAPE, "ga_ln_bwd_rows_res: null argument");
+  GA_REQUIRE(C <= 512 && (C & 3) == 0, GA_ERR_UNSUPPORTED, "ga_ln_bwd_rows_res: C=%d (multiple of 4, <= 512)", C);
+  GA_REQUIRE(res_dtype == GA_F32 || res_dtype == dtype, GA_ERR_UNSUPPORTED, "ga_ln_bwd_rows_res: residual is fp32 or the compute dtype");
+  if (M == 0) return GA_OK;
+  const int rows = C <= 128 ? 4 : (C <= 256 ? 2 : 1);
+  long long blocks = (M + 8LL * rows - 1) / (8LL * rows);
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  cudaStream_t st = (cudaStream_t)s;
+#define GA_LNR(T, TO)                                                                                                          \
+  {                                                                                                                            \
+    if (C <= 128) ln_bwd_hat_kernel<T, TO, 1, 4><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (TO*)out, (const TO*)res, (T*)shadow, M, C); \
+    else if (C <= 256) ln_bwd_hat_kernel<T, TO, 2, 2><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (TO*)out, (const TO*)res, (T*)shadow, M, C); \
+    else ln_bwd_hat_kernel<T, TO, 4, 1><<<(unsigned)blocks, 256, 0, st>>>((const T*)dxhat, (const T*)xhat, rstd, (TO*)out, (const TO*)res, (T*)shadow, M, C); \
+  }
+  if (dtype == GA_BF16 && res_dtype == GA_F32) GA_LNR(bf16, float)
+  else if (dtype == GA_BF16) GA_LNR(bf16, bf16)
+  else GA_LNR(float, float)
+#undef GA_LNR
+  return launch_ok("ln_bwd_hat_res");
 }
 
 // ---------------------------------------------------------------------------------------------- patch gathers
@@ -342,11 +373,53 @@ extern "C" int ga_stem_patchify(const float* x, void* y, int B, int H, int W, in
   return launch_ok("stem_patchify");
 }
 
-// 3x3, pad 1, stride 1 im2col (forward) and its adjoint in gather form (inverse): C % 4 == 0
+// 3x3, pad 1, stride S im2col (forward) and its adjoint in gather form (inverse): C % 4 == 0.  Output map Ho x Wo with
+// Ho = (H - 1) / S + 1 (S = 1: the Bottleneck conv; S = 2: CSWin's Merge_Block and deep stem, ga_cswin.py:256, 472)
 template <typename T>
 __global__ void im2col3_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, long long ldx,
-                               long long ldy, int inverse) {
+                               long long ldy, int inverse, int S) {
   const int C4 = C >> 2;
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+  if (S != 1) {
+    if (!inverse) {
+      const long long total = (long long)B * Ho * Wo * 9 * C4;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long p = i / C4;
+        const int tap = (int)(p % 9); p /= 9;
+        const int ox = (int)(p % Wo); p /= Wo;
+        const int oy = (int)(p % Ho);
+        const int b = (int)(p / Ho);
+        const int sy = oy * S + tap / 3 - 1, sx = ox * S + tap % 3 - 1;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = ld4(x + (((long long)b * H + sy) * W + sx) * ldx + c4 * 4);
+        st4(y + (((long long)b * Ho + oy) * Wo + ox) * ldy + tap * C + c4 * 4, v);
+      }
+    } else {
+      // x = d(col) [B*Ho*Wo, ldx>=9C]; y = d(image) [B*H*W, ldy]: pixel (yy,xx) gathers tap (ky,kx) from output (oy,ox)
+      // whenever oy*S + ky - 1 == yy and ox*S + kx - 1 == xx
+      const long long total = (long long)B * H * W * C4;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long p = i / C4;
+        const int xx = (int)(p % W); p /= W;
+        const int yy = (int)(p % H);
+        const int b = (int)(p / H);
+        float4 a = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ty = yy + 1 - tap / 3, tx = xx + 1 - tap % 3;
+          if (ty < 0 || tx < 0 || ty % S || tx % S) continue;
+          const int oy = ty / S, ox = tx / S;
+          if (oy >= Ho || ox >= Wo) continue;
+          float4 v = ld4(x + (((long long)b * Ho + oy) * Wo + ox) * ldx + tap * C + c4 * 4);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        st4(y + (((long long)b * H + yy) * W + xx) * ldy + c4 * 4, a);
+      }
+    }
+    return;
+  }
   if (!inverse) {
     const long long total = (long long)B * H * W * 9 * C4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -383,14 +456,52 @@ __global__ void im2col3_kernel(const T* __restrict__ x, T* __restrict__ y, int B
     }
   }
 }
-extern "C" int ga_im2col3(const void* x, void* y, int B, int H, int W, int C, long long ldx, long long ldy, int inverse,
-                          int dtype, ga_stream_t s) {
+extern "C" int ga_im2col3s(const void* x, void* y, int B, int H, int W, int C, int stride, long long ldx, long long ldy, int inverse,
+                           int dtype, ga_stream_t s) {
   GA_REQUIRE(x && y && (C & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0, GA_ERR_ALIGN, "ga_im2col3: C/ld must be multiples of 4");
-  const long long total = (long long)B * H * W * (C >> 2) * (inverse ? 1 : 9);
+  GA_REQUIRE(stride == 1 || stride == 2, GA_ERR_UNSUPPORTED, "ga_im2col3: stride %d (1 or 2)", stride);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const long long total = inverse ? (long long)B * H * W * (C >> 2) : (long long)B * Ho * Wo * (C >> 2) * 9;
   if (total == 0) return GA_OK;
   const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-  DISPATCH_T(dtype, { im2col3_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, B, H, W, C, ldx, ldy, inverse); });
+  DISPATCH_T(dtype, { im2col3_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, B, H, W, C, ldx, ldy, inverse, stride); });
   return launch_ok("im2col3");
+}
+extern "C" int ga_im2col3(const void* x, void* y, int B, int H, int W, int C, long long ldx, long long ldy, int inverse,
+                          int dtype, ga_stream_t s) {
+  return ga_im2col3s(x, y, B, H, W, C, 1, ldx, ldy, inverse, dtype, s);
+}
+
+// CSWin deep-stem first conv (3x3, stride S, pad 1, ga_cswin.py:463): fp32 image [B,3,H,W] with element strides ->
+// rows (b, oy, ox) of 32 columns: (ky, kx, c) in the first 27, zeros in the pad (16-byte pitch for the GEMM operand)
+template <typename T>
+__global__ void stem_im2col3_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int H, int W, int S, long long sb,
+                                    long long sc, long long sy, long long sx) {
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+  const long long total = (long long)B * Ho * Wo * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i & 31);
+    long long p = i >> 5;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float v = 0.f;
+    if (col < 27) {
+      const int c = col % 3, tap = col / 3;
+      const int yy = oy * S + tap / 3 - 1, xx = ox * S + tap % 3 - 1;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[b * sb + c * sc + yy * sy + xx * sx];
+    }
+    st_f(y + i, v);
+  }
+}
+extern "C" int ga_stem_im2col3(const float* x, void* y, int B, int H, int W, int stride, long long sb, long long sc, long long sy,
+                               long long sx, int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && y && stride >= 1, GA_ERR_SHAPE, "ga_stem_im2col3: bad arguments");
+  const long long total = (long long)B * ((H - 1) / stride + 1) * ((W - 1) / stride + 1) * 32;
+  if (total == 0) return GA_OK;
+  const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  DISPATCH_T(dtype, { stem_im2col3_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>(x, (T*)y, B, H, W, stride, sb, sc, sy, sx); });
+  return launch_ok("stem_im2col3");
 }
 
 // ---------------------------------------------------------------------------------------------- column statistics

@@ -327,8 +327,16 @@ class GA_ConvNeXt(nn.Module):
             f = self.stages[4].run(cat, (Bn, Ho, Wo))
         return f, (Bn, Ho, Wo)
 
+    def _gram_features(self, k, f, geom):
+        """Branch k's contraction conv + BN + gram layer on the shared feature rows -> [B*HW, gram_dim]."""
+        conv, bn = self.gram_contraction[k][0], self.gram_contraction[k][1]
+        g = ops.linear(f, conv.weight.reshape(self.gram_dim, f.shape[1]), conv.bias)
+        g = ops.batchnorm(g, _params(bn), self.training)
+        g, _, _, _ = self.gram_layer[k].run(g, None, geom, g.dtype, g.dtype)
+        return g
+
     def _heads(self, f, geom):
-        """The `branches` GA heads (ga_convnext.py:491-504).  Token-side work is batched over branches: one shared
+        """The `branches` GA heads (ga_convnext.py:491-504; shared with GA-CSWin, ga_cswin.py:673-693).  Token-side work is batched over branches: one shared
         normalisation of the 196 tokens (norm1's affine folded into k/v), one k/v projection GEMM of width
         branches*2E and one attention-pooling pass; class-token work ([B, C] rows) stays fp32."""
         Bn, H, W = geom
@@ -345,10 +353,7 @@ class GA_ConvNeXt(nn.Module):
         kv_tok = ops.linear(fhat, wkv, bkv)                                        # [B*HW, nb*2E]
         cls, qs, kvcs = [], [], []
         for k in range(nb):
-            conv, bn = self.gram_contraction[k][0], self.gram_contraction[k][1]
-            g = ops.linear(f, conv.weight.reshape(self.gram_dim, Cc), conv.bias)
-            g = ops.batchnorm(g, _params(bn), tr)
-            g, _, _, _ = self.gram_layer[k].run(g, None, geom, g.dtype, g.dtype)
+            g = self._gram_features(k, f, geom)
             emb, ebn = self.gram_embedding[k][0], self.gram_embedding[k][1]
             G = self.embed_groups
             glen = emb.weight.shape[1]

@@ -501,29 +501,44 @@ def stem_patchify(img: torch.Tensor, k: int, dtype) -> torch.Tensor:
 
 
 class Im2col3Fn(Function):
+    """3x3 / pad 1 / stride 1|2 patch rows of an NHWC row matrix (columns ordered (tap, c)); backward = col2im gather."""
+
     @staticmethod
-    def forward(ctx, x, geom):
+    def forward(ctx, x, geom, stride):
         Bn, H, W_ = geom
         x = rowmat(x)
         Cc = x.shape[1]
-        y = alloc_rows(x.shape[0], 9 * Cc, x.dtype, x.device)
-        L.check(_L().ga_im2col3(L.ptr(x), L.ptr(y), Bn, H, W_, Cc, L.ll(x.stride(0)), L.ll(y.stride(0)), 0, L.dt(x), L.stream()),
-                'ga_im2col3')
-        ctx.geom, ctx.Cc = geom, Cc
+        Ho, Wo = (H - 1) // stride + 1, (W_ - 1) // stride + 1
+        y = alloc_rows(Bn * Ho * Wo, 9 * Cc, x.dtype, x.device)
+        L.check(_L().ga_im2col3s(L.ptr(x), L.ptr(y), Bn, H, W_, Cc, stride, L.ll(x.stride(0)), L.ll(y.stride(0)), 0, L.dt(x),
+                                 L.stream()), 'ga_im2col3s')
+        ctx.geom, ctx.Cc, ctx.stride = geom, Cc, stride
         return y
 
     @staticmethod
     def backward(ctx, dy):
         Bn, H, W_ = ctx.geom
         dy = rowmat(dy)
-        dx = alloc_rows(dy.shape[0], ctx.Cc, dy.dtype, dy.device)
-        L.check(_L().ga_im2col3(L.ptr(dy), L.ptr(dx), Bn, H, W_, ctx.Cc, L.ll(dy.stride(0)), L.ll(dx.stride(0)), 1, L.dt(dy),
-                                L.stream()), 'ga_im2col3')
-        return dx, None
+        dx = alloc_rows(Bn * H * W_, ctx.Cc, dy.dtype, dy.device)
+        L.check(_L().ga_im2col3s(L.ptr(dy), L.ptr(dx), Bn, H, W_, ctx.Cc, ctx.stride, L.ll(dy.stride(0)), L.ll(dx.stride(0)), 1,
+                                 L.dt(dy), L.stream()), 'ga_im2col3s')
+        return dx, None, None
 
 
-def im2col3(x, geom):
-    return Im2col3Fn.apply(x, geom)
+def im2col3(x, geom, stride=1):
+    return Im2col3Fn.apply(x, geom, stride)
+
+
+def stem_im2col3(img: torch.Tensor, stride: int, dtype) -> torch.Tensor:
+    """NCHW fp32 image batch -> 3x3/pad-1 patch rows [B*Ho*Wo, 32] (27 taps*channels + zero pad); no gradient."""
+    Bn, Cin, H, W_ = img.shape
+    assert Cin == 3 and img.dtype == torch.float32
+    Ho, Wo = (H - 1) // stride + 1, (W_ - 1) // stride + 1
+    y = torch.empty(Bn * Ho * Wo, 32, dtype=dtype, device=img.device)
+    sb, sc, sy, sx = img.stride()
+    L.check(_L().ga_stem_im2col3(L.ptr(img), L.ptr(y), Bn, H, W_, stride, L.ll(sb), L.ll(sc), L.ll(sy), L.ll(sx),
+                                 BF16 if dtype == torch.bfloat16 else F32, L.stream()), 'ga_stem_im2col3')
+    return y
 
 
 # ------------------------------------------------------------------------------------------------- BatchNorm
@@ -825,6 +840,196 @@ class AttnPoolFn(Function):
 
 def attnpool(q, kv_cls, kv_tok, N, H):
     return AttnPoolFn.apply(q, kv_cls, kv_tok, N, H)
+
+
+# ------------------------------------------------------------------------------------------------- CSWin
+def _attn_fwd(qkv, lw, lb, Bn, R, Cc, split, nbr, want_lse):
+    out = torch.empty(qkv.shape[0], Cc, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(qkv.shape[0], Cc // 32, dtype=torch.float32, device=qkv.device) if want_lse else None
+    L.check(_L().ga_cswin_attn_fwd(L.ptr(qkv), L.ptr(lw), L.ptr(lb), L.ptr(out), L.ptr(lse), Bn, R, Cc, split, nbr,
+                                   L.ll(qkv.stride(0)), L.ll(out.stride(0)), L.f(32 ** -0.5), L.dt(qkv), L.stream()),
+            'ga_cswin_attn_fwd')
+    return out, lse
+
+
+def _attn_bwd(dout, qkv, out, lse, lw, lb, dlw, dlb, Bn, R, Cc, split, nbr):
+    dqkv = torch.empty_like(qkv)
+    L.check(_L().ga_cswin_attn_bwd(L.ptr(dout), L.ptr(qkv), L.ptr(out), L.ptr(lse), L.ptr(lw), L.ptr(lb), L.ptr(dqkv), L.ptr(dlw),
+                                   L.ptr(dlb), Bn, R, Cc, split, nbr, L.ll(qkv.stride(0)), L.ll(out.stride(0)),
+                                   L.ll(dout.stride(0)), L.ll(dqkv.stride(0)), L.f(32 ** -0.5), L.dt(qkv), L.stream()),
+            'ga_cswin_attn_bwd')
+    return dqkv
+
+
+class CSWinAttnFn(Function):
+    """LePEAttention of both branches on token rows (ga_cswin.py:59-136): qkv [B*R*R, 3C] -> [B*R*R, C].
+    lw [C,9] / lb [C]: the branches' get_v weights concatenated over channels."""
+
+    @staticmethod
+    def forward(ctx, qkv, lw, lb, Bn, R, split, nbr):
+        qkv = qkv.contiguous()
+        Cc = qkv.shape[1] // 3
+        lw, lb = lw.contiguous(), lb.contiguous()
+        out, lse = _attn_fwd(qkv, lw, lb, Bn, R, Cc, split, nbr, True)
+        ctx.save_for_backward(qkv, out, lse, lw, lb)
+        ctx.g = (Bn, R, Cc, split, nbr)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, lw, lb = ctx.saved_tensors
+        Bn, R, Cc, split, nbr = ctx.g
+        dout = dout.contiguous()
+        if dout.dtype != qkv.dtype:
+            dout = convert(dout, qkv.dtype)
+        dl = torch.zeros(Cc * 10, dtype=torch.float32, device=qkv.device)
+        dqkv = _attn_bwd(dout, qkv, out, lse, lw, lb, dl[:Cc * 9], dl[Cc * 9:], Bn, R, Cc, split, nbr)
+        return dqkv, dl[:Cc * 9].view(Cc, 9), dl[Cc * 9:], None, None, None, None
+
+
+def cswin_attention(qkv, lw, lb, Bn, R, split, nbr):
+    return CSWinAttnFn.apply(qkv, lw, lb, Bn, R, split, nbr)
+
+
+class CSWinBlockFn(Function):
+    """CSWinBlock on token rows (ga_cswin.py:187-212):  x + proj(attn(qkv(LN1 x)));  then  + fc2(GELU(fc1(LN2 .))).
+
+    Kernels: LN (no affine) -> GEMM qkv' -> K6 stripe attention -> GEMM proj (+bias, +x, fp32 stream + bf16 shadow)
+             -> LN -> GEMM fc1' (+bias, GELU, saves z) -> GEMM fc2 (+bias, +x1, stream + shadow).
+    Both LayerNorm affines are folded into the following weight (W' = W diag(ln_w), b' = b + W ln_b) and their
+    gradients recovered from the weight-gradient tile (ga_linear_grad_finalize).  The residual stream `x` may be fp32
+    with `xs` its bf16 shadow (autocast semantics of the reference), or x itself in the compute dtype (xs None).
+    ps1 / ps2: optional DropPath row multipliers [B] of the two residual branches.
+    """
+
+    @staticmethod
+    def forward(ctx, x, xs, n1w, n1b, wqkv, bqkv, lw, lb, wproj, bproj, n2w, n2b, w1, b1, w2, b2, ps1, ps2, geom, train, T):
+        Bn, R, split, nbr = geom
+        M, Cc = x.shape
+        assert x.is_contiguous() and M == Bn * R * R
+        mixed = x.dtype != T
+        src = xs if mixed else x
+        assert src is not None and src.dtype == T and src.is_contiguous()
+        dev = x.device
+        lib = _L()
+        HW = R * R
+
+        def ln_hat(t):
+            xh = torch.empty(M, Cc, dtype=T, device=dev)
+            mean = torch.empty(M, dtype=torch.float32, device=dev)
+            rstd = torch.empty(M, dtype=torch.float32, device=dev)
+            L.check(lib.ga_layernorm_fwd(L.ptr(t), None, None, L.ptr(xh), L.ptr(mean), L.ptr(rstd), L.ll(M), Cc, L.ll(Cc), L.ll(Cc),
+                                         L.f(1e-5), L.dt(t), L.stream()), 'ga_layernorm_fwd')
+            return xh, rstd
+        # attention half
+        xh1, rstd1 = ln_hat(src)
+        wqf = scale_matrix(wqkv, None, n1w, T)
+        bqf = gemm(n1b.unsqueeze(0), wqkv, bias=bqkv, out_dtype=torch.float32).reshape(-1)
+        qkv = gemm(xh1, wqf, bias=bqf)
+        lw, lb = lw.contiguous(), lb.contiguous()
+        att, lse = _attn_fwd(qkv, lw, lb, Bn, R, Cc, split, nbr, train)
+        x1 = torch.empty(M, Cc, dtype=x.dtype, device=dev)
+        x1s = torch.empty(M, Cc, dtype=T, device=dev) if mixed else None
+        wpc = cast_like(wproj, T)
+        gemm(att, wpc, x1, bias=bproj, rowscale=ps1, rows_per_scale=HW, residual=x, shadow=x1s)
+        # MLP half
+        xh2, rstd2 = ln_hat(x1s if mixed else x1)
+        w1f = scale_matrix(w1, None, n2w, T)
+        b1f = gemm(n2b.unsqueeze(0), w1, bias=b1, out_dtype=torch.float32).reshape(-1)
+        if train:
+            a, z = gemm(xh2, w1f, bias=b1f, act=ACT_GELU, save_z=True)
+        else:
+            a, z = gemm(xh2, w1f, bias=b1f, act=ACT_GELU), None
+        w2c = cast_like(w2, T)
+        y = torch.empty(M, Cc, dtype=x.dtype, device=dev)
+        ys = torch.empty(M, Cc, dtype=T, device=dev) if mixed else None
+        gemm(a, w2c, y, bias=b2, rowscale=ps2, rows_per_scale=HW, residual=x1, shadow=ys)
+        if train:
+            ctx.save_for_backward(xh1, rstd1, qkv, att, lse, xh2, rstd2, z, a, n1w, n1b, wqkv, wqf, lw, lb, wpc, n2w, n2b, w1, w1f,
+                                  w2c, ps1, ps2)
+            ctx.geom, ctx.T, ctx.RT = geom, T, x.dtype
+        return y, ys
+
+    @staticmethod
+    def backward(ctx, dy, dys_in):
+        (xh1, rstd1, qkv, att, lse, xh2, rstd2, z, a, n1w, n1b, wqkv, wqf, lw, lb, wpc, n2w, n2b, w1, w1f, w2c, ps1,
+         ps2) = ctx.saved_tensors
+        Bn, R, split, nbr = ctx.geom
+        T, RT = ctx.T, ctx.RT
+        M, Cc = xh1.shape
+        Hd = w1.shape[0]
+        dev = xh1.device
+        lib = _L()
+        HW = R * R
+        if dy is None:
+            dy = torch.zeros(M, Cc, dtype=RT, device=dev)
+        dy = dy.contiguous()
+        if dys_in is not None:
+            dy = dy + dys_in
+        dys = convert(dy, T) if RT != T else dy
+
+        def rows_scaled(t, ps):
+            if ps is None:
+                return t
+            o = torch.empty_like(t)
+            L.check(lib.ga_scale_rows(L.ptr(t), L.ptr(ps), L.ptr(o), L.ll(M), Cc, HW, L.dt(t), L.stream()), 'ga_scale_rows')
+            return o
+
+        sizes = [Cc, Cc, 3 * Cc * Cc, 3 * Cc, 9 * Cc, Cc, Cc * Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, 3 * Cc * Cc, Hd * Cc]
+        slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, o = [], 0
+        for n in sizes:
+            views.append(slab[o:o + n])
+            o += n
+        dn1w, dn1b, dwq, dbq, dlw, dlb, dwp, dn2w, dn2b, dw1, db1, dw2, Gq, G1 = views
+        # ---- MLP half: y = x1 + ps2 * (fc2(gelu(fc1'(xh2))) + b2)
+        d2 = rows_scaled(dys, ps2)
+        db2 = colsum(d2)
+        gemm(d2.t(), a.t(), dw2.view(Cc, Hd), accumulate=True)
+        dz = gemm(d2, w2c.t(), zin=z, zmode=ACT_GELU)
+        s1 = colsum(dz)
+        gemm(dz.t(), xh2.t(), G1.view(Hd, Cc), accumulate=True)
+        L.check(lib.ga_linear_grad_finalize(L.ptr(G1), L.ptr(s1), L.ptr(w1), None, None, L.ptr(n2w), L.ptr(n2b), L.ptr(dw1),
+                                            L.ptr(db1), None, L.ptr(dn2w), L.ptr(dn2b), Hd, Cc, L.stream()), 'linear_grad_finalize')
+        dxh2 = gemm(dz, w1f.t())
+        del dz
+        dx1 = torch.empty(M, Cc, dtype=RT, device=dev)
+        dx1s = torch.empty(M, Cc, dtype=T, device=dev) if RT != T else None
+        L.check(lib.ga_ln_bwd_rows_res(L.ptr(dxh2), L.ptr(xh2), L.ptr(rstd2), L.ptr(dy), L.ptr(dx1), L.ptr(dx1s), L.ll(M), Cc,
+                                       L.dt(dxh2), L.dt(dx1), L.stream()), 'ga_ln_bwd_rows_res')
+        # ---- attention half: x1 = x + ps1 * (proj(att) + bproj)
+        d1 = rows_scaled(dx1s if dx1s is not None else dx1, ps1)
+        dbp = colsum(d1)
+        gemm(d1.t(), att.t(), dwp.view(Cc, Cc), accumulate=True)
+        datt = gemm(d1, wpc.t())
+        dqkv = _attn_bwd(datt, qkv, att, lse, lw, lb, dlw, dlb, Bn, R, Cc, split, nbr)
+        sq = colsum(dqkv)
+        gemm(dqkv.t(), xh1.t(), Gq.view(3 * Cc, Cc), accumulate=True)
+        L.check(lib.ga_linear_grad_finalize(L.ptr(Gq), L.ptr(sq), L.ptr(wqkv), None, None, L.ptr(n1w), L.ptr(n1b), L.ptr(dwq),
+                                            L.ptr(dbq), None, L.ptr(dn1w), L.ptr(dn1b), 3 * Cc, Cc, L.stream()),
+                'linear_grad_finalize')
+        dxh1 = gemm(dqkv, wqf.t())
+        dx = torch.empty(M, Cc, dtype=RT, device=dev)
+        L.check(lib.ga_ln_bwd_rows_res(L.ptr(dxh1), L.ptr(xh1), L.ptr(rstd1), L.ptr(dx1), L.ptr(dx), None, L.ll(M), Cc,
+                                       L.dt(dxh1), L.dt(dx), L.stream()), 'ga_ln_bwd_rows_res')
+        return (dx, None, dn1w, dn1b, dwq.view(3 * Cc, Cc), dbq, dlw.view(Cc, 9), dlb, dwp.view(Cc, Cc), dbp, dn2w, dn2b,
+                dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, None, None, None, None, None)
+
+
+def cswin_block(x, p, geom, ps1=None, ps2=None, train=True, xs=None, T=None):
+    """p: reference key names of one CSWinBlock (norm1, qkv, attns.{0,1}.get_v, proj, norm2, mlp.fc1/fc2).
+    geom = (B, R, split, branches).  Returns (y, ys) like convnext_block."""
+    T = T or (xs.dtype if xs is not None else x.dtype)
+    nbr = geom[3]
+    Cc = x.shape[1]
+    if nbr == 2:
+        lw = torch.cat((p['attns.0.get_v.weight'].reshape(Cc // 2, 9), p['attns.1.get_v.weight'].reshape(Cc // 2, 9)), 0)
+        lb = torch.cat((p['attns.0.get_v.bias'], p['attns.1.get_v.bias']), 0)
+    else:
+        lw, lb = p['attns.0.get_v.weight'].reshape(Cc, 9), p['attns.0.get_v.bias']
+    return CSWinBlockFn.apply(x, xs, p['norm1.weight'], p['norm1.bias'], p['qkv.weight'], p['qkv.bias'], lw, lb,
+                              p['proj.weight'], p['proj.bias'], p['norm2.weight'], p['norm2.bias'], p['mlp.fc1.weight'],
+                              p['mlp.fc1.bias'], p['mlp.fc2.weight'], p['mlp.fc2.bias'], ps1, ps2, geom, train, T)
 
 
 # ------------------------------------------------------------------------------------------------- loss

@@ -72,6 +72,10 @@ int ga_dwconv7_ln_fwd(const void* x, const float* w49c, const float* bias, const
 /* LN backward on rows with xhat saved: dconv = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) */
 int ga_ln_bwd_rows(const void* dxhat, const void* xhat, const float* rstd, void* dconv, long long M, int C,
                    int dtype, ga_stream_t s);
+/* same with the stream gradient added: out = res + LN'(dxhat) in res_dtype (fp32 or `dtype`), plus an optional
+ * `dtype` shadow of the sum -- the residual form of a pre-norm transformer block (ga_cswin.py:198, 209-210) */
+int ga_ln_bwd_rows_res(const void* dxhat, const void* xhat, const float* rstd, const void* res, void* out, void* shadow,
+                       long long M, int C, int dtype, int res_dtype, ga_stream_t s);
 /* dwconv backward: dx = corr7(dconv, flipped w) + dres  (dx may be NULL);  dw49c += sum dconv*x(shifted);
  * dbias += sum dconv.  dw_partial: [ga_dwconv7_bwd_parts()][50][C] fp32 workspace. */
 int ga_dwconv7_bwd_parts(int B, int H, int W, int C);
@@ -98,6 +102,13 @@ int ga_stem_patchify(const float* x, void* y, int B, int H, int W, int k, long l
 /* 3x3 pad-1 im2col: NHWC rows (stride ldx) -> [B*H*W, ldy>=9C] ordered (tap,c); inverse = col2im in gather form */
 int ga_im2col3(const void* x, void* y, int B, int H, int W, int C, long long ldx, long long ldy, int inverse,
                int dtype, ga_stream_t s);
+/* the same with stride 1 or 2 (CSWin Merge_Block / deep stem, ga_cswin.py:256, 467, 472): output map ((H-1)/stride+1)^2 */
+int ga_im2col3s(const void* x, void* y, int B, int H, int W, int C, int stride, long long ldx, long long ldy,
+                int inverse, int dtype, ga_stream_t s);
+/* CSWin deep-stem first conv input (ga_cswin.py:463): fp32 image [B,3,H,W] with element strides -> 3x3/pad-1 patch rows
+ * [B*Ho*Wo, 32]: 27 columns ordered (ky,kx,c) + 5 zero columns */
+int ga_stem_im2col3(const float* x, void* y, int B, int H, int W, int stride, long long sb, long long sc, long long sy,
+                    long long sx, int dtype, ga_stream_t s);
 
 /* ---- column statistics over rows of [M,C]: BatchNorm2d (ga_convnext.py:261,270,276,283,409,420), bias grads --- */
 int ga_colstats_parts(long long M, int C);
@@ -151,6 +162,19 @@ int ga_gram_triu_bwd(const void* dout, const void* out, const float* norm, void*
 /* ---- K5: attention pooling: Q query tokens against Q+N keys  (ClassAttn ga_convnext.py:170-183; map.py:100-144)
  * q [B,Q,E] fp32 pre-scaled; kv_cls [B,Q,2E] fp32 (k | v of the query tokens); kv_tok rows [B*N, ldt] (k at col 0,
  * v at col E); H heads.  out [B,Q,E] fp32; attn [B,H,Q,Q+N] fp32 saved for backward. */
+/* ---- K6: CSWin stripe attention + LePE  (ga_cswin.py:59-136, img2windows :215, windows2img :225) --------------------
+ * qkv rows [B*R*R, 3C] (q | k | v blocks, pitch ldq); heads are 32 channels.  nbr == 2: branch 0 = channels [0,C/2) over
+ * R x split stripes, branch 1 = [C/2,C) over split x R stripes; nbr == 1: one R x R window.  <= 128 tokens per stripe.
+ * lepe_w [C,9] / lepe_b [C]: the branches' get_v depthwise 3x3 weights, concatenated over channels.
+ * out [B*R*R, C] = softmax(scale q k^T) v + dw3x3(v inside the stripe);  lse [B*R*R, C/32] fp32 (log2 units) or NULL. */
+int ga_cswin_attn_fwd(const void* qkv, const float* lepe_w, const float* lepe_b, void* out, float* lse, int B, int R,
+                      int C, int split, int nbr, long long ldq, long long ldo, float scale, int dtype, ga_stream_t s);
+/* dqkv [B*R*R, 3C] is fully overwritten; dlepe_w / dlepe_b are accumulated (+=, atomics) */
+int ga_cswin_attn_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const float* lepe_w,
+                      const float* lepe_b, void* dqkv, float* dlepe_w, float* dlepe_b, int B, int R, int C, int split,
+                      int nbr, long long ldq, long long ldo, long long lddo, long long lddq, float scale, int dtype,
+                      ga_stream_t s);
+
 int ga_attnpool_fwd(const float* q, const float* kv_cls, const void* kv_tok, float* out, float* attn, int B, int Q,
                     int N, int H, int E, long long ldt, int dtype, ga_stream_t s);
 int ga_attnpool_bwd(const float* dout, const float* q, const float* kv_cls, const void* kv_tok, const float* attn,

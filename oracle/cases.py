@@ -22,6 +22,11 @@ PARAM_COUNTS = {
 # name -> (C, H(=W), B)
 BLOCK_CASES = {'c32_h9': (32, 9, 2), 'c96_h14': (96, 14, 2), 'c192_h14': (192, 14, 1), 'c688_h7': (688, 7, 1)}
 GRAM_CASES = {'c192_h14': (192, 14, 3), 'c24_h5': (24, 5, 2)}
+# GA-CSWin: name -> (dim, reso, split, heads, last_stage, B): every stripe geometry of the T configuration
+CSWIN_BLOCK_CASES = {'s1_c64_r56_sp1': (64, 56, 1, 2, False, 1), 's2_c128_r28_sp2': (128, 28, 2, 4, False, 2),
+                     's3_c256_r14_sp7': (256, 14, 7, 8, False, 2), 's4_c512_r7_last': (512, 7, 7, 16, True, 2),
+                     'gram_c192_r14_sp7': (192, 14, 7, 6, False, 3)}
+CSWIN_MODEL_CASES = [('ga_cswin_test', 2), ('ga_CSWin_64_12211_tiny_224', 2)]
 # name -> (C, dim_embed, N tokens, B)
 CLASSATTN_CASES = {'c688_e168': (688, 168, 196, 2), 'c64_e32': (64, 32, 10, 3)}
 
@@ -62,6 +67,11 @@ def block_state(C, seed=STATE_SEED):
 def block_inputs(C, H, B, seed=11):
     g = torch.Generator().manual_seed(seed + C * 131 + H)
     return torch.randn(B, C, H, H, generator=g), torch.randn(B, C, H, H, generator=g)
+
+
+def cswin_block_inputs(dim, reso, B, seed=19):
+    g = torch.Generator().manual_seed(seed + dim * 131 + reso)
+    return torch.randn(B, reso * reso, dim, generator=g), torch.randn(B, reso * reso, dim, generator=g)
 
 
 def gram_input(C, H, B, seed=13):

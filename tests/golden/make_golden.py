@@ -269,6 +269,93 @@ def golden_map_model():
     torch.save(out, os.path.join(HERE, 'map_convnext_model.pt'))
 
 
+def golden_cswin():
+    """GA-CSWin (GA/ga_cswin.py) through the unmodified reference: CSWinBlock cases + two whole-model cases."""
+    import ga_cswin as R
+    from oracle import ga_cswin_oracle as CO
+    out = {}
+    # ---- CSWinBlock / LePEAttention (rows a15, a16): every (tokens/stripe, heads) geometry of the T configuration
+    for cname, (dim, reso, split, heads, last, B) in cases.CSWIN_BLOCK_CASES.items():
+        blk = R.CSWinBlock(dim=dim, reso=reso, num_heads=heads, split_size=split, qkv_bias=True, last_stage=last)
+        S = {}
+        CO.block_shapes(S, '', dim, reso, split, last)
+        P = cases._fill(S, cases.STATE_SEED)
+        blk.load_state_dict(P, strict=True)
+        x, dy = cases.cswin_block_inputs(dim, reso, B)
+        x.requires_grad_(True)
+        yv = blk(x)
+        yv.backward(dy)
+        grads = {k: p.grad.clone() for k, p in blk.named_parameters()}
+        Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        xo = x.detach().clone().requires_grad_(True)
+        yo = CO.cswin_block(Po, '', xo, reso, split, heads, last)
+        yo.backward(dy)
+        assert rel(yo.detach(), yv.detach()) < 1e-5, rel(yo.detach(), yv.detach())
+        assert rel(xo.grad, x.grad) < 1e-5
+        for k in grads:
+            assert close(Po[k].grad, grads[k], 2e-5), (k, rel(Po[k].grad, grads[k]))
+        out['block/' + cname] = dict(y=cases.digest(yv.detach()), dx=cases.digest(x.grad), grads=grad_digest(grads))
+        print(f'cswin block {cname}: oracle==reference')
+    # ---- whole models
+    for name, B in cases.CSWIN_MODEL_CASES:
+        spec = CO.SPECS[name]
+        torch.manual_seed(0)
+        ref = R.GA_CSWinTransformer(img_size=spec.img_size, patch_size=4, num_classes=spec.num_classes, embed_dim=spec.embed_dim,
+                                    depth=list(spec.depth), split_size=list(spec.split_size), num_heads=list(spec.num_heads),
+                                    dims=list(spec.dims), stage3_naggre=spec.naggre, gram_dim=spec.gram_dim)
+        P = CO.make_state(spec, seed=cases.STATE_SEED)
+        res = ref.load_state_dict(P, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        if name in CO.PARAM_COUNTS:
+            assert sum(p.numel() for p in ref.parameters()) == CO.PARAM_COUNTS[name], sum(p.numel() for p in ref.parameters())
+        x, y = cases.ga_inputs(B)
+        y = y % spec.num_classes
+        ref.eval()
+        with torch.no_grad():
+            r_eval = ref(x)
+            o_eval = CO.forward({k: v.clone() for k, v in P.items()}, spec, x, training=False)
+        for a, b in zip(o_eval, r_eval):
+            assert rel(a, b) < 2e-5, rel(a, b)
+        ref.train()
+        r_train = ref(x)
+        output, loss = 0, 0           # the loss expression of GA/train.py:735-745
+        for o in r_train:
+            loss = loss + F.cross_entropy(o, y)
+            output = output + o.data
+        for o in r_train:
+            loss = loss + F.kl_div(F.log_softmax(o + 0), F.log_softmax((output.detach() / len(r_train)) + 0),
+                                   reduction='mean', log_target=True) * cases.GA_LAM
+        loss.backward()
+        r_grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters()}
+        r_state = {k: v.detach().clone() for k, v in ref.state_dict().items() if 'running' in k}
+        Po = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone())
+              for k, v in P.items()}
+        o_train = CO.forward(Po, spec, x, training=True)
+        o_loss = CO.ga_loss(o_train, y, cases.GA_LAM)
+        o_loss.backward()
+        assert rel(o_loss.detach(), loss.detach()) < 1e-6
+        for a, b in zip(o_train, r_train):
+            assert rel(a.detach(), b.detach()) < 2e-5, rel(a.detach(), b.detach())
+        for k, g in r_grads.items():
+            assert close(Po[k].grad, g, 5e-5), (k, rel(Po[k].grad, g))
+        for k, v in r_state.items():
+            assert rel(Po[k], v) < 1e-5, k
+        self_err = {}
+        for mode in ('eval', 'train'):
+            ref.train(mode == 'train')
+            ref.load_state_dict(P, strict=True)
+            with torch.no_grad(), torch.autocast('cpu', dtype=torch.bfloat16):
+                o16 = ref(x)
+            base = r_eval if mode == 'eval' else [t.detach() for t in r_train]
+            self_err[mode] = max(rel(a.float(), b) for a, b in zip(o16, base))
+        print(f'{name} B={B}: oracle==reference  (loss {loss.item():.6f}; reference bf16-autocast self error '
+              f"eval {self_err['eval']:.2e} train {self_err['train']:.2e})")
+        out[f'{name}/B{B}'] = dict(ref_bf16_self_err=self_err, eval_logits=[t.clone() for t in r_eval],
+                                   train_logits=[t.detach().clone() for t in r_train], loss=loss.detach().clone(),
+                                   grads=grad_digest(r_grads), running=r_state)
+    torch.save(out, os.path.join(HERE, 'ga_cswin.pt'))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(8)
     which = sys.argv[1:] or ['modules', 'model']
@@ -278,3 +365,5 @@ if __name__ == '__main__':
         golden_ga_model()
     if 'map' in which or 'model' in which:
         golden_map_model()
+    if 'cswin' in which:
+        golden_cswin()

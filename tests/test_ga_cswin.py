@@ -1,0 +1,278 @@
+"""GA-CSWin: oracle vs committed reference fixtures and module structure on CPU;
+stripe attention / CSWinBlock / whole-model parity against the oracle and the reference fixtures on GPU."""
+import os
+
+import pytest
+import torch
+
+import imagenet_models_b200.ga_cswin as GC
+from imagenet_models_b200 import lib as L
+from imagenet_models_b200.registry import create_model
+from oracle import cases
+from oracle import ga_cswin_oracle as CO
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def gold(golden_dir):
+    return torch.load(os.path.join(golden_dir, 'ga_cswin.pt'))
+
+
+def _ctor(spec, **kw):
+    return GC.GA_CSWinTransformer(img_size=spec.img_size, patch_size=4, num_classes=spec.num_classes, embed_dim=spec.embed_dim,
+                                  depth=list(spec.depth), split_size=list(spec.split_size), num_heads=list(spec.num_heads),
+                                  dims=list(spec.dims), stage3_naggre=spec.naggre, gram_dim=spec.gram_dim, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+@pytest.mark.parametrize('cname', list(cases.CSWIN_BLOCK_CASES))
+def test_oracle_block_vs_reference_fixture(gold, cname):
+    dim, reso, split, heads, last, B = cases.CSWIN_BLOCK_CASES[cname]
+    S = {}
+    CO.block_shapes(S, '', dim, reso, split, last)
+    P = {k: v.requires_grad_(True) for k, v in cases._fill(S, cases.STATE_SEED).items()}
+    x, dy = cases.cswin_block_inputs(dim, reso, B)
+    x.requires_grad_(True)
+    y = CO.cswin_block(P, '', x, reso, split, heads, last)
+    y.backward(dy)
+    g = gold['block/' + cname]
+    assert cases.digest_close(y, g['y'], 1e-5, 1e-6)
+    assert cases.digest_close(x.grad, g['dx'], 1e-5, 1e-6)
+    for k, d in g['grads'].items():
+        assert cases.digest_close(P[k].grad, d, 3e-5, 1e-5), k
+
+
+def test_oracle_model_eval_vs_reference_fixture(gold):
+    name, B = cases.CSWIN_MODEL_CASES[0]
+    spec = CO.SPECS[name]
+    x, _ = cases.ga_inputs(B)
+    with torch.no_grad():
+        out = CO.forward(CO.make_state(spec, cases.STATE_SEED), spec, x, training=False)
+    for a, b in zip(out, gold[f'{name}/B{B}']['eval_logits']):
+        assert rel(a, b) < 2e-5
+        assert torch.equal(a.topk(5).indices, b.topk(5).indices)
+
+
+def test_lepe_is_stripe_local():
+    """The LePE conv must not read across stripe borders (zero padding inside each window, ga_cswin.py:92-103)."""
+    torch.manual_seed(0)
+    C, R, split = 32, 4, 2
+    P = {'get_v.weight': torch.randn(C, 1, 3, 3), 'get_v.bias': torch.zeros(C)}
+    q = torch.zeros(1, R * R, C)
+    v = torch.randn(1, R * R, C)
+    o = CO.lepe_attention(P, '', q, q, v, R, R, split, 1)            # uniform attention: o = mean_stripe(v) + lepe(v)
+    v2 = v.clone().reshape(1, R, R, C)
+    v2[:, :, split:] = 0                                             # wipe the other stripe
+    o2 = CO.lepe_attention(P, '', q, q, v2.reshape(1, R * R, C), R, R, split, 1)
+    left = torch.arange(R * R).reshape(R, R)[:, :split].reshape(-1)
+    assert torch.allclose(o[:, left], o2[:, left], atol=1e-6)
+
+
+@pytest.mark.parametrize('name', list(CO.SPECS))
+def test_state_dict_contract(name):
+    spec = CO.SPECS[name]
+    m = _ctor(spec)
+    sd = m.state_dict()
+    want = CO.state_shapes(spec)
+    assert sorted(sd.keys()) == sorted(want.keys())
+    for k, (shape, _) in want.items():
+        assert tuple(sd[k].shape) == shape, k
+    if name in CO.PARAM_COUNTS:
+        assert sum(p.numel() for p in m.parameters()) == CO.PARAM_COUNTS[name]
+    m.load_state_dict(CO.make_state(spec, 3), strict=True)
+
+
+def test_registry_factory_and_taps():
+    m = create_model('ga_CSWin_64_12211_tiny_224')
+    assert isinstance(m, GC.GA_CSWinTransformer) and len(m.stage3) == 21 and len(m.fc) == 5
+    assert [b.branch_num for b in (m.stage1[0], m.stage2[0], m.stage3[0], m.stage4[0], m.stage5[2])] == [2, 2, 2, 1, 2]
+    assert m.no_weight_decay() == {'pos_embed', 'cls_token'} and m.get_classifier() is m.fc
+
+
+def test_init_matches_reference_bitwise():
+    if not os.path.isdir('/root/reference/GA'):
+        pytest.skip('reference sources not present on this box')
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'oracle', 'timm_shim'))
+    sys.path.insert(0, '/root/reference/GA')
+    import ga_cswin as R
+    spec = CO.SPECS['ga_cswin_test']
+    torch.manual_seed(5)
+    ref = R.GA_CSWinTransformer(img_size=224, patch_size=4, num_classes=spec.num_classes, embed_dim=spec.embed_dim, depth=list(spec.depth),
+                                split_size=list(spec.split_size), num_heads=list(spec.num_heads), dims=list(spec.dims),
+                                stage3_naggre=spec.naggre, gram_dim=spec.gram_dim)
+    torch.manual_seed(5)
+    mine = _ctor(spec)
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert list(rs.keys()) == list(ms.keys())
+    for k in rs:
+        assert torch.equal(rs[k], ms[k]), k
+
+
+def test_cpu_tensor_raises():
+    m = _ctor(CO.SPECS['ga_cswin_test'])
+    with pytest.raises(L.GaError):
+        m(torch.zeros(1, 3, 224, 224))
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _block_case(cname, dtype):
+    from imagenet_models_b200 import ops
+    dim, reso, split, heads, last, B = cases.CSWIN_BLOCK_CASES[cname]
+    S = {}
+    CO.block_shapes(S, '', dim, reso, split, last)
+    P = cases._fill(S, cases.STATE_SEED)
+    x, dy = cases.cswin_block_inputs(dim, reso, B)
+    Pg = {k: v.cuda().requires_grad_(True) for k, v in P.items()}
+    xg = x.reshape(-1, dim).cuda().requires_grad_(True)
+    nbr = CO.block_branches(reso, split, last)
+    if dtype == torch.float32:
+        y, _ = ops.cswin_block(xg, Pg, (B, reso, split, nbr), train=True)
+    else:
+        xs = ops.to_dtype(xg, torch.bfloat16)
+        y, ys = ops.cswin_block(xg, Pg, (B, reso, split, nbr), train=True, xs=xs, T=torch.bfloat16)
+        assert ys.dtype == torch.bfloat16 and rel(ys.float(), y.detach()) < 5e-3
+    y.backward(dy.reshape(-1, dim).cuda())
+    return P, x, dy, Pg, xg, y
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cname', list(cases.CSWIN_BLOCK_CASES))
+def test_block_fp32_vs_oracle_and_reference(gold, cname):
+    dim, reso, split, heads, last, B = cases.CSWIN_BLOCK_CASES[cname]
+    P, x, dy, Pg, xg, y = _block_case(cname, torch.float32)
+    Po = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    xo = x.clone().requires_grad_(True)
+    yo = CO.cswin_block(Po, '', xo, reso, split, heads, last)
+    yo.backward(dy)
+    assert rel(y.detach().cpu().reshape(yo.shape), yo.detach()) < 1e-5
+    assert rel(xg.grad.cpu().reshape(xo.shape), xo.grad) < 2e-5
+    for k in Po:
+        assert rel(Pg[k].grad.cpu(), Po[k].grad) < 5e-5, k
+    g = gold['block/' + cname]
+    assert cases.digest_close(y.detach().cpu(), g['y'], 1e-5, 1e-6)
+    assert cases.digest_close(xg.grad.cpu(), g['dx'], 2e-5, 1e-6)
+    for k, d in g['grads'].items():
+        assert cases.digest_close(Pg[k].grad, d, 5e-5, 1e-5), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cname', list(cases.CSWIN_BLOCK_CASES))
+def test_block_bf16_vs_reference(gold, cname):
+    P, x, dy, Pg, xg, y = _block_case(cname, torch.bfloat16)
+    g = gold['block/' + cname]
+    assert cases.digest_rel_err(y.detach().cpu(), g['y']) < 2e-2
+    assert cases.digest_rel_err(xg.grad.cpu(), g['dx']) < 2e-2
+    for k, d in g['grads'].items():
+        assert cases.digest_rel_err(Pg[k].grad, d) < 3e-2, (k, cases.digest_rel_err(Pg[k].grad, d))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('R,split,nbr,C,B', [(14, 7, 2, 64, 3), (8, 2, 2, 128, 2), (7, 7, 1, 96, 2), (12, 1, 2, 64, 1), (9, 3, 2, 64, 2)])
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
+def test_stripe_attention_vs_oracle(R, split, nbr, C, B, dtype, tol):
+    """K6 alone (ragged stripe sizes incl. tokens/stripe not a multiple of 4) against lepe_attention of the oracle."""
+    from imagenet_models_b200 import ops
+    g = torch.Generator().manual_seed(R * 100 + C)
+    qkv = torch.randn(B, R * R, 3 * C, generator=g)
+    dy = torch.randn(B, R * R, C, generator=g)
+    cb = C // nbr
+    P = {f'{i}.get_v.weight': torch.randn(cb, 1, 3, 3, generator=g) * 0.3 for i in range(nbr)}
+    P.update({f'{i}.get_v.bias': torch.randn(cb, generator=g) * 0.1 for i in range(nbr)})
+    P = {k: v.requires_grad_(True) for k, v in P.items()}
+    qo = qkv.clone().to(dtype).float().requires_grad_(True)
+    q, k, v = qo[..., :C], qo[..., C:2 * C], qo[..., 2 * C:]
+    if nbr == 2:
+        h = C // 2
+        o = torch.cat((CO.lepe_attention(P, '0.', q[..., :h], k[..., :h], v[..., :h], R, R, split, h // 32),
+                       CO.lepe_attention(P, '1.', q[..., h:], k[..., h:], v[..., h:], R, split, R, h // 32)), 2)
+    else:
+        o = CO.lepe_attention(P, '0.', q, k, v, R, R, R, C // 32)
+    o.backward(dy)
+    lw = torch.cat([P[f'{i}.get_v.weight'].detach().reshape(cb, 9) for i in range(nbr)]).cuda().requires_grad_(True)
+    lb = torch.cat([P[f'{i}.get_v.bias'].detach() for i in range(nbr)]).cuda().requires_grad_(True)
+    qg = qkv.reshape(-1, 3 * C).to(dtype).cuda().requires_grad_(True)
+    og = ops.cswin_attention(qg, lw, lb, B, R, split, nbr)
+    og.backward(dy.reshape(-1, C).to(dtype).cuda())
+    assert rel(og.detach().float().cpu().reshape(o.shape), o.detach()) < tol
+    assert rel(qg.grad.float().cpu().reshape(qo.shape), qo.grad) < tol
+    dw = torch.cat([P[f'{i}.get_v.weight'].grad.reshape(cb, 9) for i in range(nbr)])
+    db = torch.cat([P[f'{i}.get_v.bias'].grad for i in range(nbr)])
+    assert rel(lw.grad.cpu(), dw) < tol and rel(lb.grad.cpu(), db) < tol
+
+
+@pytest.mark.gpu
+def test_stripe_attention_rejects_bad_geometry():
+    from imagenet_models_b200 import ops
+    q = torch.zeros(2 * 56 * 56, 3 * 64, device='cuda')
+    w, b = torch.zeros(64, 9, device='cuda'), torch.zeros(64, device='cuda')
+    with pytest.raises(L.GaError):
+        ops.cswin_attention(q, w, b, 2, 56, 7, 2)        # 392 tokens per stripe
+    with pytest.raises(L.GaError):
+        ops.cswin_attention(q[:, :144], w[:48], b[:48], 2, 56, 1, 2)   # 48 channels do not split into 32-wide heads
+
+
+def _build(name, dtype):
+    spec = CO.SPECS[name]
+    m = _ctor(spec).cuda()
+    m.load_state_dict({k: v.cuda() for k, v in CO.make_state(spec, cases.STATE_SEED).items()}, strict=True)
+    m.compute_dtype = dtype
+    return m, spec
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', range(len(cases.CSWIN_MODEL_CASES)))
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
+def test_model_eval_vs_reference(gold, case, dtype, tol):
+    name, B = cases.CSWIN_MODEL_CASES[case]
+    g = gold[f'{name}/B{B}']
+    m, spec = _build(name, dtype)
+    m.eval()
+    x, _ = cases.ga_inputs(B)
+    with torch.no_grad():
+        out = m(x.cuda())
+    assert len(out) == 5
+    for a, b in zip(out, g['eval_logits']):
+        assert a.shape == (B, spec.num_classes) and a.dtype == torch.float32
+        assert rel(a.cpu(), b) < max(tol, 0 if dtype == torch.float32 else 1.5 * g['ref_bf16_self_err']['eval']), rel(a.cpu(), b)
+        if dtype == torch.float32:
+            assert torch.equal(a.cpu().topk(5).indices, b.topk(5).indices)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', range(len(cases.CSWIN_MODEL_CASES)))
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 5e-5), (torch.bfloat16, 2e-2)])
+def test_model_train_step_vs_reference(gold, case, dtype, tol):
+    """forward + GA loss (lam=-0.8) + backward vs the reference's logits, loss, every parameter gradient and BN statistics."""
+    from imagenet_models_b200 import ops
+    name, B = cases.CSWIN_MODEL_CASES[case]
+    g = gold[f'{name}/B{B}']
+    m, spec = _build(name, dtype)
+    m.train()
+    x, y = cases.ga_inputs(B)
+    y = y % spec.num_classes
+    out = m(x.cuda())
+    ltol = tol if dtype == torch.float32 else max(tol, g['ref_bf16_self_err']['train'])
+    for a, b in zip(out, g['train_logits']):
+        assert rel(a.detach().cpu(), b) < ltol, rel(a.detach().cpu(), b)
+    loss = ops.ga_loss(torch.stack(out), y.cuda(), cases.GA_LAM)
+    assert abs(loss.item() - g['loss'].item()) < (1e-4 if dtype == torch.float32 else 3e-2) * abs(g['loss'].item())
+    loss.backward()
+    bad = []
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        if dtype == torch.float32:
+            ok = cases.digest_close(p.grad, g['grads'][k], tol, 3e-4)
+        else:
+            ok = cases.digest_rel_err(p.grad, g['grads'][k]) <= 0.15 or g['grads'][k][0] < 2e-2
+        if not ok:
+            bad.append((k, g['grads'][k][0], p.grad.double().norm().item(), cases.digest_rel_err(p.grad, g['grads'][k])))
+    assert not bad, bad[:10]
+    sd = m.state_dict()
+    for k, v in g['running'].items():
+        assert rel(sd[k].cpu(), v) < (1e-5 if dtype == torch.float32 else 1e-2), k
