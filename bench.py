@@ -139,6 +139,7 @@ def main():
     from imagenet_models_b200.registry import create_model
     import imagenet_models_b200.ga_convnext  # noqa: F401
     import imagenet_models_b200.map_convnext  # noqa: F401
+    import imagenet_models_b200.ga_cswin  # noqa: F401
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -151,7 +152,7 @@ def main():
 
     torch.manual_seed(42 + rank)                       # random_seed(seed, rank), GA/train.py:402
     model = create_model(args.model).to(dev).train()
-    gf_img, mb_img = (TRAIN_GFLOP_PER_IMG, TRAIN_MB_PER_IMG) if args.model == MODEL else ({'map_convnext_tiny': 30.4}.get(args.model), None)
+    gf_img, mb_img = (TRAIN_GFLOP_PER_IMG, TRAIN_MB_PER_IMG) if args.model == MODEL else ({'map_convnext_tiny': 30.4, 'ga_CSWin_64_12211_tiny_224': 38.3}.get(args.model), None)
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)

@@ -14,6 +14,10 @@
 // the batch before one atomic flush.
 #include "common.cuh"
 
+struct AttnGeom {
+  int units, n, n4, nt;
+};
+
 namespace {
 constexpr int HD = 32;   // head width
 constexpr int RS = 36;   // shared-memory row pitch in floats: per-thread float4 row reads are bank-conflict free
@@ -296,9 +300,6 @@ __global__ void __launch_bounds__(NT) cswin_attn_bwd_kernel(const T* __restrict_
   if (grp == 0) atomicAdd(dlb + u.cb + ch, dbacc);
 }
 
-struct AttnGeom {
-  int units, n, n4, nt;
-};
 
 int attn_geom(int B, int R, int C, int split, int nbr, AttnGeom* g) {
   GA_REQUIRE(B > 0 && R > 0 && C > 0 && (nbr == 1 || nbr == 2), GA_ERR_SHAPE, "ga_cswin_attn: bad arguments B=%d R=%d C=%d nbr=%d", B, R,
@@ -315,15 +316,23 @@ int attn_geom(int B, int R, int C, int split, int nbr, AttnGeom* g) {
 }
 }  // namespace
 
+static bool attn_use_tc(int dtype, long long ld_a, long long ld_b, long long ld_c, long long ld_d);
+int ga_attn_fwd_tc(const void* qkv, const float* lw, const float* lb, void* out, float* lse, int B, int R, int C, int split, int nbr,
+                   long long ldq, long long ldo, float scale, const AttnGeom& g, cudaStream_t st);
+int ga_attn_bwd_tc(const void* dout, const void* qkv, const void* out, const float* lse, const float* lw, const float* lb, void* dqkv,
+                   float* dlw, float* dlb, int B, int R, int C, int split, int nbr, long long ldq, long long ldo, long long lddo,
+                   long long lddq, float scale, const AttnGeom& g, int bper, int nchunk, cudaStream_t st);
+
 extern "C" int ga_cswin_attn_fwd(const void* qkv, const float* lepe_w, const float* lepe_b, void* out, float* lse, int B, int R,
                                  int C, int split, int nbr, long long ldq, long long ldo, float scale, int dtype, ga_stream_t s) {
   AttnGeom g;
   if (int rc = attn_geom(B, R, C, split, nbr, &g)) return rc;
   GA_REQUIRE(qkv && lepe_w && lepe_b && out, GA_ERR_SHAPE, "ga_cswin_attn_fwd: null argument");
   GA_REQUIRE((ldq & 3) == 0 && (ldo & 3) == 0 && ldq >= 3 * C && ldo >= C, GA_ERR_ALIGN, "ga_cswin_attn_fwd: bad pitches");
+  cudaStream_t st = (cudaStream_t)s;
+  if (attn_use_tc(dtype, ldq, ldo, 8, 8)) return ga_attn_fwd_tc(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
   const size_t smem = (size_t)(2 * g.n4 * RS + 10 * HD) * sizeof(float);
   const dim3 grid(g.units, B);
-  cudaStream_t st = (cudaStream_t)s;
 #define GA_ATTN_FWD(T, NT)                                                                                        \
   cswin_attn_fwd_kernel<T, NT><<<grid, NT, smem, st>>>((const T*)qkv, lepe_w, lepe_b, (T*)out, lse, R, C, split, nbr, ldq, ldo, \
                                                        scale * LOG2E)
@@ -350,6 +359,9 @@ extern "C" int ga_cswin_attn_bwd(const void* dout, const void* qkv, const void* 
   nchunk = (B + bper - 1) / bper;
   const dim3 grid(g.units, nchunk);
   cudaStream_t st = (cudaStream_t)s;
+  if (attn_use_tc(dtype, ldq, ldo, lddo, lddq))
+    return ga_attn_bwd_tc(dout, qkv, out, lse, lepe_w, lepe_b, dqkv, dlepe_w, dlepe_b, B, R, C, split, nbr, ldq, ldo, lddo, lddq, scale, g,
+                          bper, nchunk, st);
 #define GA_ATTN_BWD(T, NT)                                                                                                   \
   do {                                                                                                                       \
     static bool attr = false;                                                                                                \
@@ -362,4 +374,423 @@ extern "C" int ga_cswin_attn_bwd(const void* dout, const void* qkv, const void* 
 #undef GA_ATTN_BWD
   ga_count_launch();
   return ga_check_launch("cswin_attn_bwd");
+}
+
+// ================================================================================================ tensor-core path (bf16)
+// Same work decomposition, but the two matrix products of the stripe run on the tensor pipe.  A stripe is at most
+// 128 x 128 x 32, far below one tcgen05 tile (M = 128 per issue, operands in canonical swizzled shared-memory layouts,
+// accumulators in TMEM): the op is bound by the exponentials and the gather / scatter of 64-byte token rows, not by MMA
+// rate, so the products are issued as register-fragment mma.sync.m16n8k16 (bf16 in, fp32 accumulate), which lets the
+// softmax stay in the accumulator registers and feed the second product without a round trip (the S -> P fragment
+// identity).  One warp owns 16 query rows (forward, dq) or 16 key rows (dk, dv, through the transposed products).
+namespace tcattn {
+constexpr int TP = 40;   // bf16 tile row pitch (80 B): ldmatrix row addresses fall in distinct bank groups
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragment (16 rows x 16 k) of a row-major tile
+__device__ __forceinline__ void frag_a(uint32_t (&r)[4], const bf16* tile, int m0, int k0, int lane) {
+  ldsm4(r, smem_u32(tile + (m0 + (lane & 15)) * TP + k0 + (lane >> 4) * 8));
+}
+// B fragments for C = A * tile^T: 8 tile rows n0.. as the n index, all 32 k: r0,r1 = k 0..15, r2,r3 = k 16..31
+__device__ __forceinline__ void frag_b_rows(uint32_t (&r)[4], const bf16* tile, int n0, int lane) {
+  ldsm4(r, smem_u32(tile + (n0 + (lane & 7)) * TP + (lane >> 3) * 8));
+}
+// B fragments for C = A * tile: tile rows j0..j0+15 as k, columns d0..d0+15 as n: r0,r1 = n-tile d0; r2,r3 = n-tile d0+8
+__device__ __forceinline__ void frag_b_cols(uint32_t (&r)[4], const bf16* tile, int j0, int d0, int lane) {
+  ldsm4t(r, smem_u32(tile + (j0 + (lane & 7) + ((lane >> 3) & 1) * 8) * TP + d0 + (lane >> 4) * 8));
+}
+
+// Tile staging: NP rows x 4 sixteen-byte chunks = exactly 2 chunks per thread (NP = 16 NKT rows, 32 NKT threads).  The token
+// offsets of a thread's two chunks do not depend on the image, so they are computed once (stage_offsets).
+template <int NT>
+__device__ __forceinline__ void stage_offsets(int (&off)[2], const Unit& u, int R, int n) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int j = (threadIdx.x + k * NT) >> 2;
+    const int ry = j / u.ws, rx = j - ry * u.ws;
+    off[k] = j < n ? (u.y0 + ry) * R + u.x0 + rx : -1;
+  }
+}
+template <int NT>
+__device__ __forceinline__ void stage_load(uint4 (&v)[2], const bf16* __restrict__ src, long long ld, int col, long long img, const int (&off)[2]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int part = (threadIdx.x + k * NT) & 3;
+    v[k] = make_uint4(0, 0, 0, 0);
+    if (off[k] >= 0) v[k] = *reinterpret_cast<const uint4*>(src + (img + off[k]) * ld + col + part * 8);
+  }
+}
+template <int NT>
+__device__ __forceinline__ void stage_store(bf16* dst, const uint4 (&v)[2]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + k * NT;
+    *reinterpret_cast<uint4*>(dst + (idx >> 2) * TP + (idx & 3) * 8) = v[k];
+  }
+}
+
+// acc[nt][0..1] (+)= sum_tap w[tap][d] * tile[nbr(i,tap)][d] for the fragment's two rows; sign as in lepe_row
+__device__ __forceinline__ void lepe_frag(float (&acc)[4][4], const bf16* tile, const float* w, const Unit& u, int i_lo, int n, int t,
+                                          int sign) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = i_lo + h * 8;
+    if (i >= n) continue;
+    const int ry = i / u.ws, rx = i - ry * u.ws;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = ry + sign * (tap / 3 - 1), xx = rx + sign * (tap % 3 - 1);
+      if (yy < 0 || yy >= u.hs || xx < 0 || xx >= u.ws) continue;
+      const bf16* row = tile + (yy * u.ws + xx) * TP;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int d = nt * 8 + 2 * t;
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(row + d);
+        const float2 c = *reinterpret_cast<const float2*>(w + tap * HD + d);
+        acc[nt][2 * h] = fmaf(c.x, bf16lo(v), acc[nt][2 * h]);
+        acc[nt][2 * h + 1] = fmaf(c.y, bf16hi(v), acc[nt][2 * h + 1]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void store_frag(bf16* dst, long long ld, const float (&acc)[4][4], long long r_lo, long long r_hi, bool ok_lo,
+                                           bool ok_hi, int t, float mul) {
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int d = nt * 8 + 2 * t;
+    if (ok_lo) *reinterpret_cast<uint32_t*>(dst + r_lo * ld + d) = pack_bf16(acc[nt][0] * mul, acc[nt][1] * mul);
+    if (ok_hi) *reinterpret_cast<uint32_t*>(dst + r_hi * ld + d) = pack_bf16(acc[nt][2] * mul, acc[nt][3] * mul);
+  }
+}
+
+// NKT: 16-row tiles covering the stripe (4: <= 64 tokens, 7: <= 112, 8: <= 128); one warp per tile
+template <int NKT>
+__global__ void __launch_bounds__(32 * NKT) attn_fwd_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ lw,
+                                                               const float* __restrict__ lb, bf16* __restrict__ out,
+                                                               float* __restrict__ lse, int R, int C, int split, int nbr,
+                                                               long long ldq, long long ldo, float c2) {
+  constexpr int NT = 32 * NKT, NP = 16 * NKT;
+  __shared__ __align__(16) bf16 Qs[NP * TP];
+  __shared__ __align__(16) bf16 Ks[NP * TP];
+  __shared__ __align__(16) bf16 Vs[NP * TP];
+  __shared__ __align__(16) float wsm[9 * HD];
+  __shared__ float bsm[HD];
+  const Unit u = decode_unit(blockIdx.x, R, C, split, nbr);
+  const int b = blockIdx.y;
+  const int n = u.hs * u.ws;
+  {
+    int off[2];
+    stage_offsets<NT>(off, u, R, n);
+    uint4 tq[2], tk[2], tv[2];
+    const long long img = (long long)b * R * R;
+    stage_load<NT>(tq, qkv, ldq, u.cb, img, off);
+    stage_load<NT>(tk, qkv, ldq, C + u.cb, img, off);
+    stage_load<NT>(tv, qkv, ldq, 2 * C + u.cb, img, off);
+    stage_store<NT>(Qs, tq); stage_store<NT>(Ks, tk); stage_store<NT>(Vs, tv);
+  }
+  for (int idx = threadIdx.x; idx < 9 * HD; idx += NT) wsm[idx] = lw[(u.cb + (idx & 31)) * 9 + (idx >> 5)];
+  if (threadIdx.x < HD) bsm[threadIdx.x] = lb[u.cb + threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int m0 = warp * 16;
+  if (m0 >= n) return;
+  uint32_t qa[2][4];
+  frag_a(qa[0], Qs, m0, 0, lane);
+  frag_a(qa[1], Qs, m0, 16, lane);
+  float s[2 * NKT][4];
+  float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+  for (int jt = 0; jt < 2 * NKT; ++jt) {
+    uint32_t kb[4];
+    frag_b_rows(kb, Ks, jt * 8, lane);
+    s[jt][0] = s[jt][1] = s[jt][2] = s[jt][3] = 0.f;
+    mma16816(s[jt], qa[0], kb[0], kb[1]);
+    mma16816(s[jt], qa[1], kb[2], kb[3]);
+    const int j = jt * 8 + 2 * t;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s[jt][e] = (j + (e & 1) < n) ? s[jt][e] * c2 : -INFINITY;
+    mx_lo = fmaxf(mx_lo, fmaxf(s[jt][0], s[jt][1]));
+    mx_hi = fmaxf(mx_hi, fmaxf(s[jt][2], s[jt][3]));
+  }
+  mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1)); mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+  mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1)); mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+  float l_lo = 0.f, l_hi = 0.f;
+  uint32_t pa[NKT][4];
+#pragma unroll
+  for (int jt = 0; jt < 2 * NKT; ++jt) {
+    const float p0 = ex2(s[jt][0] - mx_lo), p1 = ex2(s[jt][1] - mx_lo), p2 = ex2(s[jt][2] - mx_hi), p3 = ex2(s[jt][3] - mx_hi);
+    l_lo += p0 + p1; l_hi += p2 + p3;
+    pa[jt >> 1][(jt & 1) * 2] = pack_bf16(p0, p1);
+    pa[jt >> 1][(jt & 1) * 2 + 1] = pack_bf16(p2, p3);
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1); l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1); l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  float o[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < NKT; ++kt) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t vb[4];
+      frag_b_cols(vb, Vs, kt * 16, half * 16, lane);
+      mma16816(o[2 * half], pa[kt], vb[0], vb[1]);
+      mma16816(o[2 * half + 1], pa[kt], vb[2], vb[3]);
+    }
+  }
+  const float inv_lo = 1.f / l_lo, inv_hi = 1.f / l_hi;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const float2 bb = *reinterpret_cast<const float2*>(bsm + nt * 8 + 2 * t);
+    o[nt][0] = fmaf(o[nt][0], inv_lo, bb.x); o[nt][1] = fmaf(o[nt][1], inv_lo, bb.y);
+    o[nt][2] = fmaf(o[nt][2], inv_hi, bb.x); o[nt][3] = fmaf(o[nt][3], inv_hi, bb.y);
+  }
+  const int i_lo = m0 + g, i_hi = i_lo + 8;
+  lepe_frag(o, Vs, wsm, u, i_lo, n, t, 1);
+  const bool ok_lo = i_lo < n, ok_hi = i_hi < n;
+  const long long r_lo = ok_lo ? tok_row(u, b, R, i_lo) : 0, r_hi = ok_hi ? tok_row(u, b, R, i_hi) : 0;
+  store_frag(out + u.cb, ldo, o, r_lo, r_hi, ok_lo, ok_hi, t, 1.f);
+  if (lse && t == 0) {
+    if (ok_lo) lse[r_lo * (C / HD) + u.hg] = mx_lo + log2f(l_lo);
+    if (ok_hi) lse[r_hi * (C / HD) + u.hg] = mx_hi + log2f(l_hi);
+  }
+}
+
+template <int NKT>
+__global__ void __launch_bounds__(32 * NKT, NKT <= 4 ? 4 : 2) attn_bwd_tc_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ qkv,
+                                                               const bf16* __restrict__ out, const float* __restrict__ lse,
+                                                               const float* __restrict__ lw, const float* __restrict__ lb,
+                                                               bf16* __restrict__ dqkv, float* __restrict__ dlw, float* __restrict__ dlb,
+                                                               int B, int bper, int R, int C, int split, int nbr, long long ldq,
+                                                               long long ldo, long long lddo, long long lddq, float scale) {
+  constexpr int NT = 32 * NKT, NP = 16 * NKT;
+  __shared__ __align__(16) bf16 Qs[NP * TP];
+  __shared__ __align__(16) bf16 Ks[NP * TP];
+  __shared__ __align__(16) bf16 Vs[NP * TP];
+  __shared__ __align__(16) bf16 Ds[NP * TP];
+  __shared__ __align__(16) float lse_s[NP];
+  __shared__ __align__(16) float del_s[NP];
+  __shared__ __align__(16) float wsm[9 * HD];
+  __shared__ float bsm[HD];
+  const Unit u = decode_unit(blockIdx.x, R, C, split, nbr);
+  const int n = u.hs * u.ws;
+  const float c2 = scale * LOG2E;
+  for (int idx = threadIdx.x; idx < 9 * HD; idx += NT) wsm[idx] = lw[(u.cb + (idx & 31)) * 9 + (idx >> 5)];
+  if (threadIdx.x < HD) bsm[threadIdx.x] = lb[u.cb + threadIdx.x];
+  __shared__ float red[10 * HD];
+  for (int idx = threadIdx.x; idx < 10 * HD; idx += NT) red[idx] = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  // LePE weight gradient: thread (channel pair cp, position slice) keeps all 9 taps + the bias of its two channels
+  constexpr int NS = NT / 16;
+  const int cp = threadIdx.x & 15, slice = threadIdx.x >> 4;
+  float dwacc[9][2], dbacc[2] = {0.f, 0.f};
+#pragma unroll
+  for (int q = 0; q < 9; ++q) dwacc[q][0] = dwacc[q][1] = 0.f;
+  int off[2];
+  stage_offsets<NT>(off, u, R, n);
+  const int b0 = blockIdx.y * bper;
+  const int b1 = b0 + bper < B ? b0 + bper : B;
+  for (int b = b0; b < b1; ++b) {
+    __syncthreads();
+    {
+      uint4 tq[2], tk[2], tv[2], td[2];
+      const long long img = (long long)b * R * R;
+      stage_load<NT>(tq, qkv, ldq, u.cb, img, off);
+      stage_load<NT>(tk, qkv, ldq, C + u.cb, img, off);
+      stage_load<NT>(tv, qkv, ldq, 2 * C + u.cb, img, off);
+      stage_load<NT>(td, dout, lddo, u.cb, img, off);
+      stage_store<NT>(Qs, tq); stage_store<NT>(Ks, tk); stage_store<NT>(Vs, tv); stage_store<NT>(Ds, td);
+    }
+    __syncthreads();
+    // log-sum-exp per row; padded rows get +inf so their probabilities vanish in the transposed pass
+    for (int i = threadIdx.x; i < NP; i += NT) {
+      lse_s[i] = i < n ? lse[tok_row(u, b, R, i) * (C / HD) + u.hg] : INFINITY;
+      del_s[i] = 0.f;
+    }
+    __syncthreads();
+    const int m0 = warp * 16;
+    if (m0 < n) {
+      const int i_lo = m0 + g, i_hi = i_lo + 8;
+      const bool ok_lo = i_lo < n, ok_hi = i_hi < n;
+      const long long r_lo = ok_lo ? tok_row(u, b, R, i_lo) : 0, r_hi = ok_hi ? tok_row(u, b, R, i_hi) : 0;
+      // ---- query rows m0..m0+15: dq = scale * dS K
+      {
+        uint32_t qa[2][4], da[2][4];
+        frag_a(qa[0], Qs, m0, 0, lane); frag_a(qa[1], Qs, m0, 16, lane);
+        frag_a(da[0], Ds, m0, 0, lane); frag_a(da[1], Ds, m0, 16, lane);
+        const float ls_lo = lse_s[i_lo], ls_hi = lse_s[i_hi];
+        // pass 1: P (kept as bf16 pairs) and delta_i = sum_j P_ij dP_ij  (= dO_i . (P V)_i, the softmax part of the output)
+        uint32_t ppk[2 * NKT][2];
+        float dl_lo = 0.f, dl_hi = 0.f;
+#pragma unroll
+        for (int jt = 0; jt < 2 * NKT; ++jt) {
+          uint32_t kb[4], vb[4];
+          frag_b_rows(kb, Ks, jt * 8, lane);
+          frag_b_rows(vb, Vs, jt * 8, lane);
+          float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(s, qa[0], kb[0], kb[1]); mma16816(s, qa[1], kb[2], kb[3]);
+          mma16816(dp, da[0], vb[0], vb[1]); mma16816(dp, da[1], vb[2], vb[3]);
+          const int j = jt * 8 + 2 * t;
+          float p[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) p[e] = (j + (e & 1) < n) ? ex2(fmaf(s[e], c2, -(e < 2 ? ls_lo : ls_hi))) : 0.f;
+          dl_lo = fmaf(p[0], dp[0], fmaf(p[1], dp[1], dl_lo));
+          dl_hi = fmaf(p[2], dp[2], fmaf(p[3], dp[3], dl_hi));
+          ppk[jt][0] = pack_bf16(p[0], p[1]);
+          ppk[jt][1] = pack_bf16(p[2], p[3]);
+        }
+        dl_lo += __shfl_xor_sync(0xffffffffu, dl_lo, 1); dl_lo += __shfl_xor_sync(0xffffffffu, dl_lo, 2);
+        dl_hi += __shfl_xor_sync(0xffffffffu, dl_hi, 1); dl_hi += __shfl_xor_sync(0xffffffffu, dl_hi, 2);
+        if (t == 0) { del_s[i_lo] = dl_lo; del_s[i_hi] = dl_hi; }
+        // pass 2: dS = P (dP - delta), dP recomputed on the tensor pipe
+        uint32_t dsa[NKT][4];
+#pragma unroll
+        for (int jt = 0; jt < 2 * NKT; ++jt) {
+          uint32_t vb[4];
+          frag_b_rows(vb, Vs, jt * 8, lane);
+          float dp[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(dp, da[0], vb[0], vb[1]); mma16816(dp, da[1], vb[2], vb[3]);
+          dsa[jt >> 1][(jt & 1) * 2] = pack_bf16(bf16lo(ppk[jt][0]) * (dp[0] - dl_lo), bf16hi(ppk[jt][0]) * (dp[1] - dl_lo));
+          dsa[jt >> 1][(jt & 1) * 2 + 1] = pack_bf16(bf16lo(ppk[jt][1]) * (dp[2] - dl_hi), bf16hi(ppk[jt][1]) * (dp[3] - dl_hi));
+        }
+        float dq[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dq[nt][0] = dq[nt][1] = dq[nt][2] = dq[nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < NKT; ++kt) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t kb[4];
+            frag_b_cols(kb, Ks, kt * 16, half * 16, lane);
+            mma16816(dq[2 * half], dsa[kt], kb[0], kb[1]);
+            mma16816(dq[2 * half + 1], dsa[kt], kb[2], kb[3]);
+          }
+        }
+        store_frag(dqkv + u.cb, lddq, dq, r_lo, r_hi, ok_lo, ok_hi, t, scale);
+      }
+    }
+    __syncthreads();
+    if (m0 < n) {
+      const int i_lo = m0 + g, i_hi = i_lo + 8;
+      const bool ok_lo = i_lo < n, ok_hi = i_hi < n;
+      const long long r_lo = ok_lo ? tok_row(u, b, R, i_lo) : 0, r_hi = ok_hi ? tok_row(u, b, R, i_hi) : 0;
+      // ---- key rows m0..m0+15 through the transposed products: dk = scale * dS^T Q, dv = P^T dO + lepe^T(dO)
+      {
+        uint32_t ka[2][4], va[2][4];
+        frag_a(ka[0], Ks, m0, 0, lane); frag_a(ka[1], Ks, m0, 16, lane);
+        frag_a(va[0], Vs, m0, 0, lane); frag_a(va[1], Vs, m0, 16, lane);
+        uint32_t pa[NKT][4], dsa[NKT][4];
+#pragma unroll
+        for (int it = 0; it < 2 * NKT; ++it) {
+          uint32_t qb[4], db[4];
+          frag_b_rows(qb, Qs, it * 8, lane);
+          frag_b_rows(db, Ds, it * 8, lane);
+          float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          mma16816(s, ka[0], qb[0], qb[1]); mma16816(s, ka[1], qb[2], qb[3]);
+          mma16816(dp, va[0], db[0], db[1]); mma16816(dp, va[1], db[2], db[3]);
+          const int i = it * 8 + 2 * t;
+          const float2 ls = *reinterpret_cast<const float2*>(lse_s + i);
+          const float2 dl = *reinterpret_cast<const float2*>(del_s + i);
+          float p[4], ds[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            p[e] = ex2(fmaf(s[e], c2, -((e & 1) ? ls.y : ls.x)));
+            ds[e] = p[e] * (dp[e] - ((e & 1) ? dl.y : dl.x));
+          }
+          pa[it >> 1][(it & 1) * 2] = pack_bf16(p[0], p[1]);
+          pa[it >> 1][(it & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
+          dsa[it >> 1][(it & 1) * 2] = pack_bf16(ds[0], ds[1]);
+          dsa[it >> 1][(it & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+        }
+        float dk[4][4], dv[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { dk[nt][0] = dk[nt][1] = dk[nt][2] = dk[nt][3] = 0.f; dv[nt][0] = dv[nt][1] = dv[nt][2] = dv[nt][3] = 0.f; }
+#pragma unroll
+        for (int kt = 0; kt < NKT; ++kt) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t qb[4], db[4];
+            frag_b_cols(qb, Qs, kt * 16, half * 16, lane);
+            frag_b_cols(db, Ds, kt * 16, half * 16, lane);
+            mma16816(dk[2 * half], dsa[kt], qb[0], qb[1]);
+            mma16816(dk[2 * half + 1], dsa[kt], qb[2], qb[3]);
+            mma16816(dv[2 * half], pa[kt], db[0], db[1]);
+            mma16816(dv[2 * half + 1], pa[kt], db[2], db[3]);
+          }
+        }
+        lepe_frag(dv, Ds, wsm, u, i_lo, n, t, -1);
+        store_frag(dqkv + C + u.cb, lddq, dk, r_lo, r_hi, ok_lo, ok_hi, t, scale);
+        store_frag(dqkv + 2 * C + u.cb, lddq, dv, r_lo, r_hi, ok_lo, ok_hi, t, 1.f);
+      }
+    }
+    for (int i = slice; i < n; i += NS) {
+      const int ry = i / u.ws, rx = i - ry * u.ws;
+      const uint32_t dd = *reinterpret_cast<const uint32_t*>(Ds + i * TP + 2 * cp);
+      const float d0 = bf16lo(dd), d1 = bf16hi(dd);
+      dbacc[0] += d0; dbacc[1] += d1;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = ry + tap / 3 - 1, xx = rx + tap % 3 - 1;
+        const bool ok = yy >= 0 && yy < u.hs && xx >= 0 && xx < u.ws;
+        const uint32_t vv = ok ? *reinterpret_cast<const uint32_t*>(Vs + (i + (tap / 3 - 1) * u.ws + tap % 3 - 1) * TP + 2 * cp) : 0u;
+        dwacc[tap][0] = fmaf(d0, bf16lo(vv), dwacc[tap][0]);
+        dwacc[tap][1] = fmaf(d1, bf16hi(vv), dwacc[tap][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    atomicAdd(red + tap * HD + 2 * cp, dwacc[tap][0]);
+    atomicAdd(red + tap * HD + 2 * cp + 1, dwacc[tap][1]);
+  }
+  atomicAdd(red + 9 * HD + 2 * cp, dbacc[0]);
+  atomicAdd(red + 9 * HD + 2 * cp + 1, dbacc[1]);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 10 * HD; idx += NT) {
+    const int tap = idx >> 5, ch = idx & 31;
+    if (tap < 9) atomicAdd(dlw + (u.cb + ch) * 9 + tap, red[idx]);
+    else atomicAdd(dlb + u.cb + ch, red[idx]);
+  }
+}
+}  // namespace tcattn
+
+static bool attn_use_tc(int dtype, long long ld_a, long long ld_b, long long ld_c, long long ld_d) {
+  static int simt = -1;
+  if (simt < 0) { const char* e = getenv("GA_ATTN_SIMT"); simt = (e && atoi(e)) ? 1 : 0; }
+  return dtype == GA_BF16 && !simt && ((ld_a | ld_b | ld_c | ld_d) & 7) == 0;
+}
+
+int ga_attn_fwd_tc(const void* qkv, const float* lw, const float* lb, void* out, float* lse, int B, int R, int C, int split, int nbr,
+                   long long ldq, long long ldo, float scale, const AttnGeom& g, cudaStream_t st) {
+  const dim3 grid(g.units, B);
+  const float c2 = scale * LOG2E;
+#define GA_TCF(NKT) tcattn::attn_fwd_tc_kernel<NKT><<<grid, 32 * NKT, 0, st>>>((const bf16*)qkv, lw, lb, (bf16*)out, lse, R, C, split, nbr, ldq, ldo, c2)
+  if (g.n <= 64) GA_TCF(4); else if (g.n <= 112) GA_TCF(7); else GA_TCF(8);
+#undef GA_TCF
+  ga_count_launch();
+  return ga_check_launch("cswin_attn_fwd_tc");
+}
+
+int ga_attn_bwd_tc(const void* dout, const void* qkv, const void* out, const float* lse, const float* lw, const float* lb, void* dqkv,
+                   float* dlw, float* dlb, int B, int R, int C, int split, int nbr, long long ldq, long long ldo, long long lddo,
+                   long long lddq, float scale, const AttnGeom& g, int bper, int nchunk, cudaStream_t st) {
+  const dim3 grid(g.units, nchunk);
+#define GA_TCB(NKT)                                                                                                                  \
+  tcattn::attn_bwd_tc_kernel<NKT><<<grid, 32 * NKT, 0, st>>>((const bf16*)dout, (const bf16*)qkv, (const bf16*)out, lse, lw, lb, (bf16*)dqkv, \
+                                                             dlw, dlb, B, bper, R, C, split, nbr, ldq, ldo, lddo, lddq, scale)
+  if (g.n <= 64) GA_TCB(4); else if (g.n <= 112) GA_TCB(7); else GA_TCB(8);
+#undef GA_TCB
+  ga_count_launch();
+  return ga_check_launch("cswin_attn_bwd_tc");
 }

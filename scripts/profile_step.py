@@ -23,14 +23,17 @@ def main():
     ap.add_argument('--steps', type=int, default=2)
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'step_profile.txt'))
     ap.add_argument('--fwd-only', action='store_true')
+    ap.add_argument('--model', default='ga_convnext_tiny_688')
     args = ap.parse_args()
     from imagenet_models_b200 import ops
     from imagenet_models_b200.optim import FusedAdamWEma
     from imagenet_models_b200.registry import create_model
     import imagenet_models_b200.ga_convnext  # noqa: F401
+    import imagenet_models_b200.ga_cswin  # noqa: F401
+    import imagenet_models_b200.map_convnext  # noqa: F401
     dev = torch.device('cuda')
     torch.manual_seed(0)
-    model = create_model('ga_convnext_tiny_688').to(dev).train()
+    model = create_model(args.model).to(dev).train()
     opt = FusedAdamWEma(model, lr=1e-3, weight_decay=0.05, ema_decay=0.9998)
     x = torch.randn(args.batch, 3, 224, 224, device=dev)
     y = torch.randint(0, 1000, (args.batch,), device=dev)
@@ -43,7 +46,10 @@ def main():
         opt.zero_grad()
         with torch.autocast('cuda', dtype=torch.bfloat16):
             out = model(x)
-        ops.ga_loss(torch.stack(out), y, -0.8).backward()
+        if isinstance(out[0], (list, tuple)):
+            ops.ga_loss(torch.stack([o[0] for o in out]), y, -0.8, aux=torch.stack([o[1] for o in out])).backward()
+        else:
+            ops.ga_loss(torch.stack(out), y, -0.8).backward()
         opt.step()
 
     for _ in range(3):
