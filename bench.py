@@ -127,6 +127,7 @@ def main():
     ap.add_argument('--model', default=MODEL, help='headline: ga_convnext_tiny_688; also map_convnext_tiny (config 4, use --batch 512)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='run every step eagerly instead of replaying the captured CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -156,7 +157,8 @@ def main():
     if world > 1:
         for t in list(model.parameters()) + list(model.buffers()):
             dist.broadcast(t.data, 0)
-    engine = TrainEngine(model, lr=1e-3, weight_decay=0.05, ema_decay=0.9998, ga_lam=GA_LAM, amp_dtype=torch.bfloat16)
+    engine = TrainEngine(model, lr=1e-3, weight_decay=0.05, ema_decay=0.9998, ga_lam=GA_LAM, amp_dtype=torch.bfloat16,
+                         cuda_graph=not args.no_graph, graph_warmup=3)
     B = args.batch
     x_dev = torch.randn(B, 3, 224, 224, device=dev)
     y_dev = torch.randint(0, 1000, (B,), device=dev)
@@ -194,17 +196,14 @@ def main():
         return ms.item()
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):
+    for _ in range(warm + (2 if engine.cuda_graph else 0)):     # graph mode: 3 eager steps, capture, one replay before timing
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        ops.TIMER = ops.GemmTimer()                    # CUDA events around every ga_gemm launch of the timed region
     n0 = L.launch_count()
     ms = timed(step_resident, args.steps)
-    launches = L.launch_count() - n0
-    gemm_times = ops.TIMER.summary() if rank == 0 else {}
-    ops.TIMER = None
+    launches = L.launch_count() - n0 + (engine.graph_launches * args.steps if engine._graph is not None else 0)
     clocks = sampler.stop() if rank == 0 else None
     e2e = None
     if not args.no_e2e:
@@ -214,6 +213,17 @@ def main():
         e2e = {'value': world * B * args.steps / (ms_e2e / 1e3), 'unit': 'img/s', 'ms_per_step': ms_e2e / args.steps,
                'h2d_bytes_per_step': x_host.numel() + y_host.numel() * 8, 'd2h_bytes_per_step': 4}
 
+    # per-kernel roofline: an instrumented EAGER pass after the timed region (CUDA events around every ga_gemm launch on
+    # the launching stream; a graph replay has no per-launch host hook).  All ranks run it so collectives stay matched.
+    graph_used = engine._graph is not None
+    engine.cuda_graph = False
+    n_inst = min(args.steps, 5)
+    step_resident()
+    if rank == 0:
+        ops.TIMER = ops.GemmTimer()
+    ms_inst = timed(step_resident, n_inst)
+    gemm_times = ops.TIMER.summary() if rank == 0 else {}
+    ops.TIMER = None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -227,20 +237,22 @@ def main():
     nb, M, N, K, dt, kind, byts = key
     avg_us = t_ms / n_launch * 1e3
     achieved = byts / (avg_us * 1e-6) / 1e9
-    gemm_total_ms = sum(v[1] for v in gemm_times.values()) / args.steps
+    gemm_total_ms = sum(v[1] for v in gemm_times.values()) / n_inst
+    ms_step_inst = ms_inst / n_inst
     line = {
         'metric': 'train images/sec (whole job)', 'value': img_s, 'unit': 'img/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': warm, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': f'{args.model} training step (fwd + GA loss + bwd + all-reduce + fused AdamW + EMA), bf16 autocast '
                                f'(fp32 residual stream), batch {B}/GPU, 224x224', 'global_batch': B * world,
-                   'parallelism': f'dp{world}', 'l2': 'activations per step (>10 GB) exceed the 126 MB L2; no explicit flush'},
+                   'parallelism': f'dp{world}', 'cuda_graph': graph_used, 'l2': 'activations per step (>10 GB) exceed the 126 MB L2; no explicit flush'},
         'gpu_launches': launches, 'clocks': clocks,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
                      'traffic': NCU_TRAFFIC.get((M, N, K, kind)), 'peak_source': src,
                      'kernel': f'tc::gemm_tc2_kernel (tcgen05 persistent GEMM), call site M={M} N={N} K={K} {dt} epilogue {kind}',
                      'algorithmic_bytes_per_launch': byts, 'avg_launch_us': avg_us, 'launches_timed': n_launch,
-                     'share_of_step': (t_ms / args.steps) / ms_step, 'all_gemm_share_of_step': gemm_total_ms / ms_step},
+                     'share_of_step': (t_ms / n_inst) / ms_step_inst, 'all_gemm_share_of_step': gemm_total_ms / ms_step_inst,
+                     'measured': f'{n_inst} instrumented eager steps after the timed region ({ms_step_inst:.2f} ms/step with the events)'},
         'step_roofline': {'hbm_frac': per_gpu * mb_img / 1e3 / hbm if mb_img else None, 'tensor_frac': per_gpu * gf_img / 1e3 / tf if gf_img else None,
                           'note': '268 MB/img and 32.73 GFLOP/img (BASELINE.md section 4) x img/s/GPU over the measured peaks'},
     }

@@ -12,7 +12,11 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, c
                                                         float* __restrict__ v, float* __restrict__ ema, bf16* __restrict__ p16,
                                                         const unsigned char* __restrict__ decay_flag, int seg_shift, long long n4,
                                                         float lr, float b1, float b2, float eps, float wd, float inv_bc1,
-                                                        float inv_sqrt_bc2, float ema_decay, float grad_scale) {
+                                                        float inv_sqrt_bc2, float ema_decay, float grad_scale,
+                                                        const float* __restrict__ hyper) {
+  if (hyper) {   // step-dependent scalars read from device memory so a captured CUDA graph stays valid across steps
+    lr = hyper[0]; inv_bc1 = 1.f / hyper[1]; inv_sqrt_bc2 = rsqrtf(hyper[2]); grad_scale = hyper[3];
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
     float4 gg = reinterpret_cast<const float4*>(g)[i];
@@ -46,9 +50,9 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, c
   }
 }
 
-extern "C" int ga_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16,
-                            const unsigned char* decay_flag, int seg_shift, long long n, float lr, float beta1, float beta2,
-                            float eps, float wd, float bias_c1, float bias_c2, float ema_decay, float grad_scale, ga_stream_t s) {
+static int adamw_launch(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16, const unsigned char* decay_flag,
+                        int seg_shift, long long n, float lr, float beta1, float beta2, float eps, float wd, float bias_c1, float bias_c2,
+                        float ema_decay, float grad_scale, const float* hyper, ga_stream_t s) {
   GA_REQUIRE(p && g && m && v && n >= 0 && (n & 3) == 0, GA_ERR_ALIGN, "ga_adamw_ema: n=%lld must be a multiple of 4", n);
   GA_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)ema) & 15) == 0, GA_ERR_ALIGN,
              "ga_adamw_ema: buffers must be 16-byte aligned");
@@ -59,8 +63,52 @@ extern "C" int ga_adamw_ema(float* p, const float* g, float* m, float* v, float*
   const long long cap = (long long)ga_num_sms() * 8;
   if (blocks > cap) blocks = cap;
   adamw_ema_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(p, g, m, v, ema, (bf16*)p_bf16, decay_flag, seg_shift, n4, lr, beta1,
-                                                                   beta2, eps, wd, 1.f / bias_c1, rsqrtf(bias_c2), ema_decay, grad_scale);
+                                                                   beta2, eps, wd, 1.f / bias_c1, rsqrtf(bias_c2), ema_decay, grad_scale, hyper);
   return launch_ok("adamw_ema");
+}
+extern "C" int ga_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16,
+                            const unsigned char* decay_flag, int seg_shift, long long n, float lr, float beta1, float beta2,
+                            float eps, float wd, float bias_c1, float bias_c2, float ema_decay, float grad_scale, ga_stream_t s) {
+  return adamw_launch(p, g, m, v, ema, p_bf16, decay_flag, seg_shift, n, lr, beta1, beta2, eps, wd, bias_c1, bias_c2, ema_decay, grad_scale,
+                      nullptr, s);
+}
+extern "C" int ga_adamw_ema_dev(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16,
+                                const unsigned char* decay_flag, int seg_shift, long long n, const float* hyper, float beta1,
+                                float beta2, float eps, float wd, float ema_decay, ga_stream_t s) {
+  GA_REQUIRE(hyper, GA_ERR_SHAPE, "ga_adamw_ema_dev: hyper (lr, 1-b1^t, 1-b2^t, grad_scale) is NULL");
+  return adamw_launch(p, g, m, v, ema, p_bf16, decay_flag, seg_shift, n, 0.f, beta1, beta2, eps, wd, 1.f, 1.f, ema_decay, 1.f, hyper, s);
+}
+
+// Gather per-tensor gradients into the flat gradient buffer: table[t] = {src pointer (may be NULL: zeros), flat offset,
+// element count, first chunk}; chunk c of 4096 elements belongs to the tensor found by binary search over first_chunk.
+struct GradEntry { const float* src; long long off; long long n; long long first_chunk; };
+__global__ void __launch_bounds__(256) gather_grads_kernel(const GradEntry* __restrict__ table, int count, long long chunks,
+                                                           float* __restrict__ flat) {
+  for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+    int lo = 0, hi = count - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].first_chunk <= c) lo = mid; else hi = mid - 1;
+    }
+    const GradEntry e = table[lo];
+    const long long start = (c - e.first_chunk) * 4096;
+    const long long len = e.n - start < 4096 ? e.n - start : 4096;
+    float* dst = flat + e.off + start;
+    const float* src = e.src ? e.src + start : nullptr;
+    if (src && ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0)) {
+      const long long n4 = len >> 2;
+      for (long long i = threadIdx.x; i < n4; i += 256) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
+      for (long long i = (n4 << 2) + threadIdx.x; i < len; i += 256) dst[i] = src[i];
+    } else {
+      for (long long i = threadIdx.x; i < len; i += 256) dst[i] = src ? src[i] : 0.f;
+    }
+  }
+}
+extern "C" int ga_gather_grads(const void* table, int count, long long chunks, float* flat, ga_stream_t s) {
+  GA_REQUIRE(table && flat && count > 0 && chunks > 0, GA_ERR_SHAPE, "ga_gather_grads: bad arguments");
+  long long blocks = chunks < 148LL * 16 ? chunks : 148LL * 16;
+  gather_grads_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>((const GradEntry*)table, count, chunks, flat);
+  return launch_ok("gather_grads");
 }
 
 // ema = d*ema + (1-d)*src over a flat buffer (buffers such as BatchNorm running statistics)

@@ -456,11 +456,73 @@ __global__ void im2col3_kernel(const T* __restrict__ x, T* __restrict__ y, int B
     }
   }
 }
+// 16-byte-chunk forms (C * sizeof(T) and both pitches multiples of 16 bytes): the forward gather is pure data movement
+__global__ void __launch_bounds__(256) im2col3_fwd16_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W,
+                                                            int CV, long long ldx, long long ldy, int S) {
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+  const long long total = (long long)B * Ho * Wo * 9 * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const int tap = (int)(p % 9); p /= 9;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const int sy = oy * S + tap / 3 - 1, sx = ox * S + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = x[(((long long)b * H + sy) * W + sx) * ldx + cv];
+    y[(((long long)b * Ho + oy) * Wo + ox) * ldy + tap * CV + cv] = v;
+  }
+}
+__global__ void __launch_bounds__(256) im2col3_inv8_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C,
+                                                           long long ldx, long long ldy, int S) {
+  const int C8 = C >> 3;
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+  const long long total = (long long)B * H * W * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long p = i / C8;
+    const int xx = (int)(p % W); p /= W;
+    const int yy = (int)(p % H);
+    const int b = (int)(p / H);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ty = yy + 1 - tap / 3, tx = xx + 1 - tap % 3;
+      if (ty < 0 || tx < 0 || ty % S || tx % S) continue;
+      const int oy = ty / S, ox = tx / S;
+      if (oy >= Ho || ox >= Wo) continue;
+      float v[8];
+      ld8_bf16(x + (((long long)b * Ho + oy) * Wo + ox) * ldx + tap * C + c8 * 8, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += v[e];
+    }
+    st8_bf16(y + (((long long)b * H + yy) * W + xx) * ldy + c8 * 8, a);
+  }
+}
+
 extern "C" int ga_im2col3s(const void* x, void* y, int B, int H, int W, int C, int stride, long long ldx, long long ldy, int inverse,
                            int dtype, ga_stream_t s) {
   GA_REQUIRE(x && y && (C & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0, GA_ERR_ALIGN, "ga_im2col3: C/ld must be multiples of 4");
   GA_REQUIRE(stride == 1 || stride == 2, GA_ERR_UNSUPPORTED, "ga_im2col3: stride %d (1 or 2)", stride);
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int es = dtype == GA_BF16 ? 2 : 4, per16 = 16 / es;
+  const bool v16 = (C % per16 == 0) && (ldx % per16 == 0) && (ldy % per16 == 0) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  if (v16 && !inverse) {
+    const int CV = C / per16;
+    const long long total = (long long)B * Ho * Wo * 9 * CV;
+    if (total == 0) return GA_OK;
+    const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    im2col3_fwd16_kernel<<<grid, 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)y, B, H, W, CV, ldx / per16, ldy / per16, stride);
+    return launch_ok("im2col3_fwd16");
+  }
+  if (v16 && inverse && dtype == GA_BF16) {
+    const long long total = (long long)B * H * W * (C >> 3);
+    if (total == 0) return GA_OK;
+    const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    im2col3_inv8_kernel<<<grid, 256, 0, (cudaStream_t)s>>>((const bf16*)x, (bf16*)y, B, H, W, C, ldx, ldy, stride);
+    return launch_ok("im2col3_inv8");
+  }
   const long long total = inverse ? (long long)B * H * W * (C >> 2) : (long long)B * Ho * Wo * (C >> 2) * 9;
   if (total == 0) return GA_OK;
   const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
@@ -778,6 +840,44 @@ extern "C" int ga_scale_matrix(const float* src, const float* rowscale, const fl
   if (dst_dtype == GA_BF16) scale_matrix_kernel<bf16><<<grid, 256, 0, (cudaStream_t)s>>>(src, rowscale, colscale, (bf16*)dst, rows, cols);
   else scale_matrix_kernel<float><<<grid, 256, 0, (cudaStream_t)s>>>(src, rowscale, colscale, (float*)dst, rows, cols);
   return launch_ok("scale_matrix");
+}
+// LayerNorm-affine fold of a Linear that follows the norm: Wf[n,k] = W[n,k] * g[k] (cast to the operand dtype) and
+// bf[n] = b[n] + sum_k W[n,k] * beta[k].  One warp per output row: W is read once (was: scale_matrix + an M=1 GEMM).
+template <typename TD>
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ g, const float* __restrict__ beta,
+                                                      const float* __restrict__ b, TD* __restrict__ Wf, float* __restrict__ bf, int N,
+                                                      int K, long long ldw) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float* w = W + (long long)row * K;
+  float acc = 0.f;
+  if ((K & 3) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(w + k);
+      const float4 gg = *reinterpret_cast<const float4*>(g + k);
+      const float4 bb = *reinterpret_cast<const float4*>(beta + k);
+      acc = fmaf(v.x, bb.x, fmaf(v.y, bb.y, fmaf(v.z, bb.z, fmaf(v.w, bb.w, acc))));
+      st4(Wf + (long long)row * ldw + k, make_float4(v.x * gg.x, v.y * gg.y, v.z * gg.z, v.w * gg.w));
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float v = w[k];
+      acc = fmaf(v, beta[k], acc);
+      st_f(Wf + (long long)row * ldw + k, v * g[k]);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) bf[row] = acc + (b ? b[row] : 0.f);
+}
+extern "C" int ga_fold_ln(const float* W, const float* ln_w, const float* ln_b, const float* bias, void* Wf, float* bf, int N, int K,
+                          long long ldw, int dst_dtype, ga_stream_t s) {
+  GA_REQUIRE(W && ln_w && ln_b && Wf && bf && N > 0 && K > 0 && ldw >= K, GA_ERR_SHAPE, "ga_fold_ln: bad arguments");
+  GA_REQUIRE((K & 3) || (ldw & 3) == 0, GA_ERR_ALIGN, "ga_fold_ln: ldw must be a multiple of 4 when K is");
+  const int grid = (N + 7) / 8;
+  if (dst_dtype == GA_BF16) fold_ln_kernel<bf16><<<grid, 256, 0, (cudaStream_t)s>>>(W, ln_w, ln_b, bias, (bf16*)Wf, bf, N, K, ldw);
+  else fold_ln_kernel<float><<<grid, 256, 0, (cudaStream_t)s>>>(W, ln_w, ln_b, bias, (float*)Wf, bf, N, K, ldw);
+  return launch_ok("fold_ln");
 }
 extern "C" int ga_cast_bf16(const float* src, void* dst, long long n, ga_stream_t s) {
   if (n == 0) return GA_OK;

@@ -195,16 +195,28 @@ class GroupConvMlp(nn.Module):
         self.fc1 = nn.Conv2d(in_features, hidden_features, kernel_size=1, bias=True, groups=groups)
         self.fc2 = nn.Conv2d(hidden_features, in_features, kernel_size=1, bias=True, groups=groups)
 
-    def run(self, t):
-        """t [B, C] fp32 token.  The shuffle is a strided view of the hidden activation (no copy)."""
+    ACT = ACT_GELU
+
+    def run(self, t, T=torch.float32):
+        """t [B, C] fp32 token; T: operand dtype (bf16 under autocast, like the reference's convs).  Output fp32 [B, C].
+        The channel shuffle between the two grouped convs is a re-striding of the hidden activation; with bf16 operands both
+        GEMM inputs are laid out group-major with 16-byte pitches so they run on the tcgen05 path (M is only the batch)."""
         Bn, Cc = t.shape
         g = self.groups
         hid = self.fc1.out_channels
-        a3 = t.view(Bn, g, Cc // g).transpose(0, 1)
-        h = ops.grouped_linear(a3, self.fc1.weight.view(g, hid // g, Cc // g), self.fc1.bias, act=ACT_GELU)
-        # channel_shuffle: shuffled[a*(hid/g) + b] = h[b*g + a]  (ga_convnext.py:557-566)
-        a3 = h.view(Bn, hid // g, g).permute(2, 0, 1)
-        return ops.grouped_linear(a3, self.fc2.weight.view(g, Cc // g, hid // g), self.fc2.bias)
+        cg, hg = Cc // g, hid // g
+        if T == torch.float32:
+            a3 = t.view(Bn, g, cg).transpose(0, 1)
+            h = ops.grouped_linear(a3, self.fc1.weight.view(g, hg, cg), self.fc1.bias, act=self.ACT)
+            # channel_shuffle: shuffled[a*(hid/g) + b] = h[b*g + a]  (ga_convnext.py:557-566)
+            a3 = h.view(Bn, hg, g).permute(2, 0, 1)
+            return ops.grouped_linear(a3, self.fc2.weight.view(g, cg, hg), self.fc2.bias)
+        a3 = torch.empty(g, Bn, ops.pad8(cg), dtype=T, device=t.device)[:, :, :cg]
+        a3 = a3.copy_(t.view(Bn, g, cg).transpose(0, 1))
+        h = ops.grouped_linear(a3, self.fc1.weight.view(g, hg, cg), self.fc1.bias, act=self.ACT)
+        a3 = torch.empty(g, Bn, ops.pad8(hg), dtype=T, device=t.device)[:, :, :hg]
+        a3 = a3.copy_(h.view(Bn, hg, g).permute(2, 0, 1))
+        return ops.grouped_linear(a3, self.fc2.weight.view(g, cg, hg), self.fc2.bias, out_dtype=torch.float32)
 
 
 class LayerScaleBlockClassAttn(nn.Module):
@@ -376,7 +388,7 @@ class GA_ConvNeXt(nn.Module):
             c = cls[k] + blk.gamma_1 * ops.linear(ops.to_dtype(o[k, :, 0], T), blk.attn.proj.weight, blk.attn.proj.bias,
                                                   out_dtype=torch.float32)
             h = ops.layernorm(c, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
-            c = c + blk.gamma_2 * blk.mlp.run(h)
+            c = c + blk.gamma_2 * blk.mlp.run(h, T)
             outs.append(ops.linear(ops.to_dtype(c, T), self.fc[k].weight, self.fc[k].bias, out_dtype=torch.float32))
         return outs
 

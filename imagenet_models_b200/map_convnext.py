@@ -69,14 +69,7 @@ class ClassAttention(nn.Module):
 class GroupConvMlp(_GAGroupConvMlp):
     """map.GroupConvMlp (:43-66): ReLU instead of GELU, otherwise the GA layout (grouped 1x1, shuffle, grouped 1x1)."""
 
-    def run(self, t):
-        Bn, Cc = t.shape
-        g = self.groups
-        hid = self.fc1.out_channels
-        a3 = t.view(Bn, g, Cc // g).transpose(0, 1)
-        h = ops.grouped_linear(a3, self.fc1.weight.view(g, hid // g, Cc // g), self.fc1.bias, act=ACT_RELU)
-        a3 = h.view(Bn, hid // g, g).permute(2, 0, 1)
-        return ops.grouped_linear(a3, self.fc2.weight.view(g, Cc // g, hid // g), self.fc2.bias)
+    ACT = ACT_RELU
 
 
 class CABlock(nn.Module):
@@ -207,7 +200,7 @@ class MAPHead(nn.Module):
             cls = cls + ops.linear(ops.to_dtype(o[g].reshape(Bn * nq, E), T), a.attn.proj.weight, a.attn.proj.bias,
                                    out_dtype=torch.float32)
             h = ops.layernorm(cls, a.norm2.weight, a.norm2.bias, a.norm2.eps)
-            cls = cls + a.mlp.run(h)
+            cls = cls + a.mlp.run(h, T)
             pool = cls.view(Bn, nq * L_)
             main = self.heads[g].run(pool[:, :self.out_ch].contiguous(), T)
             if training:

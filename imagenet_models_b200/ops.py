@@ -197,6 +197,17 @@ def scale_matrix(w, rowscale=None, colscale=None, dtype=torch.float32):
     return o
 
 
+def fold_ln(w, bias, ln_w, ln_b, dtype):
+    """(W diag(ln_w) in `dtype`, bias + W ln_b in fp32): LayerNorm's affine folded into the Linear that follows it."""
+    assert w.is_contiguous() and w.dim() == 2 and w.dtype == torch.float32
+    N, K = w.shape
+    wf = torch.empty(N, pad8(K), dtype=dtype, device=w.device)[:, :K] if K % 8 else torch.empty(N, K, dtype=dtype, device=w.device)
+    bf = torch.empty(N, dtype=torch.float32, device=w.device)
+    L.check(_L().ga_fold_ln(L.ptr(w), L.ptr(ln_w), L.ptr(ln_b), L.ptr(bias), L.ptr(wf), L.ptr(bf), N, K, L.ll(wf.stride(0)),
+                            BF16 if dtype == torch.bfloat16 else F32, L.stream()), 'ga_fold_ln')
+    return wf, bf
+
+
 def colsum(x: torch.Tensor, sumsq: bool = False):
     """fp32 column sums (and sums of squares) of a row matrix."""
     M, Cc = x.shape
@@ -330,8 +341,7 @@ class ConvNeXtBlockFn(Function):
         rstd = torch.empty(M, dtype=torch.float32, device=dev)
         L.check(lib.ga_dwconv7_ln_fwd(L.ptr(src), L.ptr(w49c), L.ptr(dw_b), None, None, L.ptr(xhat), L.ptr(rstd), Bn, H, W_, Cc,
                                       L.f(1e-6), L.dt(src), L.stream()), 'ga_dwconv7_ln_fwd')
-        w1f = scale_matrix(w1, None, ln_w, T)
-        b1f = gemm(ln_b.unsqueeze(0), w1, bias=b1, out_dtype=torch.float32).reshape(-1)
+        w1f, b1f = fold_ln(w1, b1, ln_w, ln_b, T)
         if train:
             a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU, save_z=True)
         else:
@@ -923,8 +933,7 @@ class CSWinBlockFn(Function):
             return xh, rstd
         # attention half
         xh1, rstd1 = ln_hat(src)
-        wqf = scale_matrix(wqkv, None, n1w, T)
-        bqf = gemm(n1b.unsqueeze(0), wqkv, bias=bqkv, out_dtype=torch.float32).reshape(-1)
+        wqf, bqf = fold_ln(wqkv, bqkv, n1w, n1b, T)
         qkv = gemm(xh1, wqf, bias=bqf)
         lw, lb = lw.contiguous(), lb.contiguous()
         att, lse = _attn_fwd(qkv, lw, lb, Bn, R, Cc, split, nbr, train)
@@ -934,8 +943,7 @@ class CSWinBlockFn(Function):
         gemm(att, wpc, x1, bias=bproj, rowscale=ps1, rows_per_scale=HW, residual=x, shadow=x1s)
         # MLP half
         xh2, rstd2 = ln_hat(x1s if mixed else x1)
-        w1f = scale_matrix(w1, None, n2w, T)
-        b1f = gemm(n2b.unsqueeze(0), w1, bias=b1, out_dtype=torch.float32).reshape(-1)
+        w1f, b1f = fold_ln(w1, b1, n2w, n2b, T)
         if train:
             a, z = gemm(xh2, w1f, bias=b1f, act=ACT_GELU, save_z=True)
         else:

@@ -43,11 +43,12 @@ class FlatState:
         self.numel = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self._tables = {}
         for p, o in zip(params, self.offsets):
             n = p.numel()
             self.flat[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat[o:o + n].view(p.shape)
-            p.grad = self.grad[o:o + n].view(p.shape)
+            p.grad = None
         # float buffers (BatchNorm running statistics) re-homed the same way, for a one-launch EMA of non-parameter state
         self.bufflat = _flatten_buffers(model, dev)
 
@@ -61,10 +62,49 @@ class FlatState:
         return flags.to(self.flat.device)
 
     def zero_grad(self):
-        self.grad.zero_()
-        for p, o in zip(self.params, self.offsets):     # autograd may have replaced .grad; re-attach the view
-            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
-                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        """Drop every .grad: autograd then *adopts* the gradient tensors our backward kernels produce instead of launching
+        one accumulate kernel per parameter; gather() collects them into the flat buffer in one launch."""
+        for p in self.params:
+            p.grad = None
+
+    def _table(self, members):
+        key = tuple(members)
+        ent = self._tables.get(key)
+        if ent is None:
+            import numpy as np
+            rec = np.zeros((len(members), 4), dtype=np.int64)
+            chunk = 0
+            for r, idx in enumerate(members):
+                n = self.params[idx].numel()
+                rec[r, 1], rec[r, 2], rec[r, 3] = self.offsets[idx], n, chunk
+                chunk += (n + 4095) // 4096
+            ent = {'rec': rec, 'chunks': chunk, 'dev': torch.empty(len(members) * 4, dtype=torch.int64, device=self.flat.device),
+                   'graph_host': torch.empty(rec.size, dtype=torch.int64, pin_memory=True)}
+            self._tables[key] = ent
+        return ent
+
+    def gather(self, members=None):
+        """p.grad of `members` (default: all) -> their slices of the flat gradient (ga_gather_grads); absent grads give zeros."""
+        members = range(len(self.params)) if members is None else members
+        ent = self._table(members)
+        rec = ent['rec']
+        for r, idx in enumerate(members):
+            g = self.params[idx].grad
+            if g is None:
+                rec[r, 0] = 0
+                continue
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                g = g.float().contiguous()
+                self.params[idx].grad = g
+            rec[r, 0] = g.data_ptr()
+        if torch.cuda.is_current_stream_capturing():
+            host = ent['graph_host']                    # the captured copy node re-reads this buffer at every replay
+        else:
+            host = torch.empty(rec.size, dtype=torch.int64, pin_memory=True)   # caching host allocator: reuse is stream-safe
+        host.numpy()[:] = rec.reshape(-1)
+        ent['dev'].copy_(host, non_blocking=True)
+        L.check(L.load().ga_gather_grads(L.ptr(ent['dev']), len(rec), L.ll(ent['chunks']), L.ptr(self.grad), L.stream()),
+                'ga_gather_grads')
 
 
 def _flatten_buffers(model: nn.Module, dev) -> torch.Tensor:
@@ -104,21 +144,41 @@ class FusedAdamWEma:
                 p.data = self.ema_flat[o:o + p.numel()].view(p.shape)
             self.ema_bufflat = _flatten_buffers(self.ema_model, self.ema_flat.device)
         self.param_groups = [{'lr': lr}]                          # what the reference's logging / schedulers read
+        self.hyper = torch.zeros(4, dtype=torch.float32, device=self.state.flat.device) if self.state.flat.is_cuda else None
 
     def zero_grad(self, set_to_none=False):
         self.state.zero_grad()
 
-    def step(self, grad_scale: float = 1.0):
+    def push_hyper(self, grad_scale: float = 1.0):
+        """Advance the step count and upload {lr, 1-b1^t, 1-b2^t, grad_scale} for a graph-captured step(device_hyper=True)."""
         self.step_count += 1
         t = self.step_count
         b1, b2 = self.betas
-        lr = self.param_groups[0]['lr']
+        host = torch.empty(4, dtype=torch.float32, pin_memory=True)
+        host[0], host[1], host[2], host[3] = self.param_groups[0]['lr'], 1 - b1 ** t, 1 - b2 ** t, grad_scale
+        self.hyper.copy_(host, non_blocking=True)
+
+    def step(self, grad_scale: float = 1.0, gathered: bool = False, device_hyper: bool = False):
+        """gathered: the flat gradient already holds this step's gradients (GradBuckets did it bucket by bucket).
+        device_hyper: read lr / bias corrections / grad_scale from self.hyper (see push_hyper) instead of scalar arguments."""
+        if not gathered:
+            self.state.gather()
+        b1, b2 = self.betas
         lib = L.load()
-        L.check(lib.ga_adamw_ema(L.ptr(self.state.flat), L.ptr(self.state.grad), L.ptr(self.m), L.ptr(self.v),
-                                 L.ptr(self.ema_flat), None, L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel), L.f(lr), L.f(b1),
-                                 L.f(b2), L.f(self.eps), L.f(self.wd), L.f(1 - b1 ** t), L.f(1 - b2 ** t),
-                                 L.f(self.ema_decay if self.ema_decay is not None else 0.0), L.f(grad_scale), L.stream()),
-                'ga_adamw_ema')
+        ema_d = self.ema_decay if self.ema_decay is not None else 0.0
+        if device_hyper:
+            L.check(lib.ga_adamw_ema_dev(L.ptr(self.state.flat), L.ptr(self.state.grad), L.ptr(self.m), L.ptr(self.v),
+                                         L.ptr(self.ema_flat), None, L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel),
+                                         L.ptr(self.hyper), L.f(b1), L.f(b2), L.f(self.eps), L.f(self.wd), L.f(ema_d), L.stream()),
+                    'ga_adamw_ema_dev')
+        else:
+            self.step_count += 1
+            t = self.step_count
+            lr = self.param_groups[0]['lr']
+            L.check(lib.ga_adamw_ema(L.ptr(self.state.flat), L.ptr(self.state.grad), L.ptr(self.m), L.ptr(self.v),
+                                     L.ptr(self.ema_flat), None, L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel), L.f(lr),
+                                     L.f(b1), L.f(b2), L.f(self.eps), L.f(self.wd), L.f(1 - b1 ** t), L.f(1 - b2 ** t), L.f(ema_d),
+                                     L.f(grad_scale), L.stream()), 'ga_adamw_ema')
         if self.ema_model is not None:
             L.check(lib.ga_ema_lerp(L.ptr(self.ema_bufflat), L.ptr(self.state.bufflat), L.ll(self.ema_bufflat.numel()),
                                     L.f(self.ema_decay), L.stream()), 'ga_ema_lerp')
@@ -170,6 +230,13 @@ class GradBuckets:
             b['pending'], b['work'] = len(b['members']), None
 
     def _launch(self, b):
+        if self._cuda:
+            self.state.gather(b['members'])        # adopt the bucket's gradients into its contiguous slice (one launch)
+        else:
+            for idx in b['members']:               # CPU (gloo tests): plain copies
+                p, o = self.state.params[idx], self.state.offsets[idx]
+                dst = self.state.grad[o:o + p.numel()]
+                dst.zero_() if p.grad is None else dst.copy_(p.grad.reshape(-1))
         buf = self.state.grad[b['lo']:b['hi']]
         if self.side is not None:
             self.side.wait_stream(torch.cuda.current_stream())

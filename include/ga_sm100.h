@@ -188,6 +188,10 @@ int ga_copy_cols(const void* src, void* dst, long long M, int C, long long lds, 
 /* fp32 -> bf16 cast of a flat buffer (weight shadows) */
 int ga_cast_bf16(const float* src, void* dst, long long n, ga_stream_t s);
 /* dst[r, c] = src[r, c] * rowscale[r] * colscale[c]  (either may be NULL): folds layer-scale / LN affine into weights */
+/* LayerNorm-affine fold into the Linear that follows (ga_convnext.py:105-107, ga_cswin.py:196-197, 210):
+ * Wf[n,k] = W[n,k]*ln_w[k] in dst_dtype (row pitch ldw), bf[n] = bias[n] + sum_k W[n,k]*ln_b[k] (bias may be NULL) */
+int ga_fold_ln(const float* W, const float* ln_w, const float* ln_b, const float* bias, void* Wf, float* bf, int N, int K,
+               long long ldw, int dst_dtype, ga_stream_t s);
 int ga_scale_matrix(const float* src, const float* rowscale, const float* colscale, void* dst, int rows, int cols,
                     int dst_dtype, ga_stream_t s);
 /* y[r,:] = x[r,:] * rowscale[r / rows_per_scale]  (DropPath mask applied to a gradient; timm drop_path) */
@@ -221,6 +225,15 @@ int ga_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, void*
                  int seg_shift, long long n, float lr, float beta1, float beta2, float eps, float wd, float bias_c1,
                  float bias_c2, float ema_decay, float grad_scale, ga_stream_t s);
 /* ema = d*ema + (1-d)*src (buffers: BatchNorm running statistics) */
+/* ga_adamw_ema with the step-dependent scalars in device memory: hyper = {lr, 1-beta1^t, 1-beta2^t, grad_scale}
+ * (so one captured CUDA graph of the training step stays valid while lr and t change) */
+int ga_adamw_ema_dev(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16,
+                     const unsigned char* decay_flag, int seg_shift, long long n, const float* hyper, float beta1,
+                     float beta2, float eps, float wd, float ema_decay, ga_stream_t s);
+/* Per-tensor gradients -> the flat gradient buffer the optimizer / all-reduce buckets read (replaces one accumulate
+ * kernel per parameter).  table: device array of `count` records {const float* src (NULL = zeros); long long flat_offset;
+ * long long numel; long long first_chunk}, chunks of 4096 elements numbered consecutively over the table. */
+int ga_gather_grads(const void* table, int count, long long chunks, float* flat, ga_stream_t s);
 int ga_ema_lerp(float* ema, const float* src, long long n, float decay, ga_stream_t s);
 
 #ifdef __cplusplus

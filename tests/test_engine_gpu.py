@@ -1,0 +1,86 @@
+"""TrainEngine on the GPU: the CUDA-graph step must train exactly like the eager step (same losses, same weights, EMA and
+BatchNorm statistics), and the adopted-gradient gather must equal per-parameter accumulation."""
+import copy
+
+import pytest
+import torch
+
+from oracle import cases
+from oracle import ga_cswin_oracle as CO
+
+
+def _model():
+    import imagenet_models_b200.ga_cswin as GC
+    spec = CO.SPECS['ga_cswin_test']
+    torch.manual_seed(3)
+    m = GC.GA_CSWinTransformer(img_size=224, patch_size=4, num_classes=spec.num_classes, embed_dim=spec.embed_dim,
+                               depth=list(spec.depth), split_size=list(spec.split_size), num_heads=list(spec.num_heads),
+                               dims=list(spec.dims), stage3_naggre=spec.naggre, gram_dim=spec.gram_dim).cuda()
+    m.load_state_dict({k: v.cuda() for k, v in CO.make_state(spec, cases.STATE_SEED).items()}, strict=True)
+    return m.train(), spec
+
+
+@pytest.mark.gpu
+def test_graph_step_matches_eager_step():
+    """AdamW turns rounding-level gradient noise into +-lr updates, so trajectories of two runs drift apart chaotically;
+    the comparison is therefore made one step at a time from bit-identical weights (warm-up steps run with lr = 0)."""
+    from imagenet_models_b200.engine import TrainEngine
+    m0, spec = _model()
+    m1 = copy.deepcopy(m0)
+    e0 = TrainEngine(m0, lr=0.0, weight_decay=0.05, ema_decay=0.99, cuda_graph=False)
+    e1 = TrainEngine(m1, lr=0.0, weight_decay=0.05, ema_decay=0.99, cuda_graph=True, graph_warmup=2)
+    g = torch.Generator().manual_seed(0)
+
+    def batch():
+        return (torch.randn(4, 3, 224, 224, generator=g).cuda(), torch.randint(0, spec.num_classes, (4,), generator=g).cuda())
+    for _ in range(2):                                   # eager in both engines; lr = 0 keeps the weights bit-identical
+        x, y = batch()
+        e0.step(x, y)
+        e1.step(x, y)
+    for p0, p1 in zip(m0.parameters(), m1.parameters()):
+        assert torch.equal(p0, p1)
+    # ---- first captured step, lr = 1e-3
+    e0.opt.param_groups[0]['lr'] = e1.opt.param_groups[0]['lr'] = 1e-3
+    x, y = batch()
+    l0, l1 = e0.step(x, y).item(), e1.step(x, y).item()
+    assert e1._graph is not None and e1.graph_launches > 100
+    assert abs(l0 - l1) <= 1e-4 * abs(l0), (l0, l1)
+    g0, g1 = e0.opt.state.grad, e1.opt.state.grad
+    assert (g0 - g1).norm().item() <= 2e-3 * g0.norm().item()
+    for p0, p1 in zip(m0.parameters(), m1.parameters()):
+        assert (p0 - p1).abs().max().item() <= 2.1e-3 + 1e-6           # at most +-lr each, whatever the noise did
+    before = [p.detach().clone() for p in m1.parameters()]
+    # ---- second replay with lr = 0: the captured optimizer must read the new lr from device memory -> weights frozen
+    e0.opt.param_groups[0]['lr'] = e1.opt.param_groups[0]['lr'] = 0.0
+    x, y = batch()
+    l0, l1 = e0.step(x, y).item(), e1.step(x, y).item()
+    assert abs(l0 - l1) <= 3e-2 * abs(l0), (l0, l1)
+    for b, p in zip(before, m1.parameters()):
+        assert torch.equal(b, p)
+    # ---- and it did train at lr = 1e-3: weights differ from the initial state
+    init = CO.make_state(spec, cases.STATE_SEED)
+    assert (m1.state_dict()['fc.0.weight'].cpu() - init['fc.0.weight']).abs().max().item() > 1e-4
+    assert e0.opt.step_count == e1.opt.step_count == 4
+    for b0, b1 in zip(m0.buffers(), m1.buffers()):                      # BatchNorm statistics advanced identically
+        if b0.is_floating_point():
+            assert (b0 - b1).norm().item() <= 1e-3 * b0.norm().item() + 1e-6
+        else:
+            assert torch.equal(b0, b1)
+
+
+@pytest.mark.gpu
+def test_gather_equals_parameter_gradients():
+    from imagenet_models_b200 import ops
+    from imagenet_models_b200.optim import FusedAdamWEma
+    m, spec = _model()
+    opt = FusedAdamWEma(m, lr=1e-3, ema_decay=None)
+    x = torch.randn(2, 3, 224, 224, device='cuda')
+    y = torch.randint(0, spec.num_classes, (2,), device='cuda')
+    opt.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+    ops.ga_loss(torch.stack(m(x)), y, -0.8).backward()
+    opt.state.grad.fill_(float('nan'))
+    opt.state.gather()
+    torch.cuda.synchronize()
+    for p, o in zip(opt.state.params, opt.state.offsets):
+        assert torch.equal(opt.state.grad[o:o + p.numel()], p.grad.reshape(-1))
