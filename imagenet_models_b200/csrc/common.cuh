@@ -117,6 +117,13 @@ __device__ __forceinline__ float gelu_f(float x) {
   const float h = gelu_h(x, &ex);
   return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
+// gelu(x) and gelu'(x) together: the reciprocal / exponential of gelu_h are shared
+__device__ __forceinline__ void gelu_both_f(float x, float* y, float* dy) {
+  float ex;
+  const float h = gelu_h(x, &ex);
+  *y = fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+  *dy = fmaf(x * 0.39894228040143268f, ex, x >= 0.f ? 1.f - h : h);
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float ex;
   const float h = gelu_h(x, &ex);

@@ -41,10 +41,13 @@ __device__ __forceinline__ void epi_store1(const EpiArgs& e, int b, int m, int n
   if (e.Zin) {
     long long zo = (long long)b * e.z_bs + (long long)m * e.ldz + n;
     float z = e.out_f32 ? ((const float*)e.Zin)[zo] : __bfloat162float(((const bf16*)e.Zin)[zo]);
-    v *= (e.zmode == GA_ACT_GELU) ? gelu_grad_f(z) : (z > 0.f ? 1.f : 0.f);
+    v *= (e.zmode == GA_ACT_MUL) ? z : (e.zmode == GA_ACT_GELU) ? gelu_grad_f(z) : (z > 0.f ? 1.f : 0.f);
   } else {
     if (e.bias) v += e.bias[(long long)b * e.bias_bs + n];
-    if (e.Z && !e.z_shadow) { if (e.out_f32) ((float*)e.Z)[off] = v; else ((bf16*)e.Z)[off] = __float2bfloat16_rn(v); }
+    if (e.Z && e.z_shadow != 1) {
+      const float zv = e.z_shadow == 2 ? gelu_grad_f(v) : v;
+      if (e.out_f32) ((float*)e.Z)[off] = zv; else ((bf16*)e.Z)[off] = __float2bfloat16_rn(zv);
+    }
     v = epi_act(v, e.act);
     if (e.colscale) v *= e.colscale[(long long)b * e.colscale_bs + n];
     if (e.rowscale) v *= e.rowscale[m / e.rows_per_scale];
@@ -53,7 +56,7 @@ __device__ __forceinline__ void epi_store1(const EpiArgs& e, int b, int m, int n
       v += e.out_f32 ? ((const float*)e.R)[ro] : __bfloat162float(((const bf16*)e.R)[ro]);
     }
   }
-  if (e.Z && e.z_shadow) ((bf16*)e.Z)[off] = __float2bfloat16_rn(v);
+  if (e.Z && e.z_shadow == 1) ((bf16*)e.Z)[off] = __float2bfloat16_rn(v);
   if (e.accumulate) atomicAdd(((float*)e.D) + off, v);
   else if (e.out_f32) ((float*)e.D)[off] = v;
   else ((bf16*)e.D)[off] = __float2bfloat16_rn(v);
@@ -67,14 +70,16 @@ __device__ __forceinline__ void epi_store4p(const EpiArgs& e, int b, int m, int 
   if (e.Zin) {
     const float zz[4] = {pre.x, pre.y, pre.z, pre.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] *= (e.zmode == GA_ACT_GELU) ? gelu_grad_f(zz[i]) : (zz[i] > 0.f ? 1.f : 0.f);
+    for (int i = 0; i < 4; ++i)
+      v[i] *= (e.zmode == GA_ACT_MUL) ? zz[i] : (e.zmode == GA_ACT_GELU) ? gelu_grad_f(zz[i]) : (zz[i] > 0.f ? 1.f : 0.f);
   } else {
     if (e.bias) {
       const float4 bb = *reinterpret_cast<const float4*>(e.bias + (long long)b * e.bias_bs + n);
       v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
     }
-    if (e.Z && !e.z_shadow) {
-      const float4 zv = make_float4(v[0], v[1], v[2], v[3]);
+    if (e.Z && e.z_shadow != 1) {
+      const float4 zv = e.z_shadow == 2 ? make_float4(gelu_grad_f(v[0]), gelu_grad_f(v[1]), gelu_grad_f(v[2]), gelu_grad_f(v[3]))
+                                        : make_float4(v[0], v[1], v[2], v[3]);
       if (e.out_f32) st4((float*)e.Z + off, zv); else st4((bf16*)e.Z + off, zv);
     }
     if (e.act == GA_ACT_GELU) {
@@ -95,7 +100,7 @@ __device__ __forceinline__ void epi_store4p(const EpiArgs& e, int b, int m, int 
     }
     if (e.R) { v[0] += pre.x; v[1] += pre.y; v[2] += pre.z; v[3] += pre.w; }
   }
-  if (e.Z && e.z_shadow) st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
+  if (e.Z && e.z_shadow == 1) st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
   if (e.accumulate) {
     float* d = (float*)e.D + off;
 #pragma unroll
@@ -512,9 +517,21 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st
       float v[4] = {acc.x, acc.y, acc.z, acc.w};
       if (EPI == EPI_BIAS_GELU_Z || EPI == EPI_BIAS_GELU) {
         v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
-        if (EPI == EPI_BIAS_GELU_Z) st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
+        if (EPI == EPI_BIAS_GELU_Z) {
+          if (e.z_shadow == 2) {       // save gelu'(z) instead of z: the backward epilogue becomes one multiply
+            float gd[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+            for (int i = 0; i < 4; ++i) gelu_both_f(v[i], &v[i], &gd[i]);
+            st4((bf16*)e.Z + off, make_float4(gd[0], gd[1], gd[2], gd[3]));
+          } else {
+            st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+        }
         st4((bf16*)e.D + off, make_float4(v[0], v[1], v[2], v[3]));
       } else if (EPI == EPI_RES_F32_SHADOW) {
         float rs = 1.f;
@@ -527,7 +544,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st
       } else if (EPI == EPI_ZIN_GELU) {
         const float zz[4] = {pre[j].x, pre[j].y, pre[j].z, pre[j].w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] *= gelu_grad_f(zz[i]);
+        for (int i = 0; i < 4; ++i) v[i] *= (e.zmode == GA_ACT_MUL) ? zz[i] : gelu_grad_f(zz[i]);
         st4((bf16*)e.D + off, make_float4(v[0], v[1], v[2], v[3]));
       } else if (EPI == EPI_PLAIN_BF16) {
         st4((bf16*)e.D + off, make_float4(v[0] + bias4.x, v[1] + bias4.y, v[2] + bias4.z, v[3] + bias4.w));
@@ -873,12 +890,12 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
     int epi = tc::EPI_GENERIC;
     if (v4 && b4 && !v1_env && wide) {
       const bool plain = !g->Z && !g->colscale && !g->rowscale && !g->R && !g->Zin && !g->accumulate;
-      if (!a_mn && !b_mn && bf_out && g->act == GA_ACT_GELU && !g->colscale && !g->rowscale && !g->R && !g->Zin && !g->accumulate && !g->z_shadow)
+      if (!a_mn && !b_mn && bf_out && g->act == GA_ACT_GELU && !g->colscale && !g->rowscale && !g->R && !g->Zin && !g->accumulate && g->z_shadow != 1)
         epi = g->Z ? tc::EPI_BIAS_GELU_Z : tc::EPI_BIAS_GELU;
       else if (!a_mn && !b_mn && !bf_out && g->act == GA_ACT_NONE && g->R && (g->ldr & 3) == 0 && !g->Zin && !g->accumulate &&
-               (!g->Z || g->z_shadow) && (!g->colscale || (((uintptr_t)g->colscale & 15) == 0 && (g->colscale_bs & 3) == 0)))
+               (!g->Z || g->z_shadow == 1) && (!g->colscale || (((uintptr_t)g->colscale & 15) == 0 && (g->colscale_bs & 3) == 0)))
         epi = tc::EPI_RES_F32_SHADOW;
-      else if (!a_mn && b_mn && bf_out && g->Zin && g->zmode == GA_ACT_GELU && (g->ldz & 3) == 0 && !g->bias && !g->Z && !g->colscale &&
+      else if (!a_mn && b_mn && bf_out && g->Zin && (g->zmode == GA_ACT_GELU || g->zmode == GA_ACT_MUL) && (g->ldz & 3) == 0 && !g->bias && !g->Z && !g->colscale &&
                !g->rowscale && !g->R && !g->accumulate)
         epi = tc::EPI_ZIN_GELU;
       else if (!a_mn && bf_out && g->act == GA_ACT_NONE && plain)

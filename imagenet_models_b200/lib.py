@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, 'libga_sm100.so')
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'ga_sm100.h')
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_MUL = 0, 1, 2, 3
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 
 

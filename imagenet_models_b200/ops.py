@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import lib as L
-from .lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32
+from .lib import ACT_GELU, ACT_MUL, ACT_NONE, ACT_RELU, BF16, F32
 
 Function = torch.autograd.Function
 
@@ -95,6 +95,8 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
     """D[b,m,n] = epi(alpha * sum_k A[b,m,k] * B[b,n,k]);  A:[M,K]|[b,M,K], B:[N,K]|[b,N,K], arbitrary strides.
 
     A batch stride of 0 (expanded tensor) broadcasts that operand.  `out` may be any strided [.., M, N] view.
+    save_z: True -> also return the pre-activation; 'grad' -> return act'(pre-activation) instead (apply it in backward
+    with zin=..., zmode=ACT_MUL: the derivative is evaluated once, next to the activation, where exp / rcp are shared).
     """
     batched = A.dim() == 3 or B.dim() == 3
     A3 = A if A.dim() == 3 else A.unsqueeze(0)
@@ -129,6 +131,10 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
         g.bias = bias.data_ptr()
         g.bias_bs = bias.stride(0) if (bias.dim() == 2 and nb > 1) else 0
     g.act = act
+    z_grad = isinstance(save_z, str)
+    if z_grad:
+        assert save_z == 'grad' and act == ACT_GELU
+        save_z = True
     if save_z is not False and save_z is not None:
         if isinstance(save_z, torch.Tensor):       # caller-provided view with D's shape and strides
             Z = save_z if save_z.dim() == 3 else save_z.unsqueeze(0)
@@ -137,6 +143,8 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
             assert out.is_contiguous() or out.dim() == 2
             Z = torch.empty_strided(out.shape, out.stride(), dtype=out.dtype, device=dev)
         g.Z = Z.data_ptr()
+        if z_grad:
+            g.z_shadow = 2
     if colscale is not None:
         assert colscale.dtype == torch.float32
         g.colscale = colscale.data_ptr()
@@ -290,6 +298,9 @@ class GemmFn(Function):
             dout = act_bwd(dout, zy, ctx.act)
         ld = dout.stride(0)
         dD3 = dout.as_strided((G, M, N), (N, ld, 1), dout.storage_offset())
+        if G > 1 and N % 8 and dout.dtype == torch.bfloat16:
+            # group stride N is not a 16-byte multiple (172-wide groups): re-pitch so both backward GEMMs stay on tcgen05
+            dD3 = torch.empty(G, M, pad8(N), dtype=dout.dtype, device=dout.device)[:, :, :N].copy_(dD3)
         dA = dW = db = None
         if ctx.needs_input_grad[0]:
             Wc = cast_like(W, A.dtype)
@@ -331,6 +342,7 @@ class ConvNeXtBlockFn(Function):
         Bn, H, W_ = geom
         M, Cc = x.shape
         assert x.is_contiguous() and M == Bn * H * W_
+        ctx.set_materialize_grads(False)            # an unused shadow output must not cost a zero fill + an add per block
         mixed = x.dtype != T
         src = xs if mixed else x
         assert src is not None and src.dtype == T and src.is_contiguous()
@@ -343,7 +355,7 @@ class ConvNeXtBlockFn(Function):
                                       L.f(1e-6), L.dt(src), L.stream()), 'ga_dwconv7_ln_fwd')
         w1f, b1f = fold_ln(w1, b1, ln_w, ln_b, T)
         if train:
-            a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU, save_z=True)
+            a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU, save_z='grad')
         else:
             a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU), None
         w2c = cast_like(w2, T)
@@ -390,7 +402,7 @@ class ConvNeXtBlockFn(Function):
                                             L.ptr(db2), L.ptr(dgam), None, None, Cc, Hd, L.stream()), 'linear_grad_finalize')
         # dz = (dys . (gamma*W2)) * gelu'(z)
         w2s = scale_matrix(w2, gamma, None, T)
-        dz = gemm(dys, w2s.t(), zin=z, zmode=ACT_GELU)
+        dz = gemm(dys, w2s.t(), zin=z, zmode=ACT_MUL)
         # fc1: G1 = dz^T xhat ; dW1 = G1*ln_w + s1 (x) ln_b ; db1 = s1 ; dln_w = coldot(W1, G1) ; dln_b = W1^T s1
         s1 = colsum(dz)
         gemm(dz.t(), xhat.t(), G1.view(Hd, Cc), accumulate=True)
@@ -917,6 +929,7 @@ class CSWinBlockFn(Function):
         Bn, R, split, nbr = geom
         M, Cc = x.shape
         assert x.is_contiguous() and M == Bn * R * R
+        ctx.set_materialize_grads(False)
         mixed = x.dtype != T
         src = xs if mixed else x
         assert src is not None and src.dtype == T and src.is_contiguous()
@@ -945,7 +958,7 @@ class CSWinBlockFn(Function):
         xh2, rstd2 = ln_hat(x1s if mixed else x1)
         w1f, b1f = fold_ln(w1, b1, n2w, n2b, T)
         if train:
-            a, z = gemm(xh2, w1f, bias=b1f, act=ACT_GELU, save_z=True)
+            a, z = gemm(xh2, w1f, bias=b1f, act=ACT_GELU, save_z='grad')
         else:
             a, z = gemm(xh2, w1f, bias=b1f, act=ACT_GELU), None
         w2c = cast_like(w2, T)
@@ -994,7 +1007,7 @@ class CSWinBlockFn(Function):
         d2 = rows_scaled(dys, ps2)
         db2 = colsum(d2)
         gemm(d2.t(), a.t(), dw2.view(Cc, Hd), accumulate=True)
-        dz = gemm(d2, w2c.t(), zin=z, zmode=ACT_GELU)
+        dz = gemm(d2, w2c.t(), zin=z, zmode=ACT_MUL)
         s1 = colsum(dz)
         gemm(dz.t(), xh2.t(), G1.view(Hd, Cc), accumulate=True)
         L.check(lib.ga_linear_grad_finalize(L.ptr(G1), L.ptr(s1), L.ptr(w1), None, None, L.ptr(n2w), L.ptr(n2b), L.ptr(dw1),

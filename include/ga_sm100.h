@@ -23,7 +23,7 @@ extern "C" {
 typedef void* ga_stream_t; /* cudaStream_t */
 
 enum { GA_F32 = 0, GA_BF16 = 1 };
-enum { GA_ACT_NONE = 0, GA_ACT_GELU = 1, GA_ACT_RELU = 2 };
+enum { GA_ACT_NONE = 0, GA_ACT_GELU = 1, GA_ACT_RELU = 2, GA_ACT_MUL = 3 /* zmode only: D = acc * Zin */ };
 enum { GA_BACKEND_AUTO = 0, GA_BACKEND_SIMT = 1, GA_BACKEND_TCGEN05 = 2 };
 
 int ga_version(void);
@@ -57,10 +57,11 @@ typedef struct GaGemm {
   const float* colscale; long long colscale_bs;
   const float* rowscale; int rows_per_scale;
   const void* R; long long ldr, r_bs;
-  const void* Zin; long long ldz, z_bs; int zmode; /* GA_ACT_GELU: *gelu'(Zin); GA_ACT_RELU: *(Zin>0) */
+  const void* Zin; long long ldz, z_bs; int zmode; /* GA_ACT_GELU: *gelu'(Zin); GA_ACT_RELU: *(Zin>0); GA_ACT_MUL: *Zin */
   int backend;    /* GA_BACKEND_* */
   int splits;     /* split-K factor for accumulate mode; 0 = auto */
-  int z_shadow;   /* 1: Z receives a bf16 copy of the FINAL value (bf16 shadow of an fp32 residual stream) */
+  int z_shadow;   /* 1: Z receives a bf16 copy of the FINAL value (bf16 shadow of an fp32 residual stream);
+                     2: Z receives act'(pre-activation) (GELU), to be applied in backward with zmode GA_ACT_MUL */
 } GaGemm;
 int ga_gemm(const GaGemm* p, ga_stream_t s);
 

@@ -78,6 +78,13 @@ def test_gemm_epilogues(dtype):
     assert rel(y3.float(), (A.float() @ B.float().t()) * zz.grad) < tol(dtype)
     y4 = ops.gemm(A, B, bias=bias, act=L.ACT_RELU)
     assert rel(y4.float(), F.relu(zr)) < tol(dtype)
+    # saved-derivative form: forward stores gelu'(z) next to gelu(z), backward multiplies by it (zmode ACT_MUL)
+    y5, gd = ops.gemm(A, B, bias=bias, act=L.ACT_GELU, save_z='grad')
+    zq = zr.clone().requires_grad_(True)
+    F.gelu(zq).sum().backward()
+    assert rel(y5.float(), F.gelu(zr)) < tol(dtype) and rel(gd.float(), zq.grad) < tol(dtype)
+    y6 = ops.gemm(A, B, zin=gd, zmode=L.ACT_MUL)
+    assert rel(y6.float(), (A.float() @ B.float().t()) * gd.float()) < tol(dtype)
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
