@@ -104,17 +104,6 @@ __device__ __forceinline__ void load_halo(uint32_t tile_s, uint64_t* bar, const 
   mbar_wait(bar, 0);
 }
 
-// sum over the P channel pairs of every pixel: part[pixel][pair] -> stat[pixel]; one warp per pixel
-__device__ __forceinline__ void reduce_pixels(const float* part, float* stat, int npix, int P) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int p = warp; p < npix; p += nw) {
-    float s = 0.f;
-    for (int k = lane; k < P; k += 32) s += part[p * P + k];
-    s = warp_sum(s);
-    if (lane == 0) stat[p] = s;
-  }
-}
-
 // MODE 0: forward  y = LN(conv(x) + bias)  (xhat, optional affine), rstd saved
 // MODE 1: dgrad    y = corr(x = dconv, flipped taps) + res
 template <typename T, typename TO, int TW, int MODE, bool BIG>
@@ -198,33 +187,63 @@ __global__ void __launch_bounds__(BIG ? 512 : (MODE == 0 ? 384 : 448), BIG ? 1 :
     continue;
   }
 
-  // ---- LayerNorm over channels (per pixel): round 1 mean, round 2 centred variance
+  // ---- LayerNorm over channels (per pixel): round 1 mean, round 2 centred variance.
+  // Each thread folds its two channels, adjacent pair-lanes fold once more by shuffle (P is even, so lane^1 is the same
+  // row's neighbouring pair), even pairs write part[pair/2][pixel]; then ONE THREAD PER PIXEL sums the P/2 partials with
+  // loads (nsl adjacent lanes per pixel when the pass has fewer pixels than threads, folded by shuffle).
   const float invC = 1.f / (float)g.C;
   const int npix = g.TR * TW;
-  if (active) {
+  const int PH = g.P >> 1;
+  const bool writer = active && !(pr & 1);
+  // reduction mapping: nsl (power of two) adjacent lanes share one pixel and split its P/2 partials
+  int nsl = 1;
+  while (nsl < 32 && nsl * 2 * npix <= (int)blockDim.x && nsl * 2 <= PH) nsl <<= 1;
+  const int rp = (int)threadIdx.x / nsl, rslice = (int)threadIdx.x & (nsl - 1);
+  float* prow = part + (size_t)(pr >> 1) * npix + trow * TW;
 #pragma unroll
-    for (int i = 0; i < TW; ++i) part[(trow * TW + i) * g.P + pr] = lo2(acc[i]) + hi2(acc[i]);
+  for (int i = 0; i < TW; ++i) {
+    float v = lo2(acc[i]) + hi2(acc[i]);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (writer) prow[i] = v;
   }
   __syncthreads();
-  reduce_pixels(part, stat, npix, g.P);
+  {
+    float a0 = 0.f, a1 = 0.f;
+    if (rp < npix) {
+      int k = rslice;
+      for (; k + nsl < PH; k += 2 * nsl) { a0 += part[(size_t)k * npix + rp]; a1 += part[(size_t)(k + nsl) * npix + rp]; }
+      if (k < PH) a0 += part[(size_t)k * npix + rp];
+    }
+    a0 += a1;
+    for (int o = nsl >> 1; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    if (rp < npix && rslice == 0) stat[rp] = a0 * invC;
+  }
   __syncthreads();
   float mean[TW];
-  if (active) {
 #pragma unroll
-    for (int i = 0; i < TW; ++i) {
-      mean[i] = stat[trow * TW + i] * invC;
-      const float d0 = lo2(acc[i]) - mean[i], d1 = hi2(acc[i]) - mean[i];
-      part[(trow * TW + i) * g.P + pr] = d0 * d0 + d1 * d1;
-    }
+  for (int i = 0; i < TW; ++i) {
+    mean[i] = active ? stat[trow * TW + i] : 0.f;
+    const float d0 = lo2(acc[i]) - mean[i], d1 = hi2(acc[i]) - mean[i];
+    float v = d0 * d0 + d1 * d1;
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    if (writer) prow[i] = v;
   }
   __syncthreads();
-  reduce_pixels(part, stat + npix, npix, g.P);
-  __syncthreads();
-  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
-    const float r = rsqrtf(stat[npix + p] * invC + eps);
-    stat[npix + p] = r;
-    const int py = y0 + r0 + p / TW, px = x0 + p % TW;
-    if (rstd_out && r0 + p / TW < g.TH && py < g.H && px < g.W) rstd_out[((size_t)b * g.H + py) * g.W + px] = r;
+  {
+    float a0 = 0.f, a1 = 0.f;
+    if (rp < npix) {
+      int k = rslice;
+      for (; k + nsl < PH; k += 2 * nsl) { a0 += part[(size_t)k * npix + rp]; a1 += part[(size_t)(k + nsl) * npix + rp]; }
+      if (k < PH) a0 += part[(size_t)k * npix + rp];
+    }
+    a0 += a1;
+    for (int o = nsl >> 1; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    if (rp < npix && rslice == 0) {
+      const float r = rsqrtf(a0 * invC + eps);
+      stat[npix + rp] = r;
+      const int py = y0 + r0 + rp / TW, px = x0 + rp % TW;
+      if (rstd_out && r0 + rp / TW < g.TH && py < g.H && px < g.W) rstd_out[((size_t)b * g.H + py) * g.W + px] = r;
+    }
   }
   __syncthreads();
   if (active && oy < g.H) {
