@@ -179,9 +179,14 @@ __global__ void __launch_bounds__(BIG ? 512 : (MODE == 0 ? 384 : 448), BIG ? 1 :
       // all TW residual loads are issued back to back (one latency per row, not one per pixel), then add + store
 #pragma unroll
       for (int i = 0; i < TW; ++i) r[i] = (res && x0 + i < g.W) ? ldg_pair<TO>(res + off0 + (size_t)i * g.C) : 0ull;
+      T* ysh = reinterpret_cast<T*>(rstd_out);      // MODE 1: the rstd slot carries an optional compute-dtype copy of dx
 #pragma unroll
       for (int i = 0; i < TW; ++i) {
-        if (x0 + i < g.W) stg_pair<TO>(y + off0 + (size_t)i * g.C, lo2(acc[i]) + lo2(r[i]), hi2(acc[i]) + hi2(r[i]));
+        if (x0 + i < g.W) {
+          const float v0 = lo2(acc[i]) + lo2(r[i]), v1 = hi2(acc[i]) + hi2(r[i]);
+          stg_pair<TO>(y + off0 + (size_t)i * g.C, v0, v1);
+          if (ysh) stg_pair<T>(ysh + off0 + (size_t)i * g.C, v0, v1);
+        }
       }
     }
     continue;
@@ -490,9 +495,17 @@ extern "C" int ga_dwconv7_ln_fwd(const void* x, const float* w49c, const float* 
 
 extern "C" int ga_dwconv7_bwd_parts(int B, int H, int W, int C) { return 32; }
 
+extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
+                               float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype, int res_dtype,
+                               ga_stream_t s);
 extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, float* dw49c,
                               float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype, int res_dtype,
                               ga_stream_t s) {
+  return ga_dwconv7_bwd2(dconv, x, dres, w49c, dx, nullptr, dw49c, dbias, dw_partial, B, H, W, C, dtype, res_dtype, s);
+}
+extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
+                               float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype, int res_dtype,
+                               ga_stream_t s) {
   cudaStream_t st = (cudaStream_t)s;
   GA_REQUIRE(dconv && w49c && B > 0, GA_ERR_SHAPE, "ga_dwconv7_bwd: bad arguments");
   GA_REQUIRE(((uintptr_t)dconv & 15) == 0 && ((uintptr_t)w49c & 7) == 0, GA_ERR_ALIGN, "ga_dwconv7_bwd: misaligned operands");
@@ -505,9 +518,9 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
     rc = dw::make_x_map(dconv, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
     if (rc) return rc;
     GA_REQUIRE(dtype == GA_BF16 || res_dtype == GA_F32, GA_ERR_UNSUPPORTED, "ga_dwconv7_bwd: fp32 gradients need an fp32 residual stream");
-    if (dtype == GA_BF16 && res_dtype == GA_BF16) rc = dw::launch_conv<bf16, bf16, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, nullptr, 0.f, st);
-    else if (dtype == GA_BF16) rc = dw::launch_conv<bf16, float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, nullptr, 0.f, st);
-    else rc = dw::launch_conv<float, float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, nullptr, 0.f, st);
+    if (dtype == GA_BF16 && res_dtype == GA_BF16) rc = dw::launch_conv<bf16, bf16, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, (float*)dx_shadow, 0.f, st);
+    else if (dtype == GA_BF16) rc = dw::launch_conv<bf16, float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, (float*)dx_shadow, 0.f, st);
+    else rc = dw::launch_conv<float, float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, (float*)dx_shadow, 0.f, st);
     if (rc) return rc;
   }
   if (dw49c || dbias) {

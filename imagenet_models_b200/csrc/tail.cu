@@ -505,6 +505,77 @@ __global__ void __launch_bounds__(256) attnpool_bwd_kernel(const float* __restri
     }
   }
 }
+// backward, coalesced form: one CTA per image; work items (key n, head h) with h fastest, so adjacent threads touch
+// adjacent head segments of the same token row (the old warp-per-(image, head) form strode lanes over rows: 2-byte accesses
+// 3 KB apart).  Reductions over keys (softmax row dot, dq) go through shared-memory atomics.
+template <typename T, int HD_MAX>
+__global__ void __launch_bounds__(256) attnpool_bwd2_kernel(const float* __restrict__ dout, const float* __restrict__ q,
+                                                            const float* __restrict__ kvc, const T* __restrict__ kvt,
+                                                            const float* __restrict__ attn, float* __restrict__ dq, float* __restrict__ dkvc,
+                                                            T* __restrict__ dkvt, int B, int Q, int N, int H, int E, long long ldt,
+                                                            long long lddt) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x;
+  const int hd = E / H, NK = Q + N, items = NK * H;
+  float* da_s = sm;                 // [NK*H]
+  float* rowdot = da_s + items;     // [H]
+  float* dq_s = rowdot + H;         // [E]
+  float* q_s = dq_s + E;            // [E]
+  float* do_s = q_s + E;            // [E]
+  for (int qi = 0; qi < Q; ++qi) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) {
+      q_s[i] = q[((long long)b * Q + qi) * E + i];
+      do_s[i] = dout[((long long)b * Q + qi) * E + i];
+      dq_s[i] = 0.f;
+    }
+    if (threadIdx.x < H) rowdot[threadIdx.x] = 0.f;
+    __syncthreads();
+    const float* arow = attn + ((long long)b * H * Q + qi) * NK;     // + h * Q * NK
+    for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
+      const int n = idx / H, h = idx - n * H;
+      float da = 0.f;
+      if (n < Q) {
+        const float* vp = kvc + ((long long)b * Q + n) * 2 * E + E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) da += do_s[h * hd + d] * vp[d];
+      } else {
+        const T* vp = kvt + ((long long)b * N + (n - Q)) * ldt + E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) da += do_s[h * hd + d] * ld_f(vp + d);
+      }
+      da_s[idx] = da;
+      atomicAdd(rowdot + h, arow[(long long)h * Q * NK + n] * da);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
+      const int n = idx / H, h = idx - n * H;
+      const float a = arow[(long long)h * Q * NK + n];
+      const float ds = a * (da_s[idx] - rowdot[h]);
+      if (n < Q) {
+        const float* kp = kvc + ((long long)b * Q + n) * 2 * E + h * hd;
+        float* gp = dkvc + ((long long)b * Q + n) * 2 * E + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) {
+          const float pk = qi == 0 ? 0.f : gp[d], pv = qi == 0 ? 0.f : gp[E + d];
+          gp[d] = pk + ds * q_s[h * hd + d]; gp[E + d] = pv + a * do_s[h * hd + d];
+          atomicAdd(dq_s + h * hd + d, ds * kp[d]);
+        }
+      } else {
+        const T* kp = kvt + ((long long)b * N + (n - Q)) * ldt + h * hd;
+        T* gp = dkvt + ((long long)b * N + (n - Q)) * lddt + h * hd;
+#pragma unroll
+        for (int d = 0; d < HD_MAX; ++d) if (d < hd) {
+          const float pk = qi == 0 ? 0.f : ld_f(gp + d), pv = qi == 0 ? 0.f : ld_f(gp + E + d);
+          st_f(gp + d, pk + ds * q_s[h * hd + d]); st_f(gp + E + d, pv + a * do_s[h * hd + d]);
+          atomicAdd(dq_s + h * hd + d, ds * ld_f(kp + d));
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < E; i += blockDim.x) dq[((long long)b * Q + qi) * E + i] = dq_s[i];
+  }
+}
 extern "C" int ga_attnpool_bwd(const float* dout, const float* q, const float* kv_cls, const void* kv_tok, const float* attn,
                                float* dq, float* dkv_cls, void* dkv_tok, int B, int Q, int N, int H, int E, long long ldt,
                                long long lddt, int dtype, ga_stream_t s) {
@@ -512,6 +583,11 @@ extern "C" int ga_attnpool_bwd(const float* dout, const float* q, const float* k
              "ga_attnpool_bwd: bad arguments");
   GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_bwd: head_dim %d > 32", E / H);
   if (B == 0) return GA_OK;
+  const size_t smem = ((size_t)(Q + N) * H + H + 3 * (size_t)E) * sizeof(float);
+  if (smem <= 48 * 1024) {
+    DISPATCH_T(dtype, { attnpool_bwd2_kernel<T, 32><<<B, 256, smem, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt); });
+    return launch_ok("attnpool_bwd2");
+  }
   const int grid = (B * H + 7) / 8;
   DISPATCH_T(dtype, { attnpool_bwd_kernel<T, 32><<<grid, 256, 0, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt); });
   return launch_ok("attnpool_bwd");

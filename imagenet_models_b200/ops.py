@@ -325,6 +325,29 @@ def grouped_linear(A3, W3, bias=None, act=ACT_NONE, out_dtype=None):
 
 
 # ------------------------------------------------------------------------------------------------- ConvNeXt block
+# The backward of block i+1 produces the stream gradient dx in fp32 AND (same kernel) its bf16 copy; block i's backward
+# needs exactly that copy as a GEMM operand.  autograd only carries dx, so the copy waits here, keyed by the tensor object
+# and its version counter: if autograd accumulated another gradient into dx (in place -> version bump, or out of place
+# -> a different tensor) the entry does not match and the copy is recomputed.  Cleared at every zero_grad.
+_shadow = {}
+
+
+def _offer_shadow(t, ts):
+    if ts is not None:
+        _shadow[id(t)] = (t, t._version, ts)
+
+
+def _take_shadow(t, T):
+    ent = _shadow.pop(id(t), None)
+    if ent is not None and ent[0] is t and ent[1] == t._version and ent[2].dtype == T:
+        return ent[2]
+    return convert(t, T)
+
+
+def clear_shadows():
+    _shadow.clear()
+
+
 class ConvNeXtBlockFn(Function):
     """dw7x7 -> LN -> fc1 -> GELU -> fc2 -> *gamma -> drop-path -> +x  on NHWC rows  (ga_convnext.py:98-112).
 
@@ -381,7 +404,7 @@ class ConvNeXtBlockFn(Function):
         dy = dy.contiguous()
         if dys_in is not None:                      # gradient that arrived through the bf16 shadow (stage boundaries)
             dy = dy + dys_in                        # type promotion keeps the sum in the stream dtype
-        dys = convert(dy, T) if RT != T else dy     # bf16 operand copy of the stream gradient
+        dys = _take_shadow(dy, T) if RT != T else dy     # bf16 operand copy of the stream gradient
         if path_scale is not None:
             t = torch.empty_like(dys)
             L.check(lib.ga_scale_rows(L.ptr(dys), L.ptr(path_scale), L.ptr(t), L.ll(M), Cc, H * W_, L.dt(dys), L.stream()),
@@ -414,10 +437,12 @@ class ConvNeXtBlockFn(Function):
         L.check(lib.ga_ln_bwd_rows(L.ptr(dxhat), L.ptr(xhat), L.ptr(rstd), L.ptr(dconv), L.ll(M), Cc, L.dt(dconv), L.stream()),
                 'ga_ln_bwd_rows')
         dx = torch.empty(M, Cc, dtype=RT, device=dev)
+        dxs = torch.empty(M, Cc, dtype=T, device=dev) if RT != T else None
         parts = lib.ga_dwconv7_bwd_parts(Bn, H, W_, Cc)
         ws = workspace(parts * 50 * Cc, dev, 'dwconv')
-        L.check(lib.ga_dwconv7_bwd(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(d49), L.ptr(ddwb), L.ptr(ws),
-                                   Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream()), 'ga_dwconv7_bwd')
+        L.check(lib.ga_dwconv7_bwd2(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(dxs), L.ptr(d49), L.ptr(ddwb),
+                                    L.ptr(ws), Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream()), 'ga_dwconv7_bwd')
+        _offer_shadow(dx, dxs)
         d_dw_w = d49.view(49, Cc).t().reshape(Cc, 1, 7, 7)
         return (dx, None, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None, None)
 

@@ -66,6 +66,8 @@ class FlatState:
         one accumulate kernel per parameter; gather() collects them into the flat buffer in one launch."""
         for p in self.params:
             p.grad = None
+        from . import ops
+        ops.clear_shadows()
 
     def _table(self, members):
         key = tuple(members)

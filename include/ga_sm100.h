@@ -84,6 +84,12 @@ int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres, const flo
                    float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype,
                    int res_dtype /* dtype of dres and dx: the residual-stream gradient */, ga_stream_t s);
 
+/* same, additionally writing dx_shadow (may be NULL): dx in the compute dtype `dtype`, the operand copy the previous
+ * block's backward GEMMs read (saves a separate fp32 -> bf16 pass over the stream gradient) */
+int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
+                    float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype,
+                    int res_dtype, ga_stream_t s);
+
 /* ---- row LayerNorm over the last dim (LayerNorm2d on NHWC rows, nn.LayerNorm)  (ga_convnext.py:51-67,233,237) */
 int ga_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,
                      long long M, int C, long long ldx, long long ldy, float eps, int dtype, ga_stream_t s);
