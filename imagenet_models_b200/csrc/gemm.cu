@@ -459,7 +459,8 @@ enum { EPI_GENERIC = 0, EPI_BIAS_GELU_Z = 1, EPI_BIAS_GELU = 2, EPI_RES_F32_SHAD
 
 // one 32-row x 32-column chunk held in this warp's staging buffer -> global memory
 template <int EPI, bool FULL>
-__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st, int lane, int batch, int m_base, int n) {
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st, int lane, int batch, int m_base, int n,
+                                               const uint2* zraw = nullptr) {
   // lane -> 4 columns (lane & 7) * 4 of rows (lane >> 3) + 4 * it, it = 0..7
   const int cl = (lane & 7) * 4;
   const int r0 = lane >> 3;
@@ -503,6 +504,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st
         pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (FULL || m < e.M) {
           if (EPI == EPI_RES_F32_SHADOW) pre[j] = ld4((const float*)e.R + (long long)batch * e.r_bs + (long long)m * e.ldr + n);
+          else if (zraw) { const uint2 u = zraw[g4 * 4 + j]; pre[j] = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y)); }
           else pre[j] = ld4((const bf16*)e.Zin + (long long)batch * e.z_bs + (long long)m * e.ldz + n);
         }
       }
@@ -664,10 +666,26 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
       const int batch = z / p.splits;
       const int m0 = m_t * BM, n0 = n_t * BN;
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
+      // x act'(z) epilogue: fetch this warp's share of the saved derivative BEFORE waiting for the accumulator, so the
+      // HBM latency of the per-element operand hides behind the MMA of this tile (it was exposed once per chunk)
+      uint2 zraw[SLICE / EPI_C][8];
+      if (EPI == EPI_ZIN_GELU) {
+#pragma unroll
+        for (int c = 0; c < SLICE / EPI_C; ++c) {
+          const int ncol = n0 + slice * SLICE + c * EPI_C + (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int m = m0 + q * 32 + (lane >> 3) + 4 * it;
+            zraw[c][it] = make_uint2(0u, 0u);
+            if (m < e.M && ncol < e.N)
+              zraw[c][it] = *reinterpret_cast<const uint2*>((const bf16*)e.Zin + (long long)batch * e.z_bs + (long long)m * e.ldz + ncol);
+          }
+        }
+      }
       mbar_wait_backoff(&tmem_full[buf], bph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < SLICE / EPI_C; ++c) {
         const int col0 = slice * SLICE + c * EPI_C;
         const bool live = (n0 + col0 < e.N);
@@ -688,8 +706,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
         }
         if (!live) continue;
         __syncwarp();
-        if (m0 + q * 32 + 32 <= e.M) epilogue_chunk<EPI, true>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4);
-        else epilogue_chunk<EPI, false>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4);
+        if (m0 + q * 32 + 32 <= e.M) epilogue_chunk<EPI, true>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4, EPI == EPI_ZIN_GELU ? zraw[c] : nullptr);
+        else epilogue_chunk<EPI, false>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4, EPI == EPI_ZIN_GELU ? zraw[c] : nullptr);
         __syncwarp();
       }
     }

@@ -52,7 +52,7 @@ def gemm_cases():
         bias = torch.randn(N, device=DEV)
         if gelu:
             out = torch.empty(M, N, device=DEV, dtype=bf)
-            fn = lambda: ops.gemm(A, W, out, bias=bias, act=L.ACT_GELU, save_z=True)
+            fn = lambda: ops.gemm(A, W, out, bias=bias, act=L.ACT_GELU, save_z='grad')
             byts = M * K * 2 + 2 * M * N * 2
         elif res:
             x = torch.randn(M, N, device=DEV)
@@ -72,7 +72,7 @@ def gemm_cases():
         W = torch.randn(K, N, device=DEV, dtype=bf) * 0.05    # B(n,k) = W[k,n]  (MN-major)
         z = torch.randn(M, N, device=DEV, dtype=bf)
         out = torch.empty(M, N, device=DEV, dtype=bf)
-        cases[name] = (lambda: ops.gemm(dy, W.t(), out, zin=z, zmode=L.ACT_GELU), M * K * 2 + 2 * M * N * 2, 2.0 * M * K * N)
+        cases[name] = (lambda: ops.gemm(dy, W.t(), out, zin=z, zmode=L.ACT_MUL), M * K * 2 + 2 * M * N * 2, 2.0 * M * K * N)
 
     def wgrad(name, M, N, K):
         dY = torch.randn(M, N, device=DEV, dtype=bf)
