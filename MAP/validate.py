@@ -17,7 +17,8 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import imagenet_models_b200.ga_convnext  # noqa: F401,E402
 import imagenet_models_b200.map_convnext  # noqa: F401,E402
-from imagenet_models_b200.engine import evaluate_batch  # noqa: E402
+import imagenet_models_b200.ga_cswin  # noqa: F401,E402
+from imagenet_models_b200.engine import EvalEngine  # noqa: E402
 from imagenet_models_b200.registry import create_model  # noqa: E402
 
 parser = argparse.ArgumentParser(description='validation on B200 (flags follow MAP/validate.py:49-125)')
@@ -30,6 +31,7 @@ parser.add_argument('--checkpoint', default='', type=str)
 parser.add_argument('--amp', action='store_true', default=False)
 parser.add_argument('--channels-last', action='store_true', default=True)
 parser.add_argument('--results-file', default='', type=str)
+parser.add_argument('--no-graph', action='store_true', help='run every batch eagerly instead of replaying a CUDA graph')
 
 
 def main():
@@ -50,12 +52,14 @@ def main():
     if args.channels_last:
         x = x.contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, model.num_classes, (B,), device='cuda', generator=g)
-    evaluate_batch(model, x, y, reduce, amp)                 # warm-up forward (MAP/validate.py:240-244)
+    engine = EvalEngine(model, reduce, amp, cuda_graph=not args.no_graph)
+    for _ in range(4):
+        engine(x, y)                                         # warm-up forwards (MAP/validate.py:240-244) + graph capture
     torch.cuda.synchronize()
     acc = torch.zeros(4, device='cuda')
     t0 = time.time()
     for _ in range(args.num_batches):
-        acc += torch.stack([t.float() for t in evaluate_batch(model, x, y, reduce, amp)])   # stays on the device
+        acc += torch.stack([t.float() for t in engine(x, y)])   # stays on the device
     if distributed:
         dist.all_reduce(acc)
     torch.cuda.synchronize()

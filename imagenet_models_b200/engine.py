@@ -129,4 +129,39 @@ def evaluate_batch(model, x, y, reduce: str = 'sum', amp_dtype=torch.bfloat16):
     loss = torch.nn.functional.cross_entropy(logits, y)
     _, pred = logits.topk(5, 1, True, True)           # timm.utils.accuracy
     hit = pred.eq(y.view(-1, 1))
-    return loss, hit[:, :1].sum(), hit.sum(), torch.tensor(y.numel(), device=y.device)
+    return loss, hit[:, :1].sum(), hit.sum(), torch.full((), y.numel(), dtype=torch.int64, device=y.device)   # no H2D copy: graph-safe
+
+
+class EvalEngine:
+    """validate()'s loop body with the forward captured in a CUDA graph per input shape (MAP/validate.py:250-311,
+    GA/train.py:838-868).  Small-batch inference is launch-bound (a T-688 forward is ~450 kernels): a replay costs one
+    launch.  __call__(x, y) -> (loss, correct@1, correct@5, count) device tensors, valid until the next call."""
+
+    def __init__(self, model, reduce: str = 'sum', amp_dtype=torch.bfloat16, cuda_graph: bool = True, graph_warmup: int = 2):
+        self.model, self.reduce, self.amp_dtype = model.eval(), reduce, amp_dtype
+        self.cuda_graph, self.graph_warmup = cuda_graph, graph_warmup
+        self._graphs = {}          # (shape, dtype) -> (graph, static x, static y, static outputs)
+        self._seen = {}
+
+    def __call__(self, x, y):
+        if not self.cuda_graph:
+            return evaluate_batch(self.model, x, y, self.reduce, self.amp_dtype)
+        key = (tuple(x.shape), x.dtype, tuple(x.stride()))
+        ent = self._graphs.get(key)
+        if ent is None:
+            n = self._seen.get(key, 0)
+            self._seen[key] = n + 1
+            if n < self.graph_warmup:
+                return evaluate_batch(self.model, x, y, self.reduce, self.amp_dtype)
+            sx, sy = torch.empty_strided(x.shape, x.stride(), dtype=x.dtype, device=x.device), torch.empty_like(y)
+            sx.copy_(x)
+            sy.copy_(y)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = evaluate_batch(self.model, sx, sy, self.reduce, self.amp_dtype)
+            ent = self._graphs[key] = (g, sx, sy, out)
+        else:
+            ent[1].copy_(x, non_blocking=True)
+            ent[2].copy_(y, non_blocking=True)
+        ent[0].replay()
+        return ent[3]

@@ -93,7 +93,8 @@ def gemm_cases():
 
 
 def dwconv_cases():
-    bf = torch.bfloat16
+    bf = torch.float32 if os.environ.get('DW_DTYPE') == 'f32' else torch.bfloat16
+    DT = L.F32 if bf == torch.float32 else L.BF16
     lib = L.load()
     cases = {}
     for s, (hw, c) in enumerate([(56, 96), (28, 192), (14, 384), (7, 688)]):
@@ -111,15 +112,15 @@ def dwconv_cases():
 
         def f_fwd(x=x, w=w, b=b, y=y, rstd=rstd, hw=hw, c=c):
             L.check(lib.ga_dwconv7_ln_fwd(L.ptr(x), L.ptr(w), L.ptr(b), None, None, L.ptr(y), L.ptr(rstd), B, hw, hw, c, L.f(1e-6),
-                                          L.BF16, L.stream()), 'fwd')
+                                          DT, L.stream()), 'fwd')
 
         def f_dgrad(x=x, w=w, dres=dres, dx=dx, hw=hw, c=c):
-            L.check(lib.ga_dwconv7_bwd(L.ptr(x), None, L.ptr(dres), L.ptr(w), L.ptr(dx), None, None, None, B, hw, hw, c, L.BF16,
+            L.check(lib.ga_dwconv7_bwd(L.ptr(x), None, L.ptr(dres), L.ptr(w), L.ptr(dx), None, None, None, B, hw, hw, c, DT,
                                        L.F32, L.stream()), 'dgrad')
 
         def f_wgrad(x=x, y=y, w=w, d49=d49, db=db, ws=ws, hw=hw, c=c):
             L.check(lib.ga_dwconv7_bwd(L.ptr(y), L.ptr(x), None, L.ptr(w), None, L.ptr(d49), L.ptr(db), L.ptr(ws), B, hw, hw, c,
-                                       L.BF16, L.F32, L.stream()), 'wgrad')
+                                       DT, L.F32, L.stream()), 'wgrad')
         fl = 2.0 * 49 * M * c
         cases[f's{s}_dw_fwd'] = (f_fwd, M * c * 4 + M * 4, fl)
         cases[f's{s}_dw_dgrad'] = (f_dgrad, M * c * (2 + 4 + 4), fl)
