@@ -27,7 +27,8 @@ TRAIN_GFLOP_PER_IMG = 32.73      # BASELINE.md section 4 (3 x 10.909 forward)
 TRAIN_MB_PER_IMG = 268.0         # GEMM-boundary-fusion convention, bf16
 GA_LAM = -0.8
 # dram__bytes_read+write per launch from profiles/r01_ncu_fc1_gelu.txt (ncu --set full) for the stage-0 fc1+GELU GEMM
-NCU_TRAFFIC = {(802816, 384, 96, 'gelu+z'): 1333.1e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/r01_ncu_gemm_sites.txt)
+NCU_TRAFFIC = {(802816, 384, 96, 'gelu+z'): 1333.5e6, (802816, 384, 96, 'lin+zin'): 1360.3e6}
 
 
 def peaks():
