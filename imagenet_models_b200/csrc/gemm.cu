@@ -899,7 +899,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
     g_last_backend = GA_BACKEND_TCGEN05;
     static int v1_env = -1;
     if (v1_env < 0) { const char* sv = getenv("GA_GEMM_V1"); v1_env = (sv && atoi(sv)) ? 1 : 0; }
-    const bool wide = g->N > 64;
+    const bool wide = g->N > 32;   // N in (32, 64] also takes the persistent kernel (half of a BN=128 tile idle; these GEMMs are HBM-bound)
     const bool wide256 = (g->N >= 512) || (g->N % 256 == 0);
     // compile-time specialised epilogues for the ConvNeXt-block GEMMs (vector path: widths and pitches multiples of 4)
     const bool v4 = ((g->N & 3) == 0) && ((g->ldd & 3) == 0) && e.d_cs == 1 && g->alpha == 1.0f;

@@ -55,12 +55,77 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
   }
 }
 
+// narrow rows (C <= 128: CSWin stem / stage 1-2, ConvNeXt stem): LPR lanes per row, 32/LPR rows per warp, ROWS rows in flight
+// per lane group so a warp keeps ROWS*32 128-bit loads outstanding instead of C/4
+template <typename T, int LPR, int ROWS>
+__global__ void __launch_bounds__(256) layernorm_fwd_narrow_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                                   const float* __restrict__ b, T* __restrict__ y,
+                                                                   float* __restrict__ mean_o, float* __restrict__ rstd_o,
+                                                                   long long M, int C, long long ldx, long long ldy, float eps) {
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  const int c = sub * 4;
+  const bool cok = c < C;
+  const float invC = 1.f / (float)C;
+  float4 ww = make_float4(1.f, 1.f, 1.f, 1.f), bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (w && cok) { ww = *reinterpret_cast<const float4*>(w + c); bb = *reinterpret_cast<const float4*>(b + c); }
+  // the trip count must be warp-uniform: the shuffles below name all 32 lanes
+  for (long long base = gw * G * ROWS; base < M; base += nw * G * ROWS) {
+    const long long r0 = base + (long long)grp * ROWS;
+    float4 v[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) v[r] = (cok && r0 + r < M) ? ld4(x + (r0 + r) * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mu[ROWS], rs[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) mu[r] = (v[r].x + v[r].y) + (v[r].z + v[r].w);
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) mu[r] += __shfl_xor_sync(0xffffffffu, mu[r], o);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      mu[r] *= invC;
+      const float a = v[r].x - mu[r], b2 = v[r].y - mu[r], c2 = v[r].z - mu[r], d = v[r].w - mu[r];
+      rs[r] = cok ? (a * a + b2 * b2) + (c2 * c2 + d * d) : 0.f;
+    }
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], o);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = r0 + r;
+      if (row >= M) continue;
+      const float rstd = rsqrtf(rs[r] * invC + eps);
+      if (sub == 0) { if (mean_o) mean_o[row] = mu[r]; if (rstd_o) rstd_o[row] = rstd; }
+      if (cok) {
+        float4 o = make_float4((v[r].x - mu[r]) * rstd, (v[r].y - mu[r]) * rstd, (v[r].z - mu[r]) * rstd, (v[r].w - mu[r]) * rstd);
+        o.x = o.x * ww.x + bb.x; o.y = o.y * ww.y + bb.y; o.z = o.z * ww.z + bb.z; o.w = o.w * ww.w + bb.w;
+        st4(y + row * ldy + c, o);
+      }
+    }
+  }
+}
+
 extern "C" int ga_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, long long M,
                                 int C, long long ldx, long long ldy, float eps, int dtype, ga_stream_t s) {
   GA_REQUIRE(x && y && M >= 0 && C > 0 && (C & 3) == 0 && (ldx & 3) == 0 && (ldy & 3) == 0, GA_ERR_ALIGN,
              "ga_layernorm_fwd: C=%d ldx=%lld ldy=%lld must be multiples of 4", C, ldx, ldy);
   GA_REQUIRE(C <= 2048, GA_ERR_UNSUPPORTED, "ga_layernorm_fwd: C=%d > 2048", C);
   if (M == 0) return GA_OK;
+  if (C <= 128) {
+    const int lpr = C <= 32 ? 8 : (C <= 64 ? 16 : 32);
+    long long blocks = (M + 8LL * (32 / lpr) * 4 - 1) / (8LL * (32 / lpr) * 4);
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    DISPATCH_T(dtype, {
+      if (lpr == 8) layernorm_fwd_narrow_kernel<T, 8, 4><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, mean, rstd, M, C, ldx, ldy, eps);
+      else if (lpr == 16) layernorm_fwd_narrow_kernel<T, 16, 4><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, mean, rstd, M, C, ldx, ldy, eps);
+      else layernorm_fwd_narrow_kernel<T, 32, 4><<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, mean, rstd, M, C, ldx, ldy, eps);
+    });
+    return launch_ok("layernorm_fwd_narrow");
+  }
   const unsigned grid = (unsigned)((M + 7) / 8);
   DISPATCH_T(dtype, {
     if (C <= 512) layernorm_fwd_kernel<T, 4><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, w, b, (T*)y, mean, rstd, M, C, ldx, ldy, eps);
@@ -146,6 +211,80 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   }
 }
 
+// narrow rows (C <= 128): LPR lanes per row, ROWS rows in flight per lane group (see layernorm_fwd_narrow_kernel)
+template <typename T, int LPR, int ROWS>
+__global__ void __launch_bounds__(256) layernorm_bwd_narrow_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                   const float* __restrict__ w, const float* __restrict__ mean,
+                                                                   const float* __restrict__ rstd, T* __restrict__ dx,
+                                                                   float* __restrict__ partial, long long M, int C, long long lddy,
+                                                                   long long ldx, long long lddx, int x_is_hat, int rows_per_cta) {
+  extern __shared__ float sacc[];  // [2][C]
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (partial) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+  }
+  const int c = sub * 4;
+  const bool cok = c < C;
+  const float invC = 1.f / (float)C;
+  float4 ww = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (w && cok) ww = *reinterpret_cast<const float4*>(w + c);
+  float4 dwv = make_float4(0, 0, 0, 0), dbv = make_float4(0, 0, 0, 0);
+  const long long rbeg = (long long)blockIdx.x * rows_per_cta;
+  long long rend = rbeg + rows_per_cta;
+  if (rend > M) rend = M;
+  // the trip count must be warp-uniform: the shuffles below name all 32 lanes
+  for (long long base = rbeg + (long long)wid * G * ROWS; base < rend; base += (long long)nw * G * ROWS) {
+    const long long r0 = base + (long long)grp * ROWS;
+    float4 g[ROWS], xh[ROWS];
+    float rs[ROWS], s1[ROWS], s2[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = r0 + r;
+      const bool ok = cok && row < rend;
+      g[r] = ok ? ld4(dy + row * lddy + c) : make_float4(0, 0, 0, 0);
+      xh[r] = ok ? ld4(x + row * ldx + c) : make_float4(0, 0, 0, 0);
+      rs[r] = row < rend ? rstd[row] : 0.f;
+      if (!x_is_hat && ok) {
+        const float mu = mean[row];
+        xh[r].x = (xh[r].x - mu) * rs[r]; xh[r].y = (xh[r].y - mu) * rs[r]; xh[r].z = (xh[r].z - mu) * rs[r]; xh[r].w = (xh[r].w - mu) * rs[r];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      dwv.x += g[r].x * xh[r].x; dwv.y += g[r].y * xh[r].y; dwv.z += g[r].z * xh[r].z; dwv.w += g[r].w * xh[r].w;
+      dbv.x += g[r].x; dbv.y += g[r].y; dbv.z += g[r].z; dbv.w += g[r].w;
+      g[r].x *= ww.x; g[r].y *= ww.y; g[r].z *= ww.z; g[r].w *= ww.w;
+      s1[r] = (g[r].x + g[r].y) + (g[r].z + g[r].w);
+      s2[r] = (g[r].x * xh[r].x + g[r].y * xh[r].y) + (g[r].z * xh[r].z + g[r].w * xh[r].w);
+    }
+#pragma unroll
+    for (int o = LPR >> 1; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+        s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+      }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const long long row = r0 + r;
+      if (!cok || row >= rend) continue;
+      const float m1 = s1[r] * invC, m2 = s2[r] * invC;
+      st4(dx + row * lddx + c, make_float4(rs[r] * (g[r].x - m1 - xh[r].x * m2), rs[r] * (g[r].y - m1 - xh[r].y * m2),
+                                           rs[r] * (g[r].z - m1 - xh[r].z * m2), rs[r] * (g[r].w - m1 - xh[r].w * m2)));
+    }
+  }
+  if (partial) {
+    if (cok) {
+      atomicAdd(&sacc[c], dwv.x); atomicAdd(&sacc[c + 1], dwv.y); atomicAdd(&sacc[c + 2], dwv.z); atomicAdd(&sacc[c + 3], dwv.w);
+      atomicAdd(&sacc[C + c], dbv.x); atomicAdd(&sacc[C + c + 1], dbv.y); atomicAdd(&sacc[C + c + 2], dbv.z); atomicAdd(&sacc[C + c + 3], dbv.w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * C + i] = sacc[i];
+  }
+}
+
 // out0[j] += sum_p partial[p][j] (j < n0), out1[j-n0] += ... (j >= n0)
 // block = 32 columns x 8 part-slices (256 threads); launch with grid ((n + 31) / 32)
 __global__ void __launch_bounds__(256) reduce_parts2_kernel(const float* __restrict__ partial, int nparts, int n,
@@ -199,11 +338,16 @@ extern "C" int ga_layernorm_bwd(const void* dy, const void* x, const float* w, c
   const int rows_per_cta = (int)((M + parts - 1) / parts);
   const size_t smem = want_param ? (size_t)2 * C * sizeof(float) : 0;
   const int x_is_hat = (mean == nullptr);
+#define GA_LNB_NARROW(LPR) layernorm_bwd_narrow_kernel<T, LPR, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta)
   DISPATCH_T(dtype, {
-    if (C <= 512) layernorm_bwd_kernel<T, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
+    if (C <= 32) GA_LNB_NARROW(8);
+    else if (C <= 64) GA_LNB_NARROW(16);
+    else if (C <= 128) GA_LNB_NARROW(32);
+    else if (C <= 512) layernorm_bwd_kernel<T, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
     else if (C <= 1024) layernorm_bwd_kernel<T, 8><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
     else layernorm_bwd_kernel<T, 16><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
   });
+#undef GA_LNB_NARROW
   int rc = launch_ok("layernorm_bwd");
   if (rc || !want_param) return rc;
   reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, dw, C, db, 1);

@@ -188,7 +188,7 @@ def test_convnext_block_vs_golden(cname, dtype, golden_dir):
 
 
 # ------------------------------------------------------------------------------------------------- rows / columns
-@pytest.mark.parametrize('M,Cc', [(1000, 96), (333, 688), (50, 2048), (64, 1536)])
+@pytest.mark.parametrize('M,Cc', [(1000, 96), (333, 688), (50, 2048), (64, 1536), (1001, 64), (77, 32), (515, 128), (9, 24)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_layernorm_fwd_bwd(M, Cc, dtype):
     x = rnd(M, Cc, dtype=dtype, seed=30).requires_grad_(True)
