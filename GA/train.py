@@ -19,6 +19,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import imagenet_models_b200.ga_convnext  # noqa: F401,E402  (registers the ga_convnext_* factories)
 import imagenet_models_b200.map_convnext  # noqa: F401,E402  (registers map_convnext_tiny / _small)
+import imagenet_models_b200.ga_cswin  # noqa: F401,E402  (GA_CSWinTransformer, ga_CSWin_64_12211_tiny_224)
 from imagenet_models_b200.engine import TrainEngine, evaluate_batch  # noqa: E402
 from imagenet_models_b200.registry import create_model  # noqa: E402
 
@@ -49,6 +50,7 @@ parser.add_argument('--log-interval', type=int, default=50)
 parser.add_argument('--initial-checkpoint', default='', type=str)
 parser.add_argument('--output', default='', type=str, help='directory for last.pth.tar (state_dict, state_dict_ema, epoch)')
 parser.add_argument('--local_rank', default=0, type=int)
+parser.add_argument('--no-cuda-graph', action='store_true', help='run every step eagerly (default: replay one captured CUDA graph per step)')
 
 
 def main():
@@ -76,7 +78,8 @@ def main():
             dist.broadcast(t.data, 0)
     engine = TrainEngine(model, lr=args.lr, weight_decay=args.weight_decay, betas=tuple(args.opt_betas), eps=args.opt_eps,
                          ema_decay=args.model_ema_decay if args.model_ema else None, ga_lam=args.GA_lam,
-                         amp_dtype=torch.bfloat16 if args.amp else None, grad_accumulation=args.grad_accumulation)
+                         amp_dtype=torch.bfloat16 if args.amp else None, grad_accumulation=args.grad_accumulation,
+                         cuda_graph=not args.no_cuda_graph)
     B, S = args.batch_size, args.img_size
     g = torch.Generator(device='cuda').manual_seed(args.seed + rank)
     for epoch in range(args.epochs):
@@ -100,7 +103,7 @@ def main():
                                  f'Time: {dt / (it + 1):.3f}s, {B * world * (it + 1) / dt:>7.2f}/s  LR: {args.lr:.3e}')
         # validate on one synthetic batch (GA sums the branch logits, GA/train.py:848-851)
         model.eval()
-        stats = torch.stack([t.float() for t in evaluate_batch(model, x, y, 'sum', torch.bfloat16 if args.amp else None)])
+        stats = torch.stack([t.float() for t in evaluate_batch(model, x, y, 'mean' if args.model.startswith('map_') else 'sum', torch.bfloat16 if args.amp else None)])
         if distributed:
             stats[1:] = stats[1:].clone()
             dist.all_reduce(stats)
