@@ -124,6 +124,57 @@ __device__ __forceinline__ void gelu_both_f(float x, float* y, float* dy) {
   *y = fmaf(-fabsf(x), h, fmaxf(x, 0.f));
   *dy = fmaf(x * 0.39894228040143268f, ex, x >= 0.f ? 1.f - h : h);
 }
+// ---- the same on two values at once with Blackwell's packed fp32x2 FMA pipe instructions (fma/mul/add.f32x2: two
+// results per issue slot; the GELU epilogues are issue-bound).  Bit-identical to the scalar forms above.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) { return ((f32x2_t)__float_as_uint(hi) << 32) | (f32x2_t)__float_as_uint(lo); }
+__device__ __forceinline__ float f2_lo(f32x2_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f2_hi(f32x2_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f32x2_t f2_splat(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// y = gelu(x), dy = gelu'(x) for the pair (x0, x1); WANT_D = false skips the derivative
+template <bool WANT_D>
+__device__ __forceinline__ void gelu_pair(float x0, float x1, float* y0, float* y1, float* d0, float* d1) {
+  const f32x2_t SIGN = 0x8000000080000000ull;
+  const f32x2_t x = f2_pack(x0, x1);
+  const f32x2_t u = x & ~SIGN;                                                  // |x|
+  const f32x2_t tin = f2_fma(f2_splat(0.23164189f), u, f2_splat(1.f));
+  float t0, t1, e0, e1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(f2_lo(tin)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(f2_hi(tin)));
+  const f32x2_t ein = f2_mul(f2_mul(u, u), f2_splat(-0.72134752f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(f2_lo(ein)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(f2_hi(ein)));
+  const f32x2_t t = f2_pack(t0, t1), ex = f2_pack(e0, e1);
+  f32x2_t poly = f2_fma(f2_splat(0.5307027145f), t, f2_splat(-0.7265760135f));
+  poly = f2_fma(poly, t, f2_splat(0.7107068705f));
+  poly = f2_fma(poly, t, f2_splat(-0.142248368f));
+  poly = f2_fma(poly, t, f2_splat(0.127414796f));
+  const f32x2_t h = f2_mul(f2_mul(poly, t), ex);
+  const f32x2_t yv = f2_fma(u ^ SIGN, h, f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));   // relu(x) - |x| h
+  *y0 = f2_lo(yv); *y1 = f2_hi(yv);
+  if (WANT_D) {
+    // Phi = x >= 0 ? 1 - h : h  =  0.5 + copysign(0.5 - h, x)   (0 < h <= 0.5)
+    const f32x2_t q = f2_fma(h, f2_splat(-1.f), f2_splat(0.5f));
+    const f32x2_t cdf = f2_add(q ^ (x & SIGN), f2_splat(0.5f));
+    const f32x2_t dv = f2_fma(f2_mul(x, f2_splat(0.39894228040143268f)), ex, cdf);
+    *d0 = f2_lo(dv); *d1 = f2_hi(dv);
+  }
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float ex;
   const float h = gelu_h(x, &ex);

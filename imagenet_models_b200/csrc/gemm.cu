@@ -522,17 +522,17 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st
         if (EPI == EPI_BIAS_GELU_Z) {
           if (e.z_shadow == 2) {       // save gelu'(z) instead of z: the backward epilogue becomes one multiply
             float gd[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) gelu_both_f(v[i], &v[i], &gd[i]);
+            gelu_pair<true>(v[0], v[1], &v[0], &v[1], &gd[0], &gd[1]);
+            gelu_pair<true>(v[2], v[3], &v[2], &v[3], &gd[2], &gd[3]);
             st4((bf16*)e.Z + off, make_float4(gd[0], gd[1], gd[2], gd[3]));
           } else {
             st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+            gelu_pair<false>(v[0], v[1], &v[0], &v[1], nullptr, nullptr);
+            gelu_pair<false>(v[2], v[3], &v[2], &v[3], nullptr, nullptr);
           }
         } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = gelu_f(v[i]);
+          gelu_pair<false>(v[0], v[1], &v[0], &v[1], nullptr, nullptr);
+          gelu_pair<false>(v[2], v[3], &v[2], &v[3], nullptr, nullptr);
         }
         st4((bf16*)e.D + off, make_float4(v[0], v[1], v[2], v[3]));
       } else if (EPI == EPI_RES_F32_SHADOW) {

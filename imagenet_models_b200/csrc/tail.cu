@@ -363,6 +363,159 @@ extern "C" int ga_gram_triu_bwd(const void* dout, const void* out, const float* 
 // Q query rows (the class / gram tokens, which are also keys) + N spatial keys.  One warp per (image, head):
 // lanes stride over keys; softmax by warp shuffles.  scores use q as given (caller pre-scales).
 // kvc [B,Q,2E] fp32: k = [..., :E], v = [..., E:];   kvt rows [B*N, ldt] (T): k at col 0, v at col E
+// ---- attention pooling, CTA-per-image form (forward and backward).
+// Two access patterns, both coalesced: (a) work items (key n, head h) with h fastest -- adjacent threads read adjacent head
+// segments of one token row -- for everything that reduces over a head's channels (scores, dP); (b) one thread per channel
+// pair walking the keys -- adjacent threads read adjacent channels -- for everything that reduces over keys (output, dq) or
+// writes per-(key, channel) results (dk, dv).  All Q queries of the image are handled in one pass over K / V, reductions
+// over keys stay in registers or warp shuffles: no atomics.  Shared memory: probabilities [Q][H][NK] (+ dP in backward).
+constexpr int AP_QMAX = 4;
+
+template <typename T>
+__device__ __forceinline__ float ap_ld(const float* kvc, const T* kvt, int b, int n, int Q, int N, int E, long long ldt, int col) {
+  // element `col` (0..2E) of key row n: class rows are fp32 [B,Q,2E], token rows are T [B*N, ldt]
+  return n < Q ? kvc[((long long)b * Q + n) * 2 * E + col] : ld_f(kvt + ((long long)b * N + (n - Q)) * ldt + col);
+}
+
+template <typename T, int HD_MAX>
+__global__ void __launch_bounds__(256) attnpool_fwd3_kernel(const float* __restrict__ q, const float* __restrict__ kvc,
+                                                            const T* __restrict__ kvt, float* __restrict__ out,
+                                                            float* __restrict__ attn, int B, int Q, int N, int H, int E, long long ldt) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, hd = E / H, NK = Q + N, items = NK * H;
+  float* p_s = sm;                      // [Q][H][NK]
+  float* q_s = p_s + Q * items;         // [Q][E]
+  for (int i = threadIdx.x; i < Q * E; i += blockDim.x) q_s[i] = q[(long long)b * Q * E + i];
+  __syncthreads();
+  // (a) scores
+  for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
+    const int n = idx / H, h = idx - n * H;
+    float kk[HD_MAX];
+#pragma unroll
+    for (int d = 0; d < HD_MAX; ++d) kk[d] = d < hd ? ap_ld<T>(kvc, kvt, b, n, Q, N, E, ldt, h * hd + d) : 0.f;
+#pragma unroll
+    for (int qi = 0; qi < AP_QMAX; ++qi) {
+      if (qi >= Q) break;
+      float sc = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD_MAX; ++d) if (d < hd) sc = fmaf(q_s[qi * E + h * hd + d], kk[d], sc);
+      p_s[(qi * H + h) * NK + n] = sc;
+    }
+  }
+  __syncthreads();
+  // softmax over keys: one warp per (query, head) row; probabilities also go to global for the backward pass
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int row = warp; row < Q * H; row += nw) {
+    float* pr = p_s + row * NK;
+    float mx = -INFINITY;
+    for (int n = lane; n < NK; n += 32) mx = fmaxf(mx, pr[n]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < NK; n += 32) { const float e = __expf(pr[n] - mx); pr[n] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    const int qi = row / H, h = row - qi * H;
+    float* arow = attn + (((long long)b * H + h) * Q + qi) * NK;
+    for (int n = lane; n < NK; n += 32) { const float a = pr[n] * inv; pr[n] = a; arow[n] = a; }
+  }
+  __syncthreads();
+  // (b) out[qi][c] = sum_n P[qi][h(c)][n] V[n][c]
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    const int h = c / hd;
+    float acc[AP_QMAX];
+#pragma unroll
+    for (int qi = 0; qi < AP_QMAX; ++qi) acc[qi] = 0.f;
+    for (int n = 0; n < NK; ++n) {
+      const float v = ap_ld<T>(kvc, kvt, b, n, Q, N, E, ldt, E + c);
+#pragma unroll
+      for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) acc[qi] = fmaf(p_s[(qi * H + h) * NK + n], v, acc[qi]);
+    }
+#pragma unroll
+    for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) out[((long long)b * Q + qi) * E + c] = acc[qi];
+  }
+}
+
+template <typename T, int HD_MAX>
+__global__ void __launch_bounds__(256) attnpool_bwd3_kernel(const float* __restrict__ dout, const float* __restrict__ q,
+                                                            const float* __restrict__ kvc, const T* __restrict__ kvt,
+                                                            const float* __restrict__ attn, float* __restrict__ dq, float* __restrict__ dkvc,
+                                                            T* __restrict__ dkvt, int B, int Q, int N, int H, int E, long long ldt,
+                                                            long long lddt) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, hd = E / H, NK = Q + N, items = NK * H;
+  float* p_s = sm;                      // [Q][H][NK] probabilities
+  float* ds_s = p_s + Q * items;        // [Q][H][NK] dP, then dS
+  float* q_s = ds_s + Q * items;        // [Q][E]
+  float* do_s = q_s + Q * E;            // [Q][E]
+  for (int i = threadIdx.x; i < Q * E; i += blockDim.x) {
+    q_s[i] = q[(long long)b * Q * E + i];
+    do_s[i] = dout[(long long)b * Q * E + i];
+  }
+  for (int i = threadIdx.x; i < Q * items; i += blockDim.x) {
+    const int row = i / NK, n = i - row * NK, qi = row / H, h = row - qi * H;
+    p_s[i] = attn[(((long long)b * H + h) * Q + qi) * NK + n];
+  }
+  __syncthreads();
+  // (a) dP[qi][h][n] = dO[qi][h] . V[n][h]
+  for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
+    const int n = idx / H, h = idx - n * H;
+    float vv[HD_MAX];
+#pragma unroll
+    for (int d = 0; d < HD_MAX; ++d) vv[d] = d < hd ? ap_ld<T>(kvc, kvt, b, n, Q, N, E, ldt, E + h * hd + d) : 0.f;
+#pragma unroll
+    for (int qi = 0; qi < AP_QMAX; ++qi) {
+      if (qi >= Q) break;
+      float da = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD_MAX; ++d) if (d < hd) da = fmaf(do_s[qi * E + h * hd + d], vv[d], da);
+      ds_s[(qi * H + h) * NK + n] = da;
+    }
+  }
+  __syncthreads();
+  // dS = P (dP - sum_n P dP): one warp per (query, head) row
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int row = warp; row < Q * H; row += nw) {
+    float rd = 0.f;
+    for (int n = lane; n < NK; n += 32) rd = fmaf(p_s[row * NK + n], ds_s[row * NK + n], rd);
+    rd = warp_sum(rd);
+    for (int n = lane; n < NK; n += 32) ds_s[row * NK + n] = p_s[row * NK + n] * (ds_s[row * NK + n] - rd);
+  }
+  __syncthreads();
+  // (b) per channel: dq[qi][c] = sum_n dS K ; dk[n][c] = sum_qi dS q ; dv[n][c] = sum_qi P dO
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    const int h = c / hd;
+    float qq[AP_QMAX], dd[AP_QMAX], dqa[AP_QMAX];
+#pragma unroll
+    for (int qi = 0; qi < AP_QMAX; ++qi) {
+      qq[qi] = qi < Q ? q_s[qi * E + c] : 0.f;
+      dd[qi] = qi < Q ? do_s[qi * E + c] : 0.f;
+      dqa[qi] = 0.f;
+    }
+    for (int n = 0; n < NK; ++n) {
+      const float k = ap_ld<T>(kvc, kvt, b, n, Q, N, E, ldt, c);
+      float dk = 0.f, dv = 0.f;
+#pragma unroll
+      for (int qi = 0; qi < AP_QMAX; ++qi) {
+        if (qi < Q) {
+          const float ds = ds_s[(qi * H + h) * NK + n], a = p_s[(qi * H + h) * NK + n];
+          dqa[qi] = fmaf(ds, k, dqa[qi]);
+          dk = fmaf(ds, qq[qi], dk);
+          dv = fmaf(a, dd[qi], dv);
+        }
+      }
+      if (n < Q) {
+        float* gp = dkvc + ((long long)b * Q + n) * 2 * E;
+        gp[c] = dk; gp[E + c] = dv;
+      } else {
+        T* gp = dkvt + ((long long)b * N + (n - Q)) * lddt;
+        st_f(gp + c, dk); st_f(gp + E + c, dv);
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) dq[((long long)b * Q + qi) * E + c] = dqa[qi];
+  }
+}
+
 template <typename T, int HD_MAX>
 __global__ void __launch_bounds__(256) attnpool_fwd_kernel(const float* __restrict__ q, const float* __restrict__ kvc, const T* __restrict__ kvt,
                                                            float* __restrict__ out, float* __restrict__ attn, int B, int Q, int N, int H,
@@ -424,6 +577,14 @@ extern "C" int ga_attnpool_fwd(const float* q, const float* kv_cls, const void* 
   GA_REQUIRE(q && kv_cls && kv_tok && out && attn && H > 0 && E % H == 0, GA_ERR_SHAPE, "ga_attnpool_fwd: bad arguments");
   GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_fwd: head_dim %d > 32", E / H);
   if (B == 0) return GA_OK;
+  const size_t smem3 = ((size_t)Q * (Q + N) * H + (size_t)Q * E) * sizeof(float);
+  if (Q <= AP_QMAX && smem3 <= 200 * 1024) {
+    DISPATCH_T(dtype, {
+      if (smem3 > 48 * 1024) cudaFuncSetAttribute(attnpool_fwd3_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+      attnpool_fwd3_kernel<T, 32><<<B, 256, smem3, (cudaStream_t)s>>>(q, kv_cls, (const T*)kv_tok, out, attn, B, Q, N, H, E, ldt);
+    });
+    return launch_ok("attnpool_fwd3");
+  }
   const int grid = (B * H + 7) / 8;
   DISPATCH_T(dtype, { attnpool_fwd_kernel<T, 32><<<grid, 256, 0, (cudaStream_t)s>>>(q, kv_cls, (const T*)kv_tok, out, attn, B, Q, N, H, E, ldt); });
   return launch_ok("attnpool_fwd");
@@ -583,6 +744,14 @@ extern "C" int ga_attnpool_bwd(const float* dout, const float* q, const float* k
              "ga_attnpool_bwd: bad arguments");
   GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_bwd: head_dim %d > 32", E / H);
   if (B == 0) return GA_OK;
+  const size_t smem3 = (2 * (size_t)Q * (Q + N) * H + 2 * (size_t)Q * E) * sizeof(float);
+  if (Q <= AP_QMAX && smem3 <= 200 * 1024) {
+    DISPATCH_T(dtype, {
+      if (smem3 > 48 * 1024) cudaFuncSetAttribute(attnpool_bwd3_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+      attnpool_bwd3_kernel<T, 32><<<B, 256, smem3, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt);
+    });
+    return launch_ok("attnpool_bwd3");
+  }
   const size_t smem = ((size_t)(Q + N) * H + H + 3 * (size_t)E) * sizeof(float);
   if (smem <= 48 * 1024) {
     DISPATCH_T(dtype, { attnpool_bwd2_kernel<T, 32><<<B, 256, smem, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt); });
