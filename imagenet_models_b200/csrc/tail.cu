@@ -370,6 +370,15 @@ extern "C" int ga_gram_triu_bwd(const void* dout, const void* out, const float* 
 // writes per-(key, channel) results (dk, dv).  All Q queries of the image are handled in one pass over K / V, reductions
 // over keys stay in registers or warp shuffles: no atomics.  Shared memory: probabilities [Q][H][NK] (+ dP in backward).
 constexpr int AP_QMAX = 4;
+template <typename T> __device__ __forceinline__ float2 ap_ld2(const T* p);
+template <> __device__ __forceinline__ float2 ap_ld2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 ap_ld2<bf16>(const bf16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(bf16lo(u), bf16hi(u));
+}
+template <typename T> __device__ __forceinline__ void ap_st2(T* p, float a, float b);
+template <> __device__ __forceinline__ void ap_st2<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> __device__ __forceinline__ void ap_st2<bf16>(bf16* p, float a, float b) { *reinterpret_cast<uint32_t*>(p) = pack_bf16(a, b); }
 
 template <typename T>
 __device__ __forceinline__ float ap_ld(const float* kvc, const T* kvt, int b, int n, int Q, int N, int E, long long ldt, int col) {
@@ -419,19 +428,48 @@ __global__ void __launch_bounds__(256) attnpool_fwd3_kernel(const float* __restr
     for (int n = lane; n < NK; n += 32) { const float a = pr[n] * inv; pr[n] = a; arow[n] = a; }
   }
   __syncthreads();
-  // (b) out[qi][c] = sum_n P[qi][h(c)][n] V[n][c]
-  for (int c = threadIdx.x; c < E; c += blockDim.x) {
-    const int h = c / hd;
-    float acc[AP_QMAX];
+  // (b) out[qi][c] = sum_n P[qi][h(c)][n] V[n][c]: thread = (channel pair, key slice); slices are summed through smem
+  {
+    const int npair = E >> 1;
+    int nsl = (int)blockDim.x / npair;
+    if (nsl < 1) nsl = 1;
+    float* red = q_s;                                   // q_s is dead from here: [nsl][Q][E] partial outputs
+    for (int w = threadIdx.x; w < npair * nsl; w += blockDim.x) {
+      const int cp = w % npair, sl = w / npair, c = 2 * cp;
+      const int h0 = c / hd, h1 = (c + 1) / hd;
+      float acc[AP_QMAX][2];
 #pragma unroll
-    for (int qi = 0; qi < AP_QMAX; ++qi) acc[qi] = 0.f;
-    for (int n = 0; n < NK; ++n) {
-      const float v = ap_ld<T>(kvc, kvt, b, n, Q, N, E, ldt, E + c);
+      for (int qi = 0; qi < AP_QMAX; ++qi) acc[qi][0] = acc[qi][1] = 0.f;
+      if (sl == 0) {
+        for (int n = 0; n < Q; ++n) {
+          const float2 v = *reinterpret_cast<const float2*>(kvc + ((long long)b * Q + n) * 2 * E + E + c);
 #pragma unroll
-      for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) acc[qi] = fmaf(p_s[(qi * H + h) * NK + n], v, acc[qi]);
+          for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) {
+            acc[qi][0] = fmaf(p_s[(qi * H + h0) * NK + n], v.x, acc[qi][0]);
+            acc[qi][1] = fmaf(p_s[(qi * H + h1) * NK + n], v.y, acc[qi][1]);
+          }
+        }
+      }
+      const T* vbase = kvt + (long long)b * N * ldt + E + c;
+#pragma unroll 4
+      for (int j = sl; j < N; j += nsl) {
+        const float2 v = ap_ld2<T>(vbase + (long long)j * ldt);
+        const int n = Q + j;
+#pragma unroll
+        for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) {
+          acc[qi][0] = fmaf(p_s[(qi * H + h0) * NK + n], v.x, acc[qi][0]);
+          acc[qi][1] = fmaf(p_s[(qi * H + h1) * NK + n], v.y, acc[qi][1]);
+        }
+      }
+#pragma unroll
+      for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) { red[(sl * Q + qi) * E + c] = acc[qi][0]; red[(sl * Q + qi) * E + c + 1] = acc[qi][1]; }
     }
-#pragma unroll
-    for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) out[((long long)b * Q + qi) * E + c] = acc[qi];
+    __syncthreads();
+    for (int i = threadIdx.x; i < Q * E; i += blockDim.x) {
+      float a = 0.f;
+      for (int sl = 0; sl < nsl; ++sl) a += red[sl * Q * E + i];
+      out[(long long)b * Q * E + i] = a;
+    }
   }
 }
 
@@ -481,38 +519,66 @@ __global__ void __launch_bounds__(256) attnpool_bwd3_kernel(const float* __restr
     for (int n = lane; n < NK; n += 32) ds_s[row * NK + n] = p_s[row * NK + n] * (ds_s[row * NK + n] - rd);
   }
   __syncthreads();
-  // (b) per channel: dq[qi][c] = sum_n dS K ; dk[n][c] = sum_qi dS q ; dv[n][c] = sum_qi P dO
-  for (int c = threadIdx.x; c < E; c += blockDim.x) {
-    const int h = c / hd;
-    float qq[AP_QMAX], dd[AP_QMAX], dqa[AP_QMAX];
-#pragma unroll
-    for (int qi = 0; qi < AP_QMAX; ++qi) {
-      qq[qi] = qi < Q ? q_s[qi * E + c] : 0.f;
-      dd[qi] = qi < Q ? do_s[qi * E + c] : 0.f;
-      dqa[qi] = 0.f;
-    }
-    for (int n = 0; n < NK; ++n) {
-      const float k = ap_ld<T>(kvc, kvt, b, n, Q, N, E, ldt, c);
-      float dk = 0.f, dv = 0.f;
+  // (b) thread = (channel pair, key slice): dq[qi][c] = sum_n dS K ; dk[n][c] = sum_qi dS q ; dv[n][c] = sum_qi P dO
+  {
+    const int npair = E >> 1;
+    int nsl = (int)blockDim.x / npair;
+    if (nsl < 1) nsl = 1;
+    float* red = sm + 2 * Q * items + 2 * Q * E;        // [nsl][Q][E] partial dq
+    for (int w = threadIdx.x; w < npair * nsl; w += blockDim.x) {
+      const int cp = w % npair, sl = w / npair, c = 2 * cp;
+      const int h0 = c / hd, h1 = (c + 1) / hd;
+      float qq[AP_QMAX][2], dd[AP_QMAX][2], dqa[AP_QMAX][2];
 #pragma unroll
       for (int qi = 0; qi < AP_QMAX; ++qi) {
-        if (qi < Q) {
-          const float ds = ds_s[(qi * H + h) * NK + n], a = p_s[(qi * H + h) * NK + n];
-          dqa[qi] = fmaf(ds, k, dqa[qi]);
-          dk = fmaf(ds, qq[qi], dk);
-          dv = fmaf(a, dd[qi], dv);
+        qq[qi][0] = qi < Q ? q_s[qi * E + c] : 0.f;  qq[qi][1] = qi < Q ? q_s[qi * E + c + 1] : 0.f;
+        dd[qi][0] = qi < Q ? do_s[qi * E + c] : 0.f; dd[qi][1] = qi < Q ? do_s[qi * E + c + 1] : 0.f;
+        dqa[qi][0] = dqa[qi][1] = 0.f;
+      }
+      if (sl == 0) {
+        for (int n = 0; n < Q; ++n) {
+          const float2 k = *reinterpret_cast<const float2*>(kvc + ((long long)b * Q + n) * 2 * E + c);
+          float dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+#pragma unroll
+          for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) {
+            const float s0 = ds_s[(qi * H + h0) * NK + n], s1 = ds_s[(qi * H + h1) * NK + n];
+            const float a0 = p_s[(qi * H + h0) * NK + n], a1 = p_s[(qi * H + h1) * NK + n];
+            dqa[qi][0] = fmaf(s0, k.x, dqa[qi][0]); dqa[qi][1] = fmaf(s1, k.y, dqa[qi][1]);
+            dk0 = fmaf(s0, qq[qi][0], dk0); dk1 = fmaf(s1, qq[qi][1], dk1);
+            dv0 = fmaf(a0, dd[qi][0], dv0); dv1 = fmaf(a1, dd[qi][1], dv1);
+          }
+          float* gp = dkvc + ((long long)b * Q + n) * 2 * E;
+          *reinterpret_cast<float2*>(gp + c) = make_float2(dk0, dk1);
+          *reinterpret_cast<float2*>(gp + E + c) = make_float2(dv0, dv1);
         }
       }
-      if (n < Q) {
-        float* gp = dkvc + ((long long)b * Q + n) * 2 * E;
-        gp[c] = dk; gp[E + c] = dv;
-      } else {
-        T* gp = dkvt + ((long long)b * N + (n - Q)) * lddt;
-        st_f(gp + c, dk); st_f(gp + E + c, dv);
-      }
-    }
+      const T* kbase = kvt + (long long)b * N * ldt + c;
+      T* gbase = dkvt + (long long)b * N * lddt + c;
+#pragma unroll 4
+      for (int j = sl; j < N; j += nsl) {
+        const float2 k = ap_ld2<T>(kbase + (long long)j * ldt);
+        const int n = Q + j;
+        float dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
 #pragma unroll
-    for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) dq[((long long)b * Q + qi) * E + c] = dqa[qi];
+        for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) {
+          const float s0 = ds_s[(qi * H + h0) * NK + n], s1 = ds_s[(qi * H + h1) * NK + n];
+          const float a0 = p_s[(qi * H + h0) * NK + n], a1 = p_s[(qi * H + h1) * NK + n];
+          dqa[qi][0] = fmaf(s0, k.x, dqa[qi][0]); dqa[qi][1] = fmaf(s1, k.y, dqa[qi][1]);
+          dk0 = fmaf(s0, qq[qi][0], dk0); dk1 = fmaf(s1, qq[qi][1], dk1);
+          dv0 = fmaf(a0, dd[qi][0], dv0); dv1 = fmaf(a1, dd[qi][1], dv1);
+        }
+        ap_st2<T>(gbase + (long long)j * lddt, dk0, dk1);
+        ap_st2<T>(gbase + (long long)j * lddt + E, dv0, dv1);
+      }
+#pragma unroll
+      for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) { red[(sl * Q + qi) * E + c] = dqa[qi][0]; red[(sl * Q + qi) * E + c + 1] = dqa[qi][1]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Q * E; i += blockDim.x) {
+      float a = 0.f;
+      for (int sl = 0; sl < nsl; ++sl) a += red[sl * Q * E + i];
+      dq[(long long)b * Q * E + i] = a;
+    }
   }
 }
 
@@ -577,8 +643,9 @@ extern "C" int ga_attnpool_fwd(const float* q, const float* kv_cls, const void* 
   GA_REQUIRE(q && kv_cls && kv_tok && out && attn && H > 0 && E % H == 0, GA_ERR_SHAPE, "ga_attnpool_fwd: bad arguments");
   GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_fwd: head_dim %d > 32", E / H);
   if (B == 0) return GA_OK;
-  const size_t smem3 = ((size_t)Q * (Q + N) * H + (size_t)Q * E) * sizeof(float);
-  if (Q <= AP_QMAX && smem3 <= 200 * 1024) {
+  const int ap_nsl = (256 / (E / 2)) < 1 ? 1 : 256 / (E / 2);
+  const size_t smem3 = ((size_t)Q * (Q + N) * H + (size_t)ap_nsl * Q * E) * sizeof(float);
+  if (Q <= AP_QMAX && (E & 1) == 0 && (ldt & 1) == 0 && smem3 <= 200 * 1024) {
     DISPATCH_T(dtype, {
       if (smem3 > 48 * 1024) cudaFuncSetAttribute(attnpool_fwd3_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
       attnpool_fwd3_kernel<T, 32><<<B, 256, smem3, (cudaStream_t)s>>>(q, kv_cls, (const T*)kv_tok, out, attn, B, Q, N, H, E, ldt);
@@ -744,8 +811,9 @@ extern "C" int ga_attnpool_bwd(const float* dout, const float* q, const float* k
              "ga_attnpool_bwd: bad arguments");
   GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_bwd: head_dim %d > 32", E / H);
   if (B == 0) return GA_OK;
-  const size_t smem3 = (2 * (size_t)Q * (Q + N) * H + 2 * (size_t)Q * E) * sizeof(float);
-  if (Q <= AP_QMAX && smem3 <= 200 * 1024) {
+  const int ap_nsl = (256 / (E / 2)) < 1 ? 1 : 256 / (E / 2);
+  const size_t smem3 = (2 * (size_t)Q * (Q + N) * H + (2 + (size_t)ap_nsl) * Q * E) * sizeof(float);
+  if (Q <= AP_QMAX && (E & 1) == 0 && ((ldt | lddt) & 1) == 0 && smem3 <= 200 * 1024) {
     DISPATCH_T(dtype, {
       if (smem3 > 48 * 1024) cudaFuncSetAttribute(attnpool_bwd3_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
       attnpool_bwd3_kernel<T, 32><<<B, 256, smem3, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt);
