@@ -33,7 +33,7 @@ parser.add_argument('-b', '--batch-size', type=int, default=128, help='per-proce
 parser.add_argument('--img-size', type=int, default=224)
 parser.add_argument('--epochs', type=int, default=1)
 parser.add_argument('--steps-per-epoch', type=int, default=50, help='synthetic data: steps per epoch')
-parser.add_argument('--opt', default='adamw', type=str, help="only 'adamw' is fused here (LAMB is next, SURVEY 8f-2)")
+parser.add_argument('--opt', default='adamw', type=str, help="'adamw' or 'lamb' (timm.optim.Lamb semantics, the recipes' optimizer)")
 parser.add_argument('--lr', type=float, default=1e-3)
 parser.add_argument('--weight-decay', type=float, default=0.05)
 parser.add_argument('--opt-eps', type=float, default=1e-8)
@@ -56,8 +56,8 @@ parser.add_argument('--no-cuda-graph', action='store_true', help='run every step
 def main():
     logging.basicConfig(level=logging.INFO, format='%(message)s')
     args = parser.parse_args()
-    if args.opt.lower() != 'adamw':
-        raise SystemExit(f"--opt {args.opt}: only adamw has a fused sm_100a step in this build")
+    if args.opt.lower() not in ('adamw', 'lamb'):
+        raise SystemExit(f"--opt {args.opt}: adamw and lamb have fused sm_100a steps in this build")
     distributed = int(os.environ.get('WORLD_SIZE', '1')) > 1
     local_rank = int(os.environ.get('LOCAL_RANK', args.local_rank))
     torch.cuda.set_device(local_rank)
@@ -79,7 +79,7 @@ def main():
     engine = TrainEngine(model, lr=args.lr, weight_decay=args.weight_decay, betas=tuple(args.opt_betas), eps=args.opt_eps,
                          ema_decay=args.model_ema_decay if args.model_ema else None, ga_lam=args.GA_lam,
                          amp_dtype=torch.bfloat16 if args.amp else None, grad_accumulation=args.grad_accumulation,
-                         cuda_graph=not args.no_cuda_graph)
+                         cuda_graph=not args.no_cuda_graph, opt=args.opt.lower())
     B, S = args.batch_size, args.img_size
     g = torch.Generator(device='cuda').manual_seed(args.seed + rank)
     for epoch in range(args.epochs):

@@ -207,3 +207,115 @@ extern "C" int ga_loss_fwd_bwd(const float* logits, const float* aux, const long
   ga_loss_kernel<<<B, 256, smem, (cudaStream_t)s>>>(logits, aux, target, loss, dlogits, daux, nb, B, ncls, lam, grad_scale);
   return launch_ok("ga_loss");
 }
+
+// ---------------------------------------------------------------------------------------------- LAMB (timm.optim.Lamb)
+// The published recipes train with `--opt lamb` (GA/README.md:26).  timm's Lamb (absent dependency, restated in
+// oracle/lamb_oracle.py):  global-norm clip g /= max(1, ||g|| / max_grad_norm);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+// u = (m / bc1) / (sqrt(v) / sqrt(bc2) + eps) + wd p;  decayed tensors only: u *= ||p|| / ||u|| (1 when either norm is 0);
+// p -= lr u.  Three passes over the flat state: (1) ||g||^2, (2) moments + update (written over the gradient buffer) +
+// per-tensor ||p||^2, ||u||^2, (3) apply with the trust ratio (+ EMA).  Chunk table as in ga_gather_grads: one CTA works
+// inside one tensor, so the per-tensor norms cost two atomics per CTA.
+struct LambEntry { long long off; long long n; long long first_chunk; long long decay; };
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n4, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+__device__ __forceinline__ int lamb_find(const LambEntry* table, int count, long long c) {
+  int lo = 0, hi = count - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].first_chunk <= c) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// hyper = {lr, 1-b1^t, 1-b2^t, grad_scale}; gnorm_sq: sum of squares of the UNSCALED flat gradient
+__global__ void __launch_bounds__(256) lamb_update_kernel(const LambEntry* __restrict__ table, int count, long long chunks,
+                                                          const float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                          float* __restrict__ v, float* __restrict__ norms, const float* __restrict__ hyper,
+                                                          const float* __restrict__ gnorm_sq, float b1, float b2, float eps, float wd,
+                                                          float max_grad_norm) {
+  __shared__ float red[32];
+  const float inv_bc1 = 1.f / hyper[1], inv_sqrt_bc2 = rsqrtf(hyper[2]), gs = hyper[3];
+  const float gn = sqrtf(*gnorm_sq) * gs;
+  const float clip = (max_grad_norm > 0.f && gn > max_grad_norm) ? max_grad_norm / gn : 1.f;
+  const float gmul = gs * clip;
+  for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+    const int t = lamb_find(table, count, c);
+    const LambEntry e = table[t];
+    const long long start = (c - e.first_chunk) * 4096;
+    const long long len = e.n - start < 4096 ? e.n - start : 4096;
+    const long long base = e.off + start;
+    const float wdt = e.decay ? wd : 0.f;
+    float pn = 0.f, un = 0.f;
+    for (long long i = threadIdx.x; i < len; i += 256) {
+      const float gi = g[base + i] * gmul, pi = p[base + i];
+      const float mi = b1 * m[base + i] + (1.f - b1) * gi;
+      const float vi = b2 * v[base + i] + (1.f - b2) * gi * gi;
+      m[base + i] = mi;
+      v[base + i] = vi;
+      const float u = (mi * inv_bc1) / (sqrtf(vi) * inv_sqrt_bc2 + eps) + wdt * pi;
+      g[base + i] = u;
+      pn += pi * pi;
+      un += u * u;
+    }
+    pn = block_sum(pn, red);
+    un = block_sum(un, red);
+    if (threadIdx.x == 0 && e.decay) { atomicAdd(norms + 2 * t, pn); atomicAdd(norms + 2 * t + 1, un); }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) lamb_apply_kernel(const LambEntry* __restrict__ table, int count, long long chunks,
+                                                         float* __restrict__ p, const float* __restrict__ u, float* __restrict__ ema,
+                                                         const float* __restrict__ norms, const float* __restrict__ hyper, float ema_decay) {
+  const float lr = hyper[0];
+  for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+    const int t = lamb_find(table, count, c);
+    const LambEntry e = table[t];
+    float trust = 1.f;
+    if (e.decay) {
+      const float wn = sqrtf(norms[2 * t]), un = sqrtf(norms[2 * t + 1]);
+      trust = (wn > 0.f && un > 0.f) ? wn / un : 1.f;
+    }
+    const long long start = (c - e.first_chunk) * 4096;
+    const long long len = e.n - start < 4096 ? e.n - start : 4096;
+    const long long base = e.off + start;
+    const float step = lr * trust;
+    for (long long i = threadIdx.x; i < len; i += 256) {
+      const float pi = p[base + i] - step * u[base + i];
+      p[base + i] = pi;
+      if (ema) ema[base + i] = ema_decay * ema[base + i] + (1.f - ema_decay) * pi;
+    }
+  }
+}
+
+extern "C" int ga_lamb_ema(float* p, float* g, float* m, float* v, float* ema, const void* table, int count, long long chunks,
+                           long long n_flat, float* scratch /* [1 + 2*count] */, const float* hyper, float beta1, float beta2,
+                           float eps, float wd, float max_grad_norm, float ema_decay, ga_stream_t s) {
+  GA_REQUIRE(p && g && m && v && table && scratch && hyper && count > 0 && chunks > 0 && (n_flat & 3) == 0, GA_ERR_SHAPE,
+             "ga_lamb_ema: bad arguments");
+  cudaStream_t st = (cudaStream_t)s;
+  cudaMemsetAsync(scratch, 0, (size_t)(1 + 2 * count) * sizeof(float), st);
+  const long long n4 = n_flat >> 2;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n4, scratch);
+  int rc = launch_ok("lamb_sumsq");
+  if (rc) return rc;
+  long long cb = chunks < 148LL * 16 ? chunks : 148LL * 16;
+  lamb_update_kernel<<<(unsigned)cb, 256, 0, st>>>((const LambEntry*)table, count, chunks, p, g, m, v, scratch + 1, hyper, scratch, beta1,
+                                                   beta2, eps, wd, max_grad_norm);
+  rc = launch_ok("lamb_update");
+  if (rc) return rc;
+  lamb_apply_kernel<<<(unsigned)cb, 256, 0, st>>>((const LambEntry*)table, count, chunks, p, g, ema, scratch + 1, hyper, ema_decay);
+  return launch_ok("lamb_apply");
+}

@@ -14,20 +14,25 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .optim import FusedAdamWEma, GradBuckets
+from .optim import FusedAdamWEma, FusedLambEma, GradBuckets
 
 
 class TrainEngine:
     def __init__(self, model, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, ema_decay: Optional[float] = 0.9998,
                  ga_lam: float = -0.8, amp_dtype=torch.bfloat16, grad_accumulation: int = 1, bucket_mb: float = 25.0,
-                 cuda_graph: bool = False, graph_warmup: int = 3):
+                 cuda_graph: bool = False, graph_warmup: int = 3, opt: str = 'adamw'):
         """cuda_graph: after `graph_warmup` eager steps the whole step (zero-grad, forward, loss, backward, gradient gather and,
         on one GPU, the optimizer) is captured once into a CUDA graph and replayed, which removes the ~1.5k per-step kernel
         launches from the CPU's critical path.  With several ranks the all-reduce and the optimizer run after the replay
         (NVSwitch moves the 190 MB of gradients in well under a millisecond; overlap with backward is traded for launch cost).
         Needs fixed batch shapes; drop-path masks are drawn inside the graph from the graph-safe generator."""
         self.model = model
-        self.opt = FusedAdamWEma(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay)
+        if opt == 'lamb':          # timm.optim.Lamb, the optimizer of the published recipes (GA/README.md:26)
+            self.opt = FusedLambEma(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay)
+        elif opt == 'adamw':
+            self.opt = FusedAdamWEma(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay)
+        else:
+            raise ValueError(f"optimizer '{opt}': 'adamw' and 'lamb' are fused here")
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.buckets = GradBuckets(self.opt.state, bucket_mb=bucket_mb) if self.world > 1 else None
         self.ga_lam, self.amp_dtype, self.accum = ga_lam, amp_dtype, max(1, grad_accumulation)
@@ -65,7 +70,7 @@ class TrainEngine:
             n0 = L.launch_count()
             with torch.cuda.graph(g):
                 self.opt.zero_grad()
-                self._sloss = self._forward_backward(self._sx, self._sy)
+                self._sloss = self._forward_backward(self._sx, self._sy).detach()
                 self.opt.state.gather()
                 if self.world == 1:
                     self.opt.step(gathered=True, device_hyper=True)
@@ -112,7 +117,9 @@ class TrainEngine:
             scale = self.buckets.finish() if self.buckets is not None else 1.0
             self.opt.step(grad_scale=scale, gathered=self.buckets is not None)
         self.micro += 1
-        return loss
+        # detached: a caller holding the loss must not keep this step's autograd graph (and its AccumulateGrad nodes, bound to
+        # the eager stream) alive into the CUDA-graph capture of a later step
+        return loss.detach()
 
 
 @torch.no_grad()

@@ -186,6 +186,44 @@ class FusedAdamWEma:
                                     L.f(self.ema_decay), L.stream()), 'ga_ema_lerp')
 
 
+class FusedLambEma(FusedAdamWEma):
+    """timm.optim.Lamb semantics (the optimizer of the published recipes, GA/README.md:26) + ModelEmaV2 over the flat state:
+    global-norm clip, Adam moments, per-tensor trust ratio on the decayed tensors; three launches (ga_lamb_ema).
+    Same interface as FusedAdamWEma (step / push_hyper / zero_grad / param_groups)."""
+
+    def __init__(self, model: nn.Module, lr=5e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.05, ema_decay: Optional[float] = None,
+                 filter_bias_and_bn=True, max_grad_norm: float = 1.0):
+        super().__init__(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay,
+                         filter_bias_and_bn=filter_bias_and_bn)
+        import numpy as np
+        st = self.state
+        rec = np.zeros((len(st.params), 4), dtype=np.int64)
+        chunk = 0
+        for r, (name, p_, o) in enumerate(zip(st.names, st.params, st.offsets)):
+            decay = bool(weight_decay) and not (filter_bias_and_bn and (p_.ndim <= 1 or name.endswith('.bias')))
+            rec[r] = (o, p_.numel(), chunk, int(decay))
+            chunk += (p_.numel() + 4095) // 4096
+        self.max_grad_norm = max_grad_norm
+        self._chunks = chunk
+        self._table = torch.from_numpy(rec.reshape(-1)).to(st.flat.device)
+        self._scratch = torch.zeros(1 + 2 * len(st.params), dtype=torch.float32, device=st.flat.device)
+
+    def step(self, grad_scale: float = 1.0, gathered: bool = False, device_hyper: bool = False):
+        if not gathered:
+            self.state.gather()
+        if not device_hyper:
+            self.push_hyper(grad_scale)
+        b1, b2 = self.betas
+        L.check(L.load().ga_lamb_ema(L.ptr(self.state.flat), L.ptr(self.state.grad), L.ptr(self.m), L.ptr(self.v), L.ptr(self.ema_flat),
+                                     L.ptr(self._table), len(self.state.params), L.ll(self._chunks), L.ll(self.state.numel),
+                                     L.ptr(self._scratch), L.ptr(self.hyper), L.f(b1), L.f(b2), L.f(self.eps), L.f(self.wd),
+                                     L.f(self.max_grad_norm), L.f(self.ema_decay if self.ema_decay is not None else 0.0), L.stream()),
+                'ga_lamb_ema')
+        if self.ema_model is not None:
+            L.check(L.load().ga_ema_lerp(L.ptr(self.ema_bufflat), L.ptr(self.state.bufflat), L.ll(self.ema_bufflat.numel()),
+                                         L.f(self.ema_decay), L.stream()), 'ga_ema_lerp')
+
+
 class GradBuckets:
     """Overlapped data-parallel gradient all-reduce (mean) over contiguous slices of the flat gradient.
 

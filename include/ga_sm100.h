@@ -241,6 +241,14 @@ int ga_adamw_ema_dev(float* p, const float* g, float* m, float* v, float* ema, v
  * kernel per parameter).  table: device array of `count` records {const float* src (NULL = zeros); long long flat_offset;
  * long long numel; long long first_chunk}, chunks of 4096 elements numbered consecutively over the table. */
 int ga_gather_grads(const void* table, int count, long long chunks, float* flat, ga_stream_t s);
+/* LAMB as timm.optim.Lamb does it (GA/README.md:26 trains with --opt lamb; GA/train.py:466 create_optimizer_v2) + EMA:
+ * global gradient-norm clip (max_grad_norm, 0 = off), Adam moments with bias correction, update + wd*p, per-tensor trust
+ * ratio ||p||/||update|| for decayed tensors, p -= lr*trust*update.  table: device array of `count` records
+ * {long long flat_offset, numel, first_chunk (4096-element chunks), decay (0/1)}; hyper = {lr, 1-b1^t, 1-b2^t, grad_scale}
+ * in device memory; scratch: 1 + 2*count floats; g is overwritten with the update. */
+int ga_lamb_ema(float* p, float* g, float* m, float* v, float* ema, const void* table, int count, long long chunks,
+                long long n_flat, float* scratch, const float* hyper, float beta1, float beta2, float eps, float wd,
+                float max_grad_norm, float ema_decay, ga_stream_t s);
 int ga_ema_lerp(float* ema, const float* src, long long n, float decay, ga_stream_t s);
 
 #ifdef __cplusplus

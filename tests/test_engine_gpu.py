@@ -86,3 +86,37 @@ def test_gather_equals_parameter_gradients():
     torch.cuda.synchronize()
     for p, o in zip(opt.state.params, opt.state.offsets):
         assert torch.equal(opt.state.grad[o:o + p.numel()], p.grad.reshape(-1))
+
+
+@pytest.mark.gpu
+def test_fused_lamb_matches_the_restated_timm_algorithm():
+    """ga_lamb_ema (3 launches over the flat state) vs oracle/lamb_oracle.py over 4 steps, incl. the global-norm clip,
+    the no-decay group (biases: no trust ratio) and the EMA."""
+    import torch.nn as nn
+    from imagenet_models_b200.optim import FusedLambEma
+    from oracle.lamb_oracle import lamb_step
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(37, 64), nn.GELU(), nn.Linear(64, 5000), nn.LayerNorm(5000), nn.Linear(5000, 3)).cuda()
+    ref_p = [p.detach().cpu().clone() for p in net.parameters()]
+    names = [n for n, _ in net.named_parameters()]
+    decay = [not (p.ndim <= 1 or n.endswith('.bias')) for n, p in zip(names, ref_p)]
+    m = [torch.zeros_like(p) for p in ref_p]
+    v = [torch.zeros_like(p) for p in ref_p]
+    ema = [p.clone() for p in ref_p]
+    opt = FusedLambEma(net, lr=5e-3, weight_decay=0.05, ema_decay=0.9, max_grad_norm=1.0)
+    g = torch.Generator().manual_seed(1)
+    for step in range(1, 5):
+        scale = 3.0 if step == 1 else 0.01            # step 1 exceeds max_grad_norm (clip active), later steps do not
+        grads = [torch.randn(p.shape, generator=g) * scale for p in ref_p]
+        opt.zero_grad()
+        for p, gr in zip(net.parameters(), grads):
+            p.grad = gr.cuda()
+        opt.step()
+        lamb_step(ref_p, grads, m, v, decay, step, lr=5e-3, eps=1e-6, weight_decay=0.05, max_grad_norm=1.0)
+        for e, p in zip(ema, ref_p):
+            e.mul_(0.9).add_(p, alpha=0.1)
+    for n, p, r in zip(names, net.parameters(), ref_p):
+        assert (p.detach().cpu() - r).norm().item() <= 2e-5 * r.norm().item() + 1e-7, n
+    for n, p, r in zip(names, opt.ema_model.parameters(), ema):
+        assert (p.detach().cpu() - r).norm().item() <= 2e-5 * r.norm().item() + 1e-7, n
+    assert opt.step_count == 4
