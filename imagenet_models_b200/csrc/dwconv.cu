@@ -434,6 +434,17 @@ static int plan(int B, int H, int W, int C, int dtype, bool wgrad, Plan* p, int 
     else { limit = 225 * 1024; th = fit(tw, limit); if (th < 1 && tw == 14) { tw = 7; th = fit(7, limit); } if (th < 1) { tw = 4; th = fit(4, limit); } }
   }
   {
+    // measured on B200 (scripts/kernel_bench.py dwconv, GA_DW_TH sweep 2..14): short tiles win for the conv / data-gradient
+    // kernels (more CTAs in flight hide the halo-load latency; the extra halo rows are L2 hits: 56x56x96 fwd 360 -> 307 us,
+    // 7x7x688 fwd 132 -> 88 us), taller ones for the weight gradient (fewer folds and atomics per pixel: 436 -> 374 us)
+    if (!wgrad) {
+      const int pref = H >= 28 ? 4 : 2;
+      if (th > pref) th = pref;
+    } else if (H >= 28 && fit(tw, 225 * 1024) >= 10) {
+      th = 10;                                   // two passes of 5 rows: 240-thread CTAs, still two per SM at C <= 192
+    }
+  }
+  {
     const char* eh = getenv("GA_DW_TH");
     if (eh) { int v = atoi(eh); if (v >= 1 && v <= 14) th = v; }
   }
