@@ -348,6 +348,22 @@ def clear_shadows():
     _shadow.clear()
 
 
+def _stream_grad(dy, dys_in, M, Cc, RT, T, dev):
+    """Gradient of a block's two outputs (stream y in RT, shadow ys in T) -> (dy in RT, its T copy for the GEMM operands).
+    The last block of a stage feeds only its shadow onward (next stage's LayerNorm, the aggregator): dy is then absent and
+    the shadow gradient IS the gradient -- one widening copy instead of zero-fill + mixed-dtype add + narrowing copy."""
+    if dy is None and dys_in is None:
+        dy = torch.zeros(M, Cc, dtype=RT, device=dev)
+        return dy, (convert(dy, T) if RT != T else dy)
+    if dy is None:
+        dys = rowmat(dys_in) if dys_in.is_contiguous() else dys_in.contiguous()
+        return (convert(dys, RT) if RT != T else dys), dys
+    dy = dy.contiguous()
+    if dys_in is not None:                      # tapped blocks: both outputs are consumed
+        dy = dy + dys_in                        # type promotion keeps the sum in the stream dtype
+    return dy, (_take_shadow(dy, T) if RT != T else dy)
+
+
 class ConvNeXtBlockFn(Function):
     """dw7x7 -> LN -> fc1 -> GELU -> fc2 -> *gamma -> drop-path -> +x  on NHWC rows  (ga_convnext.py:98-112).
 
@@ -399,12 +415,7 @@ class ConvNeXtBlockFn(Function):
         Hd = w1.shape[0]
         dev = src.device
         lib = _L()
-        if dy is None:
-            dy = torch.zeros(M, Cc, dtype=RT, device=dev)
-        dy = dy.contiguous()
-        if dys_in is not None:                      # gradient that arrived through the bf16 shadow (stage boundaries)
-            dy = dy + dys_in                        # type promotion keeps the sum in the stream dtype
-        dys = _take_shadow(dy, T) if RT != T else dy     # bf16 operand copy of the stream gradient
+        dy, dys = _stream_grad(dy, dys_in, M, Cc, RT, T, dev)
         if path_scale is not None:
             t = torch.empty_like(dys)
             L.check(lib.ga_scale_rows(L.ptr(dys), L.ptr(path_scale), L.ptr(t), L.ll(M), Cc, H * W_, L.dt(dys), L.stream()),
@@ -1007,12 +1018,7 @@ class CSWinBlockFn(Function):
         dev = xh1.device
         lib = _L()
         HW = R * R
-        if dy is None:
-            dy = torch.zeros(M, Cc, dtype=RT, device=dev)
-        dy = dy.contiguous()
-        if dys_in is not None:
-            dy = dy + dys_in
-        dys = convert(dy, T) if RT != T else dy
+        dy, dys = _stream_grad(dy, dys_in, M, Cc, RT, T, dev)
 
         def rows_scaled(t, ps):
             if ps is None:
