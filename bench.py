@@ -255,7 +255,7 @@ def main():
                      'share_of_step': (t_ms / n_inst) / ms_step_inst, 'all_gemm_share_of_step': gemm_total_ms / ms_step_inst,
                      'measured': f'{n_inst} instrumented eager steps after the timed region ({ms_step_inst:.2f} ms/step with the events)'},
         'step_roofline': {'hbm_frac': per_gpu * mb_img / 1e3 / hbm if mb_img else None, 'tensor_frac': per_gpu * gf_img / 1e3 / tf if gf_img else None,
-                          'note': '268 MB/img and 32.73 GFLOP/img (BASELINE.md section 4) x img/s/GPU over the measured peaks'},
+                          'note': f'{mb_img} MB/img (SURVEY 8d convention) and {gf_img} training GFLOP/img x img/s/GPU over the measured peaks'},
     }
     if e2e:
         line['e2e'] = e2e
