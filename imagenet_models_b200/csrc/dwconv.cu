@@ -99,7 +99,7 @@ __device__ __forceinline__ void load_halo(uint32_t tile_s, uint64_t* bar, const 
     const uint32_t box_bytes = (uint32_t)((g.TH + 6) * (TW + 6) * g.cbox * sizeof(T));
     mbar_expect_tx(bar, box_bytes * g.nbox);
     for (int j = 0; j < g.nbox; ++j)
-      tma_load_4d(tile_s + (uint32_t)((size_t)j * g.box_stride * sizeof(T)), map, bar, j * g.cbox, x0 - 3, y0 - 3, b);
+      tma_load_4d(tile_s + (uint32_t)((size_t)j * g.box_stride * sizeof(T)), map, bar, g.c0 + j * g.cbox, x0 - 3, y0 - 3, b);
   }
   mbar_wait(bar, 0);
 }
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(BIG ? 512 : (MODE == 0 ? 384 : 448), BIG ? 1 :
   u64 acc[TW];
   {
     u64 init = 0ull;
-    if (MODE == 0 && bias && active) init = *reinterpret_cast<const u64*>(bias + c);
+    if (MODE != 1 && bias && active) init = *reinterpret_cast<const u64*>(bias + g.c0 + c);
 #pragma unroll
     for (int i = 0; i < TW; ++i) acc[i] = init;
   }
@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(BIG ? 512 : (MODE == 0 ? 384 : 448), BIG ? 1 :
     uint32_t rowaddr = tile_s + (uint32_t)(((size_t)box * g.box_stride + (size_t)row * (TW + 6) * g.cbox + cc) * sizeof(T));
     const uint32_t row_pitch = (uint32_t)(TW + 6) * cbs;
     // taps walk forward (conv) or backward (data gradient = correlation with the flipped kernel)
-    const float* wk = w49c + c + (MODE == 0 ? 0 : 48 * g.C);
-    const int wstep = (MODE == 0) ? g.C : -g.C;
+    const float* wk = w49c + g.c0 + c + (MODE != 1 ? 0 : 48 * g.Cfull);
+    const int wstep = (MODE != 1) ? g.Cfull : -g.Cfull;
 #pragma unroll 1
     for (int ky = 0; ky < 7; ++ky) {
       u64 wv[7];
@@ -172,20 +172,20 @@ __global__ void __launch_bounds__(BIG ? 512 : (MODE == 0 ? 384 : 448), BIG ? 1 :
   }
 
   const int oy = y0 + row;
-  if (MODE == 1) {
+  if (MODE != 0) {       // 1: data gradient (+ residual); 2: conv + bias only (channel-sliced forward, LayerNorm done separately)
     if (active && oy < g.H) {
-      const size_t off0 = (((size_t)b * g.H + oy) * g.W + x0) * g.C + c;
+      const size_t off0 = (((size_t)b * g.H + oy) * g.W + x0) * g.Cfull + g.c0 + c;
       u64 r[TW];
       // all TW residual loads are issued back to back (one latency per row, not one per pixel), then add + store
 #pragma unroll
-      for (int i = 0; i < TW; ++i) r[i] = (res && x0 + i < g.W) ? ldg_pair<TO>(res + off0 + (size_t)i * g.C) : 0ull;
+      for (int i = 0; i < TW; ++i) r[i] = (res && x0 + i < g.W) ? ldg_pair<TO>(res + off0 + (size_t)i * g.Cfull) : 0ull;
       T* ysh = reinterpret_cast<T*>(rstd_out);      // MODE 1: the rstd slot carries an optional compute-dtype copy of dx
 #pragma unroll
       for (int i = 0; i < TW; ++i) {
         if (x0 + i < g.W) {
           const float v0 = lo2(acc[i]) + lo2(r[i]), v1 = hi2(acc[i]) + hi2(r[i]);
-          stg_pair<TO>(y + off0 + (size_t)i * g.C, v0, v1);
-          if (ysh) stg_pair<T>(ysh + off0 + (size_t)i * g.C, v0, v1);
+          stg_pair<TO>(y + off0 + (size_t)i * g.Cfull, v0, v1);
+          if (ysh) stg_pair<T>(ysh + off0 + (size_t)i * g.Cfull, v0, v1);
         }
       }
     }
@@ -496,6 +496,26 @@ extern "C" int ga_dwconv7_ln_fwd(const void* x, const float* w49c, const float* 
              "ga_dwconv7_ln_fwd: x must be 16-byte, weights 8-byte aligned");
   dw::Plan p;
   int rc = dw::plan(B, H, W, C, dtype, false, &p, 384);
+  if (rc == GA_ERR_UNSUPPORTED) {
+    // the full-width halo does not fit one CTA (fp32 at C >= 976): conv + bias in channel slices, then a row LayerNorm pass
+    int nslice = 2;
+    for (;; ++nslice) {
+      GA_REQUIRE(nslice <= 16, GA_ERR_UNSUPPORTED, "dwconv7: C=%d does not fit shared memory even in 16 channel slices", C);
+      if (C % nslice || (C / nslice) % 8) continue;
+      if (dw::plan(B, H, W, C / nslice, dtype, false, &p, 448) == GA_OK) break;
+    }
+    CUtensorMap tm;
+    rc = dw::make_x_map(x, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
+    if (rc) return rc;
+    p.g.Cfull = C;
+    for (int sl = 0; sl < nslice; ++sl) {
+      p.g.c0 = sl * (C / nslice);
+      rc = dtype == GA_BF16 ? dw::launch_conv<bf16, bf16, 2>(p, tm, w49c, bias, nullptr, nullptr, nullptr, y, nullptr, 0.f, (cudaStream_t)s)
+                            : dw::launch_conv<float, float, 2>(p, tm, w49c, bias, nullptr, nullptr, nullptr, y, nullptr, 0.f, (cudaStream_t)s);
+      if (rc) return rc;
+    }
+    return ga_layernorm_fwd(y, ln_w, ln_b, y, nullptr, rstd, (long long)B * H * W, C, C, C, eps, dtype, s);
+  }
   if (rc) return rc;
   CUtensorMap tm;
   rc = dw::make_x_map(x, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
@@ -523,16 +543,26 @@ extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dre
   int rc;
   if (dx) {
     dw::Plan p;
-    rc = dw::plan(B, H, W, C, dtype, false, &p, 448);
-    if (rc) return rc;
+    int nslice = 1;
+    for (;; ++nslice) {            // fp32 at C >= 976: cover the channels in equal slices
+      GA_REQUIRE(nslice <= 16, GA_ERR_UNSUPPORTED, "dwconv7: C=%d does not fit shared memory even in 16 channel slices", C);
+      if (C % nslice || (C / nslice) % 8) continue;
+      rc = dw::plan(B, H, W, C / nslice, dtype, false, &p, 448);
+      if (rc == GA_OK) break;
+      if (rc != GA_ERR_UNSUPPORTED) return rc;
+    }
     CUtensorMap tm;
     rc = dw::make_x_map(dconv, B, H, W, C, dtype, p.g.cbox, p.tw, p.g.TH, &tm);
     if (rc) return rc;
+    p.g.Cfull = C;
+    for (int sl = 0; sl < nslice; ++sl) {
+    p.g.c0 = sl * (C / nslice);
     GA_REQUIRE(dtype == GA_BF16 || res_dtype == GA_F32, GA_ERR_UNSUPPORTED, "ga_dwconv7_bwd: fp32 gradients need an fp32 residual stream");
     if (dtype == GA_BF16 && res_dtype == GA_BF16) rc = dw::launch_conv<bf16, bf16, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, (float*)dx_shadow, 0.f, st);
     else if (dtype == GA_BF16) rc = dw::launch_conv<bf16, float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, (float*)dx_shadow, 0.f, st);
     else rc = dw::launch_conv<float, float, 1>(p, tm, w49c, nullptr, nullptr, nullptr, dres, dx, (float*)dx_shadow, 0.f, st);
     if (rc) return rc;
+    }
   }
   if (dw49c || dbias) {
     GA_REQUIRE(x && dw_partial, GA_ERR_SHAPE, "ga_dwconv7_bwd: weight gradient needs x and a partial workspace");

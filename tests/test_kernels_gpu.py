@@ -127,7 +127,7 @@ def test_gemm_rejects_cpu():
 
 
 # ------------------------------------------------------------------------------------------------- K1 dwconv + LN
-@pytest.mark.parametrize('Bn,H,Cc', [(2, 56, 96), (2, 28, 192), (3, 14, 384), (2, 7, 688), (2, 14, 192), (1, 9, 32), (2, 14, 128)])
+@pytest.mark.parametrize('Bn,H,Cc', [(2, 56, 96), (2, 28, 192), (3, 14, 384), (2, 7, 688), (2, 14, 192), (1, 9, 32), (2, 14, 128), (1, 7, 976), (1, 14, 1024)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_dwconv_ln_fwd_bwd(Bn, H, Cc, dtype):
     x = rnd(Bn * H * H, Cc, dtype=dtype, seed=20)
