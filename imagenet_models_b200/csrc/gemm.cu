@@ -25,6 +25,7 @@ struct EpiArgs {
   const void* R; long long ldr, r_bs;
   const void* Zin; long long ldz, z_bs; int zmode;
   int z_shadow;  // Z receives a bf16 copy of the final value instead of the pre-activation
+  float* colsum;  // x act' epilogue only: colsum[n] += sum_m D[m,n] (the bias gradient of the layer whose dz this GEMM produces)
   int M, N;
 };
 
@@ -459,8 +460,9 @@ enum { EPI_GENERIC = 0, EPI_BIAS_GELU_Z = 1, EPI_BIAS_GELU = 2, EPI_RES_F32_SHAD
 
 // one 32-row x 32-column chunk held in this warp's staging buffer -> global memory
 template <int EPI, bool FULL>
-__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st, int lane, int batch, int m_base, int n,
-                                               const uint2* zraw = nullptr) {
+__device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* st, int lane, int batch, int m_base, int n,
+                                                 const uint2* zraw = nullptr) {
+  float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);     // x act' epilogue: sums of this lane's 4 columns over its 8 rows
   // lane -> 4 columns (lane & 7) * 4 of rows (lane >> 3) + 4 * it, it = 0..7
   const int cl = (lane & 7) * 4;
   const int r0 = lane >> 3;
@@ -483,9 +485,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st
         }
       }
     }
-    return;
+    return csum;
   }
-  if (n >= e.N) return;
+  if (n >= e.N) return csum;
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
   if (EPI == EPI_BIAS_GELU_Z || EPI == EPI_BIAS_GELU || EPI == EPI_RES_F32_SHADOW || EPI == EPI_PLAIN_BF16) {
     if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + (long long)batch * e.bias_bs + n);
@@ -548,6 +550,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] *= (e.zmode == GA_ACT_MUL) ? zz[i] : gelu_grad_f(zz[i]);
         st4((bf16*)e.D + off, make_float4(v[0], v[1], v[2], v[3]));
+        csum.x += v[0]; csum.y += v[1]; csum.z += v[2]; csum.w += v[3];
       } else if (EPI == EPI_PLAIN_BF16) {
         st4((bf16*)e.D + off, make_float4(v[0] + bias4.x, v[1] + bias4.y, v[2] + bias4.z, v[3] + bias4.w));
       } else if (EPI == EPI_ACCUM) {
@@ -555,6 +558,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, const float* st
       }
     }
   }
+  return csum;
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -661,10 +665,32 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
     const int slice = ew >> 2;                // which quarter of the BN columns
     float* st = staging + (size_t)ew * 32 * ST_LD;
     uint32_t lt = 0;
+    // fused column sums (bias gradient) of the x act' epilogue: each lane keeps the sums of its 4 columns per chunk across
+    // the tiles of one column block and flushes (2 shuffles + one 16-byte red per 8 lanes) when the block changes
+    float4 csum[SLICE / EPI_C];
+    int cs_n0 = -1;
+    const bool want_cs = (EPI == EPI_ZIN_GELU) && e.colsum != nullptr;
+    auto cs_flush = [&]() {
+#pragma unroll
+      for (int c = 0; c < SLICE / EPI_C; ++c) {
+        float4 v = csum[c];
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+          v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+          v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+        }
+        const int ncol = cs_n0 + slice * SLICE + c * EPI_C + (lane & 7) * 4;
+        if (lane < 8 && cs_n0 >= 0 && ncol < e.N) atomicAdd(reinterpret_cast<float4*>(e.colsum + ncol), v);
+        csum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+#pragma unroll
+    for (int c = 0; c < SLICE / EPI_C; ++c) csum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const int n_t = t % nt, m_t = (t / nt) % mt, z = t / (nt * mt);
       const int batch = z / p.splits;
       const int m0 = m_t * BM, n0 = n_t * BN;
+      if (want_cs && n0 != cs_n0) { cs_flush(); cs_n0 = n0; }
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       // x act'(z) epilogue: fetch this warp's share of the saved derivative BEFORE waiting for the accumulator, so the
       // HBM latency of the per-element operand hides behind the MMA of this tile (it was exposed once per chunk)
@@ -706,11 +732,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
         }
         if (!live) continue;
         __syncwarp();
-        if (m0 + q * 32 + 32 <= e.M) epilogue_chunk<EPI, true>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4, EPI == EPI_ZIN_GELU ? zraw[c] : nullptr);
-        else epilogue_chunk<EPI, false>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4, EPI == EPI_ZIN_GELU ? zraw[c] : nullptr);
+        float4 cs;
+        if (m0 + q * 32 + 32 <= e.M) cs = epilogue_chunk<EPI, true>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4, EPI == EPI_ZIN_GELU ? zraw[c] : nullptr);
+        else cs = epilogue_chunk<EPI, false>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4, EPI == EPI_ZIN_GELU ? zraw[c] : nullptr);
+        if (EPI == EPI_ZIN_GELU) { csum[c].x += cs.x; csum[c].y += cs.y; csum[c].z += cs.z; csum[c].w += cs.w; }
         __syncwarp();
       }
     }
+    if (want_cs) cs_flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -887,6 +916,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
   e.rowscale = g->rowscale; e.rows_per_scale = g->rows_per_scale > 0 ? g->rows_per_scale : 1;
   e.R = g->R; e.ldr = g->ldr; e.r_bs = g->r_bs;
   e.Zin = g->Zin; e.ldz = g->ldz; e.z_bs = g->z_bs; e.zmode = g->zmode; e.z_shadow = g->z_shadow;
+  e.colsum = g->colsum;
   e.M = g->M; e.N = g->N;
 
   bool a_mn = false, b_mn = false;
@@ -924,6 +954,8 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
       epi = tc::EPI_ACCUM;
 #define GA_TC2(BN_, AM, BM_, EP) return tc::launch2<BN_, AM, BM_, EP>(g, e, st)
 #define GA_TC_BN(AM, BM_, EP) { if (wide256) GA_TC2(256, AM, BM_, EP); else GA_TC2(128, AM, BM_, EP); }
+    GA_REQUIRE(!g->colsum || (epi == tc::EPI_ZIN_GELU && wide && !v1_env && g->batch == 1 && (((uintptr_t)g->colsum) & 15) == 0),
+               GA_ERR_UNSUPPORTED, "ga_gemm: colsum is fused only into the tcgen05 x act' epilogue (bf16, N %% 4 == 0, N > 32)");
     if (wide && !v1_env) {
       switch (epi) {
         case tc::EPI_BIAS_GELU_Z: GA_TC_BN(false, false, tc::EPI_BIAS_GELU_Z)
@@ -948,6 +980,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
     GA_TC_CASE(true, true)
 #undef GA_TC_CASE
   }
+  GA_REQUIRE(!g->colsum, GA_ERR_UNSUPPORTED, "ga_gemm: colsum is fused only into the tcgen05 x act' epilogue");
   g_last_backend = GA_BACKEND_SIMT;
   dim3 grid((g->M + 63) / 64, (g->N + 63) / 64, g->batch);
   GA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, GA_ERR_SHAPE, "ga_gemm(simt): grid too large");

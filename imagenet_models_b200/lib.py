@@ -37,6 +37,7 @@ class GaGemm(C.Structure):
         ('R', C.c_void_p), ('ldr', C.c_longlong), ('r_bs', C.c_longlong),
         ('Zin', C.c_void_p), ('ldz', C.c_longlong), ('z_bs', C.c_longlong), ('zmode', C.c_int),
         ('backend', C.c_int), ('splits', C.c_int), ('z_shadow', C.c_int),
+        ('colsum', C.c_void_p),
     ]
 
 

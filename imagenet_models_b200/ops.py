@@ -91,7 +91,7 @@ TIMER = None      # set to a GemmTimer() to time GEMM launches
 
 def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None, rowscale=None, rows_per_scale=1,
          residual=None, zin=None, zmode=ACT_NONE, alpha=1.0, accumulate=False, out_dtype=None, backend=L.BACKEND_AUTO,
-         splits=0, shadow=None):
+         splits=0, shadow=None, colsum=None):
     """D[b,m,n] = epi(alpha * sum_k A[b,m,k] * B[b,n,k]);  A:[M,K]|[b,M,K], B:[N,K]|[b,N,K], arbitrary strides.
 
     A batch stride of 0 (expanded tensor) broadcasts that operand.  `out` may be any strided [.., M, N] view.
@@ -163,6 +163,9 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
     if shadow is not None:                       # bf16 copy of the final value, same row layout as D
         assert save_z is False and shadow.dtype == torch.bfloat16 and shadow.stride() == out.stride()
         g.Z, g.z_shadow = shadow.data_ptr(), 1
+    if colsum is not None:                       # fp32 [N], zeroed by the caller: += column sums of D (x act' epilogue only)
+        assert colsum.dtype == torch.float32 and colsum.numel() == N and colsum.is_contiguous()
+        g.colsum = colsum.data_ptr()
     g.backend, g.splits = backend, splits
     if TIMER is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -214,6 +217,19 @@ def fold_ln(w, bias, ln_w, ln_b, dtype):
     L.check(_L().ga_fold_ln(L.ptr(w), L.ptr(ln_w), L.ptr(ln_b), L.ptr(bias), L.ptr(wf), L.ptr(bf), N, K, L.ll(wf.stride(0)),
                             BF16 if dtype == torch.bfloat16 else F32, L.stream()), 'ga_fold_ln')
     return wf, bf
+
+
+def gemm_dz(dy, w_t, zgrad, sbuf):
+    """dz = (dy @ w_t^T) * zgrad together with its column sums (the bias gradient).  On the tcgen05 path the sums come out of
+    the GEMM epilogue (`sbuf`, a zeroed fp32 [N] view, receives them); otherwise dz is re-read by the column-sum kernel."""
+    N = w_t.shape[0]
+    if dy.dtype == torch.bfloat16 and N % 4 == 0 and N > 32 and sbuf.data_ptr() % 16 == 0:
+        try:
+            return gemm(dy, w_t, zin=zgrad, zmode=ACT_MUL, colsum=sbuf), sbuf
+        except L.GaError:
+            pass                                   # not fusable for these operands (checked before any launch)
+    dz = gemm(dy, w_t, zin=zgrad, zmode=ACT_MUL)
+    return dz, colsum(dz)
 
 
 def colsum(x: torch.Tensor, sumsq: bool = False):
@@ -422,13 +438,13 @@ class ConvNeXtBlockFn(Function):
                     'ga_scale_rows')
             dys = t
         # one zeroed slab for every parameter gradient of the block
-        sizes = [49 * Cc, Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, Cc, Cc, Cc * Hd, Hd * Cc]
+        sizes = [49 * Cc, Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, Cc, Cc, Cc * Hd, Hd * Cc, Hd]
         slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
         views, o = [], 0
         for n in sizes:
             views.append(slab[o:o + n])
             o += n
-        d49, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgam, G2, G1 = views
+        d49, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgam, G2, G1, s1buf = views
         # fc2: G2 = dys^T a ; dW2 = gamma*G2 ; db2 = gamma*s2 ; dgamma = rowdot(W2, G2) + b2*s2
         s2 = colsum(dys)
         gemm(dys.t(), a.t(), G2.view(Cc, Hd), accumulate=True)
@@ -436,9 +452,8 @@ class ConvNeXtBlockFn(Function):
                                             L.ptr(db2), L.ptr(dgam), None, None, Cc, Hd, L.stream()), 'linear_grad_finalize')
         # dz = (dys . (gamma*W2)) * gelu'(z)
         w2s = scale_matrix(w2, gamma, None, T)
-        dz = gemm(dys, w2s.t(), zin=z, zmode=ACT_MUL)
+        dz, s1 = gemm_dz(dys, w2s.t(), z, s1buf)
         # fc1: G1 = dz^T xhat ; dW1 = G1*ln_w + s1 (x) ln_b ; db1 = s1 ; dln_w = coldot(W1, G1) ; dln_b = W1^T s1
-        s1 = colsum(dz)
         gemm(dz.t(), xhat.t(), G1.view(Hd, Cc), accumulate=True)
         L.check(lib.ga_linear_grad_finalize(L.ptr(G1), L.ptr(s1), L.ptr(w1), None, None, L.ptr(ln_w), L.ptr(ln_b), L.ptr(dw1),
                                             L.ptr(db1), None, L.ptr(dlnw), L.ptr(dlnb), Hd, Cc, L.stream()), 'linear_grad_finalize')
@@ -1027,19 +1042,18 @@ class CSWinBlockFn(Function):
             L.check(lib.ga_scale_rows(L.ptr(t), L.ptr(ps), L.ptr(o), L.ll(M), Cc, HW, L.dt(t), L.stream()), 'ga_scale_rows')
             return o
 
-        sizes = [Cc, Cc, 3 * Cc * Cc, 3 * Cc, 9 * Cc, Cc, Cc * Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, 3 * Cc * Cc, Hd * Cc]
+        sizes = [Cc, Cc, 3 * Cc * Cc, 3 * Cc, 9 * Cc, Cc, Cc * Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, 3 * Cc * Cc, Hd * Cc, Hd]
         slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
         views, o = [], 0
         for n in sizes:
             views.append(slab[o:o + n])
             o += n
-        dn1w, dn1b, dwq, dbq, dlw, dlb, dwp, dn2w, dn2b, dw1, db1, dw2, Gq, G1 = views
+        dn1w, dn1b, dwq, dbq, dlw, dlb, dwp, dn2w, dn2b, dw1, db1, dw2, Gq, G1, s1buf = views
         # ---- MLP half: y = x1 + ps2 * (fc2(gelu(fc1'(xh2))) + b2)
         d2 = rows_scaled(dys, ps2)
         db2 = colsum(d2)
         gemm(d2.t(), a.t(), dw2.view(Cc, Hd), accumulate=True)
-        dz = gemm(d2, w2c.t(), zin=z, zmode=ACT_MUL)
-        s1 = colsum(dz)
+        dz, s1 = gemm_dz(d2, w2c.t(), z, s1buf)
         gemm(dz.t(), xh2.t(), G1.view(Hd, Cc), accumulate=True)
         L.check(lib.ga_linear_grad_finalize(L.ptr(G1), L.ptr(s1), L.ptr(w1), None, None, L.ptr(n2w), L.ptr(n2b), L.ptr(dw1),
                                             L.ptr(db1), None, L.ptr(dn2w), L.ptr(dn2b), Hd, Cc, L.stream()), 'linear_grad_finalize')

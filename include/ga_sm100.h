@@ -62,6 +62,8 @@ typedef struct GaGemm {
   int splits;     /* split-K factor for accumulate mode; 0 = auto */
   int z_shadow;   /* 1: Z receives a bf16 copy of the FINAL value (bf16 shadow of an fp32 residual stream);
                      2: Z receives act'(pre-activation) (GELU), to be applied in backward with zmode GA_ACT_MUL */
+  float* colsum;  /* optional, with Zin on the tcgen05 path only: colsum[n] += sum_m D[m,n] (fp32, 16-byte aligned; the bias
+                     gradient of the layer whose dz this GEMM produces); GA_ERR_UNSUPPORTED when it cannot be fused */
 } GaGemm;
 int ga_gemm(const GaGemm* p, ga_stream_t s);
 

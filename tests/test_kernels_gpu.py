@@ -85,6 +85,17 @@ def test_gemm_epilogues(dtype):
     assert rel(y5.float(), F.gelu(zr)) < tol(dtype) and rel(gd.float(), zq.grad) < tol(dtype)
     y6 = ops.gemm(A, B, zin=gd, zmode=L.ACT_MUL)
     assert rel(y6.float(), (A.float() @ B.float().t()) * gd.float()) < tol(dtype)
+    # the same with the bias gradient (column sums of the result) fused into the epilogue; several row tiles and column blocks
+    M2, N2 = 1000, 768
+    A2, Bt = rnd(M2, K, dtype=dtype, seed=16), rnd(K, N2, dtype=dtype, seed=17, scale=0.2)
+    g2 = rnd(M2, N2, dtype=dtype, seed=18)
+    sbuf = torch.zeros(N2, device=DEV)
+    dz, s1 = ops.gemm_dz(A2, Bt.t(), g2, sbuf)
+    ref = (A2.float() @ Bt.float()) * g2.float()
+    assert rel(dz.float(), ref) < tol(dtype)
+    assert rel(s1, ref.sum(0)) < (1e-5 if dtype == torch.float32 else 3e-3)
+    if dtype == torch.bfloat16:
+        assert s1.data_ptr() == sbuf.data_ptr()      # came out of the GEMM epilogue, not from a second pass
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
