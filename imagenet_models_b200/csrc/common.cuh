@@ -117,14 +117,7 @@ __device__ __forceinline__ float gelu_f(float x) {
   const float h = gelu_h(x, &ex);
   return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
-// gelu(x) and gelu'(x) together: the reciprocal / exponential of gelu_h are shared
-__device__ __forceinline__ void gelu_both_f(float x, float* y, float* dy) {
-  float ex;
-  const float h = gelu_h(x, &ex);
-  *y = fmaf(-fabsf(x), h, fmaxf(x, 0.f));
-  *dy = fmaf(x * 0.39894228040143268f, ex, x >= 0.f ? 1.f - h : h);
-}
-// ---- the same on two values at once with Blackwell's packed fp32x2 FMA pipe instructions (fma/mul/add.f32x2: two
+// ---- gelu and gelu' on two values at once with Blackwell's packed fp32x2 FMA pipe instructions (fma/mul/add.f32x2: two
 // results per issue slot; the GELU epilogues are issue-bound).  Bit-identical to the scalar forms above.
 typedef unsigned long long f32x2_t;
 __device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) { return ((f32x2_t)__float_as_uint(hi) << 32) | (f32x2_t)__float_as_uint(lo); }
