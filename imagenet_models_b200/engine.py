@@ -122,6 +122,38 @@ class TrainEngine:
         return loss.detach()
 
 
+class DevicePrefetcher:
+    """timm `PrefetchLoader` semantics (create_loader(..., use_prefetcher=True), GA/train.py:598-626): the NEXT batch's uint8
+    host-to-device copy and its normalisation (x - mean*255) / (std*255) run on a side stream under the current step, so PCIe
+    time disappears from the step.  submit(pinned uint8 [B,3,H,W], pinned int64 [B]) -> later get() -> (float x, y)."""
+
+    def __init__(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), device='cuda'):
+        self.device = torch.device(device)
+        self.mean = torch.tensor(mean, device=self.device).view(1, 3, 1, 1) * 255
+        self.std = torch.tensor(std, device=self.device).view(1, 3, 1, 1) * 255
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._pending = None
+
+    def submit(self, x_u8: torch.Tensor, y: torch.Tensor):
+        assert self._pending is None, 'one batch in flight'
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            x = x_u8.to(self.device, non_blocking=True).float().sub_(self.mean).div_(self.std)
+            yd = y.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending = (x, yd, ev)
+
+    def get(self):
+        x, y, ev = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        x.record_stream(cur)
+        y.record_stream(cur)
+        return x, y
+
+
 @torch.no_grad()
 def evaluate_batch(model, x, y, reduce: str = 'sum', amp_dtype=torch.bfloat16):
     """-> (loss, correct@1, correct@5, count) as device tensors (no host sync).  reduce: 'sum' (GA) | 'mean' (MAP)."""

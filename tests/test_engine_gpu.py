@@ -149,3 +149,21 @@ def test_every_other_factory_trains(name):
     m.eval()
     out = evaluate_batch(m, x, y, 'mean' if name.startswith('map_') else 'sum', amp_dtype=None)
     assert all(torch.isfinite(t.float()).all().item() for t in out)
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_matches_direct_normalisation():
+    from imagenet_models_b200.engine import DevicePrefetcher
+    pf = DevicePrefetcher()
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randint(0, 256, (4, 3, 32, 32), dtype=torch.uint8, generator=g).pin_memory(),
+                torch.randint(0, 1000, (4,), generator=g).pin_memory()) for _ in range(3)]
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1) * 255
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1) * 255
+    pf.submit(*batches[0])
+    for i in range(3):
+        x, y = pf.get()
+        if i + 1 < 3:
+            pf.submit(*batches[i + 1])                 # next copy runs under whatever the main stream does with x
+        ref = (batches[i][0].float() - mean) / std
+        assert torch.allclose(x.cpu(), ref, atol=1e-6) and torch.equal(y.cpu(), batches[i][1])
