@@ -476,7 +476,7 @@ __device__ __forceinline__ void store_frag(bf16* dst, long long ld, const float 
 
 // NKT: 16-row tiles covering the stripe (4: <= 64 tokens, 7: <= 112, 8: <= 128); one warp per tile
 template <int NKT>
-__global__ void __launch_bounds__(32 * NKT) attn_fwd_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ lw,
+__global__ void __launch_bounds__(32 * NKT, NKT <= 4 ? 1 : 3) attn_fwd_tc_kernel(const bf16* __restrict__ qkv, const float* __restrict__ lw,
                                                                const float* __restrict__ lb, bf16* __restrict__ out,
                                                                float* __restrict__ lse, int R, int C, int split, int nbr,
                                                                long long ldq, long long ldo, float c2) {
