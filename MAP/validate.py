@@ -55,6 +55,8 @@ def main():
     engine = EvalEngine(model, reduce, amp, cuda_graph=not args.no_graph)
     for _ in range(4):
         engine(x, y)                                         # warm-up forwards (MAP/validate.py:240-244) + graph capture
+    if distributed:
+        dist.all_reduce(torch.zeros(1, device='cuda'))       # NCCL communicator set-up stays out of the timed loop
     torch.cuda.synchronize()
     acc = torch.zeros(4, device='cuda')
     t0 = time.time()
