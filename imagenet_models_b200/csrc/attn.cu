@@ -12,6 +12,8 @@
 // Backward recomputes the probabilities from the saved log-sum-exp (one pass per query row for dq, one per key row
 // for dk / dv), adds the transposed LePE stencil to dv and accumulates the LePE weight gradient per CTA over a slice of
 // the batch before one atomic flush.
+#include <cuda.h>
+
 #include "common.cuh"
 
 struct AttnGeom {
@@ -322,6 +324,17 @@ int ga_attn_fwd_tc(const void* qkv, const float* lw, const float* lb, void* out,
 int ga_attn_bwd_tc(const void* dout, const void* qkv, const void* out, const float* lse, const float* lw, const float* lb, void* dqkv,
                    float* dlw, float* dlb, int B, int R, int C, int split, int nbr, long long ldq, long long ldo, long long lddo,
                    long long lddq, float scale, const AttnGeom& g, int bper, int nchunk, cudaStream_t st);
+int ga_attn_fwd_tc5(const void* qkv, const float* lw, const float* lb, void* out, float* lse, int B, int R, int C, int split, int nbr,
+                    long long ldq, long long ldo, float scale, const AttnGeom& g, cudaStream_t st);
+
+// forward backend for bf16 stripes of <= 112 tokens: 0 = register-fragment mma.sync (default, faster today), 1 = tcgen05 + TMEM +
+// TMA (tc5 below); -1 = read GA_ATTN_TCGEN05 from the environment on first use
+static int g_attn_tcgen05 = -1;
+extern "C" int ga_cswin_attn_fwd_backend(int tcgen05) {
+  const int prev = g_attn_tcgen05;
+  g_attn_tcgen05 = tcgen05;
+  return prev;
+}
 
 extern "C" int ga_cswin_attn_fwd(const void* qkv, const float* lepe_w, const float* lepe_b, void* out, float* lse, int B, int R,
                                  int C, int split, int nbr, long long ldq, long long ldo, float scale, int dtype, ga_stream_t s) {
@@ -330,7 +343,11 @@ extern "C" int ga_cswin_attn_fwd(const void* qkv, const float* lepe_w, const flo
   GA_REQUIRE(qkv && lepe_w && lepe_b && out, GA_ERR_SHAPE, "ga_cswin_attn_fwd: null argument");
   GA_REQUIRE((ldq & 3) == 0 && (ldo & 3) == 0 && ldq >= 3 * C && ldo >= C, GA_ERR_ALIGN, "ga_cswin_attn_fwd: bad pitches");
   cudaStream_t st = (cudaStream_t)s;
-  if (attn_use_tc(dtype, ldq, ldo, 8, 8)) return ga_attn_fwd_tc(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
+  if (attn_use_tc(dtype, ldq, ldo, 8, 8)) {
+    if (g_attn_tcgen05 < 0) { const char* e5 = getenv("GA_ATTN_TCGEN05"); g_attn_tcgen05 = (e5 && atoi(e5)) ? 1 : 0; }
+    if (g_attn_tcgen05 && g.n <= 112) return ga_attn_fwd_tc5(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
+    return ga_attn_fwd_tc(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
+  }
   const size_t smem = (size_t)(2 * g.n4 * RS + 10 * HD) * sizeof(float);
   const dim3 grid(g.units, B);
 #define GA_ATTN_FWD(T, NT)                                                                                        \
@@ -793,4 +810,253 @@ int ga_attn_bwd_tc(const void* dout, const void* qkv, const void* out, const flo
 #undef GA_TCB
   ga_count_launch();
   return ga_check_launch("cswin_attn_bwd_tc");
+}
+
+// ================================================================================================ tcgen05 / TMEM / TMA forward
+// The same unit of work on the 5th-generation tensor cores: one CTA = (image, branch, stripe, head), 128 threads.
+//   * Q, K, V of the stripe arrive by TMA: one 4-D box {64 channels, ws, hs, 1} per tensor over the [B, R, R, 3C] qkv rows lands
+//     as a K-major SWIZZLE_128B tile (128-byte rows = 64 bf16, of which this head's 32 are used; rows = stripe tokens in
+//     (y, x) order), so the window gather of img2windows is the tensor map and the tile is directly a UMMA operand.
+//   * S = Q K^T: two tcgen05.mma (M=128, N=112, K=16 each, descriptor advanced 32 B inside the swizzle atom) into TMEM columns
+//     [0,112); every thread owns one query row = one TMEM lane, reads it back with tcgen05.ld, does the softmax in registers
+//     and writes P (bf16) into shared memory in the K-major swizzled layout (two 64-wide k-blocks).
+//   * O = P V: seven tcgen05.mma (M=128, N=64, K=16) with V as the MN-major operand straight from its TMA tile, into TMEM
+//     columns [128,192); the epilogue scales by 1/l, adds the LePE stencil (read from the swizzled V tile) and stores.
+// Rows / keys beyond the stripe's n tokens: V rows >= n are zero-filled before the TMA (0 * garbage must not make NaN), score
+// columns >= n are masked by index.
+namespace tc5 {
+constexpr uint32_t TILE_BYTES = 128 * 128;      // 128 rows x 128 B
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// SWIZZLE_128B descriptor (see gemm.cu): K-major lbo 16 / sbo 1024; MN-major lbo 8192 / sbo 1024
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+// byte offset of the 16-byte chunk `ch16` (0..7) of row r inside a [rows x 128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz(int r, int ch16) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((ch16 ^ (r & 7)) << 4)); }
+
+__global__ void __launch_bounds__(128) attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                                                           const float* __restrict__ lw, const float* __restrict__ lb,
+                                                           bf16* __restrict__ out, float* __restrict__ lse, int R, int C, int split,
+                                                           int nbr, long long ldo, float c2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* Qt = sm;
+  uint8_t* Kt = Qt + TILE_BYTES;
+  uint8_t* Vt = Kt + TILE_BYTES;
+  uint8_t* Pt = Vt + TILE_BYTES;                 // two k-blocks of [128 x 64]
+  float* wsm = (float*)(Pt + 2 * TILE_BYTES);    // [9][32]
+  float* bsm = wsm + 9 * HD;
+  uint64_t* bars = (uint64_t*)(bsm + HD);        // tma, s, o
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3);
+
+  const Unit u = decode_unit(blockIdx.x, R, C, split, nbr);
+  const int b = blockIdx.y;
+  const int n = u.hs * u.ws;
+  const int t = threadIdx.x, warp = t >> 5;
+  const bool br1 = (nbr == 2) && (u.hs != R);    // branch 1 stripes are split x R
+
+  // zero V rows >= n (TMA fills rows < n only), stage the LePE weights
+  for (int idx = t; idx < (128 - n) * 8; idx += 128) {
+    const int r = n + (idx >> 3);
+    *reinterpret_cast<uint4*>(Vt + r * 128 + (idx & 7) * 16) = make_uint4(0, 0, 0, 0);   // whole rows: swizzle stays inside the row
+  }
+  for (int idx = t; idx < 9 * HD; idx += 128) wsm[idx] = lw[(u.cb + (idx & 31)) * 9 + (idx >> 5)];
+  if (t < HD) bsm[t] = lb[u.cb + t];
+  if (t == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill before async-proxy (TMA / UMMA) accesses
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (t == 0) {
+    const CUtensorMap* tm = br1 ? &tm1 : &tm0;
+    mbar_expect_tx(&bars[0], 3u * (uint32_t)n * 128u);
+    tma_load_4d(smem_u32(Qt), tm, &bars[0], u.cb, u.x0, u.y0, b);
+    tma_load_4d(smem_u32(Kt), tm, &bars[0], C + u.cb, u.x0, u.y0, b);
+    tma_load_4d(smem_u32(Vt), tm, &bars[0], 2 * C + u.cb, u.x0, u.y0, b);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint64_t qd = make_desc(smem_u32(Qt), 16, 1024), kd = make_desc(smem_u32(Kt), 16, 1024);
+    constexpr uint32_t id_s = idesc_bf16(128, 112, false, false);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) umma_bf16(tS, qd + (uint64_t)((k * 32) >> 4), kd + (uint64_t)((k * 32) >> 4), id_s, k > 0 ? 1u : 0u);
+    umma_commit(&bars[1]);
+  }
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  // ---- softmax of row t (TMEM lane t); the stripe has n <= 112 keys
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tS + lane_addr + (uint32_t)(c * 32), r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (c * 32 + j < n) mx = fmaxf(mx, __uint_as_float(r[j]));
+  }
+  const float mxs = mx * c2;
+  float l = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tS + lane_addr + (uint32_t)(c * 32), r);
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float p0 = (c * 32 + j < n) ? ex2(fmaf(__uint_as_float(r[j]), c2, -mxs)) : 0.f;
+      const float p1 = (c * 32 + j + 1 < n) ? ex2(fmaf(__uint_as_float(r[j + 1]), c2, -mxs)) : 0.f;
+      l += p0 + p1;
+      pk[j >> 1] = pack_bf16(p0, p1);
+    }
+    uint8_t* blk = Pt + (c >> 1) * TILE_BYTES;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<uint4*>(blk + swz(t, (c & 1) * 4 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (t == 0) {
+    constexpr uint32_t id_o = idesc_bf16(128, 64, false, true);
+#pragma unroll
+    for (int ks = 0; ks < 7; ++ks) {            // 112 keys = 7 steps of 16
+      const int kb = ks >> 2, kk = ks & 3;
+      const uint64_t pd = make_desc(smem_u32(Pt + kb * TILE_BYTES), 16, 1024) + (uint64_t)((kk * 32) >> 4);
+      const uint64_t vd = make_desc(smem_u32(Vt + kb * 8192), 8192, 1024) + (uint64_t)((kk * 16 * 128) >> 4);
+      umma_bf16(tO, pd, vd, id_o, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(&bars[2]);
+  }
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  uint32_t r[32];
+  tmem_ld32(tO + lane_addr, r);                 // .sync.aligned: every lane of the warp takes part, also rows >= n
+  if (t < n) {
+    const float inv = 1.f / l;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = fmaf(__uint_as_float(r[d]), inv, bsm[d]);
+    const int ry = t / u.ws, rx = t - ry * u.ws;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = ry + tap / 3 - 1, xx = rx + tap % 3 - 1;
+      if (yy < 0 || yy >= u.hs || xx < 0 || xx >= u.ws) continue;
+      const int j = yy * u.ws + xx;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+        ld8_bf16(reinterpret_cast<const bf16*>(Vt + swz(j, q)), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[q * 8 + e] = fmaf(wsm[tap * HD + q * 8 + e], v[e], o[q * 8 + e]);
+      }
+    }
+    const long long row = tok_row(u, b, R, t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) st8_bf16(out + row * ldo + u.cb + q * 8, o + q * 8);
+    if (lse) lse[row * (C / HD) + u.hg] = mxs + log2f(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+}  // namespace tc5
+
+int ga_attn_fwd_tc5(const void* qkv, const float* lw, const float* lb, void* out, float* lse, int B, int R, int C, int split, int nbr,
+                    long long ldq, long long ldo, float scale, const AttnGeom& g, cudaStream_t st) {
+  GA_REQUIRE(g.n <= 112 && (ldq & 7) == 0 && (ldo & 7) == 0 && (((uintptr_t)qkv | (uintptr_t)out) & 15) == 0, GA_ERR_UNSUPPORTED,
+             "ga_cswin_attn_fwd (tcgen05): stripes of at most 112 tokens, 16-byte aligned rows");
+  CUtensorMap tm0, tm1;
+  const uint64_t dims[4] = {(uint64_t)(3 * C), (uint64_t)R, (uint64_t)R, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)ldq * 2, (uint64_t)R * ldq * 2, (uint64_t)R * R * ldq * 2};
+  const uint32_t box0[4] = {64, (uint32_t)(nbr == 1 ? R : split), (uint32_t)R, 1};
+  const uint32_t box1[4] = {64, (uint32_t)R, (uint32_t)(nbr == 1 ? R : split), 1};
+  int rc = ga_tensor_map(&tm0, GA_BF16, 4, qkv, dims, strides, box0, 1);
+  if (rc) return rc;
+  rc = ga_tensor_map(&tm1, GA_BF16, 4, qkv, dims, strides, box1, 1);
+  if (rc) return rc;
+  const size_t smem = 1024 + 5 * (size_t)tc5::TILE_BYTES + (10 * HD) * sizeof(float) + 64;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tc5::attn_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  const dim3 grid(g.units, B);
+  tc5::attn_fwd_tc5_kernel<<<grid, 128, smem, st>>>(tm0, tm1, lw, lb, (bf16*)out, lse, R, C, split, nbr, ldo, scale * LOG2E);
+  ga_count_launch();
+  return ga_check_launch("cswin_attn_fwd_tc5");
 }

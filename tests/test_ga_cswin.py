@@ -207,6 +207,38 @@ def test_stripe_attention_vs_oracle(R, split, nbr, C, B, dtype, tol):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('R,split,nbr,C,B', [(14, 7, 2, 64, 3), (28, 2, 2, 128, 2), (7, 7, 1, 96, 2), (9, 3, 2, 64, 2)])
+def test_stripe_attention_tcgen05_forward_matches_mma_sync_and_oracle(R, split, nbr, C, B):
+    """The tcgen05 / TMEM / TMA forward (opt-in backend) against the default kernel and the oracle on the same bf16 inputs."""
+    from imagenet_models_b200 import ops
+    lib = L.load()
+    g = torch.Generator().manual_seed(R * 7 + C)
+    qkv = torch.randn(B * R * R, 3 * C, generator=g).bfloat16().cuda()
+    lw = (torch.randn(C, 9, generator=g) * 0.3).cuda()
+    lb = (torch.randn(C, generator=g) * 0.1).cuda()
+    prev = lib.ga_cswin_attn_fwd_backend(0)
+    try:
+        o0, l0 = ops._attn_fwd(qkv, lw, lb, B, R, C, split, nbr, True)
+        lib.ga_cswin_attn_fwd_backend(1)
+        o1, l1 = ops._attn_fwd(qkv, lw, lb, B, R, C, split, nbr, True)
+    finally:
+        lib.ga_cswin_attn_fwd_backend(prev)
+    assert rel(o1.float(), o0.float()) < 6e-3 and rel(l1, l0) < 1e-4
+    cb = C // nbr
+    P = {f'{i}.get_v.weight': lw[i * cb:(i + 1) * cb].cpu().reshape(cb, 1, 3, 3) for i in range(nbr)}
+    P.update({f'{i}.get_v.bias': lb[i * cb:(i + 1) * cb].cpu() for i in range(nbr)})
+    qf = qkv.float().cpu().reshape(B, R * R, 3 * C)
+    q, k, v = qf[..., :C], qf[..., C:2 * C], qf[..., 2 * C:]
+    if nbr == 2:
+        h = C // 2
+        ref = torch.cat((CO.lepe_attention(P, '0.', q[..., :h], k[..., :h], v[..., :h], R, R, split, h // 32),
+                         CO.lepe_attention(P, '1.', q[..., h:], k[..., h:], v[..., h:], R, split, R, h // 32)), 2)
+    else:
+        ref = CO.lepe_attention(P, '0.', q, k, v, R, R, R, C // 32)
+    assert rel(o1.float().cpu().reshape(ref.shape), ref) < 1.5e-2
+
+
+@pytest.mark.gpu
 def test_stripe_attention_rejects_bad_geometry():
     from imagenet_models_b200 import ops
     q = torch.zeros(2 * 56 * 56, 3 * 64, device='cuda')
