@@ -327,8 +327,9 @@ int ga_attn_bwd_tc(const void* dout, const void* qkv, const void* out, const flo
 int ga_attn_fwd_tc5(const void* qkv, const float* lw, const float* lb, void* out, float* lse, int B, int R, int C, int split, int nbr,
                     long long ldq, long long ldo, float scale, const AttnGeom& g, cudaStream_t st);
 
-// forward backend for bf16 stripes of <= 112 tokens: 0 = register-fragment mma.sync (default, faster today), 1 = tcgen05 + TMEM +
-// TMA (tc5 below); -1 = read GA_ATTN_TCGEN05 from the environment on first use
+// forward backend for bf16 stripes of <= 112 tokens: 0 = register-fragment mma.sync, 1 = tcgen05 + TMEM + TMA (tc5 below),
+// 2 = auto (tcgen05 for 65..112-token stripes with an even head count, else mma.sync); -1 = GA_ATTN_TCGEN05 from the
+// environment on first use, auto when unset
 static int g_attn_tcgen05 = -1;
 extern "C" int ga_cswin_attn_fwd_backend(int tcgen05) {
   const int prev = g_attn_tcgen05;
@@ -344,8 +345,11 @@ extern "C" int ga_cswin_attn_fwd(const void* qkv, const float* lepe_w, const flo
   GA_REQUIRE((ldq & 3) == 0 && (ldo & 3) == 0 && ldq >= 3 * C && ldo >= C, GA_ERR_ALIGN, "ga_cswin_attn_fwd: bad pitches");
   cudaStream_t st = (cudaStream_t)s;
   if (attn_use_tc(dtype, ldq, ldo, 8, 8)) {
-    if (g_attn_tcgen05 < 0) { const char* e5 = getenv("GA_ATTN_TCGEN05"); g_attn_tcgen05 = (e5 && atoi(e5)) ? 1 : 0; }
-    if (g_attn_tcgen05 && g.n <= 112) return ga_attn_fwd_tc5(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
+    if (g_attn_tcgen05 < 0) { const char* e5 = getenv("GA_ATTN_TCGEN05"); g_attn_tcgen05 = e5 ? (atoi(e5) ? 1 : 0) : 2; }
+    // 2 = auto: the tcgen05 kernel where it is at least as fast as the register-fragment one (measured, scripts/attn_bench.py):
+    // long stripes (65..112 tokens fill the M = 128 tile) with an even number of heads per branch (no idle warpgroup)
+    const bool tc5_auto = g_attn_tcgen05 == 2 && g.n > 64 && ((C / nbr / HD) & 1) == 0;
+    if ((g_attn_tcgen05 == 1 || tc5_auto) && g.n <= 112) return ga_attn_fwd_tc5(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
     return ga_attn_fwd_tc(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
   }
   const size_t smem = (size_t)(2 * g.n4 * RS + 10 * HD) * sizeof(float);
@@ -905,7 +909,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn, bool 
 // byte offset of the 16-byte chunk `ch16` (0..7) of row r inside a [rows x 128 B] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t swz(int r, int ch16) { return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((ch16 ^ (r & 7)) << 4)); }
 
-__global__ void __launch_bounds__(128) attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+// One CTA = (image, branch, stripe, PAIR of heads), 256 threads: warpgroup g (threads 128 g ..) owns head 2*pair + g, thread
+// (t & 127) owns query row / TMEM lane (t & 127).  The 64-channel TMA box feeds both heads (k-steps 0,1 -> head A; 2,3 -> head B).
+// TMEM (256 columns): S_A [0,128), S_B [128,256); O_g overwrites the first 64 columns of S_g once the softmax has consumed it.
+// Shared memory: Q, K, V tiles (48 KB) + P_A (32 KB); P_B overlays Q and K, which are dead after the S products.
+__global__ void __launch_bounds__(256) attn_fwd_tc5_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                                                            const float* __restrict__ lw, const float* __restrict__ lb,
                                                            bf16* __restrict__ out, float* __restrict__ lse, int R, int C, int split,
                                                            int nbr, long long ldo, float c2) {
@@ -914,55 +922,75 @@ __global__ void __launch_bounds__(128) attn_fwd_tc5_kernel(const __grid_constant
   uint8_t* Qt = sm;
   uint8_t* Kt = Qt + TILE_BYTES;
   uint8_t* Vt = Kt + TILE_BYTES;
-  uint8_t* Pt = Vt + TILE_BYTES;                 // two k-blocks of [128 x 64]
-  float* wsm = (float*)(Pt + 2 * TILE_BYTES);    // [9][32]
-  float* bsm = wsm + 9 * HD;
-  uint64_t* bars = (uint64_t*)(bsm + HD);        // tma, s, o
+  uint8_t* Pa = Vt + TILE_BYTES;                 // two k-blocks of [128 x 64]
+  float* wsm = (float*)(Pa + 2 * TILE_BYTES);    // [9][64]
+  float* bsm = wsm + 9 * 64;                     // [64]
+  uint64_t* bars = (uint64_t*)(bsm + 64);        // tma, s, o
   uint32_t* tmem_slot = (uint32_t*)(bars + 3);
 
-  const Unit u = decode_unit(blockIdx.x, R, C, split, nbr);
+  // unit -> (branch, stripe, head pair)
+  const int hb = C / nbr / HD, hp = (hb + 1) >> 1;
+  int br = 0, stp = 0, pair = blockIdx.x;
+  if (nbr == 2) {
+    const int nst = R / split;
+    br = blockIdx.x / (nst * hp);
+    const int rem = blockIdx.x - br * nst * hp;
+    stp = rem / hp;
+    pair = rem - stp * hp;
+  }
+  Unit u;
+  if (nbr == 1) { u.hs = R; u.ws = R; u.y0 = 0; u.x0 = 0; }
+  else if (br == 0) { u.hs = R; u.ws = split; u.y0 = 0; u.x0 = stp * split; }
+  else { u.hs = split; u.ws = R; u.y0 = stp * split; u.x0 = 0; }
   const int b = blockIdx.y;
   const int n = u.hs * u.ws;
-  const int t = threadIdx.x, warp = t >> 5;
-  const bool br1 = (nbr == 2) && (u.hs != R);    // branch 1 stripes are split x R
+  const int t = threadIdx.x, wg = t >> 7, row = t & 127, warp4 = (t >> 5) & 3;
+  const int head = 2 * pair + wg;                // head of this warpgroup inside the branch
+  const bool hvalid = head < hb;
+  const int cb0 = br * (C / nbr) + 2 * pair * HD;   // first channel of the pair
+  u.cb = cb0 + wg * HD;
+  u.hg = br * hb + head;
 
-  // zero V rows >= n (TMA fills rows < n only), stage the LePE weights
-  for (int idx = t; idx < (128 - n) * 8; idx += 128) {
+  for (int idx = t; idx < (128 - n) * 8; idx += 256) {
     const int r = n + (idx >> 3);
     *reinterpret_cast<uint4*>(Vt + r * 128 + (idx & 7) * 16) = make_uint4(0, 0, 0, 0);   // whole rows: swizzle stays inside the row
   }
-  for (int idx = t; idx < 9 * HD; idx += 128) wsm[idx] = lw[(u.cb + (idx & 31)) * 9 + (idx >> 5)];
-  if (t < HD) bsm[t] = lb[u.cb + t];
+  for (int idx = t; idx < 9 * 64; idx += 256) {
+    const int c = cb0 + (idx & 63);
+    wsm[idx] = c < (br + 1) * (C / nbr) ? lw[c * 9 + (idx >> 6)] : 0.f;
+  }
+  if (t < 64) bsm[t] = cb0 + t < (br + 1) * (C / nbr) ? lb[cb0 + t] : 0.f;
   if (t == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if ((t >> 5) == 0) tmem_alloc(tmem_slot, 256);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill before async-proxy (TMA / UMMA) accesses
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+  const uint32_t tS = tmem_base + (uint32_t)(wg * 128), tO = tS;
 
   if (t == 0) {
-    const CUtensorMap* tm = br1 ? &tm1 : &tm0;
+    const CUtensorMap* tm = (nbr == 2 && br == 1) ? &tm1 : &tm0;
     mbar_expect_tx(&bars[0], 3u * (uint32_t)n * 128u);
-    tma_load_4d(smem_u32(Qt), tm, &bars[0], u.cb, u.x0, u.y0, b);
-    tma_load_4d(smem_u32(Kt), tm, &bars[0], C + u.cb, u.x0, u.y0, b);
-    tma_load_4d(smem_u32(Vt), tm, &bars[0], 2 * C + u.cb, u.x0, u.y0, b);
+    tma_load_4d(smem_u32(Qt), tm, &bars[0], cb0, u.x0, u.y0, b);
+    tma_load_4d(smem_u32(Kt), tm, &bars[0], C + cb0, u.x0, u.y0, b);
+    tma_load_4d(smem_u32(Vt), tm, &bars[0], 2 * C + cb0, u.x0, u.y0, b);
     mbar_wait(&bars[0], 0);
     tc_fence_after();
     const uint64_t qd = make_desc(smem_u32(Qt), 16, 1024), kd = make_desc(smem_u32(Kt), 16, 1024);
     constexpr uint32_t id_s = idesc_bf16(128, 112, false, false);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) umma_bf16(tS, qd + (uint64_t)((k * 32) >> 4), kd + (uint64_t)((k * 32) >> 4), id_s, k > 0 ? 1u : 0u);
+    for (int k = 0; k < 4; ++k)                 // k-steps 0,1: head A channels; 2,3: head B channels
+      umma_bf16(tmem_base + (uint32_t)((k >> 1) * 128), qd + (uint64_t)((k * 32) >> 4), kd + (uint64_t)((k * 32) >> 4), id_s, (k & 1) ? 1u : 0u);
     umma_commit(&bars[1]);
   }
   mbar_wait(&bars[1], 0);
   tc_fence_after();
-  // ---- softmax of row t (TMEM lane t); the stripe has n <= 112 keys
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  // ---- softmax of row `row` of this warpgroup's head; the stripe has n <= 112 keys
+  const uint32_t lane_addr = (uint32_t)(warp4 * 32) << 16;
   float mx = -INFINITY;
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
@@ -973,6 +1001,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc5_kernel(const __grid_constant
   }
   const float mxs = mx * c2;
   float l = 0.f;
+  uint8_t* Pt = wg == 0 ? Pa : Qt;              // P_B overlays Q | K
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     uint32_t r[32];
@@ -988,7 +1017,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc5_kernel(const __grid_constant
     uint8_t* blk = Pt + (c >> 1) * TILE_BYTES;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<uint4*>(blk + swz(t, (c & 1) * 4 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      *reinterpret_cast<uint4*>(blk + swz(row, (c & 1) * 4 + q)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
@@ -997,24 +1026,28 @@ __global__ void __launch_bounds__(128) attn_fwd_tc5_kernel(const __grid_constant
   if (t == 0) {
     constexpr uint32_t id_o = idesc_bf16(128, 64, false, true);
 #pragma unroll
-    for (int ks = 0; ks < 7; ++ks) {            // 112 keys = 7 steps of 16
-      const int kb = ks >> 2, kk = ks & 3;
-      const uint64_t pd = make_desc(smem_u32(Pt + kb * TILE_BYTES), 16, 1024) + (uint64_t)((kk * 32) >> 4);
-      const uint64_t vd = make_desc(smem_u32(Vt + kb * 8192), 8192, 1024) + (uint64_t)((kk * 16 * 128) >> 4);
-      umma_bf16(tO, pd, vd, id_o, ks > 0 ? 1u : 0u);
+    for (int g2 = 0; g2 < 2; ++g2) {
+      const uint8_t* Pg = g2 == 0 ? Pa : Qt;
+#pragma unroll
+      for (int ks = 0; ks < 7; ++ks) {          // 112 keys = 7 steps of 16
+        const int kb = ks >> 2, kk = ks & 3;
+        const uint64_t pd = make_desc(smem_u32(Pg + kb * TILE_BYTES), 16, 1024) + (uint64_t)((kk * 32) >> 4);
+        const uint64_t vd = make_desc(smem_u32(Vt + kb * 8192), 8192, 1024) + (uint64_t)((kk * 16 * 128) >> 4);
+        umma_bf16(tmem_base + (uint32_t)(g2 * 128), pd, vd, id_o, ks > 0 ? 1u : 0u);
+      }
     }
     umma_commit(&bars[2]);
   }
   mbar_wait(&bars[2], 0);
   tc_fence_after();
   uint32_t r[32];
-  tmem_ld32(tO + lane_addr, r);                 // .sync.aligned: every lane of the warp takes part, also rows >= n
-  if (t < n) {
+  tmem_ld32(tO + lane_addr + (uint32_t)(wg * 32), r);   // O columns wg*32.. = this head's 32 channels of the 64-wide product
+  if (row < n && hvalid) {
     const float inv = 1.f / l;
     float o[HD];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = fmaf(__uint_as_float(r[d]), inv, bsm[d]);
-    const int ry = t / u.ws, rx = t - ry * u.ws;
+    for (int d = 0; d < HD; ++d) o[d] = fmaf(__uint_as_float(r[d]), inv, bsm[wg * HD + d]);
+    const int ry = row / u.ws, rx = row - ry * u.ws;
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int yy = ry + tap / 3 - 1, xx = rx + tap % 3 - 1;
@@ -1023,19 +1056,19 @@ __global__ void __launch_bounds__(128) attn_fwd_tc5_kernel(const __grid_constant
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float v[8];
-        ld8_bf16(reinterpret_cast<const bf16*>(Vt + swz(j, q)), v);
+        ld8_bf16(reinterpret_cast<const bf16*>(Vt + swz(j, wg * 4 + q)), v);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[q * 8 + e] = fmaf(wsm[tap * HD + q * 8 + e], v[e], o[q * 8 + e]);
+        for (int e = 0; e < 8; ++e) o[q * 8 + e] = fmaf(wsm[tap * 64 + wg * HD + q * 8 + e], v[e], o[q * 8 + e]);
       }
     }
-    const long long row = tok_row(u, b, R, t);
+    const long long grow = tok_row(u, b, R, row);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) st8_bf16(out + row * ldo + u.cb + q * 8, o + q * 8);
-    if (lse) lse[row * (C / HD) + u.hg] = mxs + log2f(l);
+    for (int q = 0; q < 4; ++q) st8_bf16(out + grow * ldo + u.cb + q * 8, o + q * 8);
+    if (lse) lse[grow * (C / HD) + u.hg] = mxs + log2f(l);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if ((t >> 5) == 0) tmem_dealloc(tmem_base, 256);
 }
 }  // namespace tc5
 
@@ -1052,11 +1085,12 @@ int ga_attn_fwd_tc5(const void* qkv, const float* lw, const float* lb, void* out
   if (rc) return rc;
   rc = ga_tensor_map(&tm1, GA_BF16, 4, qkv, dims, strides, box1, 1);
   if (rc) return rc;
-  const size_t smem = 1024 + 5 * (size_t)tc5::TILE_BYTES + (10 * HD) * sizeof(float) + 64;
+  const size_t smem = 1024 + 5 * (size_t)tc5::TILE_BYTES + (10 * 64) * sizeof(float) + 64;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(tc5::attn_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  const dim3 grid(g.units, B);
-  tc5::attn_fwd_tc5_kernel<<<grid, 128, smem, st>>>(tm0, tm1, lw, lb, (bf16*)out, lse, R, C, split, nbr, ldo, scale * LOG2E);
+  const int hb = C / nbr / HD, hp = (hb + 1) / 2;
+  const dim3 grid(nbr == 1 ? hp : 2 * (R / split) * hp, B);      // one CTA per pair of heads
+  tc5::attn_fwd_tc5_kernel<<<grid, 256, smem, st>>>(tm0, tm1, lw, lb, (bf16*)out, lse, R, C, split, nbr, ldo, scale * LOG2E);
   ga_count_launch();
   return ga_check_launch("cswin_attn_fwd_tc5");
 }

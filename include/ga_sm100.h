@@ -178,9 +178,9 @@ int ga_gram_triu_bwd(const void* dout, const void* out, const float* norm, void*
  * out [B*R*R, C] = softmax(scale q k^T) v + dw3x3(v inside the stripe);  lse [B*R*R, C/32] fp32 (log2 units) or NULL. */
 int ga_cswin_attn_fwd(const void* qkv, const float* lepe_w, const float* lepe_b, void* out, float* lse, int B, int R,
                       int C, int split, int nbr, long long ldq, long long ldo, float scale, int dtype, ga_stream_t s);
-/* bf16 forward backend for stripes of <= 112 tokens: 0 = register-fragment mma.sync kernel (default), 1 = tcgen05 kernel (Q/K/V
- * by 4-D TMA boxes straight into UMMA operand tiles, S and O accumulated in TMEM); returns the previous setting.
- * Also selectable with GA_ATTN_TCGEN05=1 in the environment. */
+/* bf16 forward backend for stripes of <= 112 tokens: 0 = register-fragment mma.sync kernel, 1 = tcgen05 kernel (Q/K/V by 4-D TMA
+ * boxes straight into UMMA operand tiles, S and O accumulated in TMEM, two heads per CTA), 2 = auto (default: tcgen05 for
+ * 65..112-token stripes with an even head count per branch); returns the previous setting.  GA_ATTN_TCGEN05=0/1 forces one. */
 int ga_cswin_attn_fwd_backend(int tcgen05);
 /* dqkv [B*R*R, 3C] is fully overwritten; dlepe_w / dlepe_b are accumulated (+=, atomics) */
 int ga_cswin_attn_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const float* lepe_w,
