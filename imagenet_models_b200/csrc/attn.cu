@@ -327,29 +327,19 @@ int ga_attn_bwd_tc(const void* dout, const void* qkv, const void* out, const flo
 int ga_attn_fwd_tc5(const void* qkv, const float* lw, const float* lb, void* out, float* lse, int B, int R, int C, int split, int nbr,
                     long long ldq, long long ldo, float scale, const AttnGeom& g, cudaStream_t st);
 
-// forward backend for bf16 stripes of <= 112 tokens: 0 = register-fragment mma.sync, 1 = tcgen05 + TMEM + TMA (tc5 below),
-// 2 = auto (tcgen05 for 65..112-token stripes with an even head count, else mma.sync); -1 = GA_ATTN_TCGEN05 from the
-// environment on first use, auto when unset
-static int g_attn_tcgen05 = -1;
-extern "C" int ga_cswin_attn_fwd_backend(int tcgen05) {
-  const int prev = g_attn_tcgen05;
-  g_attn_tcgen05 = tcgen05;
-  return prev;
-}
-
 extern "C" int ga_cswin_attn_fwd(const void* qkv, const float* lepe_w, const float* lepe_b, void* out, float* lse, int B, int R,
-                                 int C, int split, int nbr, long long ldq, long long ldo, float scale, int dtype, ga_stream_t s) {
+                                 int C, int split, int nbr, long long ldq, long long ldo, float scale, int dtype, int backend,
+                                 ga_stream_t s) {
   AttnGeom g;
   if (int rc = attn_geom(B, R, C, split, nbr, &g)) return rc;
   GA_REQUIRE(qkv && lepe_w && lepe_b && out, GA_ERR_SHAPE, "ga_cswin_attn_fwd: null argument");
   GA_REQUIRE((ldq & 3) == 0 && (ldo & 3) == 0 && ldq >= 3 * C && ldo >= C, GA_ERR_ALIGN, "ga_cswin_attn_fwd: bad pitches");
   cudaStream_t st = (cudaStream_t)s;
   if (attn_use_tc(dtype, ldq, ldo, 8, 8)) {
-    if (g_attn_tcgen05 < 0) { const char* e5 = getenv("GA_ATTN_TCGEN05"); g_attn_tcgen05 = e5 ? (atoi(e5) ? 1 : 0) : 2; }
-    // 2 = auto: the tcgen05 kernel where it is at least as fast as the register-fragment one (measured, scripts/attn_bench.py):
+    // auto: the tcgen05 kernel where it is at least as fast as the register-fragment one (measured, scripts/attn_bench.py):
     // long stripes (65..112 tokens fill the M = 128 tile) with an even number of heads per branch (no idle warpgroup)
-    const bool tc5_auto = g_attn_tcgen05 == 2 && g.n > 64 && ((C / nbr / HD) & 1) == 0;
-    if ((g_attn_tcgen05 == 1 || tc5_auto) && g.n <= 112) return ga_attn_fwd_tc5(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
+    const bool tc5_auto = backend == GA_BACKEND_AUTO && g.n > 64 && ((C / nbr / HD) & 1) == 0;
+    if ((backend == GA_BACKEND_TCGEN05 || tc5_auto) && g.n <= 112) return ga_attn_fwd_tc5(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
     return ga_attn_fwd_tc(qkv, lepe_w, lepe_b, out, lse, B, R, C, split, nbr, ldq, ldo, scale, g, st);
   }
   const size_t smem = (size_t)(2 * g.n4 * RS + 10 * HD) * sizeof(float);

@@ -881,8 +881,6 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------ entry point
-static int g_last_backend = 0;
-extern "C" int ga_gemm_last_backend(void) { return g_last_backend; }
 
 static bool tc_eligible(const GaGemm* g, bool* a_mn, bool* b_mn) {
   if (g->in_dtype != GA_BF16) return false;
@@ -926,7 +924,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
   if (g->backend == GA_BACKEND_TCGEN05)
     GA_REQUIRE(use_tc, GA_ERR_ALIGN, "ga_gemm: operands not eligible for the tcgen05 path (bf16, 16B-aligned, unit stride)");
   if (use_tc) {
-    g_last_backend = GA_BACKEND_TCGEN05;
+    if (g->backend_used) *g->backend_used = GA_BACKEND_TCGEN05;
     static int v1_env = -1;
     if (v1_env < 0) { const char* sv = getenv("GA_GEMM_V1"); v1_env = (sv && atoi(sv)) ? 1 : 0; }
     const bool wide = g->N > 32;   // N in (32, 64] also takes the persistent kernel (half of a BN=128 tile idle; these GEMMs are HBM-bound)
@@ -981,7 +979,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
 #undef GA_TC_CASE
   }
   GA_REQUIRE(!g->colsum, GA_ERR_UNSUPPORTED, "ga_gemm: colsum is fused only into the tcgen05 x act' epilogue");
-  g_last_backend = GA_BACKEND_SIMT;
+  if (g->backend_used) *g->backend_used = GA_BACKEND_SIMT;
   dim3 grid((g->M + 63) / 64, (g->N + 63) / 64, g->batch);
   GA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, GA_ERR_SHAPE, "ga_gemm(simt): grid too large");
   if (g->in_dtype == GA_F32)

@@ -43,7 +43,26 @@ int ga_num_sms() {
 }
 
 extern "C" int ga_version(void) { return 100; }
-extern "C" const char* ga_last_error(void) { return g_err; }
+// message of the calling thread's last failed call, copied into the caller's buffer (always NUL-terminated); returns its length
+extern "C" int ga_last_error(char* buf, size_t n) {
+  const size_t len = strlen(g_err);
+  if (buf && n) {
+    const size_t c = len < n - 1 ? len : n - 1;
+    memcpy(buf, g_err, c);
+    buf[c] = 0;
+  }
+  return (int)len;
+}
+
+// bytes of caller-owned scratch an entry point needs for the given shape (kernels never allocate)
+extern "C" long long ga_workspace_bytes(int op, long long a, long long b, long long c, long long d) {
+  switch (op) {
+    case GA_WS_DWCONV7_BWD: return (long long)ga_dwconv7_bwd_parts((int)a, (int)b, (int)c, (int)d) * 50 * d * (long long)sizeof(float);
+    case GA_WS_COLSTATS: return (long long)ga_colstats_parts(a, (int)b) * 2 * b * (long long)sizeof(float);
+    case GA_WS_LAYERNORM_BWD: return (long long)ga_layernorm_bwd_parts(a, (int)b) * 2 * b * (long long)sizeof(float);
+    default: ga_set_error("ga_workspace_bytes: unknown op %d", op); return -1;
+  }
+}
 extern "C" long long ga_launch_count(void) { return g_launches.load(); }
 
 // ---- tensor-map cache (immutable entries, mutex guarded; SURVEY.md 8b threading contract) -------------------

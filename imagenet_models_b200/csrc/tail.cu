@@ -359,6 +359,83 @@ extern "C" int ga_gram_triu_bwd(const void* dout, const void* out, const float* 
   return launch_ok("gram_triu_bwd");
 }
 
+// Two-term bf16 form of the same vector: hi = bf16(v), lo = bf16(v - hi), so hi + lo carries ~16 mantissa bits.  The
+// embedding conv that consumes it feeds a train-mode BatchNorm over the batch only ([B, C, 1, 1]); that BatchNorm divides by
+// a standard deviation ~15-25x below the activations' magnitude and multiplies the operand rounding by the same factor
+// (measured on the reference itself: 2.4e-3 before the BatchNorm, 3-6e-2 after it), so this one operand gets two GEMM passes.
+__global__ void __launch_bounds__(512) gram_triu_fwd_split_kernel(const float* __restrict__ G, bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                                  float* __restrict__ norm_o, int C, int glen, int gld,
+                                                                  long long out_bs, int nt) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const float* Gb = G + (long long)b * C * C;
+  float ss = 0.f;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int i = idx / C, j = idx - i * C;
+    if (j >= i) { const float v = Gb[idx]; ss += v * v; }
+  }
+  ss = block_sum(ss, red);
+  const float nrm = fmaxf(sqrtf(ss), 1e-12f);
+  if (threadIdx.x == 0) norm_o[b] = nrm;
+  const float inv = 1.f / nrm;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int i = idx / C, j = idx - i * C;
+    if (j >= i) {
+      const int t = triu_pos(triu_row_start(i, C) + (j - i), C * (C + 1) / 2, nt);
+      const long long o = (long long)b * out_bs + (long long)(t / glen) * gld + t % glen;
+      const float v = Gb[idx] * inv;
+      const bf16 h = __float2bfloat16(v);
+      hi[o] = h;
+      lo[o] = __float2bfloat16(v - __bfloat162float(h));
+    }
+  }
+}
+extern "C" int ga_gram_triu_fwd_split(const float* G, void* hi, void* lo, float* norm, int B, int C, int glen, int gld,
+                                      long long out_bs, int interleave, ga_stream_t s) {
+  GA_REQUIRE(G && hi && lo && norm && C > 0 && glen > 0 && gld >= glen, GA_ERR_SHAPE, "ga_gram_triu_fwd_split: bad arguments");
+  if (B == 0) return GA_OK;
+  gram_triu_fwd_split_kernel<<<B, 512, 0, (cudaStream_t)s>>>(G, (bf16*)hi, (bf16*)lo, norm, C, glen, gld, out_bs, interleave);
+  return launch_ok("gram_triu_fwd_split");
+}
+
+template <typename TS>
+__global__ void __launch_bounds__(512) gram_triu_bwd_split_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ hi,
+                                                                  const bf16* __restrict__ lo, const float* __restrict__ norm,
+                                                                  TS* __restrict__ S, int C, int glen, int gld, long long out_bs, int nt) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const bf16* hb = hi + (long long)b * out_bs;
+  const bf16* lb = lo + (long long)b * out_bs;
+  const bf16* db = dout + (long long)b * out_bs;
+  const int tri = C * (C + 1) / 2;
+  float dot = 0.f;
+  for (int t = threadIdx.x; t < tri; t += blockDim.x) {
+    const long long o = (long long)(t / glen) * gld + t % glen;
+    dot += (ld_f(hb + o) + ld_f(lb + o)) * ld_f(db + o);
+  }
+  dot = block_sum(dot, red);
+  const float inv = 1.f / norm[b];
+  TS* Sb = S + (long long)b * C * C;
+  for (int idx = threadIdx.x; idx < C * C; idx += blockDim.x) {
+    const int i = idx / C, j = idx - i * C;
+    const int l = i < j ? i : j, h = i < j ? j : i;
+    const int t = triu_pos(triu_row_start(l, C) + (h - l), tri, nt);
+    const long long o = (long long)(t / glen) * gld + t % glen;
+    float v = (ld_f(db + o) - (ld_f(hb + o) + ld_f(lb + o)) * dot) * inv;
+    if (i == j) v *= 2.f;
+    st_f(Sb + idx, v);
+  }
+}
+extern "C" int ga_gram_triu_bwd_split(const void* dout, const void* hi, const void* lo, const float* norm, void* S, int B, int C,
+                                      int glen, int gld, long long out_bs, int s_dtype, int interleave, ga_stream_t s) {
+  GA_REQUIRE(dout && hi && lo && norm && S, GA_ERR_SHAPE, "ga_gram_triu_bwd_split: bad arguments");
+  if (B == 0) return GA_OK;
+  cudaStream_t st = (cudaStream_t)s;
+  if (s_dtype == GA_BF16) gram_triu_bwd_split_kernel<bf16><<<B, 512, 0, st>>>((const bf16*)dout, (const bf16*)hi, (const bf16*)lo, norm, (bf16*)S, C, glen, gld, out_bs, interleave);
+  else gram_triu_bwd_split_kernel<float><<<B, 512, 0, st>>>((const bf16*)dout, (const bf16*)hi, (const bf16*)lo, norm, (float*)S, C, glen, gld, out_bs, interleave);
+  return launch_ok("gram_triu_bwd_split");
+}
+
 // ---------------------------------------------------------------------------------------------- attention pooling
 // Q query rows (the class / gram tokens, which are also keys) + N spatial keys.  One warp per (image, head):
 // lanes stride over keys; softmax by warp shuffles.  scores use q as given (caller pre-scales).

@@ -369,9 +369,7 @@ class GA_ConvNeXt(nn.Module):
             emb, ebn = self.gram_embedding[k][0], self.gram_embedding[k][1]
             G = self.embed_groups
             glen = emb.weight.shape[1]
-            gv = ops.gram_vector(g, Bn, HW, float(H), T, G)                        # [B, G*pad8(glen)] in T (fp32: unpadded)
-            a3 = gv.view(Bn, G, -1)[:, :, :glen].transpose(0, 1)
-            c = ops.grouped_linear(a3, emb.weight.view(G, Cc // G, glen), emb.bias, out_dtype=torch.float32)  # [B, C] fp32
+            c = ops.gram_embed(g, emb.weight.view(G, Cc // G, glen), emb.bias, Bn, HW, float(H))   # get_gram + embedding, [B, C] fp32
             c = ops.batchnorm(c, _params(ebn), tr)
             blk = self.ga[k]
             cn = ops.layernorm(c, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)

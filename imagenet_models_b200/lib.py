@@ -37,6 +37,7 @@ class GaGemm(C.Structure):
         ('R', C.c_void_p), ('ldr', C.c_longlong), ('r_bs', C.c_longlong),
         ('Zin', C.c_void_p), ('ldz', C.c_longlong), ('z_bs', C.c_longlong), ('zmode', C.c_int),
         ('backend', C.c_int), ('splits', C.c_int), ('z_shadow', C.c_int),
+        ('backend_used', C.POINTER(C.c_int)),
         ('colsum', C.c_void_p),
     ]
 
@@ -58,18 +59,81 @@ def exported_symbols():
 
 
 _lib = None
+_timed = None
+_UNTIMED = ('ga_last_error', 'ga_launch_count', 'ga_version', 'ga_workspace_bytes')
 
 
-def load() -> C.CDLL:
+class CallTimer:
+    """Optional CUDA-event instrumentation of EVERY C-ABI call (bench.py's live per-kernel roofline): events are recorded on
+    the launching stream around each `ga_*` entry point, keyed by (entry point, integer arguments = the call site's shape).
+    Enabled with start_timing(); read with summary() after a synchronize."""
+
+    def __init__(self, lib):
+        self._lib, self.records = lib, []
+
+    @staticmethod
+    def _sig(name, args):
+        if name == 'ga_gemm':
+            g = args[0]._obj
+            return (g.batch, g.M, g.N, g.K, g.in_dtype, g.out_dtype, g.act, int(bool(g.Z)), int(g.z_shadow), int(bool(g.R)),
+                    int(bool(g.Zin)), g.accumulate, int(g.a_cs != 1), int(g.b_cs != 1))
+        sig = []
+        for a in args:
+            if isinstance(a, int):
+                sig.append(a)
+            elif isinstance(a, (C.c_int, C.c_longlong)):
+                sig.append(a.value)
+        return tuple(sig)
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith('ga_') or name in _UNTIMED or name.endswith('_parts'):
+            return fn
+
+        def timed(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            self.records.append((name, self._sig(name, args), e0, e1))
+            return rc
+        return timed
+
+    def summary(self):
+        """{(entry point, signature): (calls, total ms)}"""
+        agg = {}
+        for name, sig, e0, e1 in self.records:
+            n, t = agg.get((name, sig), (0, 0.0))
+            agg[(name, sig)] = (n + 1, t + e0.elapsed_time(e1))
+        return agg
+
+
+def start_timing() -> 'CallTimer':
+    global _timed
+    _timed = CallTimer(load_raw())
+    return _timed
+
+
+def stop_timing():
+    global _timed
+    _timed = None
+
+
+def load_raw() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
                                '(there is no CPU or PyTorch fallback for the GA kernels)')
         _lib = C.CDLL(LIB_PATH)
-        _lib.ga_last_error.restype = C.c_char_p
         _lib.ga_launch_count.restype = C.c_longlong
+        _lib.ga_workspace_bytes.restype = C.c_longlong
     return _lib
+
+
+def load():
+    """The library handle every op calls through (a CallTimer proxy while start_timing() is active)."""
+    return _timed if _timed is not None else load_raw()
 
 
 class GaError(RuntimeError):
@@ -78,7 +142,9 @@ class GaError(RuntimeError):
 
 def check(rc: int, what: str):
     if rc != 0:
-        raise GaError(f'{what} failed (code {rc}): {load().ga_last_error().decode()}')
+        buf = C.create_string_buffer(512)
+        load_raw().ga_last_error(buf, C.c_size_t(len(buf)))
+        raise GaError(f'{what} failed (code {rc}): {buf.value.decode()}')
 
 
 def stream() -> C.c_void_p:

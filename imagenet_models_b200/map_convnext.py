@@ -178,9 +178,7 @@ class MAPHead(nn.Module):
             r = ops.batchnorm(r, _bn(gt.ch_reduction[1]), training)
             G, glen = gt.num_groups, gt.bp_reduction[0].weight.shape[1]
             # x/(hw) then X X^T (map.py:217-218): alpha = 1/(hw)^2 = 1/(div^2 * hw) with div = sqrt(hw)
-            gv = ops.gram_vector(r, Bn, HW, float(HW) ** 0.5, T, G, interleave=nt)
-            a3 = gv.view(Bn, G, -1)[:, :, :glen].transpose(0, 1)
-            t = ops.grouped_linear(a3, gt.bp_reduction[0].weight.view(G, L_ * nt // G, glen), None, out_dtype=torch.float32)
+            t = ops.gram_embed(r, gt.bp_reduction[0].weight.view(G, L_ * nt // G, glen), None, Bn, HW, float(HW) ** 0.5, interleave=nt)
             t = ops.batchnorm(t, _bn(gt.bp_reduction[1]), training)               # [B, L*nt] fp32, channel c*nt + j = token j
             tok = t.view(Bn, L_, nt).permute(0, 2, 1)
             cls = torch.cat((tok, tok.mean(dim=1, keepdim=True)), dim=1).contiguous()   # + self-distillation token

@@ -9,11 +9,14 @@
  *  - activations are NHWC-contiguous ("channels_last" storage), dtype GA_F32 or GA_BF16;
  *    parameters and all statistics are fp32;
  *  - every call launches on the given stream and returns immediately (no sync, no allocation);
- *  - return 0 on success, non-zero otherwise; ga_last_error() has the message;
+ *  - return 0 on success, non-zero otherwise; ga_last_error(buf, n) copies the calling thread's message;
+ *  - no process-global mutable state: backends are per-call arguments, the only caches are the immutable tensor-map /
+ *    function-attribute caches (mutex guarded);
  *    nothing throws or exits across this boundary.
  */
 #ifndef GA_SM100_H
 #define GA_SM100_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -27,11 +30,14 @@ enum { GA_ACT_NONE = 0, GA_ACT_GELU = 1, GA_ACT_RELU = 2, GA_ACT_MUL = 3 /* zmod
 enum { GA_BACKEND_AUTO = 0, GA_BACKEND_SIMT = 1, GA_BACKEND_TCGEN05 = 2 };
 
 int ga_version(void);
-const char* ga_last_error(void);
+/* message of the calling thread's last failed call, copied into buf (NUL-terminated, truncated to n); returns its length */
+int ga_last_error(char* buf, size_t n);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long ga_launch_count(void);
-/* GA_BACKEND_* of the last ga_gemm call */
-int ga_gemm_last_backend(void);
+/* bytes of caller-owned fp32 scratch an entry point needs: GA_WS_DWCONV7_BWD (B, H, W, C) -> dw_partial;
+ * GA_WS_COLSTATS (M, C, 0, 0) -> ga_colstats / ga_bn_bwd_reduce workspace; GA_WS_LAYERNORM_BWD (M, C, 0, 0).  -1 = unknown op */
+enum { GA_WS_DWCONV7_BWD = 1, GA_WS_COLSTATS = 2, GA_WS_LAYERNORM_BWD = 3 };
+long long ga_workspace_bytes(int op, long long a, long long b, long long c, long long d);
 
 /* ---- GEMM with fused epilogue: every nn.Linear / 1x1 / k=s conv on the path --------------------------------
  *   D[b][m][n] = epi( alpha * sum_k A[b](m,k) * B[b](n,k) )
@@ -62,6 +68,7 @@ typedef struct GaGemm {
   int splits;     /* split-K factor for accumulate mode; 0 = auto */
   int z_shadow;   /* 1: Z receives a bf16 copy of the FINAL value (bf16 shadow of an fp32 residual stream);
                      2: Z receives act'(pre-activation) (GELU), to be applied in backward with zmode GA_ACT_MUL */
+  int* backend_used; /* optional out: GA_BACKEND_* this call ran on */
   float* colsum;  /* optional, with Zin on the tcgen05 path only: colsum[n] += sum_m D[m,n] (fp32, 16-byte aligned; the bias
                      gradient of the layer whose dz this GEMM produces); GA_ERR_UNSUPPORTED when it cannot be fused */
 } GaGemm;
@@ -168,6 +175,13 @@ int ga_gram_triu_fwd(const float* G, void* out, float* norm, int B, int C, int g
 int ga_gram_triu_bwd(const void* dout, const void* out, const float* norm, void* S, int B, int C, int glen, int gld,
                      long long out_bs, int io_dtype, int s_dtype, int interleave, ga_stream_t s);
 
+/* the same vector as two bf16 terms hi + lo (~16 mantissa bits) for the embedding conv that feeds a train-mode BatchNorm over
+ * the batch (gram_embedding ga_convnext.py:417-420, bp_reduction map.py:203-206): that BatchNorm amplifies operand rounding ~20x */
+int ga_gram_triu_fwd_split(const float* G, void* hi, void* lo, float* norm, int B, int C, int glen, int gld,
+                           long long out_bs, int interleave, ga_stream_t s);
+int ga_gram_triu_bwd_split(const void* dout, const void* hi, const void* lo, const float* norm, void* S, int B, int C,
+                           int glen, int gld, long long out_bs, int s_dtype, int interleave, ga_stream_t s);
+
 /* ---- K5: attention pooling: Q query tokens against Q+N keys  (ClassAttn ga_convnext.py:170-183; map.py:100-144)
  * q [B,Q,E] fp32 pre-scaled; kv_cls [B,Q,2E] fp32 (k | v of the query tokens); kv_tok rows [B*N, ldt] (k at col 0,
  * v at col E); H heads.  out [B,Q,E] fp32; attn [B,H,Q,Q+N] fp32 saved for backward. */
@@ -175,13 +189,13 @@ int ga_gram_triu_bwd(const void* dout, const void* out, const float* norm, void*
  * qkv rows [B*R*R, 3C] (q | k | v blocks, pitch ldq); heads are 32 channels.  nbr == 2: branch 0 = channels [0,C/2) over
  * R x split stripes, branch 1 = [C/2,C) over split x R stripes; nbr == 1: one R x R window.  <= 128 tokens per stripe.
  * lepe_w [C,9] / lepe_b [C]: the branches' get_v depthwise 3x3 weights, concatenated over channels.
- * out [B*R*R, C] = softmax(scale q k^T) v + dw3x3(v inside the stripe);  lse [B*R*R, C/32] fp32 (log2 units) or NULL. */
+ * out [B*R*R, C] = softmax(scale q k^T) v + dw3x3(v inside the stripe);  lse [B*R*R, C/32] fp32 (log2 units) or NULL.
+ * backend (bf16, stripes of <= 112 tokens): GA_BACKEND_AUTO = tcgen05 kernel (Q/K/V by 4-D TMA boxes straight into UMMA operand
+ * tiles, S and O accumulated in TMEM, two heads per CTA) for 65..112-token stripes with an even head count per branch, else the
+ * register-fragment mma.sync kernel; GA_BACKEND_SIMT forces the mma.sync kernel, GA_BACKEND_TCGEN05 the tcgen05 one. */
 int ga_cswin_attn_fwd(const void* qkv, const float* lepe_w, const float* lepe_b, void* out, float* lse, int B, int R,
-                      int C, int split, int nbr, long long ldq, long long ldo, float scale, int dtype, ga_stream_t s);
-/* bf16 forward backend for stripes of <= 112 tokens: 0 = register-fragment mma.sync kernel, 1 = tcgen05 kernel (Q/K/V by 4-D TMA
- * boxes straight into UMMA operand tiles, S and O accumulated in TMEM, two heads per CTA), 2 = auto (default: tcgen05 for
- * 65..112-token stripes with an even head count per branch); returns the previous setting.  GA_ATTN_TCGEN05=0/1 forces one. */
-int ga_cswin_attn_fwd_backend(int tcgen05);
+                      int C, int split, int nbr, long long ldq, long long ldo, float scale, int dtype, int backend,
+                      ga_stream_t s);
 /* dqkv [B*R*R, 3C] is fully overwritten; dlepe_w / dlepe_b are accumulated (+=, atomics) */
 int ga_cswin_attn_bwd(const void* dout, const void* qkv, const void* out, const float* lse, const float* lepe_w,
                       const float* lepe_b, void* dqkv, float* dlepe_w, float* dlepe_b, int B, int R, int C, int split,

@@ -56,6 +56,39 @@ def ga_inputs(B, seed=42, size=224):
     return torch.randn(B, 3, size, size, generator=g), torch.randint(0, 1000, (B,), generator=g)
 
 
+def ga_inputs_diverse(B, seed=42, size=224):
+    """Images that differ from one another (per-image sinusoid patterns, colour offsets, noise levels): with i.i.d. noise
+    images every sample has the same statistics, train-mode BatchNorm over the batch then divides by a vanishing standard
+    deviation and amplifies rounding ~25x (gram_embedding BN over [B, C, 1, 1]); real images are not like that."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, size), torch.linspace(-1, 1, size), indexing='ij')
+    imgs = []
+    for _ in range(B):
+        f = torch.rand(3, 2, generator=g) * 12 + 1
+        ph = torch.rand(3, generator=g) * 6.28
+        amp = torch.rand(3, generator=g) * 1.5 + 0.2
+        mean = torch.randn(3, generator=g) * 0.7
+        noise = torch.randn(3, size, size, generator=g) * (0.1 + torch.rand(1, generator=g) * 0.9)
+        pat = torch.stack([amp[c] * torch.sin(f[c, 0] * xx * 3.14 + f[c, 1] * yy * 3.14 + ph[c]) for c in range(3)])
+        imgs.append(pat + mean[:, None, None] + noise)
+    return torch.stack(imgs), torch.randint(0, 1000, (B,), generator=g)
+
+
+# whole-model parity cases at the BASELINE.json shapes: key -> (model, B, state profile, input kind)
+#   config1: BASELINE config 1 (fp32 training step, batch 8; the fp64 Gram branch of get_gram is active: training and B < 128)
+#   bf16:    the bf16 training fixture, batch 16
+# Both use mutually different images and trained-magnitude layer scales (see ga_inputs_diverse / make_state(profile='trained')).
+GA_PARITY_CASES = {'config1': ('ga_convnext_tiny_688', 8, 'trained', 'diverse'),
+                   'bf16': ('ga_convnext_tiny_688', 16, 'trained', 'diverse')}
+# parameters whose gradient does not pass through any Bottleneck ReLU (everything after stages.4): compared with the reference
+# directly; the rest is compared with the oracle evaluated at the implementation's own ReLU decisions (oracle _relu docstring)
+GA_TAIL_PREFIXES = ('gram_contraction.', 'gram_layer.', 'gram_embedding.', 'ga.', 'fc.')
+
+
+def parity_inputs(kind, B, size=224):
+    return ga_inputs_diverse(B, size=size) if kind == 'diverse' else ga_inputs(B, size=size)
+
+
 def block_state(C, seed=STATE_SEED):
     return _fill({'conv_dw.weight': ((C, 1, 7, 7), 'w'), 'conv_dw.bias': ((C,), 'b'),
                   'norm.weight': ((C,), 'g'), 'norm.bias': ((C,), 'b'),

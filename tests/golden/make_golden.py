@@ -269,6 +269,88 @@ def golden_map_model():
     torch.save(out, os.path.join(HERE, 'map_convnext_model.pt'))
 
 
+def golden_ga_parity():
+    """Whole-model fixtures at the BASELINE.json shapes (oracle/cases.py GA_PARITY_CASES): config 1 (fp32 training step, batch 8,
+    fp64 Gram branch) and the bf16 training fixture (batch 16); mutually different images, trained-magnitude layer scales."""
+    import numpy as np
+    import ga_convnext as R  # noqa: F401
+    import timm
+
+    def ga_loss_ref(outs, y):
+        output, loss = 0, 0           # the loss expression of GA/train.py:735-745
+        for o in outs:
+            loss = loss + F.cross_entropy(o, y)
+            output = output + o.data
+        for o in outs:
+            loss = loss + F.kl_div(F.log_softmax(o + 0), F.log_softmax((output.detach() / len(outs)) + 0),
+                                   reduction='mean', log_target=True) * cases.GA_LAM
+        return loss
+
+    def run_ref(name, P, x, y):
+        ref = timm.create_model(name)
+        ref.load_state_dict(P, strict=True)
+        ref.train()
+        masks = {}
+        for key, act in (('bn1', ref.stages[4].act1), ('bn2', ref.stages[4].act2), ('out', ref.stages[4].act3)):
+            act.register_forward_hook(lambda m, i, o, key=key: masks.__setitem__(key, (o.detach() > 0)))
+        outs = ref(x)
+        loss = ga_loss_ref(outs, y)
+        loss.backward()
+        return ref, outs, loss, {k: p.grad.detach().clone() for k, p in ref.named_parameters()}, dict(masks)   # copy: later forwards re-fire the hooks
+
+    out = {}
+    for key, (name, B, profile, kind) in cases.GA_PARITY_CASES.items():
+        spec = O.SPECS[name]
+        P = O.make_state(spec, seed=cases.STATE_SEED, profile=profile)
+        x, y = cases.parity_inputs(kind, B)
+        ref, r_train, loss, r_grads, r_masks = run_ref(name, P, x, y)
+        r_state = {k: v.detach().clone() for k, v in ref.state_dict().items() if 'running' in k}
+        ref.eval()
+        ref.load_state_dict(P, strict=True)
+        with torch.no_grad():
+            r_eval = ref(x)
+        # oracle == reference, with the oracle evaluated at the reference's ReLU decisions (they agree anyway unless a
+        # pre-activation sits within fp32 rounding of zero)
+        Po = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone())
+              for k, v in P.items()}
+        o_train = O.forward(Po, spec, x, training=True, relu_masks=r_masks)
+        o_loss = O.ga_loss(o_train, y, cases.GA_LAM)
+        o_loss.backward()
+        assert rel(o_loss.detach(), loss.detach()) < 1e-6
+        for a, b in zip(o_train, r_train):
+            assert rel(a.detach(), b.detach()) < 2e-5, rel(a.detach(), b.detach())
+        worst = 0.0
+        for k, g in r_grads.items():
+            assert close(Po[k].grad, g, 5e-5), (k, rel(Po[k].grad, g))
+            if g.norm() > 1e-3:
+                worst = max(worst, rel(Po[k].grad, g))
+        # the reference against ITSELF on inputs perturbed by 1e-7 relative: the noise floor of any fp32 comparison here,
+        # and how many ReLU decisions of the Bottleneck flip
+        gen = torch.Generator().manual_seed(5)
+        _, p_train, _, p_grads, p_masks = run_ref(name, P, x * (1 + 1e-7 * torch.randn(x.shape, generator=gen)), y)
+        noise_g = sorted(rel(p_grads[k], g) for k, g in r_grads.items() if g.norm() > 1e-3)
+        flips = sum(int((p_masks[k] != r_masks[k]).sum()) for k in r_masks)
+        self_noise = dict(logits=max(rel(a.detach(), b.detach()) for a, b in zip(p_train, r_train)),
+                          grads_median=noise_g[len(noise_g) // 2], grads_max=noise_g[-1], relu_flips=flips,
+                          relu_decisions=sum(m.numel() for m in r_masks.values()))
+        # information only: how far the reference's OWN bf16 autocast (CPU) is from its fp32 result on this fixture
+        m2 = timm.create_model(name)
+        m2.load_state_dict(P, strict=True)
+        m2.train()
+        with torch.no_grad(), torch.autocast('cpu', dtype=torch.bfloat16):
+            o16 = m2(x)
+        self_err = max(rel(a.float(), b.detach()) for a, b in zip(o16, r_train))
+        print(f'{key}: {name} B={B} {profile}/{kind}: oracle==reference (loss {loss.item():.6f}, worst gradient {worst:.2e}); '
+              f'reference vs itself at 1e-7 input noise: logits {self_noise["logits"]:.2e}, gradients median '
+              f'{self_noise["grads_median"]:.2e} max {self_noise["grads_max"]:.2e}, {flips} of {self_noise["relu_decisions"]} ReLU '
+              f'decisions flipped; reference bf16-autocast train logits are {self_err:.2e} from its fp32 logits')
+        out[key] = dict(eval_logits=[t.clone() for t in r_eval], train_logits=[t.detach().clone() for t in r_train],
+                        loss=loss.detach().clone(), grads=grad_digest(r_grads), running=r_state,
+                        relu_masks={k: torch.from_numpy(np.packbits(m.numpy().reshape(-1))) for k, m in r_masks.items()},
+                        ref_bf16_train_self_err=self_err, ref_self_noise=self_noise)
+    torch.save(out, os.path.join(HERE, 'ga_convnext_parity.pt'))
+
+
 def golden_cswin():
     """GA-CSWin (GA/ga_cswin.py) through the unmodified reference: CSWinBlock cases + two whole-model cases."""
     import ga_cswin as R
@@ -367,3 +449,5 @@ if __name__ == '__main__':
         golden_map_model()
     if 'cswin' in which:
         golden_cswin()
+    if 'parity' in which:
+        golden_ga_parity()

@@ -211,18 +211,17 @@ def test_stripe_attention_vs_oracle(R, split, nbr, C, B, dtype, tol):
 def test_stripe_attention_tcgen05_forward_matches_mma_sync_and_oracle(R, split, nbr, C, B):
     """The tcgen05 / TMEM / TMA forward (opt-in backend) against the default kernel and the oracle on the same bf16 inputs."""
     from imagenet_models_b200 import ops
-    lib = L.load()
     g = torch.Generator().manual_seed(R * 7 + C)
     qkv = torch.randn(B * R * R, 3 * C, generator=g).bfloat16().cuda()
     lw = (torch.randn(C, 9, generator=g) * 0.3).cuda()
     lb = (torch.randn(C, generator=g) * 0.1).cuda()
-    prev = lib.ga_cswin_attn_fwd_backend(0)
     try:
+        ops.ATTN_BACKEND = L.BACKEND_SIMT            # register-fragment mma.sync kernel (per-call backend argument)
         o0, l0 = ops._attn_fwd(qkv, lw, lb, B, R, C, split, nbr, True)
-        lib.ga_cswin_attn_fwd_backend(1)
+        ops.ATTN_BACKEND = L.BACKEND_TCGEN05
         o1, l1 = ops._attn_fwd(qkv, lw, lb, B, R, C, split, nbr, True)
     finally:
-        lib.ga_cswin_attn_fwd_backend(prev if prev >= 0 else 2)
+        ops.ATTN_BACKEND = L.BACKEND_AUTO
     assert rel(o1.float(), o0.float()) < 6e-3 and rel(l1, l0) < 1e-4
     cb = C // nbr
     P = {f'{i}.get_v.weight': lw[i * cb:(i + 1) * cb].cpu().reshape(cb, 1, 3, 3) for i in range(nbr)}

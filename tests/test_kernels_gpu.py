@@ -41,7 +41,7 @@ def test_gemm_plain(M, N, K, dtype):
     ref = A.float() @ B.float().t()
     assert rel(D.float(), ref) < tol(dtype)
     if dtype == torch.bfloat16 and K % 8 == 0:
-        assert L.load().ga_gemm_last_backend() == L.BACKEND_TCGEN05
+        assert ops.LAST_GEMM_BACKEND == L.BACKEND_TCGEN05
 
 
 @pytest.mark.parametrize('a_mn,b_mn', [(False, True), (True, False), (True, True)])
@@ -52,7 +52,7 @@ def test_gemm_tc_majors(a_mn, b_mn, M, N, K):
     A = rnd(K, M, dtype=dtype, seed=3).t() if a_mn else rnd(M, K, dtype=dtype, seed=3)
     B = rnd(K, N, dtype=dtype, seed=4).t() if b_mn else rnd(N, K, dtype=dtype, seed=4)
     D = ops.gemm(A, B, out_dtype=torch.float32)
-    assert L.load().ga_gemm_last_backend() == L.BACKEND_TCGEN05
+    assert ops.LAST_GEMM_BACKEND == L.BACKEND_TCGEN05
     ref = A.float() @ B.float().t()
     assert rel(D, ref) < 1e-2 * 0.2   # fp32 output of bf16 products: only accumulation-order error
 
