@@ -489,11 +489,26 @@ static int launch_conv(const Plan& p, const CUtensorMap& tm, const float* w, con
 
 }  // namespace dw
 
+// second-generation bf16 kernels (dwconv3.cu); GA_ERR_UNSUPPORTED = shape not taken, fall through to the kernels above
+int ga_dwconv7_ln_fwd_v3(const void* x, const float* w49c, const float* bias, void* y, float* rstd, int B, int H, int W, int C,
+                         float eps, cudaStream_t st);
+int ga_dwconv7_bwd_v3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dxs, float* partial,
+                      int nparts, int B, int H, int W, int C, int res_dtype, cudaStream_t st);
+// GA_DW_V3=0 (read once, immutable afterwards) keeps the first-generation kernels for A/B timing in scripts/kernel_bench.py
+static bool dw_v3_enabled() {
+  static const bool on = [] { const char* e = getenv("GA_DW_V3"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+
 extern "C" int ga_dwconv7_ln_fwd(const void* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
                                  void* y, float* rstd, int B, int H, int W, int C, float eps, int dtype, ga_stream_t s) {
   GA_REQUIRE(x && w49c && y && B > 0 && H > 0 && W > 0, GA_ERR_SHAPE, "ga_dwconv7_ln_fwd: bad arguments");
   GA_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w49c & 7) == 0 && ((uintptr_t)bias & 7) == 0, GA_ERR_ALIGN,
              "ga_dwconv7_ln_fwd: x must be 16-byte, weights 8-byte aligned");
+  if (dtype == GA_BF16 && !ln_w && !ln_b && dw_v3_enabled()) {
+    const int rc3 = ga_dwconv7_ln_fwd_v3(x, w49c, bias, y, rstd, B, H, W, C, eps, (cudaStream_t)s);
+    if (rc3 != GA_ERR_UNSUPPORTED) return rc3;
+  }
   dw::Plan p;
   int rc = dw::plan(B, H, W, C, dtype, false, &p, 384);
   if (rc == GA_ERR_UNSUPPORTED) {
@@ -541,6 +556,19 @@ extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dre
   GA_REQUIRE(dconv && w49c && B > 0, GA_ERR_SHAPE, "ga_dwconv7_bwd: bad arguments");
   GA_REQUIRE(((uintptr_t)dconv & 15) == 0 && ((uintptr_t)w49c & 7) == 0, GA_ERR_ALIGN, "ga_dwconv7_bwd: misaligned operands");
   int rc;
+  if (dtype == GA_BF16 && dx && x && dw_partial && (dw49c || dbias) && ((uintptr_t)x & 15) == 0 && dw_v3_enabled()) {
+    // one fused kernel: data gradient (+ residual, + bf16 shadow), weight gradient and bias gradient from one staged dconv halo
+    const int nparts = ga_dwconv7_bwd_parts(B, H, W, C);
+    cudaMemsetAsync(dw_partial, 0, (size_t)nparts * 50 * C * sizeof(float), st);
+    rc = ga_dwconv7_bwd_v3(dconv, x, dres, w49c, dx, dx_shadow, dw_partial, nparts, B, H, W, C, res_dtype, st);
+    if (rc == GA_OK) {
+      const int n = 50 * C;
+      dw::reduce_parts_kernel<<<(n + 255) / 256, 256, 0, st>>>(dw_partial, nparts, n, dw49c, 49 * C, dbias);
+      ga_count_launch();
+      return ga_check_launch("dwconv7_wgrad_reduce");
+    }
+    if (rc != GA_ERR_UNSUPPORTED) return rc;
+  }
   if (dx) {
     dw::Plan p;
     int nslice = 1;

@@ -714,11 +714,14 @@ extern "C" int ga_stem_im2col3(const float* x, void* y, int B, int H, int W, int
 // CTA (strip of 128 columns as 32 lanes x 4, row slice): 8 warps stride rows; result -> partial[slice][2][C]
 // MODE 0: s1 = sum x, s2 = sum x^2
 // MODE 1: BN backward: d = dy * (relu ? y>0 : 1); s1 = sum d; s2 = sum d * (x-mean)*invstd
+// MODE 2: s1 = sum (x - p), s2 = sum (x - p)^2 with the pivot p = row 0 of x (also written to pivot_out): BatchNorm statistics
+//         without the cancellation of E[x^2] - E[x]^2 (a batch whose rows differ by 5 % of their magnitude loses 4e-5 there)
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ yact,
                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                                        float* __restrict__ partial, long long M, int C, long long ldx,
-                                                       long long lddy, long long ldy, int rows_per_cta, int relu) {
+                                                       long long lddy, long long ldy, int rows_per_cta, int relu,
+                                                       float* __restrict__ pivot_out = nullptr) {
   __shared__ float4 sh[2][8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + lane * 4;
@@ -727,6 +730,10 @@ __global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, 
   if (c < C) {
     float4 mu = make_float4(0, 0, 0, 0), is = make_float4(1, 1, 1, 1);
     if (MODE == 1) { mu = *reinterpret_cast<const float4*>(mean + c); is = *reinterpret_cast<const float4*>(invstd + c); }
+    if (MODE == 2) {
+      mu = ld4(x + c);
+      if (blockIdx.y == 0 && wid == 0) *reinterpret_cast<float4*>(pivot_out + c) = mu;
+    }
     long long rend = r0 + rows_per_cta;
     if (rend > M) rend = M;
     long long r = r0 + wid;
@@ -742,6 +749,10 @@ __global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, 
     for (; r < rend; r += 8) {
       float4 v = ld4(x + r * ldx + c);
       if (MODE == 0) {
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+      } else if (MODE == 2) {
+        v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
         a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
         q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
       } else {
@@ -787,8 +798,24 @@ extern "C" int ga_colstats(const void* x, float* sum, float* sumsq, float* parti
   return launch_ok("colstats_reduce");
 }
 
+// sums of (x - pivot) and (x - pivot)^2 with pivot = row 0 (pivot[C] written), for ga_bn_finalize(pivot != NULL)
+extern "C" int ga_colstats_shifted(const void* x, float* pivot, float* sum, float* sumsq, float* partial, long long M, int C,
+                                   long long ldx, int dtype, ga_stream_t s) {
+  GA_REQUIRE(x && pivot && sum && sumsq && partial && M > 0 && (C & 3) == 0 && (ldx & 3) == 0, GA_ERR_ALIGN,
+             "ga_colstats_shifted: C=%d ldx=%lld must be multiples of 4", C, ldx);
+  const int parts = ga_colstats_parts(M, C);
+  const int rows_per_cta = (int)((M + parts - 1) / parts);
+  dim3 grid((C + 127) / 128, parts);
+  DISPATCH_T(dtype, { colstats_kernel<T, 2><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, partial, M, C, ldx, 0, 0, rows_per_cta, 0, pivot); });
+  int rc = launch_ok("colstats_shifted");
+  if (rc) return rc;
+  reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, sum, C, sumsq, 0);
+  return launch_ok("colstats_reduce");
+}
+
 // BatchNorm (training) finalize: from sum/sumsq over M rows -> mean, invstd, scale, shift; running stats (momentum, unbiased var)
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ w,
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ pivot,
+                                   const float* __restrict__ w,
                                    const float* __restrict__ b, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_o, float* __restrict__ invstd_o, float* __restrict__ scale_o,
                                    float* __restrict__ shift_o, long long M, int C, float momentum, float eps, int training) {
@@ -796,8 +823,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   if (c >= C) return;
   float mean, var;
   if (training) {
-    mean = sum[c] / (float)M;
-    var = fmaxf(sumsq[c] / (float)M - mean * mean, 0.f);
+    const float m0 = sum[c] / (float)M;                         // mean of (x - pivot) when a pivot is given
+    var = fmaxf(sumsq[c] / (float)M - m0 * m0, 0.f);
+    mean = pivot ? pivot[c] + m0 : m0;
     if (running_mean) {
       const float unb = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
@@ -814,11 +842,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   scale_o[c] = sc;
   shift_o[c] = (b ? b[c] : 0.f) - mean * sc;
 }
-extern "C" int ga_bn_finalize(const float* sum, const float* sumsq, const float* w, const float* b, float* running_mean,
+extern "C" int ga_bn_finalize(const float* sum, const float* sumsq, const float* pivot, const float* w, const float* b, float* running_mean,
                               float* running_var, float* mean, float* invstd, float* scale, float* shift, long long M, int C,
                               float momentum, float eps, int training, ga_stream_t s) {
   GA_REQUIRE(scale && shift && C > 0, GA_ERR_SHAPE, "ga_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(sum, sumsq, w, b, running_mean, running_var, mean, invstd, scale, shift, M, C, momentum, eps, training);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(sum, sumsq, pivot, w, b, running_mean, running_var, mean, invstd, scale, shift, M, C, momentum, eps, training);
   return launch_ok("bn_finalize");
 }
 

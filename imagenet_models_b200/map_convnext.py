@@ -170,7 +170,7 @@ class MAPHead(nn.Module):
             w = torch.cat((a.attn.k.weight, a.attn.v.weight), 0)
             wkv.append(w * a.norm1.weight[None, :])
             bkv.append(w @ a.norm1.bias + torch.cat((a.attn.k.bias, a.attn.v.bias), 0))
-        kv_tok = ops.linear(fhat, torch.cat(wkv, 0), torch.cat(bkv, 0))            # [B*HW, nb*2E]
+        kv_tok = ops.linear(fhat, torch.cat(wkv, 0), torch.cat(bkv, 0), out_dtype=torch.float32)   # [B*HW, nb*2E]; fp32 like GA_ConvNeXt._heads
         cls_all, qs, kvcs = [], [], []
         for c in caps:
             gt, a = c.gram_token_extraction, c.attention[0]

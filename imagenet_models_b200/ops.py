@@ -88,7 +88,7 @@ class GemmTimer:
 
 TIMER = None      # set to a GemmTimer() to time GEMM launches
 LAST_GEMM_BACKEND = 0   # lib.BACKEND_* the most recent gemm() ran on (reported by the call itself through GaGemm.backend_used)
-RELU_TAP = None   # tests set this to a list: every fused BatchNorm+ReLU appends its 0/1 decisions (rows [M, C] bool), in call order
+RELU_TAP = None   # tests set this to a list: every ReLU appends (kind, 0/1 decisions): ('bn', rows [M, C]) per fused BatchNorm+ReLU, ('se', [B, R])
 
 
 def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None, rowscale=None, rows_per_scale=1,
@@ -314,6 +314,9 @@ class GemmFn(Function):
         G, M, K = A.shape
         N = W.shape[1]
         dout = rowmat(dout)
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2] and ctx.act == ACT_NONE and dout.dtype == torch.float32 and N * G % 4 == 0:
+            db = colsum(dout)              # bias gradient from the fp32 gradient, before it is rounded to the operand dtype
         if dout.dtype != A.dtype:
             dout = convert(dout, A.dtype)
         if ctx.act != ACT_NONE:
@@ -323,7 +326,7 @@ class GemmFn(Function):
         if G > 1 and N % 8 and dout.dtype == torch.bfloat16:
             # group stride N is not a 16-byte multiple (172-wide groups): re-pitch so both backward GEMMs stay on tcgen05
             dD3 = torch.empty(G, M, pad8(N), dtype=dout.dtype, device=dout.device)[:, :, :N].copy_(dD3)
-        dA = dW = db = None
+        dA = dW = None
         if ctx.needs_input_grad[0]:
             Wc = cast_like(W, A.dtype)
             dA = torch.empty(G, M, K, dtype=A.dtype, device=A.device) if (G > 1 or K % 8) else alloc_rows(M, K, A.dtype, A.device).unsqueeze(0)
@@ -331,7 +334,7 @@ class GemmFn(Function):
         if ctx.needs_input_grad[1]:
             dW = torch.zeros(G, N, K, dtype=torch.float32, device=A.device)
             gemm(dD3.transpose(1, 2), A.transpose(1, 2), dW, accumulate=True)   # dW[g,n,k] = sum_m dD[g,m,n] A[g,m,k]
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if ctx.has_bias and ctx.needs_input_grad[2] and db is None:
             db = colsum(dout)
         return dA, dW, db, None, None
 
@@ -452,7 +455,9 @@ class ConvNeXtBlockFn(Function):
             o += n
         d49, ddwb, dlnw, dlnb, dw1, db1, dw2, db2, dgam, G2, G1, s1buf = views
         # fc2: G2 = dys^T a ; dW2 = gamma*G2 ; db2 = gamma*s2 ; dgamma = rowdot(W2, G2) + b2*s2
-        s2 = colsum(dys)
+        # the column sums (bias / layer-scale gradients) come from the fp32 stream gradient, not its bf16 operand copy: a sum
+        # over 800 k rows of mean-free terms is where operand rounding shows (2-4e-2 on fc2.bias with the bf16 sums)
+        s2 = colsum(dy if (path_scale is None and dy.dtype == torch.float32 and Cc % 4 == 0) else dys)
         gemm(dys.t(), a.t(), G2.view(Cc, Hd), accumulate=True)
         L.check(lib.ga_linear_grad_finalize(L.ptr(G2), L.ptr(s2), L.ptr(w2), L.ptr(b2), L.ptr(gamma), None, None, L.ptr(dw2),
                                             L.ptr(db2), L.ptr(dgam), None, None, Cc, Hd, L.stream()), 'linear_grad_finalize')
@@ -625,10 +630,16 @@ def _bn_stats(x, w, b, rm, rv, training, momentum, eps):
     M, Cc = x.shape
     dev = x.device
     st = torch.empty(4, Cc, dtype=torch.float32, device=dev)   # mean, invstd, scale, shift
-    s = q = None
+    s = q = pv = None
     if training:
-        s, q = colsum(x, sumsq=True)
-    L.check(_L().ga_bn_finalize(L.ptr(s), L.ptr(q), L.ptr(w), L.ptr(b), L.ptr(rm), L.ptr(rv), L.ptr(st[0]), L.ptr(st[1]),
+        # sums of (x - row 0): the variance then has no E[x^2] - E[x]^2 cancellation (the gram_embedding BatchNorm sees a batch
+        # whose rows differ by ~5 % of their magnitude; the plain form cost 2e-5 on the fp32 logits)
+        sq = torch.empty(3, Cc, dtype=torch.float32, device=dev)
+        pv, s, q = sq[0], sq[1], sq[2]
+        ws = workspace(_L().ga_colstats_parts(L.ll(M), Cc) * 2 * Cc, dev, 'colstats')
+        L.check(_L().ga_colstats_shifted(L.ptr(x), L.ptr(pv), L.ptr(s), L.ptr(q), L.ptr(ws), L.ll(M), Cc, L.ll(x.stride(0)), L.dt(x),
+                                         L.stream()), 'ga_colstats_shifted')
+    L.check(_L().ga_bn_finalize(L.ptr(s), L.ptr(q), L.ptr(pv), L.ptr(w), L.ptr(b), L.ptr(rm), L.ptr(rv), L.ptr(st[0]), L.ptr(st[1]),
                                 L.ptr(st[2]), L.ptr(st[3]), L.ll(M), Cc, L.f(momentum), L.f(eps), int(training), L.stream()),
             'ga_bn_finalize')
     return st
@@ -656,7 +667,7 @@ class BatchNormFn(Function):
         ctx.save_for_backward(x, st, xb, stb, y if relu else None)
         ctx.training, ctx.relu = training, relu
         if relu and RELU_TAP is not None:
-            RELU_TAP.append(y.detach() > 0)
+            RELU_TAP.append(('bn', y.detach() > 0))
         return y
 
     @staticmethod
@@ -814,6 +825,8 @@ class SEFn(Function):
                                L.ptr(gate), Bn, HW, Cc, R, L.ll(x.stride(0)), L.ll(y.stride(0)), L.dt(x), L.stream()), 'ga_se_fwd')
         ctx.save_for_backward(x, w1m, w2m, pooled, hidden, gate)
         ctx.dims = (Bn, HW, Cc, R, w1.shape, w2.shape)
+        if RELU_TAP is not None:
+            RELU_TAP.append(('se', hidden.detach() > 0))
         return y
 
     @staticmethod

@@ -131,9 +131,12 @@ int ga_colstats_parts(long long M, int C);
 /* sum[c] (=|+=) sum_m x[m,c]; sumsq[c] likewise with x^2 (either may be NULL); partial: [parts][2][C] */
 int ga_colstats(const void* x, float* sum, float* sumsq, float* partial, long long M, int C, long long ldx,
                 int accumulate, int dtype, ga_stream_t s);
-/* training: mean/invstd from the sums, running stats updated (momentum, unbiased var); eval: from running stats.
- * scale = w*invstd, shift = b - mean*scale */
-int ga_bn_finalize(const float* sum, const float* sumsq, const float* w, const float* b, float* running_mean,
+/* the same sums of (x - pivot), pivot[c] = x[0,c] (written): BatchNorm statistics without the E[x^2] - E[x]^2 cancellation */
+int ga_colstats_shifted(const void* x, float* pivot, float* sum, float* sumsq, float* partial, long long M, int C,
+                        long long ldx, int dtype, ga_stream_t s);
+/* training: mean/invstd from the sums (of x - pivot when pivot != NULL), running stats updated (momentum, unbiased var);
+ * eval: from running stats.  scale = w*invstd, shift = b - mean*scale */
+int ga_bn_finalize(const float* sum, const float* sumsq, const float* pivot, const float* w, const float* b, float* running_mean,
                    float* running_var, float* mean, float* invstd, float* scale, float* shift, long long M, int C,
                    float momentum, float eps, int training, ga_stream_t s);
 /* y = act( x*scale[c] + shift[c]  (+ x2*scale2[c] + shift2[c]) ): BN apply (+ReLU) and the Bottleneck merge

@@ -244,14 +244,14 @@ def bottleneck(P: State, x: Tensor, training: bool, relu_masks=None) -> Tensor:
     """stages.4: 1x1+BN+ReLU, 3x3+BN+ReLU, SE, 1x1+BN, + (1x1+BN shortcut), ReLU (ga_convnext.py:294-318).
 
     DropPath on the residual branch (:310-311) is identity in eval / at rate 0, the parity contract.
-    relu_masks: optional {'bn1', 'bn2', 'out'} 0/1 tensors (NCHW) replacing the three large ReLU decisions (see _relu).
+    relu_masks: optional {'bn1', 'bn2', 'out', 'se'} 0/1 tensors (NCHW; 'se' [B, R, 1, 1]) replacing the ReLU decisions (see _relu).
     """
     pre = 'stages.4.'
     y = _relu(batchnorm(P, pre + 'bn1', F.conv2d(x, P[pre + 'conv1.weight']), training), relu_masks, 'bn1')
     y = _relu(batchnorm(P, pre + 'bn2', F.conv2d(y, P[pre + 'conv2.weight'], padding=1), training), relu_masks, 'bn2')
     # timm SEModule: mean over HW -> fc1 -> ReLU -> fc2 -> sigmoid gate
     s = y.mean((2, 3), keepdim=True)
-    s = F.relu(F.conv2d(s, P[pre + 'se.fc1.weight'], P[pre + 'se.fc1.bias']))
+    s = _relu(F.conv2d(s, P[pre + 'se.fc1.weight'], P[pre + 'se.fc1.bias']), relu_masks, 'se')
     s = F.conv2d(s, P[pre + 'se.fc2.weight'], P[pre + 'se.fc2.bias'])
     y = y * torch.sigmoid(s)
     y = batchnorm(P, pre + 'bn3', F.conv2d(y, P[pre + 'conv3.weight']), training)

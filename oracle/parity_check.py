@@ -63,13 +63,16 @@ def measure(key, dtype, fixture=None):
     res['tail_grads'] = live(tail)
     res['upstream_grads_raw'] = live(up)
     # ---- ReLU decisions: ours vs the reference's
-    assert len(taps) == 3, len(taps)
+    bn_taps = [t for kind, t in taps if kind == 'bn']
+    se_taps = [t for kind, t in taps if kind == 'se']
+    assert len(bn_taps) == 3 and len(se_taps) == 1, (len(bn_taps), len(se_taps))
     H = W = 14
     masks = {}
-    for kname, t in zip(('bn1', 'bn2', 'out'), taps):
+    for kname, t in zip(('bn1', 'bn2', 'out'), bn_taps):
         masks[kname] = t.view(B, H, W, -1).permute(0, 3, 1, 2).cpu()
+    masks['se'] = se_taps[0].view(B, -1, 1, 1).cpu()
     flips = 0
-    for kname, packed in g['relu_masks'].items():
+    for kname, packed in g['relu_masks'].items():                  # the three large ReLUs (the SE one is not in the fixture)
         refm = torch.from_numpy(np.unpackbits(packed.numpy())[:masks[kname].numel()].astype(bool)).view(masks[kname].shape)
         flips += int((refm != masks[kname]).sum())
     res['relu_flips_vs_reference'] = flips

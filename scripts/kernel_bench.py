@@ -121,7 +121,13 @@ def dwconv_cases():
         def f_wgrad(x=x, y=y, w=w, d49=d49, db=db, ws=ws, hw=hw, c=c):
             L.check(lib.ga_dwconv7_bwd(L.ptr(y), L.ptr(x), None, L.ptr(w), None, L.ptr(d49), L.ptr(db), L.ptr(ws), B, hw, hw, c,
                                        DT, L.F32, L.stream()), 'wgrad')
+        dxs = torch.empty(M, c, device=DEV, dtype=bf)
+
+        def f_bwd2(x=x, y=y, w=w, dres=dres, dx=dx, dxs=dxs, d49=d49, db=db, ws=ws, hw=hw, c=c):
+            L.check(lib.ga_dwconv7_bwd2(L.ptr(y), L.ptr(x), L.ptr(dres), L.ptr(w), L.ptr(dx), L.ptr(dxs), L.ptr(d49), L.ptr(db), L.ptr(ws),
+                                        B, hw, hw, c, DT, L.F32, L.stream()), 'bwd2')
         fl = 2.0 * 49 * M * c
+        cases[f's{s}_dw_bwd2'] = (f_bwd2, M * c * (2 + 2 + 4 + 4 + 2), 2 * fl)      # the training call: dgrad + wgrad + dbias
         cases[f's{s}_dw_fwd'] = (f_fwd, M * c * 4 + M * 4, fl)
         cases[f's{s}_dw_dgrad'] = (f_dgrad, M * c * (2 + 4 + 4), fl)
         cases[f's{s}_dw_wgrad'] = (f_wgrad, M * c * 4, fl)

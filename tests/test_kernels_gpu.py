@@ -176,6 +176,47 @@ def test_dwconv_ln_fwd_bwd(Bn, H, Cc, dtype):
     assert rel(db, bg.grad) < (2e-5 if dtype == torch.float32 else 5e-3)
 
 
+@pytest.mark.parametrize('Bn,H,W,Cc', [(48, 56, 56, 96), (16, 28, 28, 192), (8, 14, 14, 384), (4, 7, 7, 688), (3, 12, 12, 192), (2, 24, 20, 96),
+                                       (2, 14, 14, 512), (2, 9, 13, 256)])
+def test_dwconv_bf16_second_generation_kernels(Bn, H, W, Cc):
+    """dwconv3.cu at the training shapes' structure: fp32 residual-stream gradient + bf16 shadow (ga_dwconv7_bwd2), several tiles
+    per CTA (batch 48 at 56x56), channel slices + cluster LayerNorm (C = 384, 512, 688), widths that are no multiple of 7."""
+    dtype = torch.bfloat16
+    M = Bn * H * W
+    x = rnd(M, Cc, dtype=dtype, seed=30)
+    w = rnd(Cc, 1, 7, 7, seed=31, scale=0.15)
+    b = rnd(Cc, seed=32, scale=0.1)
+    w49c = w.reshape(Cc, 49).t().contiguous()
+    xhat = torch.empty_like(x)
+    rstd = torch.empty(M, device=DEV)
+    lib = L.load()
+    L.check(lib.ga_dwconv7_ln_fwd(L.ptr(x), L.ptr(w49c), L.ptr(b), None, None, L.ptr(xhat), L.ptr(rstd), Bn, H, W, Cc, L.f(1e-6),
+                                  L.dt(x), L.stream()), 'fwd')
+    xr = x.float().view(Bn, H, W, Cc).permute(0, 3, 1, 2)
+    conv = F.conv2d(xr, w, b, padding=3, groups=Cc).permute(0, 2, 3, 1).reshape(-1, Cc)
+    ref = F.layer_norm(conv, (Cc,), None, None, 1e-6)
+    assert rel(xhat.float(), ref) < tol(dtype)
+    assert rel(rstd, torch.rsqrt(conv.var(dim=1, unbiased=False) + 1e-6)) < 1e-2
+    dconv = rnd(M, Cc, dtype=dtype, seed=33)
+    dres = rnd(M, Cc, dtype=torch.float32, seed=34)
+    dx = torch.empty(M, Cc, device=DEV)
+    dxs = torch.empty(M, Cc, device=DEV, dtype=dtype)
+    d49 = torch.zeros(49, Cc, device=DEV)
+    db = torch.zeros(Cc, device=DEV)
+    ws = torch.empty(lib.ga_dwconv7_bwd_parts(Bn, H, W, Cc) * 50 * Cc, device=DEV)
+    L.check(lib.ga_dwconv7_bwd2(L.ptr(dconv), L.ptr(x), L.ptr(dres), L.ptr(w49c), L.ptr(dx), L.ptr(dxs), L.ptr(d49), L.ptr(db), L.ptr(ws),
+                                Bn, H, W, Cc, L.BF16, L.F32, L.stream()), 'bwd2')
+    xg = xr.clone().requires_grad_(True)
+    wg = w.clone().requires_grad_(True)
+    bg = b.clone().requires_grad_(True)
+    F.conv2d(xg, wg, bg, padding=3, groups=Cc).backward(dconv.float().view(Bn, H, W, Cc).permute(0, 3, 1, 2))
+    dx_ref = xg.grad.permute(0, 2, 3, 1).reshape(-1, Cc) + dres
+    assert rel(dx, dx_ref) < 1e-5                          # fp32 accumulation of exact bf16 products + fp32 residual
+    assert rel(dxs.float(), dx_ref) < tol(dtype)
+    assert rel(d49, wg.grad.reshape(Cc, 49).t()) < 1e-4
+    assert rel(db, bg.grad) < 1e-4
+
+
 @pytest.mark.parametrize('cname', ['c32_h9', 'c96_h14', 'c192_h14', 'c688_h7'])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_convnext_block_vs_golden(cname, dtype, golden_dir):
