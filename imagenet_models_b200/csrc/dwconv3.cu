@@ -260,6 +260,8 @@ dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_consta
   const uint32_t cen_s = halo_s + ((HALO_BYTES + 127) & ~127u);
   const uint32_t fold_s = cen_s + ((CEN_BYTES + 127) & ~127u);          // u64 [7][RS][P]
   const uint32_t accum_s = fold_s + 7 * RS * P * 8;                     // float2 [50][P]: this CTA's weight / bias gradient sums
+  const uint32_t wsm_s = accum_s + 50 * P * 8;                          // float2 [49][P]: the slice's taps (ncu: the per-ky LDG of the
+                                                                         // taps was 28 % long-scoreboard stall; the CTA walks several tiles)
 
   const int sl = blockIdx.y, c0 = sl * CB;
   const int pr = threadIdx.x % P, rs = threadIdx.x / P;
@@ -267,12 +269,17 @@ dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_consta
   const int c = c0 + 2 * pr;
   const bool cvalid = c < g.C;
   for (int i = threadIdx.x; i < 50 * P; i += NT) sts_f2(accum_s + (uint32_t)(i * 8), 0.f, 0.f);
+  for (int i = threadIdx.x; i < 49 * P; i += NT) {
+    const int tap = i / P, cc = c0 + 2 * (i - tap * P);
+    const u64 v = cc < g.C ? ldg_w2(w49c + (size_t)tap * g.C + cc) : 0ull;
+    sts_u64(wsm_s + (uint32_t)(i * 8), v);
+  }
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const float* wp = w49c + (cvalid ? c : 0);
+  const uint32_t wbase = wsm_s + (uint32_t)(pr * 8);
   const uint32_t hbase = halo_s + (uint32_t)(row * ROWB + strip * 7 * PIXB + pr * 4);
   const uint32_t cbase = cen_s + (uint32_t)((row * TW + strip * 7) * PIXB + pr * 4);
   const long long t_begin = (long long)blockIdx.x * g.tpc;
@@ -296,14 +303,12 @@ dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_consta
 #pragma unroll
     for (int i = 0; i < 7; ++i) xc[i] = lds_bf2(cbase + (uint32_t)(i * PIXB));
     float ds0 = 0.f, ds1 = 0.f;
-    const float* wq = wp + (size_t)48 * g.C;
 #pragma unroll
     for (int ky = 0; ky < 7; ++ky) {
       u64 wv[7], a7[7];
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
-        wv[kx] = ldg_w2(wq);                 // flipped taps: 48, 47, ... (tail-slice pairs read channel 0; their dconv is zero fill)
-        wq -= g.C;
+        wv[kx] = lds_u64(wbase + (uint32_t)((48 - (ky * 7 + kx)) * P * 8));      // flipped taps
         a7[kx] = 0ull;
       }
 #pragma unroll
@@ -438,7 +443,7 @@ static int launch_bwd(const void* dconv, const void* x, const void* dres, const 
                       int nparts, int B, int H, int W, int C, cudaStream_t st) {
   constexpr int P = CB / 2, RS = TH * (TW / 7), NT = RS * P;
   constexpr size_t HALO = (size_t)(TH + 6) * (TW + 6) * CB * 2, CEN = (size_t)TH * TW * CB * 2;
-  constexpr size_t SMEM = 128 + 128 + ((HALO + 127) & ~(size_t)127) + ((CEN + 127) & ~(size_t)127) + (size_t)7 * RS * P * 8 + (size_t)50 * P * 8;
+  constexpr size_t SMEM = 128 + 128 + ((HALO + 127) & ~(size_t)127) + ((CEN + 127) & ~(size_t)127) + (size_t)7 * RS * P * 8 + (size_t)99 * P * 8;
   static_assert(SMEM <= 227 * 1024, "dwconv7 bwd3 tile does not fit shared memory");
   Geo3 g;
   g.B = B; g.H = H; g.W = W; g.C = C;
