@@ -63,6 +63,7 @@ def main():
     torch.cuda.set_device(local_rank)
     rank, world = 0, 1
     if distributed:
+        os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')     # the step's NCCL calls are captured in a CUDA graph
         dist.init_process_group(backend='nccl', init_method='env://')
         rank, world = dist.get_rank(), dist.get_world_size()
     torch.manual_seed(args.seed + rank)                      # timm random_seed(seed, rank), GA/train.py:402

@@ -231,6 +231,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')     # the step's NCCL calls are captured in a CUDA graph
         dist.init_process_group('nccl', init_method='env://')
     dev = torch.device('cuda', local)
     L.load()

@@ -20,12 +20,11 @@ from .optim import FusedAdamWEma, FusedLambEma, GradBuckets
 class TrainEngine:
     def __init__(self, model, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, ema_decay: Optional[float] = 0.9998,
                  ga_lam: float = -0.8, amp_dtype=torch.bfloat16, grad_accumulation: int = 1, bucket_mb: float = 25.0,
-                 cuda_graph: bool = False, graph_warmup: int = 3, opt: str = 'adamw'):
-        """cuda_graph: after `graph_warmup` eager steps the whole step (zero-grad, forward, loss, backward, gradient gather and,
-        on one GPU, the optimizer) is captured once into a CUDA graph and replayed, which removes the ~1.5k per-step kernel
-        launches from the CPU's critical path.  With several ranks the all-reduce and the optimizer run after the replay
-        (NVSwitch moves the 190 MB of gradients in well under a millisecond; overlap with backward is traded for launch cost).
-        Needs fixed batch shapes; drop-path masks are drawn inside the graph from the graph-safe generator."""
+                 cuda_graph: bool = False, graph_warmup: int = 3, opt: str = 'adamw', broadcast_buffers: bool = True):
+        """cuda_graph: after `graph_warmup` eager steps the whole step (zero-grad, forward, loss, backward, the bucketed gradient
+        all-reduce on its side stream, gradient gather, optimizer + EMA) is captured once into a CUDA graph and replayed, which
+        removes the ~1.5k per-step kernel launches from the CPU's critical path.  Needs fixed batch shapes; drop-path masks
+        are drawn inside the graph from the graph-safe generator."""
         self.model = model
         if opt == 'lamb':          # timm.optim.Lamb, the optimizer of the published recipes (GA/README.md:26)
             self.opt = FusedLambEma(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, ema_decay=ema_decay)
@@ -35,6 +34,9 @@ class TrainEngine:
             raise ValueError(f"optimizer '{opt}': 'adamw' and 'lamb' are fused here")
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.buckets = GradBuckets(self.opt.state, bucket_mb=bucket_mb) if self.world > 1 else None
+        # DistributedDataParallel(broadcast_buffers=True) (GA/train.py:514, --no-ddp-bb turns it off): rank 0's BatchNorm running
+        # statistics replace every rank's before each forward.  All float buffers live in one flat tensor -> one small broadcast.
+        self.broadcast_buffers = bool(broadcast_buffers) and self.world > 1
         self.ga_lam, self.amp_dtype, self.accum = ga_lam, amp_dtype, max(1, grad_accumulation)
         self.micro = 0
         self.cuda_graph = bool(cuda_graph) and self.accum == 1
@@ -45,7 +47,22 @@ class TrainEngine:
     def model_ema(self):
         return self.opt.ema_model
 
+    def distribute_bn(self, reduce: bool = True):
+        """timm.utils.distribute_bn at epoch end (GA/train.py:665-668): average (reduce=True) or broadcast rank 0's BatchNorm
+        running statistics, for the model and its EMA copy."""
+        if self.world == 1:
+            return
+        flats = [self.opt.state.bufflat] + ([self.opt.ema_bufflat] if self.opt.ema_model is not None else [])
+        for f in flats:
+            if reduce:
+                dist.all_reduce(f)
+                f.div_(self.world)
+            else:
+                dist.broadcast(f, 0)
+
     def _forward_backward(self, x, y):
+        if self.broadcast_buffers:
+            dist.broadcast(self.opt.state.bufflat, 0)
         if self.amp_dtype is not None:
             with torch.autocast('cuda', dtype=self.amp_dtype):
                 out = self.model(x)
@@ -64,28 +81,31 @@ class TrainEngine:
             self._sx, self._sy = torch.empty_like(x), torch.empty_like(y)
             self._sx.copy_(x)
             self._sy.copy_(y)
-            if self.buckets is not None:
-                self.buckets.enabled = False
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
-            with torch.cuda.graph(g):
+            # several ranks: the bucketed all-reduce is captured too -- every bucket's NCCL call sits on the side stream, forked
+            # from the capture stream by the grad-ready hook that completes the bucket and joined before the optimizer, so the
+            # replayed step overlaps the reduction with the rest of backward exactly like the eager path (GA/train.py:505-515).
+            # thread_local: the NCCL watchdog thread's event queries must not invalidate the capture.
+            kw = {'capture_error_mode': 'thread_local'} if self.world > 1 else {}
+            with torch.cuda.graph(g, **kw):
                 self.opt.zero_grad()
+                if self.buckets is not None:
+                    self.buckets.enabled = True
+                    self.buckets.prepare()
                 self._sloss = self._forward_backward(self._sx, self._sy).detach()
-                self.opt.state.gather()
-                if self.world == 1:
-                    self.opt.step(gathered=True, device_hyper=True)
+                if self.buckets is not None:
+                    self.buckets.finish()
+                else:
+                    self.opt.state.gather()
+                self.opt.step(gathered=True, device_hyper=True)
             self.graph_launches = L.launch_count() - n0
             self._graph = g
         else:
             self._sx.copy_(x, non_blocking=True)
             self._sy.copy_(y, non_blocking=True)
-        if self.world == 1:
-            self.opt.push_hyper(1.0)
-            self._graph.replay()
-        else:
-            self._graph.replay()
-            dist.all_reduce(self.opt.state.grad)
-            self.opt.step(grad_scale=1.0 / self.world, gathered=True)
+        self.opt.push_hyper(1.0 / self.world)          # lr, bias corrections and the 1/world gradient scale, read by the captured optimizer
+        self._graph.replay()
         return self._sloss
 
     def step(self, x, y):
@@ -103,6 +123,8 @@ class TrainEngine:
             self.buckets.enabled = last
             if last:
                 self.buckets.prepare()
+        if self.broadcast_buffers:
+            dist.broadcast(self.opt.state.bufflat, 0)
         if self.amp_dtype is not None:
             with torch.autocast('cuda', dtype=self.amp_dtype):
                 out = self.model(x)

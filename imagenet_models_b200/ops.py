@@ -40,6 +40,7 @@ def rowmat(t: torch.Tensor) -> torch.Tensor:
 
 
 _ws_cache = {}
+_ws_retired = []
 
 
 def workspace(n_floats: int, device, tag: str) -> torch.Tensor:
@@ -47,6 +48,8 @@ def workspace(n_floats: int, device, tag: str) -> torch.Tensor:
     key = (tag, str(device))
     t = _ws_cache.get(key)
     if t is None or t.numel() < n_floats:
+        if t is not None:
+            _ws_retired.append(t)      # a captured CUDA graph may have this address baked in: never hand it back to the allocator
         t = torch.empty(max(int(n_floats), 1 << 16), dtype=torch.float32, device=device)
         _ws_cache[key] = t
     return t
@@ -1217,6 +1220,10 @@ class GALossFn(Function):
     @staticmethod
     def forward(ctx, logits, aux, target, lam):
         nb, Bn, ncls = logits.shape
+        if target.dtype != torch.int64 or tuple(target.shape) != (Bn,) or not target.is_cuda:
+            raise L.GaError(f'ga_loss: hard labels must be a CUDA int64 tensor of shape ({Bn},), got {target.dtype} {tuple(target.shape)}; '
+                            'soft targets (mixup / smoothing / BCE) go through ga_soft_loss')
+        target = target.contiguous()
         logits = logits.contiguous().float()
         loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
         dl = torch.empty_like(logits)

@@ -141,8 +141,9 @@ class FusedAdamWEma:
             self.ema_model = copy.deepcopy(model).eval()          # same layout -> same offsets
             for p in self.ema_model.parameters():
                 p.requires_grad_(False)
-            ema_params = [p for p in self.ema_model.parameters()]
-            for p, o in zip(ema_params, self.state.offsets):
+            ema_named = dict(self.ema_model.named_parameters())      # same names as the model; frozen parameters are not in the flat state
+            for name, o in zip(self.state.names, self.state.offsets):
+                p = ema_named[name]
                 p.data = self.ema_flat[o:o + p.numel()].view(p.shape)
             self.ema_bufflat = _flatten_buffers(self.ema_model, self.ema_flat.device)
         self.param_groups = [{'lr': lr}]                          # what the reference's logging / schedulers read

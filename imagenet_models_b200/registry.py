@@ -43,7 +43,9 @@ def create_model(model_name: str, pretrained: bool = False, checkpoint_path: str
     model = _ENTRYPOINTS[model_name](pretrained=pretrained, **kwargs)
     if checkpoint_path:
         import torch
-        ckpt = torch.load(checkpoint_path, map_location='cpu')
+        # timm's CheckpointSaver pickles an argparse.Namespace ('args') and optimizer state next to the weights
+        # (GA/train.py:649): that needs the full unpickler, like timm.models.load_checkpoint does for trusted files
+        ckpt = torch.load(checkpoint_path, map_location='cpu', weights_only=False)
         sd = ckpt.get('state_dict_ema') or ckpt.get('state_dict') or ckpt.get('model') or ckpt
         sd = {(k[7:] if k.startswith('module.') else k): v for k, v in sd.items()}
         model.load_state_dict(sd, strict=True)

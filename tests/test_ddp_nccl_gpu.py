@@ -1,0 +1,102 @@
+"""Two ranks over NCCL on two GPUs (skipped on a one-GPU box): the data-parallel training step of imagenet_models_b200.engine --
+bucketed all-reduce overlapped with backward (eager) and the SAME buckets captured inside the step's CUDA graph -- against ONE
+process on the concatenated batch.  Reference behaviour: DistributedDataParallel gradient averaging (GA/train.py:505-515).
+BatchNorm runs on its running statistics (model.eval() with gradients enabled), the only mode in which a sharded batch and the
+whole batch define the same function; fp32 compute so the comparison is about the collective, not about rounding."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import cases
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+B_PER_RANK, STEPS, LR = 4, 5, 1e-3
+
+
+def _model():
+    import imagenet_models_b200.ga_convnext  # noqa: F401
+    from imagenet_models_b200.registry import create_model
+    from oracle import ga_convnext_oracle as O
+    name = 'ga_convnext_tiny_688'
+    m = create_model(name).cuda()
+    P = O.make_state(O.SPECS[name], cases.STATE_SEED, profile='trained')
+    m.load_state_dict({k: v.cuda() for k, v in P.items()}, strict=True)
+    return m.eval()                     # BatchNorm on running statistics, no drop path; gradients still flow
+
+
+def _batches(world):
+    g = torch.Generator().manual_seed(123)
+    return [cases.ga_inputs_diverse(B_PER_RANK * world, seed=1000 + s) for s in range(STEPS)]
+
+
+def _worker(rank, world, port, use_graph, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      TORCH_NCCL_ASYNC_ERROR_HANDLING='0')
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world)
+    from imagenet_models_b200.engine import TrainEngine
+    m = _model()
+    eng = TrainEngine(m, lr=LR, weight_decay=0.05, ema_decay=0.99, ga_lam=cases.GA_LAM, amp_dtype=None, cuda_graph=use_graph,
+                      graph_warmup=2, bucket_mb=25.0)
+    m.eval()
+    grads = []
+    for x, y in _batches(world):
+        xs = x[rank * B_PER_RANK:(rank + 1) * B_PER_RANK].cuda()
+        ys = y[rank * B_PER_RANK:(rank + 1) * B_PER_RANK].cuda()
+        eng.step(xs, ys)
+        grads.append((eng.opt.state.grad / world).cpu().clone())        # the optimizer folds 1/world into its gradient scale
+    torch.cuda.synchronize()
+    out = {'rank': rank, 'grads': [g.numpy() for g in grads], 'flat': eng.opt.state.flat.cpu().numpy(),
+           'graph': eng._graph is not None, 'nbuckets': len(eng.buckets.buckets)}
+    q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_two_rank_nccl_step_matches_one_process_on_the_whole_batch(use_graph):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs (gpurun --gpus 2)')
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, use_graph, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=600) for _ in range(world)], key=lambda o: o['rank'])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # single process, whole batch
+    from imagenet_models_b200.engine import TrainEngine
+    torch.cuda.set_device(0)
+    m = _model()
+    eng = TrainEngine(m, lr=LR, weight_decay=0.05, ema_decay=0.99, ga_lam=cases.GA_LAM, amp_dtype=None, cuda_graph=False)
+    m.eval()
+    ref_grads = []
+    for x, y in _batches(world):
+        eng.step(x.cuda(), y.cuda())
+        ref_grads.append(eng.opt.state.grad.cpu().clone())
+    ref_flat = eng.opt.state.flat.cpu()
+    assert outs[0]['graph'] == use_graph and outs[0]['nbuckets'] >= 2
+    for o in outs:
+        g0 = torch.from_numpy(o['grads'][0])
+        # step 1 starts from identical weights: reduced gradient == whole-batch gradient (summation order only)
+        assert (g0 - ref_grads[0]).norm().item() <= 2e-5 * ref_grads[0].norm().item(), (g0 - ref_grads[0]).norm().item() / ref_grads[0].norm().item()
+        # later steps start from weights that differ by optimizer round-off (AdamW turns 1e-7 gradient noise into +-lr on
+        # near-zero gradients), so the bound is per step: nobody moves more than lr per step away from the single process
+        assert (torch.from_numpy(o['flat']) - ref_flat).abs().max().item() <= STEPS * LR * 1.05
+    assert (torch.from_numpy(outs[0]['flat']) - torch.from_numpy(outs[1]['flat'])).abs().max().item() == 0.0   # replicas stay bit-identical

@@ -115,3 +115,22 @@ def test_loss_matches_manual():
     base = sum(torch.nn.functional.cross_entropy(o, y) for o in outs)
     assert torch.allclose(O.ga_loss(outs, y, 0.0), base)
     assert not torch.allclose(O.ga_loss(outs, y, -0.8), base)
+
+
+def test_create_model_loads_a_timm_format_checkpoint(tmp_path):
+    """timm's CheckpointSaver writes an argparse.Namespace and optimizer state beside the weights (GA/train.py:649); such a
+    file must load through create_model(checkpoint_path=...) with strict key matching, EMA weights preferred."""
+    import argparse
+    from imagenet_models_b200.registry import create_model
+    import imagenet_models_b200.ga_convnext  # noqa: F401
+    m = create_model('ga_convnext_tiny_688')
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    ema = {('module.' + k): (v + 1 if v.is_floating_point() else v.clone()) for k, v in sd.items()}     # DDP-prefixed, different values
+    ck = {'epoch': 3, 'arch': 'ga_convnext_tiny_688', 'state_dict': sd, 'state_dict_ema': ema, 'version': 2,
+          'args': argparse.Namespace(model='ga_convnext_tiny_688', lr=5e-3), 'optimizer': {'state': {}, 'param_groups': [{'lr': 5e-3}]},
+          'metric': 83.2}
+    path = tmp_path / 'checkpoint-3.pth.tar'
+    torch.save(ck, path)
+    m2 = create_model('ga_convnext_tiny_688', checkpoint_path=str(path))
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, ema['module.' + k]), k
