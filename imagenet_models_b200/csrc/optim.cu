@@ -147,10 +147,13 @@ __device__ __forceinline__ void log_softmax_row(float* row, int ncls, float* red
   __syncthreads();
 }
 
+// Classification term per branch: hard labels (cross entropy), dense targets [B, ncls] (timm SoftTargetCrossEntropy: mixup /
+// cutmix / label smoothing, GA/train.py:615-624) or BCE-with-logits on dense targets, mean over B*ncls (timm BinaryCrossEntropy,
+// --bce-loss of every published recipe, GA/train.py:618-619).  mode: 0 = CE (hard or dense), 1 = BCE.
 __global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ logits, const float* __restrict__ aux,
-                                                      const long long* __restrict__ target, float* __restrict__ loss,
-                                                      float* __restrict__ dlogits, float* __restrict__ daux, int nb, int B, int ncls,
-                                                      float lam, float grad_scale) {
+                                                      const long long* __restrict__ target, const float* __restrict__ dense, int mode,
+                                                      float* __restrict__ loss, float* __restrict__ dlogits, float* __restrict__ daux,
+                                                      int nb, int B, int ncls, float lam, float grad_scale) {
   extern __shared__ float sm[];  // [(nb+2)][ncls]: nb branch rows, the mean row, one aux row
   __shared__ float red[32];
   const int b = blockIdx.x;
@@ -167,7 +170,15 @@ __global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ 
   }
   __syncthreads();
   for (int k = 0; k <= nb; ++k) log_softmax_row(sm + (size_t)k * ncls, ncls, red);
-  const int y = (int)target[b];
+  const int y = target ? (int)target[b] : -1;
+  const float* trow = dense ? dense + (size_t)b * ncls : nullptr;
+  float tsum = 1.f;
+  if (trow && mode == 0) {                 // sum of the dense target row (1 for mixup / smoothing targets, kept general)
+    float a = 0.f;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) a += trow[c];
+    tsum = block_sum(a, red);
+    __syncthreads();
+  }
   const float invB = 1.f / (float)B, inv_bc = 1.f / ((float)B * (float)ncls);
   float local = 0.f;
   for (int k = 0; k < nb; ++k) {
@@ -175,12 +186,22 @@ __global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ 
     for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
       const float p = expf(lp[c]), qv = expf(lq[c]);
       local += lam * inv_bc * qv * (lq[c] - lp[c]);
-      if (c == y) local += -lp[c] * invB;
+      float gcls;
+      if (mode == 1) {
+        const float z = logits[((size_t)k * B + b) * ncls + c], t = trow ? trow[c] : (c == y ? 1.f : 0.f);
+        local += (fmaxf(z, 0.f) - z * t + log1pf(expf(-fabsf(z)))) * inv_bc;
+        gcls = (1.f / (1.f + expf(-z)) - t) * inv_bc;
+      } else if (trow) {
+        local += -trow[c] * lp[c] * invB;
+        gcls = (p * tsum - trow[c]) * invB;
+      } else {
+        if (c == y) local += -lp[c] * invB;
+        gcls = (p - (c == y ? 1.f : 0.f)) * invB;          // dCE/dz = (p - onehot)/B
+      }
       if (dlogits) {
-        // dCE/dz = (p - onehot)/B ; d/dz_k of -lam/(B C) * sum_c q_c logp_k,c = -lam/(B C) * (q_c - p_c)
-        const float gce = (p - (c == y ? 1.f : 0.f)) * invB;
+        // d/dz_k of -lam/(B C) * sum_c q_c logp_k,c = -lam/(B C) * (q_c - p_c)
         const float gkl = -lam * inv_bc * (qv - p);
-        dlogits[((size_t)k * B + b) * ncls + c] = (gce + gkl) * grad_scale;
+        dlogits[((size_t)k * B + b) * ncls + c] = (gcls + gkl) * grad_scale;
       }
     }
     if (aux) {
@@ -198,14 +219,23 @@ __global__ void __launch_bounds__(256) ga_loss_kernel(const float* __restrict__ 
   local = block_sum(local, red);
   if (threadIdx.x == 0) atomicAdd(loss, local);
 }
-extern "C" int ga_loss_fwd_bwd(const float* logits, const float* aux, const long long* target, float* loss, float* dlogits,
-                               float* daux, int nb, int B, int ncls, float lam, float grad_scale, ga_stream_t s) {
-  GA_REQUIRE(logits && target && loss && nb > 0 && B > 0 && ncls > 0, GA_ERR_SHAPE, "ga_loss_fwd_bwd: bad arguments");
+static int loss_launch(const float* logits, const float* aux, const long long* target, const float* dense, int mode, float* loss,
+                       float* dlogits, float* daux, int nb, int B, int ncls, float lam, float grad_scale, ga_stream_t s) {
   const size_t smem = (size_t)(nb + 2) * ncls * sizeof(float);
   GA_REQUIRE(smem <= 200 * 1024, GA_ERR_UNSUPPORTED, "ga_loss_fwd_bwd: (nb+2)*ncls too large for shared memory");
   cudaFuncSetAttribute(ga_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ga_loss_kernel<<<B, 256, smem, (cudaStream_t)s>>>(logits, aux, target, loss, dlogits, daux, nb, B, ncls, lam, grad_scale);
+  ga_loss_kernel<<<B, 256, smem, (cudaStream_t)s>>>(logits, aux, target, dense, mode, loss, dlogits, daux, nb, B, ncls, lam, grad_scale);
   return launch_ok("ga_loss");
+}
+extern "C" int ga_loss_fwd_bwd(const float* logits, const float* aux, const long long* target, float* loss, float* dlogits,
+                               float* daux, int nb, int B, int ncls, float lam, float grad_scale, ga_stream_t s) {
+  GA_REQUIRE(logits && target && loss && nb > 0 && B > 0 && ncls > 0, GA_ERR_SHAPE, "ga_loss_fwd_bwd: bad arguments");
+  return loss_launch(logits, aux, target, nullptr, 0, loss, dlogits, daux, nb, B, ncls, lam, grad_scale, s);
+}
+extern "C" int ga_loss_dense_fwd_bwd(const float* logits, const float* aux, const float* dense_target, int bce, float* loss,
+                                     float* dlogits, float* daux, int nb, int B, int ncls, float lam, float grad_scale, ga_stream_t s) {
+  GA_REQUIRE(logits && dense_target && loss && nb > 0 && B > 0 && ncls > 0, GA_ERR_SHAPE, "ga_loss_dense_fwd_bwd: bad arguments");
+  return loss_launch(logits, aux, nullptr, dense_target, bce ? 1 : 0, loss, dlogits, daux, nb, B, ncls, lam, grad_scale, s);
 }
 
 // ---------------------------------------------------------------------------------------------- LAMB (timm.optim.Lamb)

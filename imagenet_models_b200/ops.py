@@ -91,7 +91,7 @@ class GemmTimer:
 
 TIMER = None      # set to a GemmTimer() to time GEMM launches
 LAST_GEMM_BACKEND = 0   # lib.BACKEND_* the most recent gemm() ran on (reported by the call itself through GaGemm.backend_used)
-RELU_TAP = None   # tests set this to a list: every ReLU appends (kind, 0/1 decisions): ('bn', rows [M, C]) per fused BatchNorm+ReLU, ('se', [B, R])
+RELU_TAP = None   # tests set this to a list: every ReLU appends (kind, 0/1 decisions): ('bn', rows [M, C]) per fused BatchNorm+ReLU, ('se', [B, R]), ('gemm', rows [M, G*N]) per ReLU epilogue
 
 
 def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None, rowscale=None, rows_per_scale=1,
@@ -309,6 +309,8 @@ class GemmFn(Function):
             gemm(A, Wc, D3, bias=b2, act=act)
         ctx.save_for_backward(A, W, z if z is not None else (out if act == ACT_RELU else None))
         ctx.act, ctx.has_bias = act, bias is not None
+        if act == ACT_RELU and RELU_TAP is not None:
+            RELU_TAP.append(('gemm', out.detach() > 0))
         return out
 
     @staticmethod
@@ -1244,3 +1246,46 @@ class GALossFn(Function):
 
 def ga_loss(logits, target, lam, aux=None):
     return GALossFn.apply(logits, aux, target, lam)
+
+
+class GADenseLossFn(Function):
+    """The same loss with DENSE targets [B, ncls] (mixup / cutmix / label smoothing -> timm SoftTargetCrossEntropy) or, bce=True,
+    BCE-with-logits averaged over B*ncls (timm BinaryCrossEntropy, --bce-loss; GA/train.py:615-624)."""
+
+    @staticmethod
+    def forward(ctx, logits, aux, target, lam, bce):
+        nb, Bn, ncls = logits.shape
+        if target.dtype != torch.float32 or tuple(target.shape) != (Bn, ncls) or not target.is_cuda:
+            raise L.GaError(f'ga_soft_loss: dense targets must be a CUDA fp32 tensor of shape ({Bn}, {ncls})')
+        target = target.contiguous()
+        logits = logits.contiguous().float()
+        loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        dl = torch.empty_like(logits)
+        da = None
+        if aux is not None:
+            aux = aux.contiguous().float()
+            da = torch.empty_like(aux)
+        L.check(_L().ga_loss_dense_fwd_bwd(L.ptr(logits), L.ptr(aux), L.ptr(target), int(bool(bce)), L.ptr(loss), L.ptr(dl), L.ptr(da), nb, Bn,
+                                           ncls, L.f(lam), L.f(1.0), L.stream()), 'ga_loss_dense_fwd_bwd')
+        ctx.save_for_backward(dl, da)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        dl, da = ctx.saved_tensors
+        return dl * g, (da * g if da is not None else None), None, None, None
+
+
+def ga_soft_loss(logits, dense_target, lam, aux=None, bce=False):
+    return GADenseLossFn.apply(logits, aux, dense_target, lam, bce)
+
+
+def smooth_one_hot(target, ncls, smoothing=0.0, bce_target_thresh=None):
+    """Dense targets from hard labels exactly as timm builds them: LabelSmoothingCrossEntropy == soft CE on
+    onehot*(1-s) + s/C; BinaryCrossEntropy(smoothing, target_threshold) uses off = s/C, on = 1 - s + off, then the threshold."""
+    off = smoothing / ncls
+    t = torch.full((target.shape[0], ncls), off, dtype=torch.float32, device=target.device)
+    t.scatter_(1, target.view(-1, 1), 1.0 - smoothing + off)
+    if bce_target_thresh is not None:
+        t = t.gt(bce_target_thresh).float()
+    return t

@@ -246,6 +246,10 @@ int ga_linear_grad_finalize(const float* G, const float* s, const float* W, cons
  * logits, aux: [nb][B][ncls] fp32; dlogits / daux same shape (may be NULL), scaled by grad_scale; loss[0] += value */
 int ga_loss_fwd_bwd(const float* logits, const float* aux, const long long* target, float* loss, float* dlogits,
                     float* daux, int nb, int B, int ncls, float lam, float grad_scale, ga_stream_t s);
+/* the same with DENSE targets [B, ncls] fp32 (mixup / cutmix / label smoothing: timm SoftTargetCrossEntropy, GA/train.py:615-624)
+ * or, bce != 0, BCE-with-logits averaged over B*ncls (timm BinaryCrossEntropy, --bce-loss, GA/train.py:618-619) */
+int ga_loss_dense_fwd_bwd(const float* logits, const float* aux, const float* dense_target, int bce, float* loss,
+                          float* dlogits, float* daux, int nb, int B, int ncls, float lam, float grad_scale, ga_stream_t s);
 
 /* ---- K7: fused multi-tensor AdamW + EMA over flat fp32 buffers  (GA/train.py:466,499,760-761; timm ModelEmaV2)
  * torch.optim.AdamW update of p from g (scaled by grad_scale) with state m, v; bias_c1 = 1-beta1^t, bias_c2 = 1-beta2^t.

@@ -85,6 +85,12 @@ GA_PARITY_CASES = {'config1': ('ga_convnext_tiny_688', 8, 'trained', 'diverse'),
 GA_TAIL_PREFIXES = ('gram_contraction.', 'gram_layer.', 'gram_embedding.', 'ga.', 'fc.')
 
 
+MAP_PARITY_CASES = {'map': ('map_convnext_tiny', 8, 'trained', 'diverse')}
+CSWIN_PARITY_CASES = {'cswin': ('ga_CSWin_64_12211_tiny_224', 8, 'trained', 'diverse')}
+MAP_TAIL_PREFIXES = ('head.heads.', 'head.self_dt_heads.')      # after the CABlock MLP's ReLU
+CSWIN_TAIL_PREFIXES = ('',)                                      # GA-CSWin has no ReLU at all: every gradient is compared raw
+
+
 def parity_inputs(kind, B, size=224):
     return ga_inputs_diverse(B, size=size) if kind == 'diverse' else ga_inputs(B, size=size)
 

@@ -160,8 +160,10 @@ def state_shapes(spec: CSWinSpec) -> Dict[str, Tuple[Tuple[int, ...], str]]:
     return S
 
 
-def make_state(spec: CSWinSpec, seed: int = 0, dtype=torch.float32) -> State:
-    """Sensitised deterministic state (same recipe as ga_convnext_oracle.make_state)."""
+def make_state(spec: CSWinSpec, seed: int = 0, dtype=torch.float32, profile: str = 'sensitised') -> State:
+    """Sensitised deterministic state (same recipe as ga_convnext_oracle.make_state).  CSWin blocks have no layer scale; profile
+    'trained' scales the weights of every residual branch's last Linear (attention `proj`, `mlp.fc2`) by 0.3, the role the layer
+    scale plays in the ConvNeXt fixtures: 31 unscaled residual branches otherwise let every rounding error through at full size."""
     import math
     import zlib
     P: State = {}
@@ -172,6 +174,8 @@ def make_state(spec: CSWinSpec, seed: int = 0, dtype=torch.float32) -> State:
             for s in shape[1:]:
                 fan_in *= s
             t = torch.randn(shape, generator=g) * (1.0 / math.sqrt(fan_in))
+            if profile == 'trained' and (name.endswith('.proj.weight') or name.endswith('.mlp.fc2.weight')) and 'ga.' not in name:
+                t = t * 0.3
         elif kind in ('b', 'rm'):
             t = torch.randn(shape, generator=g) * 0.1
         elif kind in ('g', 'rv'):

@@ -122,8 +122,9 @@ def state_shapes(spec: MAPSpec) -> Dict[str, Tuple[Tuple[int, ...], str]]:
     return S
 
 
-def make_state(spec: MAPSpec, seed: int = 0) -> State:
-    """Sensitised deterministic state (see ga_convnext_oracle.make_state)."""
+def make_state(spec: MAPSpec, seed: int = 0, profile: str = 'sensitised') -> State:
+    """Sensitised deterministic state (see ga_convnext_oracle.make_state); profile 'trained' draws the ConvNeXt-block layer
+    scales (`*.gamma`) from U(0.1, 0.3) instead of U(0.5, 1.5)."""
     P: State = {}
     for name, (shape, kind) in state_shapes(spec).items():
         g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 31))
@@ -136,6 +137,8 @@ def make_state(spec: MAPSpec, seed: int = 0) -> State:
             P[name] = torch.randn(shape, generator=g) * 0.1
         elif kind in ('g', 'rv'):
             P[name] = 0.5 + torch.rand(shape, generator=g)
+            if profile == 'trained' and name.endswith('.gamma'):
+                P[name] = P[name] * 0.2
         elif kind == 'rm':
             P[name] = torch.randn(shape, generator=g) * 0.1
         elif kind == 'idx':
@@ -218,18 +221,21 @@ def class_attention(P: State, spec: MAPSpec, pre: str, u: Tensor, n_q: int) -> T
     return F.linear(o, P[pre + 'proj.weight'], P[pre + 'proj.bias'])
 
 
-def group_conv_mlp(P: State, pre: str, t: Tensor, groups: int) -> Tensor:
-    """map.GroupConvMlp (map.py:56-66) on tokens [B, n, C]: grouped 1x1 -> ReLU -> channel shuffle -> grouped 1x1."""
+def group_conv_mlp(P: State, pre: str, t: Tensor, groups: int, relu_mask=None) -> Tensor:
+    """map.GroupConvMlp (map.py:56-66) on tokens [B, n, C]: grouped 1x1 -> ReLU -> channel shuffle -> grouped 1x1.
+    relu_mask: optional 0/1 tensor [B, hidden, n, 1] replacing the ReLU decisions (mask-pinned gradient check, see
+    ga_convnext_oracle._relu)."""
     B, n, C = t.shape
     x = t.permute(0, 2, 1).unsqueeze(-1)
-    x = F.relu(F.conv2d(x, P[pre + 'fc1.weight'], P[pre + 'fc1.bias'], groups=groups))
+    x = F.conv2d(x, P[pre + 'fc1.weight'], P[pre + 'fc1.bias'], groups=groups)
+    x = F.relu(x) if relu_mask is None else x * relu_mask.to(x.dtype)
     hid = x.shape[1]
     x = x.reshape(B, hid // groups, groups, n, 1).permute(0, 2, 1, 3, 4).reshape(B, hid, n, 1)
     x = F.conv2d(x, P[pre + 'fc2.weight'], P[pre + 'fc2.bias'], groups=groups)
     return x.squeeze(-1).permute(0, 2, 1)
 
 
-def cap(P: State, spec: MAPSpec, g: int, x: Tensor, training: bool) -> Tensor:
+def cap(P: State, spec: MAPSpec, g: int, x: Tensor, training: bool, relu_masks=None) -> Tensor:
     """CAP.forward (map.py:262-278): gram tokens + their mean token -> CABlock -> [B, all_tokens*last_dim]."""
     pre = f'head.mmcap.mmcap.{g}.'
     cls = gram_tokens(P, spec, pre + 'gram_token_extraction.', x, training)
@@ -241,7 +247,7 @@ def cap(P: State, spec: MAPSpec, g: int, x: Tensor, training: bool) -> Tensor:
     u = F.layer_norm(u, (C,), P[a + 'norm1.weight'], P[a + 'norm1.bias'], 1e-6)
     cls = cls + class_attention(P, spec, a + 'attn.', u, spec.all_tokens)
     h = F.layer_norm(cls, (C,), P[a + 'norm2.weight'], P[a + 'norm2.bias'], 1e-6)
-    cls = cls + group_conv_mlp(P, a + 'mlp.', h, spec.mlp_groups)
+    cls = cls + group_conv_mlp(P, a + 'mlp.', h, spec.mlp_groups, None if relu_masks is None else relu_masks.get(f'mlp{g}'))
     return cls.reshape(B, -1)
 
 
@@ -251,14 +257,14 @@ def norm_head(P: State, pre: str, x: Tensor) -> Tensor:
     return F.linear(x, P[pre + 'head.weight'], P[pre + 'head.bias'])
 
 
-def forward(P: State, spec: MAPSpec, x: Tensor, training: bool = False):
+def forward(P: State, spec: MAPSpec, x: Tensor, training: bool = False, relu_masks=None):
     """map_convnext ConvNeXt.forward with global_pool='mmcap' (:137-140) + MAPHead.forward (map.py:512-539).
     eval: list of n_groups logits; train: list of [main logits, self-distillation logits] pairs."""
     f = multi_scale(P, features(P, spec, x), training)
     out = []
     w = spec.last_dim * spec.n_tokens
     for g in range(spec.n_groups):
-        pool = cap(P, spec, g, f, training)
+        pool = cap(P, spec, g, f, training, relu_masks)
         main = norm_head(P, f'head.heads.{g}.', pool[:, :w])
         if training:
             out.append([main, norm_head(P, f'head.self_dt_heads.{g}.', pool[:, w:])])

@@ -269,15 +269,53 @@ def golden_map_model():
     torch.save(out, os.path.join(HERE, 'map_convnext_model.pt'))
 
 
-def golden_ga_parity():
-    """Whole-model fixtures at the BASELINE.json shapes (oracle/cases.py GA_PARITY_CASES): config 1 (fp32 training step, batch 8,
-    fp64 Gram branch) and the bf16 training fixture (batch 16); mutually different images, trained-magnitude layer scales."""
+def golden_parity(family):
+    """Whole-model training-step fixtures at the BASELINE.json shapes (oracle/cases.py *_PARITY_CASES): GA-ConvNeXt config 1
+    (fp32, batch 8, fp64 Gram branch) and its batch-16 bf16 fixture, MAP-ConvNeXt-T and GA-CSWin-T at batch 8; mutually
+    different images, trained-magnitude residual-branch scales.  Stores the reference's logits, loss, gradient digests,
+    BatchNorm statistics, ReLU decisions, and its own noise floor (1e-7 input perturbation) and bf16-autocast deviation."""
     import numpy as np
-    import ga_convnext as R  # noqa: F401
     import timm
+    from oracle import parity_check as PC
+    fam = PC.FAMILIES[family]()
+    if family == 'ga':
+        import ga_convnext  # noqa: F401
+    elif family == 'map':
+        import models.map_convnext  # noqa: F401
 
-    def ga_loss_ref(outs, y):
-        output, loss = 0, 0           # the loss expression of GA/train.py:735-745
+    def build(name):
+        if family == 'cswin':
+            import ga_cswin as R
+            s_ = fam.spec(name)
+            return R.GA_CSWinTransformer(img_size=224, patch_size=4, num_classes=s_.num_classes, embed_dim=s_.embed_dim,
+                                         depth=list(s_.depth), split_size=list(s_.split_size), num_heads=list(s_.num_heads),
+                                         dims=list(s_.dims), stage3_naggre=s_.naggre, gram_dim=s_.gram_dim)
+        ref = timm.create_model(name)
+        if family == 'map':
+            for m in ref.modules():                # parity contract: every drop rate 0 (map.py:149 hard-codes 0.05)
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+        return ref
+
+    def relu_modules(ref):
+        if family == 'ga':
+            return {'bn1': ref.stages[4].act1, 'bn2': ref.stages[4].act2, 'out': ref.stages[4].act3}
+        if family == 'map':
+            return {f'mlp{g}': ref.head.mmcap.mmcap[g].attention[0].mlp.act for g in range(len(ref.head.mmcap.mmcap))}
+        return {}
+
+    def ref_loss(outs, y):
+        if family == 'map':                        # the expression of MAP/train.py:792-839 (distill_tokens == 0)
+            loss, agg = 0, 0
+            for yh, ym in outs:
+                agg = agg + yh
+                loss = loss + F.cross_entropy(yh, y) + F.kl_div(F.log_softmax(ym, dim=1), F.log_softmax(yh, dim=1).detach(),
+                                                                reduction='sum', log_target=True) / yh.numel()
+            for yh, ym in outs:
+                loss = loss + F.kl_div(F.log_softmax(yh, dim=1), F.log_softmax(agg.detach() / len(outs), dim=1),
+                                       reduction='mean', log_target=True) * cases.MAP_DEC_LAM
+            return loss
+        output, loss = 0, 0                        # the loss expression of GA/train.py:735-745
         for o in outs:
             loss = loss + F.cross_entropy(o, y)
             output = output + o.data
@@ -287,23 +325,26 @@ def golden_ga_parity():
         return loss
 
     def run_ref(name, P, x, y):
-        ref = timm.create_model(name)
+        ref = build(name)
         ref.load_state_dict(P, strict=True)
         ref.train()
         masks = {}
-        for key, act in (('bn1', ref.stages[4].act1), ('bn2', ref.stages[4].act2), ('out', ref.stages[4].act3)):
+        for key, act in relu_modules(ref).items():
             act.register_forward_hook(lambda m, i, o, key=key: masks.__setitem__(key, (o.detach() > 0)))
         outs = ref(x)
-        loss = ga_loss_ref(outs, y)
+        loss = ref_loss(outs, y)
         loss.backward()
-        return ref, outs, loss, {k: p.grad.detach().clone() for k, p in ref.named_parameters()}, dict(masks)   # copy: later forwards re-fire the hooks
+        grads = {k: p.grad.detach().clone() for k, p in ref.named_parameters() if p.grad is not None}
+        return ref, outs, loss, grads, dict(masks)   # copy: later forwards re-fire the hooks
 
     out = {}
-    for key, (name, B, profile, kind) in cases.GA_PARITY_CASES.items():
-        spec = O.SPECS[name]
-        P = O.make_state(spec, seed=cases.STATE_SEED, profile=profile)
+    for key, (name, B, profile, kind) in fam.cases_.items():
+        spec = fam.spec(name)
+        P = fam.O.make_state(spec, seed=cases.STATE_SEED, profile=profile)
         x, y = cases.parity_inputs(kind, B)
+        y = fam.labels(y, spec)
         ref, r_train, loss, r_grads, r_masks = run_ref(name, P, x, y)
+        r_flat = [t.detach() for t in fam.flat(r_train)]
         r_state = {k: v.detach().clone() for k, v in ref.state_dict().items() if 'running' in k}
         ref.eval()
         ref.load_state_dict(P, strict=True)
@@ -313,42 +354,43 @@ def golden_ga_parity():
         # pre-activation sits within fp32 rounding of zero)
         Po = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'running' not in k else v.clone())
               for k, v in P.items()}
-        o_train = O.forward(Po, spec, x, training=True, relu_masks=r_masks)
-        o_loss = O.ga_loss(o_train, y, cases.GA_LAM)
+        kw = {'relu_masks': r_masks} if r_masks else {}
+        o_train = fam.O.forward(Po, spec, x, training=True, **kw)
+        o_loss = fam.oracle_loss(o_train, y)
         o_loss.backward()
         assert rel(o_loss.detach(), loss.detach()) < 1e-6
-        for a, b in zip(o_train, r_train):
-            assert rel(a.detach(), b.detach()) < 2e-5, rel(a.detach(), b.detach())
+        for a, b in zip(fam.flat(o_train), r_flat):
+            assert rel(a.detach(), b) < 2e-5, rel(a.detach(), b)
         worst = 0.0
         for k, g in r_grads.items():
             assert close(Po[k].grad, g, 5e-5), (k, rel(Po[k].grad, g))
             if g.norm() > 1e-3:
                 worst = max(worst, rel(Po[k].grad, g))
         # the reference against ITSELF on inputs perturbed by 1e-7 relative: the noise floor of any fp32 comparison here,
-        # and how many ReLU decisions of the Bottleneck flip
+        # and how many ReLU decisions flip
         gen = torch.Generator().manual_seed(5)
         _, p_train, _, p_grads, p_masks = run_ref(name, P, x * (1 + 1e-7 * torch.randn(x.shape, generator=gen)), y)
         noise_g = sorted(rel(p_grads[k], g) for k, g in r_grads.items() if g.norm() > 1e-3)
         flips = sum(int((p_masks[k] != r_masks[k]).sum()) for k in r_masks)
-        self_noise = dict(logits=max(rel(a.detach(), b.detach()) for a, b in zip(p_train, r_train)),
+        self_noise = dict(logits=max(rel(a.detach(), b) for a, b in zip(fam.flat(p_train), r_flat)),
                           grads_median=noise_g[len(noise_g) // 2], grads_max=noise_g[-1], relu_flips=flips,
                           relu_decisions=sum(m.numel() for m in r_masks.values()))
         # information only: how far the reference's OWN bf16 autocast (CPU) is from its fp32 result on this fixture
-        m2 = timm.create_model(name)
+        m2 = build(name)
         m2.load_state_dict(P, strict=True)
         m2.train()
         with torch.no_grad(), torch.autocast('cpu', dtype=torch.bfloat16):
             o16 = m2(x)
-        self_err = max(rel(a.float(), b.detach()) for a, b in zip(o16, r_train))
-        print(f'{key}: {name} B={B} {profile}/{kind}: oracle==reference (loss {loss.item():.6f}, worst gradient {worst:.2e}); '
+        self_err = max(rel(a.float(), b) for a, b in zip(fam.flat(o16), r_flat))
+        print(f'{family}/{key}: {name} B={B} {profile}/{kind}: oracle==reference (loss {loss.item():.6f}, worst gradient {worst:.2e}); '
               f'reference vs itself at 1e-7 input noise: logits {self_noise["logits"]:.2e}, gradients median '
               f'{self_noise["grads_median"]:.2e} max {self_noise["grads_max"]:.2e}, {flips} of {self_noise["relu_decisions"]} ReLU '
               f'decisions flipped; reference bf16-autocast train logits are {self_err:.2e} from its fp32 logits')
-        out[key] = dict(eval_logits=[t.clone() for t in r_eval], train_logits=[t.detach().clone() for t in r_train],
+        out[key] = dict(eval_logits=[t.clone() for t in r_eval], train_logits=[t.clone() for t in r_flat],
                         loss=loss.detach().clone(), grads=grad_digest(r_grads), running=r_state,
                         relu_masks={k: torch.from_numpy(np.packbits(m.numpy().reshape(-1))) for k, m in r_masks.items()},
                         ref_bf16_train_self_err=self_err, ref_self_noise=self_noise)
-    torch.save(out, os.path.join(HERE, 'ga_convnext_parity.pt'))
+    torch.save(out, os.path.join(HERE, fam.golden))
 
 
 def golden_cswin():
@@ -449,5 +491,6 @@ if __name__ == '__main__':
         golden_map_model()
     if 'cswin' in which:
         golden_cswin()
-    if 'parity' in which:
-        golden_ga_parity()
+    for fam in ('ga', 'map', 'cswin'):
+        if f'parity_{fam}' in which or 'parity' in which:
+            golden_parity(fam)

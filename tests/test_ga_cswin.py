@@ -258,11 +258,10 @@ def _build(name, dtype):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', range(len(cases.CSWIN_MODEL_CASES)))
-@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
-def test_model_eval_vs_reference(gold, case, dtype, tol):
+def test_model_eval_vs_reference_fp32(gold, case):
     name, B = cases.CSWIN_MODEL_CASES[case]
     g = gold[f'{name}/B{B}']
-    m, spec = _build(name, dtype)
+    m, spec = _build(name, torch.float32)
     m.eval()
     x, _ = cases.ga_inputs(B)
     with torch.no_grad():
@@ -270,40 +269,35 @@ def test_model_eval_vs_reference(gold, case, dtype, tol):
     assert len(out) == 5
     for a, b in zip(out, g['eval_logits']):
         assert a.shape == (B, spec.num_classes) and a.dtype == torch.float32
-        assert rel(a.cpu(), b) < max(tol, 0 if dtype == torch.float32 else 1.5 * g['ref_bf16_self_err']['eval']), rel(a.cpu(), b)
-        if dtype == torch.float32:
-            assert torch.equal(a.cpu().topk(5).indices, b.topk(5).indices)
+        assert rel(a.cpu(), b) < 2e-5, rel(a.cpu(), b)
+        assert torch.equal(a.cpu().topk(5).indices, b.topk(5).indices)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('case', range(len(cases.CSWIN_MODEL_CASES)))
-@pytest.mark.parametrize('dtype,tol', [(torch.float32, 5e-5), (torch.bfloat16, 2e-2)])
-def test_model_train_step_vs_reference(gold, case, dtype, tol):
-    """forward + GA loss (lam=-0.8) + backward vs the reference's logits, loss, every parameter gradient and BN statistics."""
+def test_model_train_step_vs_reference_fp32_batch2(gold, case):
+    """forward + GA loss (lam=-0.8) + backward vs the reference's logits, loss, every parameter gradient and BN statistics in fp32
+    on the batch-2 fixtures; the bf16 contract (2e-2, asserted directly) and the batch-8 fp32 one are
+    tests/test_parity_baseline_shapes.py (train-mode BatchNorm over two samples is a sign function: not meaningful in bf16)."""
     from imagenet_models_b200 import ops
     name, B = cases.CSWIN_MODEL_CASES[case]
     g = gold[f'{name}/B{B}']
-    m, spec = _build(name, dtype)
+    m, spec = _build(name, torch.float32)
     m.train()
     x, y = cases.ga_inputs(B)
     y = y % spec.num_classes
     out = m(x.cuda())
-    ltol = tol if dtype == torch.float32 else max(tol, g['ref_bf16_self_err']['train'])
     for a, b in zip(out, g['train_logits']):
-        assert rel(a.detach().cpu(), b) < ltol, rel(a.detach().cpu(), b)
+        assert rel(a.detach().cpu(), b) < 5e-5, rel(a.detach().cpu(), b)
     loss = ops.ga_loss(torch.stack(out), y.cuda(), cases.GA_LAM)
-    assert abs(loss.item() - g['loss'].item()) < (1e-4 if dtype == torch.float32 else 3e-2) * abs(g['loss'].item())
+    assert abs(loss.item() - g['loss'].item()) < 1e-4 * abs(g['loss'].item())
     loss.backward()
     bad = []
     for k, p in m.named_parameters():
         assert p.grad is not None, k
-        if dtype == torch.float32:
-            ok = cases.digest_close(p.grad, g['grads'][k], tol, 3e-4)
-        else:
-            ok = cases.digest_rel_err(p.grad, g['grads'][k]) <= 0.15 or g['grads'][k][0] < 2e-2
-        if not ok:
+        if not cases.digest_close(p.grad, g['grads'][k], 5e-5, 3e-4):
             bad.append((k, g['grads'][k][0], p.grad.double().norm().item(), cases.digest_rel_err(p.grad, g['grads'][k])))
     assert not bad, bad[:10]
     sd = m.state_dict()
     for k, v in g['running'].items():
-        assert rel(sd[k].cpu(), v) < (1e-5 if dtype == torch.float32 else 1e-2), k
+        assert rel(sd[k].cpu(), v) < 1e-5, k

@@ -91,34 +91,30 @@ def test_eval_logits_vs_reference(gmap, dtype, tol):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('dtype,tol', [(torch.float32, 5e-5), (torch.bfloat16, 2e-2)])
-def test_train_step_vs_reference(gmap, dtype, tol):
-    """forward (pairs) + multi_group_loss (dec_lam=-0.8) + backward vs the reference's logits, loss, gradients, BN stats."""
+def test_train_step_vs_reference_fp32_batch2(gmap):
+    """forward (pairs) + multi_group_loss (dec_lam=-0.8) + backward vs the reference's logits, loss, gradients, BN stats, fp32, on
+    the batch-2 fixture (train-mode BatchNorm over two samples is a sign function, so bf16 is not meaningful here: the bf16
+    training contract -- 2e-2 asserted directly -- is tests/test_parity_baseline_shapes.py on the batch-8 fixture)."""
     from imagenet_models_b200 import ops
     name, B = cases.MAP_MODEL_CASES[0]
     g = gmap[f'{name}/B{B}']
-    m = _build(name, dtype).train()
+    m = _build(name, torch.float32).train()
     x, y = cases.ga_inputs(B)
     out = m(x.cuda())
-    ltol = tol if dtype == torch.float32 else max(tol, g['ref_bf16_self_err']['train'])
     for (a1, a2), (b1, b2) in zip(out, g['train_logits']):
-        assert rel(a1.detach().cpu(), b1) < ltol and rel(a2.detach().cpu(), b2) < ltol
+        assert rel(a1.detach().cpu(), b1) < 5e-5 and rel(a2.detach().cpu(), b2) < 5e-5
     loss = ops.ga_loss(torch.stack([o[0] for o in out]), y.cuda(), cases.MAP_DEC_LAM, aux=torch.stack([o[1] for o in out]))
-    assert abs(loss.item() - g['loss'].item()) < (1e-4 if dtype == torch.float32 else 3e-2) * abs(g['loss'].item())
+    assert abs(loss.item() - g['loss'].item()) < 1e-4 * abs(g['loss'].item())
     loss.backward()
     bad = []
     for k, p in m.named_parameters():
         assert p.grad is not None, k
-        if dtype == torch.float32:
-            ok = cases.digest_close(p.grad, g['grads'][k], tol, 3e-4)
-        else:
-            ok = cases.digest_rel_err(p.grad, g['grads'][k]) <= 0.15 or g['grads'][k][0] < 2e-2
-        if not ok:
+        if not cases.digest_close(p.grad, g['grads'][k], 5e-5, 3e-4):
             bad.append((k, g['grads'][k][0], p.grad.double().norm().item()))
     assert not bad, bad[:10]
     sd = m.state_dict()
     for k, v in g['running'].items():
-        assert rel(sd[k].cpu(), v) < (1e-5 if dtype == torch.float32 else 1e-2), k
+        assert rel(sd[k].cpu(), v) < 1e-5, k
 
 
 def test_cpu_tensor_raises():
