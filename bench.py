@@ -339,8 +339,7 @@ def main():
             del m, ev, xi
             torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     ms_step = ms / args.steps
     img_s = world * B * args.steps / (ms / 1e3)
@@ -396,9 +395,22 @@ def main():
                                 'sample': '3 training steps (fwd + GA loss + bwd) of batch 8 (BASELINE config 1), fp32, after 1 warm-up, on all '
                                           'host threads; ' + ('the unmodified reference module staged in baseline/_ref' if kind == 'reference'
                                                               else 'oracle port (baseline/_ref not staged)')}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Several ranks: leave without ncclCommDestroy.  destroy_process_group() blocks for ever once a CUDA graph holding NCCL
+    kernels of that communicator exists (probed on 2 x B200, scripts/nccl_graph_probe.py: capture, replays, eager collectives and
+    barrier all complete, destroy_process_group() never returns), so the ranks synchronise, flush and exit."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -328,6 +328,30 @@ __global__ void __launch_bounds__(256) lamb_apply_kernel(const LambEntry* __rest
   }
 }
 
+// Global-norm gradient clipping for the AdamW path (timm dispatch_clip_grad(mode='norm') = torch.nn.utils.clip_grad_norm_,
+// GA/train.py:321-327,758): hyper[3] (the gradient scale the optimizer kernel applies) is multiplied by
+// min(1, max_norm / (||g * hyper[3]|| + 1e-6)).  push_hyper() rewrites hyper[3] before every step.
+__global__ void clip_scale_kernel(const float* __restrict__ sumsq, float* __restrict__ hyper, float max_norm, float* __restrict__ norm_out) {
+  const float norm = sqrtf(*sumsq) * hyper[3];
+  if (norm_out) *norm_out = norm;
+  const float coef = max_norm / (norm + 1e-6f);
+  if (coef < 1.f) hyper[3] *= coef;
+}
+extern "C" int ga_grad_clip_scale(const float* g, long long n, float max_norm, float* hyper, float* scratch /* [2]: sumsq, norm */,
+                                  ga_stream_t s) {
+  GA_REQUIRE(g && hyper && scratch && n > 0 && (n & 3) == 0 && max_norm > 0.f, GA_ERR_SHAPE, "ga_grad_clip_scale: bad arguments");
+  cudaStream_t st = (cudaStream_t)s;
+  cudaMemsetAsync(scratch, 0, 2 * sizeof(float), st);
+  const long long n4 = n >> 2;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > 148LL * 8) blocks = 148LL * 8;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, n4, scratch);
+  int rc = launch_ok("clip_sumsq");
+  if (rc) return rc;
+  clip_scale_kernel<<<1, 1, 0, st>>>(scratch, hyper, max_norm, scratch + 1);
+  return launch_ok("clip_scale");
+}
+
 extern "C" int ga_lamb_ema(float* p, float* g, float* m, float* v, float* ema, const void* table, int count, long long chunks,
                            long long n_flat, float* scratch /* [1 + 2*count] */, const float* hyper, float beta1, float beta2,
                            float eps, float wd, float max_grad_norm, float ema_decay, ga_stream_t s) {

@@ -1180,3 +1180,45 @@ extern "C" int ga_act_bwd(const void* dy, const void* zy, void* dz, long long M,
   DISPATCH_T(dtype, { act_bwd_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)zy, (T*)dz, M, C, lddy, ldz, lddz, act); });
   return launch_ok("act_bwd");
 }
+
+
+// ---------------------------------------------------------------------------------------------- input batch preparation
+// uint8 NCHW -> fp32 NCHW, normalised, optionally mixed with the batch in reverse order (timm Mixup: x.flip(0)); 4 pixels / thread
+__global__ void __launch_bounds__(256) prep_batch_kernel(const unsigned char* __restrict__ x, float* __restrict__ y, int B, long long plane,
+                                                         int W, float m0, float m1, float m2, float r0, float r1, float r2, int mode,
+                                                         float lam, int y0, int y1, int x0, int x1) {
+  const long long per_img = 3 * plane;
+  const long long total4 = (long long)B * per_img / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 4;
+    const int b = (int)(e / per_img);
+    const long long r = e - (long long)b * per_img;
+    const int c = (int)(r / plane);
+    const long long p = r - (long long)c * plane;
+    const float mu = c == 0 ? m0 : (c == 1 ? m1 : m2), rs = c == 0 ? r0 : (c == 1 ? r1 : r2);
+    const uchar4 a = *reinterpret_cast<const uchar4*>(x + e);
+    float v[4] = {(float)a.x, (float)a.y, (float)a.z, (float)a.w};
+    if (mode) {
+      const uchar4 o = *reinterpret_cast<const uchar4*>(x + (long long)(B - 1 - b) * per_img + r);
+      const float w[4] = {(float)o.x, (float)o.y, (float)o.z, (float)o.w};
+      const int py = (int)(p / W), px = (int)(p - (long long)py * W);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (mode == 1) v[k] = lam * v[k] + (1.f - lam) * w[k];
+        else if (py >= y0 && py < y1 && px + k >= x0 && px + k < x1) v[k] = w[k];
+      }
+    }
+    *reinterpret_cast<float4*>(y + e) = make_float4((v[0] - mu) * rs, (v[1] - mu) * rs, (v[2] - mu) * rs, (v[3] - mu) * rs);
+  }
+}
+extern "C" int ga_prep_batch(const unsigned char* x, float* y, int B, int H, int W, const float* mean3, const float* std3, int mode,
+                             float lam, int y0, int y1, int x0, int x1, ga_stream_t s) {
+  GA_REQUIRE(x && y && mean3 && std3 && B > 0 && (W & 3) == 0, GA_ERR_SHAPE, "ga_prep_batch: bad arguments (W must be a multiple of 4)");
+  const long long plane = (long long)H * W, total4 = (long long)B * 3 * plane / 4;
+  long long blocks = (total4 + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  prep_batch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(x, y, B, plane, W, mean3[0] * 255.f, mean3[1] * 255.f, mean3[2] * 255.f,
+                                                                   1.f / (std3[0] * 255.f), 1.f / (std3[1] * 255.f), 1.f / (std3[2] * 255.f),
+                                                                   mode, lam, y0, y1, x0, x1);
+  return launch_ok("prep_batch");
+}

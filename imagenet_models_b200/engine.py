@@ -17,10 +17,15 @@ from . import ops
 from .optim import FusedAdamWEma, FusedLambEma, GradBuckets
 
 
+DDP_IN_GRAPH_DEFAULT = 0      # see TrainEngine(ddp_in_graph=...)
+
+
 class TrainEngine:
     def __init__(self, model, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8, ema_decay: Optional[float] = 0.9998,
                  ga_lam: float = -0.8, amp_dtype=torch.bfloat16, grad_accumulation: int = 1, bucket_mb: float = 25.0,
-                 cuda_graph: bool = False, graph_warmup: int = 3, opt: str = 'adamw', broadcast_buffers: bool = True):
+                 cuda_graph: bool = False, graph_warmup: int = 3, opt: str = 'adamw', broadcast_buffers: bool = True,
+                 ddp_in_graph: Optional[bool] = None, loss: str = 'ce', smoothing: float = 0.0, bce_target_thresh: Optional[float] = None,
+                 clip_grad: Optional[float] = None):
         """cuda_graph: after `graph_warmup` eager steps the whole step (zero-grad, forward, loss, backward, the bucketed gradient
         all-reduce on its side stream, gradient gather, optimizer + EMA) is captured once into a CUDA graph and replayed, which
         removes the ~1.5k per-step kernel launches from the CPU's critical path.  Needs fixed batch shapes; drop-path masks
@@ -37,9 +42,23 @@ class TrainEngine:
         # DistributedDataParallel(broadcast_buffers=True) (GA/train.py:514, --no-ddp-bb turns it off): rank 0's BatchNorm running
         # statistics replace every rank's before each forward.  All float buffers live in one flat tensor -> one small broadcast.
         self.broadcast_buffers = bool(broadcast_buffers) and self.world > 1
+        # classification term: 'ce' hard labels (LabelSmoothingCrossEntropy when smoothing > 0; SoftTargetCrossEntropy when the
+        # loader hands dense mixup targets), 'bce' = timm BinaryCrossEntropy (--bce-loss of the published recipes)
+        assert loss in ('ce', 'bce')
+        self.loss_kind, self.smoothing, self.bce_thresh = loss, smoothing, bce_target_thresh
+        self.clip_grad = clip_grad            # global-norm clip (timm dispatch_clip_grad mode 'norm'); LAMB clips inside its own step
+        if clip_grad is not None and opt == 'adamw':
+            self.opt.clip_grad = float(clip_grad)
         self.ga_lam, self.amp_dtype, self.accum = ga_lam, amp_dtype, max(1, grad_accumulation)
         self.micro = 0
         self.cuda_graph = bool(cuda_graph) and self.accum == 1
+        # several ranks + CUDA graph: True captures the bucketed NCCL all-reduce (side stream) and the optimizer inside the step
+        # graph; False replays forward / backward / gather and then runs ONE all-reduce of the flat gradient and the optimizer
+        # eagerly.  GA_DDP_IN_GRAPH=0/1 overrides the default.
+        if ddp_in_graph is None:
+            import os
+            ddp_in_graph = os.environ.get('GA_DDP_IN_GRAPH', '%d' % DDP_IN_GRAPH_DEFAULT) == '1'
+        self.ddp_in_graph = bool(ddp_in_graph)
         self.graph_warmup, self._calls, self._graph = graph_warmup, 0, None
         self.graph_launches = 0                     # kernels captured per replay (ga_launch_count delta at capture)
 
@@ -60,52 +79,72 @@ class TrainEngine:
             else:
                 dist.broadcast(f, 0)
 
-    def _forward_backward(self, x, y):
-        if self.broadcast_buffers:
+    def _loss(self, out, y):
+        pairs = isinstance(out[0], (list, tuple))            # MAP train mode: [main, self-distillation] pairs per group
+        main = torch.stack([o[0] for o in out]) if pairs else torch.stack(out)
+        aux = torch.stack([o[1] for o in out]) if pairs else None
+        dense = y.dtype != torch.int64
+        if not dense and self.loss_kind == 'ce' and self.smoothing == 0.0:
+            return ops.ga_loss(main, y, self.ga_lam, aux=aux)
+        if not dense:
+            y = ops.smooth_one_hot(y, main.shape[-1], self.smoothing, self.bce_thresh if self.loss_kind == 'bce' else None)
+        elif self.loss_kind == 'bce' and self.bce_thresh is not None:
+            y = y.gt(self.bce_thresh).float()
+        return ops.ga_soft_loss(main, y, self.ga_lam, aux=aux, bce=self.loss_kind == 'bce')
+
+    def _forward_backward(self, x, y, broadcast=True):
+        if self.broadcast_buffers and broadcast:
             dist.broadcast(self.opt.state.bufflat, 0)
         if self.amp_dtype is not None:
             with torch.autocast('cuda', dtype=self.amp_dtype):
                 out = self.model(x)
         else:
             out = self.model(x)
-        if isinstance(out[0], (list, tuple)):            # MAP train mode: [main, self-distillation] pairs per group
-            loss = ops.ga_loss(torch.stack([o[0] for o in out]), y, self.ga_lam, aux=torch.stack([o[1] for o in out]))
-        else:
-            loss = ops.ga_loss(torch.stack(out), y, self.ga_lam)
+        loss = self._loss(out, y)
         loss.backward()
         return loss
 
     def _graph_step(self, x, y):
         from . import lib as L
+        in_graph = self.world == 1 or self.ddp_in_graph
         if self._graph is None:
             self._sx, self._sy = torch.empty_like(x), torch.empty_like(y)
             self._sx.copy_(x)
             self._sy.copy_(y)
             g = torch.cuda.CUDAGraph()
             n0 = L.launch_count()
-            # several ranks: the bucketed all-reduce is captured too -- every bucket's NCCL call sits on the side stream, forked
-            # from the capture stream by the grad-ready hook that completes the bucket and joined before the optimizer, so the
-            # replayed step overlaps the reduction with the rest of backward exactly like the eager path (GA/train.py:505-515).
-            # thread_local: the NCCL watchdog thread's event queries must not invalidate the capture.
-            kw = {'capture_error_mode': 'thread_local'} if self.world > 1 else {}
+            # several ranks, ddp_in_graph: the bucketed all-reduce is captured too -- every bucket's NCCL call sits on the side
+            # stream, forked from the capture stream by the grad-ready hook that completes the bucket and joined before the
+            # optimizer, so the replayed step overlaps the reduction with the rest of backward exactly like the eager path
+            # (GA/train.py:505-515).  thread_local: the NCCL watchdog thread's event queries must not invalidate the capture.
+            kw = {'capture_error_mode': 'thread_local'} if (self.world > 1 and in_graph) else {}
             with torch.cuda.graph(g, **kw):
                 self.opt.zero_grad()
                 if self.buckets is not None:
-                    self.buckets.enabled = True
-                    self.buckets.prepare()
-                self._sloss = self._forward_backward(self._sx, self._sy).detach()
-                if self.buckets is not None:
+                    self.buckets.enabled = in_graph
+                    if in_graph:
+                        self.buckets.prepare()
+                self._sloss = self._forward_backward(self._sx, self._sy, broadcast=in_graph).detach()
+                if self.buckets is not None and in_graph:
                     self.buckets.finish()
                 else:
                     self.opt.state.gather()
-                self.opt.step(gathered=True, device_hyper=True)
+                if in_graph:
+                    self.opt.step(gathered=True, device_hyper=True)
             self.graph_launches = L.launch_count() - n0
             self._graph = g
         else:
             self._sx.copy_(x, non_blocking=True)
             self._sy.copy_(y, non_blocking=True)
-        self.opt.push_hyper(1.0 / self.world)          # lr, bias corrections and the 1/world gradient scale, read by the captured optimizer
-        self._graph.replay()
+        if in_graph:
+            self.opt.push_hyper(1.0 / self.world)      # lr, bias corrections and the 1/world gradient scale, read by the captured optimizer
+            self._graph.replay()
+        else:
+            if self.broadcast_buffers:
+                dist.broadcast(self.opt.state.bufflat, 0)
+            self._graph.replay()
+            dist.all_reduce(self.opt.state.grad)
+            self.opt.step(grad_scale=1.0 / self.world, gathered=True)
         return self._sloss
 
     def step(self, x, y):
@@ -130,10 +169,7 @@ class TrainEngine:
                 out = self.model(x)
         else:
             out = self.model(x)
-        if isinstance(out[0], (list, tuple)):            # MAP train mode: [main, self-distillation] pairs per group
-            loss = ops.ga_loss(torch.stack([o[0] for o in out]), y, self.ga_lam, aux=torch.stack([o[1] for o in out]))
-        else:
-            loss = ops.ga_loss(torch.stack(out), y, self.ga_lam)
+        loss = self._loss(out, y)
         (loss / self.accum if self.accum > 1 else loss).backward()
         if last:
             scale = self.buckets.finish() if self.buckets is not None else 1.0
@@ -144,36 +180,103 @@ class TrainEngine:
         return loss.detach()
 
 
+class Mixup:
+    """timm.data.Mixup (mode 'batch') on the device, GA/train.py:545-557: per batch one lambda ~ Beta(alpha, alpha); mixup blends
+    the batch with itself in reverse order, cutmix pastes a random box from it (lambda corrected to the box area); the targets
+    become lam * smooth_one_hot(y) + (1 - lam) * smooth_one_hot(y.flip(0)).  The host RNG is numpy's, as in timm.
+    draw() -> (mode, lam, (y0, y1, x0, x1)) for DevicePrefetcher / ga_prep_batch; targets() builds the dense targets.
+    timm is absent from this image, so this follows its published algorithm (parity unpinned)."""
+
+    def __init__(self, mixup_alpha=0.8, cutmix_alpha=1.0, prob=1.0, switch_prob=0.5, label_smoothing=0.1, num_classes=1000, seed=None):
+        import numpy as np
+        self.mixup_alpha, self.cutmix_alpha, self.prob, self.switch_prob = mixup_alpha, cutmix_alpha, prob, switch_prob
+        self.smoothing, self.num_classes = label_smoothing, num_classes
+        self.rng = np.random.RandomState(seed)
+        self.enabled = True
+
+    def draw(self, H, W):
+        r = self.rng
+        if not self.enabled or r.rand() >= self.prob or (self.mixup_alpha <= 0 and self.cutmix_alpha <= 0):
+            return 0, 1.0, (0, 0, 0, 0)
+        use_cutmix = self.cutmix_alpha > 0 and (self.mixup_alpha <= 0 or r.rand() < self.switch_prob)
+        lam = float(r.beta(self.cutmix_alpha, self.cutmix_alpha) if use_cutmix else r.beta(self.mixup_alpha, self.mixup_alpha))
+        if not use_cutmix:
+            return 1, lam, (0, 0, 0, 0)
+        ratio = (1.0 - lam) ** 0.5                                     # timm rand_bbox
+        ch, cw = int(H * ratio), int(W * ratio)
+        cy, cx = r.randint(0, H), r.randint(0, W)
+        y0, y1 = max(cy - ch // 2, 0), min(cy + ch // 2, H)
+        x0, x1 = max(cx - cw // 2, 0), min(cx + cw // 2, W)
+        lam = 1.0 - (y1 - y0) * (x1 - x0) / float(H * W)               # correct_lam
+        return 2, lam, (y0, y1, x0, x1)
+
+    def targets(self, y, lam):
+        t = ops.smooth_one_hot(y, self.num_classes, self.smoothing)
+        return t if lam == 1.0 else t * lam + t.flip(0) * (1.0 - lam)
+
+
 class DevicePrefetcher:
     """timm `PrefetchLoader` semantics (create_loader(..., use_prefetcher=True), GA/train.py:598-626): the NEXT batch's uint8
-    host-to-device copy and its normalisation (x - mean*255) / (std*255) run on a side stream under the current step, so PCIe
-    time disappears from the step.  submit(pinned uint8 [B,3,H,W], pinned int64 [B]) -> later get() -> (float x, y)."""
+    host-to-device copy and its normalisation (x - mean*255) / (std*255) -- and, with a Mixup, the mixing with the reversed
+    batch -- run on a side stream under the current step, as ONE kernel (ga_prep_batch) behind the copy.
+    submit(pinned uint8 [B,3,H,W], pinned int64 [B]) -> later get() -> (float x, y or dense targets)."""
 
-    def __init__(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), device='cuda'):
+    def __init__(self, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), device='cuda', mixup: Optional[Mixup] = None):
+        import ctypes as C
         self.device = torch.device(device)
-        self.mean = torch.tensor(mean, device=self.device).view(1, 3, 1, 1) * 255
-        self.std = torch.tensor(std, device=self.device).view(1, 3, 1, 1) * 255
+        self.mean = (C.c_float * 3)(*mean)
+        self.std = (C.c_float * 3)(*std)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.mixup = mixup
         self._pending = None
 
     def submit(self, x_u8: torch.Tensor, y: torch.Tensor):
+        from . import lib as L
         assert self._pending is None, 'one batch in flight'
+        assert x_u8.dtype == torch.uint8 and x_u8.dim() == 4 and x_u8.shape[1] == 3 and x_u8.is_contiguous()
+        Bn, _, H, W = x_u8.shape
+        mode, lam, box = (0, 1.0, (0, 0, 0, 0)) if self.mixup is None else self.mixup.draw(H, W)
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
-            x = x_u8.to(self.device, non_blocking=True).float().sub_(self.mean).div_(self.std)
+            xd = x_u8.to(self.device, non_blocking=True)
             yd = y.to(self.device, non_blocking=True)
+            x = torch.empty(Bn, 3, H, W, dtype=torch.float32, device=self.device)
+            L.check(L.load().ga_prep_batch(L.ptr(xd), L.ptr(x), Bn, H, W, self.mean, self.std, mode, L.f(lam), box[0], box[1], box[2],
+                                           box[3], L.stream()), 'ga_prep_batch')
+            if self.mixup is not None:
+                yd = self.mixup.targets(yd, lam if mode else 1.0)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self._pending = (x, yd, ev)
+        self._pending = (x, yd, ev, xd)
 
     def get(self):
-        x, y, ev = self._pending
+        x, y, ev, xd = self._pending
         self._pending = None
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(ev)
         x.record_stream(cur)
         y.record_stream(cur)
         return x, y
+
+
+class CosineSchedule:
+    """timm CosineLRScheduler as the recipes use it (--sched cosine --warmup-epochs W --warmup-lr L0 --min-lr Lmin, stepped per
+    epoch; GA/train.py:518-531): linear warm-up from warmup_lr to lr over `warmup_epochs`, then
+    min_lr + 0.5 (lr - min_lr) (1 + cos(pi * epoch / epochs)).  timm is absent: its published formula, parity unpinned."""
+
+    def __init__(self, optimizer, base_lr, epochs, warmup_epochs=0, warmup_lr=1e-6, min_lr=1e-5):
+        self.opt, self.base, self.epochs = optimizer, base_lr, max(1, epochs)
+        self.warm, self.warm_lr, self.min_lr = warmup_epochs, warmup_lr, min_lr
+        self.step(0)
+
+    def lr_at(self, epoch):
+        import math
+        if epoch < self.warm:
+            return self.warm_lr + epoch * (self.base - self.warm_lr) / self.warm
+        return self.min_lr + 0.5 * (self.base - self.min_lr) * (1 + math.cos(math.pi * min(epoch, self.epochs) / self.epochs))
+
+    def step(self, epoch):
+        self.opt.param_groups[0]['lr'] = self.lr_at(epoch)
 
 
 @torch.no_grad()

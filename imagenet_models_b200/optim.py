@@ -146,11 +146,26 @@ class FusedAdamWEma:
                 p = ema_named[name]
                 p.data = self.ema_flat[o:o + p.numel()].view(p.shape)
             self.ema_bufflat = _flatten_buffers(self.ema_model, self.ema_flat.device)
+        self.clip_grad = None                                     # global-norm clip (set by TrainEngine(clip_grad=...))
+        self._clip_scratch = torch.zeros(2, dtype=torch.float32, device=self.state.flat.device)
         self.param_groups = [{'lr': lr}]                          # what the reference's logging / schedulers read
         self.hyper = torch.zeros(4, dtype=torch.float32, device=self.state.flat.device) if self.state.flat.is_cuda else None
 
     def zero_grad(self, set_to_none=False):
         self.state.zero_grad()
+
+    def state_dict(self):
+        """Flat moments + step count + lr (what resume needs; timm's resume_checkpoint(optimizer=...) restores the same things)."""
+        return {'m': self.m.detach().cpu(), 'v': self.v.detach().cpu(), 'step_count': self.step_count,
+                'param_groups': [dict(g) for g in self.param_groups], 'names': list(self.state.names),
+                'offsets': list(self.state.offsets)}
+
+    def load_state_dict(self, sd):
+        assert list(sd['names']) == list(self.state.names) and list(sd['offsets']) == list(self.state.offsets), 'optimizer state of another model'
+        self.m.copy_(sd['m'])
+        self.v.copy_(sd['v'])
+        self.step_count = int(sd['step_count'])
+        self.param_groups[0].update(sd['param_groups'][0])
 
     def push_hyper(self, grad_scale: float = 1.0):
         """Advance the step count and upload {lr, 1-b1^t, 1-b2^t, grad_scale} for a graph-captured step(device_hyper=True)."""
@@ -169,6 +184,12 @@ class FusedAdamWEma:
         b1, b2 = self.betas
         lib = L.load()
         ema_d = self.ema_decay if self.ema_decay is not None else 0.0
+        if self.clip_grad is not None and not device_hyper:       # clipping rescales hyper[3] on the device: take that path
+            self.push_hyper(grad_scale)
+            device_hyper = True
+        if self.clip_grad is not None:
+            L.check(lib.ga_grad_clip_scale(L.ptr(self.state.grad), L.ll(self.state.numel), L.f(self.clip_grad), L.ptr(self.hyper),
+                                           L.ptr(self._clip_scratch), L.stream()), 'ga_grad_clip_scale')
         if device_hyper:
             L.check(lib.ga_adamw_ema_dev(L.ptr(self.state.flat), L.ptr(self.state.grad), L.ptr(self.m), L.ptr(self.v),
                                          L.ptr(self.ema_flat), None, L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel),

@@ -264,6 +264,14 @@ int ga_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, void*
 int ga_adamw_ema_dev(float* p, const float* g, float* m, float* v, float* ema, void* p_bf16,
                      const unsigned char* decay_flag, int seg_shift, long long n, const float* hyper, float beta1,
                      float beta2, float eps, float wd, float ema_decay, ga_stream_t s);
+/* global-norm clipping for the AdamW path (torch.nn.utils.clip_grad_norm_ via timm dispatch_clip_grad, GA/train.py:321-327):
+ * hyper[3] *= min(1, max_norm / (||g|| * hyper[3] + 1e-6));  scratch[0] = sum g^2, scratch[1] = the (scaled) norm */
+int ga_grad_clip_scale(const float* g, long long n, float max_norm, float* hyper, float* scratch, ga_stream_t s);
+/* input pipeline step in front of the stem (timm PrefetchLoader + Mixup, GA/train.py:545-557,598-626): uint8 NCHW batch ->
+ * fp32 (x - mean*255) / (std*255), optionally mixed with the batch in reverse order: mode 1 mixup out = lam*a + (1-lam)*b,
+ * mode 2 cutmix (b inside the box [y0,y1) x [x0,x1)).  One pass. */
+int ga_prep_batch(const unsigned char* x, float* y, int B, int H, int W, const float* mean3, const float* std3, int mode,
+                  float lam, int y0, int y1, int x0, int x1, ga_stream_t s);
 /* Per-tensor gradients -> the flat gradient buffer the optimizer / all-reduce buckets read (replaces one accumulate
  * kernel per parameter).  table: device array of `count` records {const float* src (NULL = zeros); long long flat_offset;
  * long long numel; long long first_chunk}, chunks of 4096 elements numbered consecutively over the table. */

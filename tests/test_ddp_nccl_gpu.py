@@ -48,8 +48,8 @@ def _worker(rank, world, port, use_graph, q):
     dist.init_process_group('nccl', rank=rank, world_size=world)
     from imagenet_models_b200.engine import TrainEngine
     m = _model()
-    eng = TrainEngine(m, lr=LR, weight_decay=0.05, ema_decay=0.99, ga_lam=cases.GA_LAM, amp_dtype=None, cuda_graph=use_graph,
-                      graph_warmup=2, bucket_mb=25.0)
+    eng = TrainEngine(m, lr=LR, weight_decay=0.05, ema_decay=0.99, ga_lam=cases.GA_LAM, amp_dtype=None, cuda_graph=use_graph != 'eager',
+                      graph_warmup=2, bucket_mb=25.0, ddp_in_graph=use_graph == 'graph+nccl')
     m.eval()
     grads = []
     for x, y in _batches(world):
@@ -62,11 +62,14 @@ def _worker(rank, world, port, use_graph, q):
            'graph': eng._graph is not None, 'nbuckets': len(eng.buckets.buckets)}
     q.put(out)
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    import time
+    time.sleep(2.0)            # let the queue's feeder thread hand the result over before the hard exit
+    os._exit(0)                # not destroy_process_group(): it blocks once a CUDA graph holds NCCL kernels (scripts/nccl_graph_probe.py)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('use_graph', [False, True])
+@pytest.mark.parametrize('use_graph', ['eager', 'graph', 'graph+nccl'])
 def test_two_rank_nccl_step_matches_one_process_on_the_whole_batch(use_graph):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs (gpurun --gpus 2)')
@@ -91,7 +94,7 @@ def test_two_rank_nccl_step_matches_one_process_on_the_whole_batch(use_graph):
         eng.step(x.cuda(), y.cuda())
         ref_grads.append(eng.opt.state.grad.cpu().clone())
     ref_flat = eng.opt.state.flat.cpu()
-    assert outs[0]['graph'] == use_graph and outs[0]['nbuckets'] >= 2
+    assert outs[0]['graph'] == (use_graph != 'eager') and outs[0]['nbuckets'] >= 2
     for o in outs:
         g0 = torch.from_numpy(o['grads'][0])
         # step 1 starts from identical weights: reduced gradient == whole-batch gradient (summation order only)
