@@ -556,11 +556,9 @@ extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dre
   GA_REQUIRE(dconv && w49c && B > 0, GA_ERR_SHAPE, "ga_dwconv7_bwd: bad arguments");
   GA_REQUIRE(((uintptr_t)dconv & 15) == 0 && ((uintptr_t)w49c & 7) == 0, GA_ERR_ALIGN, "ga_dwconv7_bwd: misaligned operands");
   int rc;
-  // measured (scripts/kernel_bench.py, B=256, fused vs the two first-generation kernels): 56x56x96 574 vs 654 us, 14x14x384 233 vs
-  // 241, 7x7x688 131 vs 205; 28x28x192 386 vs 366 (768-thread CTAs, one per SM) -> that shape keeps the two-kernel path.
-  // GA_DW_BWD3 = 1 / 0 (read once) forces the fused kernel everywhere / nowhere for A/B timing.
+  // GA_DW_BWD3 = 0 (read once) keeps the two first-generation kernels for A/B timing (scripts/kernel_bench.py)
   static const int bwd3_mode = [] { const char* e = getenv("GA_DW_BWD3"); return e ? atoi(e) : -1; }();
-  const bool bwd3 = bwd3_mode == 1 || (bwd3_mode != 0 && (W <= 14 || C == 96));
+  const bool bwd3 = bwd3_mode != 0;
   if (dtype == GA_BF16 && dx && x && dw_partial && (dw49c || dbias) && ((uintptr_t)x & 15) == 0 && dw_v3_enabled() && bwd3) {
     // one fused kernel: data gradient (+ residual, + bf16 shadow), weight gradient and bias gradient from one staged dconv halo
     const int nparts = ga_dwconv7_bwd_parts(B, H, W, C);

@@ -466,7 +466,8 @@ __device__ __forceinline__ float ap_ld(const float* kvc, const T* kvt, int b, in
 template <typename T, int HD_MAX>
 __global__ void __launch_bounds__(256) attnpool_fwd3_kernel(const float* __restrict__ q, const float* __restrict__ kvc,
                                                             const T* __restrict__ kvt, float* __restrict__ out,
-                                                            float* __restrict__ attn, int B, int Q, int N, int H, int E, long long ldt) {
+                                                            float* __restrict__ attn, int B, int Q, int N, int H, int E, long long ldt,
+                                                            const float* __restrict__ drop_mask) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, hd = E / H, NK = Q + N, items = NK * H;
   float* p_s = sm;                      // [Q][H][NK]
@@ -502,7 +503,10 @@ __global__ void __launch_bounds__(256) attnpool_fwd3_kernel(const float* __restr
     const float inv = 1.f / sum;
     const int qi = row / H, h = row - qi * H;
     float* arow = attn + (((long long)b * H + h) * Q + qi) * NK;
-    for (int n = lane; n < NK; n += 32) { const float a = pr[n] * inv; pr[n] = a; arow[n] = a; }
+    // attention dropout (map.py:138): the saved probabilities stay undropped (the softmax derivative needs them), the
+    // product with V uses P * mask, mask = 0 or 1/(1-p) in the layout of `attn`
+    const float* mrow = drop_mask ? drop_mask + (((long long)b * H + h) * Q + qi) * NK : nullptr;
+    for (int n = lane; n < NK; n += 32) { const float a = pr[n] * inv; arow[n] = a; pr[n] = mrow ? a * mrow[n] : a; }
   }
   __syncthreads();
   // (b) out[qi][c] = sum_n P[qi][h(c)][n] V[n][c]: thread = (channel pair, key slice); slices are summed through smem
@@ -555,7 +559,7 @@ __global__ void __launch_bounds__(256) attnpool_bwd3_kernel(const float* __restr
                                                             const float* __restrict__ kvc, const T* __restrict__ kvt,
                                                             const float* __restrict__ attn, float* __restrict__ dq, float* __restrict__ dkvc,
                                                             T* __restrict__ dkvt, int B, int Q, int N, int H, int E, long long ldt,
-                                                            long long lddt) {
+                                                            long long lddt, const float* __restrict__ drop_mask) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, hd = E / H, NK = Q + N, items = NK * H;
   float* p_s = sm;                      // [Q][H][NK] probabilities
@@ -583,6 +587,7 @@ __global__ void __launch_bounds__(256) attnpool_bwd3_kernel(const float* __restr
       float da = 0.f;
 #pragma unroll
       for (int d = 0; d < HD_MAX; ++d) if (d < hd) da = fmaf(do_s[qi * E + h * hd + d], vv[d], da);
+      if (drop_mask) da *= drop_mask[(((long long)b * H + h) * Q + qi) * NK + n];      // d(P * mask) -> dP
       ds_s[(qi * H + h) * NK + n] = da;
     }
   }
@@ -619,7 +624,11 @@ __global__ void __launch_bounds__(256) attnpool_bwd3_kernel(const float* __restr
 #pragma unroll
           for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) {
             const float s0 = ds_s[(qi * H + h0) * NK + n], s1 = ds_s[(qi * H + h1) * NK + n];
-            const float a0 = p_s[(qi * H + h0) * NK + n], a1 = p_s[(qi * H + h1) * NK + n];
+            float a0 = p_s[(qi * H + h0) * NK + n], a1 = p_s[(qi * H + h1) * NK + n];
+            if (drop_mask) {
+              a0 *= drop_mask[(((long long)b * H + h0) * Q + qi) * NK + n];
+              a1 *= drop_mask[(((long long)b * H + h1) * Q + qi) * NK + n];
+            }
             dqa[qi][0] = fmaf(s0, k.x, dqa[qi][0]); dqa[qi][1] = fmaf(s1, k.y, dqa[qi][1]);
             dk0 = fmaf(s0, qq[qi][0], dk0); dk1 = fmaf(s1, qq[qi][1], dk1);
             dv0 = fmaf(a0, dd[qi][0], dv0); dv1 = fmaf(a1, dd[qi][1], dv1);
@@ -639,7 +648,11 @@ __global__ void __launch_bounds__(256) attnpool_bwd3_kernel(const float* __restr
 #pragma unroll
         for (int qi = 0; qi < AP_QMAX; ++qi) if (qi < Q) {
           const float s0 = ds_s[(qi * H + h0) * NK + n], s1 = ds_s[(qi * H + h1) * NK + n];
-          const float a0 = p_s[(qi * H + h0) * NK + n], a1 = p_s[(qi * H + h1) * NK + n];
+          float a0 = p_s[(qi * H + h0) * NK + n], a1 = p_s[(qi * H + h1) * NK + n];
+          if (drop_mask) {
+            a0 *= drop_mask[(((long long)b * H + h0) * Q + qi) * NK + n];
+            a1 *= drop_mask[(((long long)b * H + h1) * Q + qi) * NK + n];
+          }
           dqa[qi][0] = fmaf(s0, k.x, dqa[qi][0]); dqa[qi][1] = fmaf(s1, k.y, dqa[qi][1]);
           dk0 = fmaf(s0, qq[qi][0], dk0); dk1 = fmaf(s1, qq[qi][1], dk1);
           dv0 = fmaf(a0, dd[qi][0], dv0); dv1 = fmaf(a1, dd[qi][1], dv1);
@@ -716,7 +729,7 @@ __global__ void __launch_bounds__(256) attnpool_fwd_kernel(const float* __restri
   }
 }
 extern "C" int ga_attnpool_fwd(const float* q, const float* kv_cls, const void* kv_tok, float* out, float* attn, int B, int Q, int N,
-                               int H, int E, long long ldt, int dtype, ga_stream_t s) {
+                               int H, int E, long long ldt, int dtype, const float* drop_mask, ga_stream_t s) {
   GA_REQUIRE(q && kv_cls && kv_tok && out && attn && H > 0 && E % H == 0, GA_ERR_SHAPE, "ga_attnpool_fwd: bad arguments");
   GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_fwd: head_dim %d > 32", E / H);
   if (B == 0) return GA_OK;
@@ -725,10 +738,11 @@ extern "C" int ga_attnpool_fwd(const float* q, const float* kv_cls, const void* 
   if (Q <= AP_QMAX && (E & 1) == 0 && (ldt & 1) == 0 && smem3 <= 200 * 1024) {
     DISPATCH_T(dtype, {
       if (smem3 > 48 * 1024) cudaFuncSetAttribute(attnpool_fwd3_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-      attnpool_fwd3_kernel<T, 32><<<B, 256, smem3, (cudaStream_t)s>>>(q, kv_cls, (const T*)kv_tok, out, attn, B, Q, N, H, E, ldt);
+      attnpool_fwd3_kernel<T, 32><<<B, 256, smem3, (cudaStream_t)s>>>(q, kv_cls, (const T*)kv_tok, out, attn, B, Q, N, H, E, ldt, drop_mask);
     });
     return launch_ok("attnpool_fwd3");
   }
+  GA_REQUIRE(!drop_mask, GA_ERR_UNSUPPORTED, "ga_attnpool_fwd: attention dropout needs the CTA-per-image kernel (Q <= 4, even E)");
   const int grid = (B * H + 7) / 8;
   DISPATCH_T(dtype, { attnpool_fwd_kernel<T, 32><<<grid, 256, 0, (cudaStream_t)s>>>(q, kv_cls, (const T*)kv_tok, out, attn, B, Q, N, H, E, ldt); });
   return launch_ok("attnpool_fwd");
@@ -883,7 +897,7 @@ __global__ void __launch_bounds__(256) attnpool_bwd2_kernel(const float* __restr
 }
 extern "C" int ga_attnpool_bwd(const float* dout, const float* q, const float* kv_cls, const void* kv_tok, const float* attn,
                                float* dq, float* dkv_cls, void* dkv_tok, int B, int Q, int N, int H, int E, long long ldt,
-                               long long lddt, int dtype, ga_stream_t s) {
+                               long long lddt, int dtype, const float* drop_mask, ga_stream_t s) {
   GA_REQUIRE(dout && q && kv_cls && kv_tok && attn && dq && dkv_cls && dkv_tok && H > 0 && E % H == 0, GA_ERR_SHAPE,
              "ga_attnpool_bwd: bad arguments");
   GA_REQUIRE(E / H <= 32, GA_ERR_UNSUPPORTED, "ga_attnpool_bwd: head_dim %d > 32", E / H);
@@ -893,10 +907,11 @@ extern "C" int ga_attnpool_bwd(const float* dout, const float* q, const float* k
   if (Q <= AP_QMAX && (E & 1) == 0 && ((ldt | lddt) & 1) == 0 && smem3 <= 200 * 1024) {
     DISPATCH_T(dtype, {
       if (smem3 > 48 * 1024) cudaFuncSetAttribute(attnpool_bwd3_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-      attnpool_bwd3_kernel<T, 32><<<B, 256, smem3, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt);
+      attnpool_bwd3_kernel<T, 32><<<B, 256, smem3, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt, drop_mask);
     });
     return launch_ok("attnpool_bwd3");
   }
+  GA_REQUIRE(!drop_mask, GA_ERR_UNSUPPORTED, "ga_attnpool_bwd: attention dropout needs the CTA-per-image kernel (Q <= 4, even E)");
   const size_t smem = ((size_t)(Q + N) * H + H + 3 * (size_t)E) * sizeof(float);
   if (smem <= 48 * 1024) {
     DISPATCH_T(dtype, { attnpool_bwd2_kernel<T, 32><<<B, 256, smem, (cudaStream_t)s>>>(dout, q, kv_cls, (const T*)kv_tok, attn, dq, dkv_cls, (T*)dkv_tok, B, Q, N, H, E, ldt, lddt); });

@@ -197,8 +197,9 @@ class GroupConvMlp(nn.Module):
 
     ACT = ACT_GELU
 
-    def run(self, t, T=torch.float32):
+    def run(self, t, T=torch.float32, drop: float = 0.0):
         """t [B, C] fp32 token; T: operand dtype (bf16 under autocast, like the reference's convs).  Output fp32 [B, C].
+        drop: dropout on the hidden activation after the nonlinearity (map.GroupConvMlp.drop, map.py:61; 0 for GA).
         The channel shuffle between the two grouped convs is a re-striding of the hidden activation; with bf16 operands both
         GEMM inputs are laid out group-major with 16-byte pitches so they run on the tcgen05 path (M is only the batch)."""
         Bn, Cc = t.shape
@@ -208,12 +209,16 @@ class GroupConvMlp(nn.Module):
         if T == torch.float32:
             a3 = t.view(Bn, g, cg).transpose(0, 1)
             h = ops.grouped_linear(a3, self.fc1.weight.view(g, hg, cg), self.fc1.bias, act=self.ACT)
+            if drop > 0.0:
+                h = torch.nn.functional.dropout(h, drop, True)
             # channel_shuffle: shuffled[a*(hid/g) + b] = h[b*g + a]  (ga_convnext.py:557-566)
             a3 = h.view(Bn, hg, g).permute(2, 0, 1)
             return ops.grouped_linear(a3, self.fc2.weight.view(g, cg, hg), self.fc2.bias)
         a3 = torch.empty(g, Bn, ops.pad8(cg), dtype=T, device=t.device)[:, :, :cg]
         a3 = a3.copy_(t.view(Bn, g, cg).transpose(0, 1))
         h = ops.grouped_linear(a3, self.fc1.weight.view(g, hg, cg), self.fc1.bias, act=self.ACT)
+        if drop > 0.0:
+            h = torch.nn.functional.dropout(h, drop, True)
         a3 = torch.empty(g, Bn, ops.pad8(hg), dtype=T, device=t.device)[:, :, :hg]
         a3 = a3.copy_(h.view(Bn, hg, g).permute(2, 0, 1))
         return ops.grouped_linear(a3, self.fc2.weight.view(g, cg, hg), self.fc2.bias, out_dtype=torch.float32)

@@ -3,8 +3,10 @@
 Same factories (`map_convnext_tiny`, `map_convnext_small`), attribute names and state_dict keys (332 entries for tiny,
 incl. `head.mmcap.mmcap.*.gram_token_extraction.bp_index`); the module tree only holds parameters, the arithmetic runs
 through `ops.*` (libga_sm100.so) on NHWC row matrices.  train mode returns `[main logits, self-distillation logits]`
-pairs per group, eval mode the main logits (map.py:519-537).  Dropout (attn_drop/drop 0.05, map.py:149,464) is not
-applied: the kernels implement the deterministic path (the reference's eval behaviour and its train behaviour at drop 0).
+pairs per group, eval mode the main logits (map.py:519-537).  In train mode the CABlock dropouts of the reference are
+applied with its defaults (attn_drop = drop = 0.05, map.py:149): on the attention probabilities inside the attention-pooling
+kernel (mask from torch's Philox generator), on the proj output and on the MLP hidden activation; `MAPHead.drop` /
+`MAPHead.attn_drop` = 0 gives the deterministic path the parity tests use.
 """
 from __future__ import annotations
 
@@ -144,6 +146,7 @@ class MAPHead(nn.Module):
         self.mmcap = MAP(channels, last_dim, num_heads, mlp_ratio, mlp_groups, n_tokens, n_groups, gram_group, bp_dim, ca_dim)
         self.heads = nn.ModuleList([NormHead(last_dim * n_tokens, num_classes) for _ in range(n_groups)])
         self.self_dt_heads = nn.ModuleList([NormHead(last_dim, num_classes) for _ in range(n_groups)])
+        self.drop, self.attn_drop = 0.05, 0.05          # CABlock defaults (map.py:149); train mode only
 
     def run(self, feats, geoms, T, training):
         """feats: compute-dtype row matrices [stem, s0, s1, s2, s3] with geoms (B,H,W).  -> list of logits (pairs in train)."""
@@ -190,15 +193,20 @@ class MAPHead(nn.Module):
             cls_all.append(cls)
         q = torch.stack(qs).view(nb, Bn, nq, E)
         kvc = torch.stack(kvcs).view(nb, Bn, nq, 2 * E)
-        o = ops.attnpool(q, kvc, kv_tok, HW, heads)                                # [nb, B, nq, E]
+        p_att = self.attn_drop if training else 0.0
+        p_drop = self.drop if training else 0.0
+        mask = ops.dropout_mask((nb, Bn, heads, nq, nq + HW), p_att, f.device) if p_att > 0.0 else None
+        o = ops.attnpool(q, kvc, kv_tok, HW, heads, mask)                          # [nb, B, nq, E]
         out = []
         for g, c in enumerate(caps):
             a = c.attention[0]
             cls = cls_all[g].view(Bn * nq, L_)
-            cls = cls + ops.linear(ops.to_dtype(o[g].reshape(Bn * nq, E), T), a.attn.proj.weight, a.attn.proj.bias,
-                                   out_dtype=torch.float32)
+            pr = ops.linear(ops.to_dtype(o[g].reshape(Bn * nq, E), T), a.attn.proj.weight, a.attn.proj.bias, out_dtype=torch.float32)
+            if p_drop > 0.0:
+                pr = torch.nn.functional.dropout(pr, p_drop, True)                 # proj_drop (map.py:141)
+            cls = cls + pr
             h = ops.layernorm(cls, a.norm2.weight, a.norm2.bias, a.norm2.eps)
-            cls = cls + a.mlp.run(h, T)
+            cls = cls + a.mlp.run(h, T, drop=p_drop)
             pool = cls.view(Bn, nq * L_)
             main = self.heads[g].run(pool[:, :self.out_ch].contiguous(), T)
             if training:

@@ -991,25 +991,29 @@ def gram_embed(x, W3, bias, Bn, HW, div, interleave=1):
 # ------------------------------------------------------------------------------------------------- attention pooling
 class AttnPoolFn(Function):
     """Class attention for nb branches at once: q [nb,B,Q,E] fp32 (pre-scaled), kv_cls [nb,B,Q,2E] fp32,
-    kv_tok [B*N, nb*2E] (branch k owns columns [k*2E, (k+1)*2E)).  -> out [nb,B,Q,E] fp32."""
+    kv_tok [B*N, nb*2E] (branch k owns columns [k*2E, (k+1)*2E)).  -> out [nb,B,Q,E] fp32.
+    drop_mask: optional [nb,B,H,Q,Q+N] fp32 attention-dropout multipliers (0 or 1/(1-p)), applied after the softmax."""
 
     @staticmethod
-    def forward(ctx, q, kv_cls, kv_tok, N, H):
+    def forward(ctx, q, kv_cls, kv_tok, N, H, drop_mask):
         nb, Bn, Q, E = q.shape
         q, kv_cls, kv_tok = q.contiguous(), kv_cls.contiguous(), rowmat(kv_tok)
         dev = q.device
         out = torch.empty(nb, Bn, Q, E, dtype=torch.float32, device=dev)
         attn = torch.empty(nb, Bn, H, Q, Q + N, dtype=torch.float32, device=dev)
+        if drop_mask is not None:
+            assert tuple(drop_mask.shape) == tuple(attn.shape) and drop_mask.dtype == torch.float32 and drop_mask.is_contiguous()
         for k in range(nb):
             L.check(_L().ga_attnpool_fwd(L.ptr(q[k]), L.ptr(kv_cls[k]), L.ptr(kv_tok[:, k * 2 * E:]), L.ptr(out[k]), L.ptr(attn[k]),
-                                         Bn, Q, N, H, E, L.ll(kv_tok.stride(0)), L.dt(kv_tok), L.stream()), 'ga_attnpool_fwd')
-        ctx.save_for_backward(q, kv_cls, kv_tok, attn)
+                                         Bn, Q, N, H, E, L.ll(kv_tok.stride(0)), L.dt(kv_tok),
+                                         L.ptr(drop_mask[k]) if drop_mask is not None else None, L.stream()), 'ga_attnpool_fwd')
+        ctx.save_for_backward(q, kv_cls, kv_tok, attn, drop_mask)
         ctx.dims = (N, H)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, kv_cls, kv_tok, attn = ctx.saved_tensors
+        q, kv_cls, kv_tok, attn, drop_mask = ctx.saved_tensors
         N, H = ctx.dims
         nb, Bn, Q, E = q.shape
         dout = dout.contiguous()
@@ -1019,12 +1023,18 @@ class AttnPoolFn(Function):
         for k in range(nb):
             L.check(_L().ga_attnpool_bwd(L.ptr(dout[k]), L.ptr(q[k]), L.ptr(kv_cls[k]), L.ptr(kv_tok[:, k * 2 * E:]), L.ptr(attn[k]),
                                          L.ptr(dq[k]), L.ptr(dkvc[k]), L.ptr(dkvt[:, k * 2 * E:]), Bn, Q, N, H, E,
-                                         L.ll(kv_tok.stride(0)), L.ll(dkvt.stride(0)), L.dt(kv_tok), L.stream()), 'ga_attnpool_bwd')
-        return dq, dkvc, dkvt, None, None
+                                         L.ll(kv_tok.stride(0)), L.ll(dkvt.stride(0)), L.dt(kv_tok),
+                                         L.ptr(drop_mask[k]) if drop_mask is not None else None, L.stream()), 'ga_attnpool_bwd')
+        return dq, dkvc, dkvt, None, None, None
 
 
-def attnpool(q, kv_cls, kv_tok, N, H):
-    return AttnPoolFn.apply(q, kv_cls, kv_tok, N, H)
+def attnpool(q, kv_cls, kv_tok, N, H, drop_mask=None):
+    return AttnPoolFn.apply(q, kv_cls, kv_tok, N, H, drop_mask)
+
+
+def dropout_mask(shape, p, device):
+    """Inverted-dropout multipliers (0 or 1/(1-p)) from torch's generator (Philox on CUDA, graph-capturable)."""
+    return torch.empty(shape, dtype=torch.float32, device=device).bernoulli_(1.0 - p).div_(1.0 - p)
 
 
 # ------------------------------------------------------------------------------------------------- CSWin

@@ -206,10 +206,12 @@ int ga_cswin_attn_bwd(const void* dout, const void* qkv, const void* out, const 
                       ga_stream_t s);
 
 int ga_attnpool_fwd(const float* q, const float* kv_cls, const void* kv_tok, float* out, float* attn, int B, int Q,
-                    int N, int H, int E, long long ldt, int dtype, ga_stream_t s);
+                    int N, int H, int E, long long ldt, int dtype,
+                    const float* drop_mask /* attention dropout (map.py:138): [B,H,Q,Q+N] multipliers 0 or 1/(1-p), or NULL */,
+                    ga_stream_t s);
 int ga_attnpool_bwd(const float* dout, const float* q, const float* kv_cls, const void* kv_tok, const float* attn,
                     float* dq, float* dkv_cls, void* dkv_tok, int B, int Q, int N, int H, int E, long long ldt,
-                    long long lddt, int dtype, ga_stream_t s);
+                    long long lddt, int dtype, const float* drop_mask, ga_stream_t s);
 
 /* ---- small fused pieces -------------------------------------------------------------------------------------*/
 /* dst[m, c] = src[m, c] for c < C with row strides and dtype conversion (concat slices, casts) */

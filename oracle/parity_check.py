@@ -77,7 +77,9 @@ class _MAP(_GA):
     def model(self, name):
         import imagenet_models_b200.map_convnext  # noqa: F401
         from imagenet_models_b200.registry import create_model
-        return create_model(name)
+        m = create_model(name)
+        m.head.drop = m.head.attn_drop = 0.0           # parity contract: every drop rate 0 (the fixture zeroes the reference's Dropouts)
+        return m
 
     def impl_loss(self, out, y):
         from imagenet_models_b200 import ops

@@ -1,8 +1,10 @@
-"""Two ranks over NCCL on two GPUs (skipped on a one-GPU box): the data-parallel training step of imagenet_models_b200.engine --
-bucketed all-reduce overlapped with backward (eager) and the SAME buckets captured inside the step's CUDA graph -- against ONE
-process on the concatenated batch.  Reference behaviour: DistributedDataParallel gradient averaging (GA/train.py:505-515).
-BatchNorm runs on its running statistics (model.eval() with gradients enabled), the only mode in which a sharded batch and the
-whole batch define the same function; fp32 compute so the comparison is about the collective, not about rounding."""
+"""Two ranks over NCCL on two GPUs (skipped on a one-GPU box): the data-parallel training step of imagenet_models_b200.engine in
+its three forms -- 'eager' (bucketed all-reduce overlapped with backward from grad-ready hooks), 'graph' (forward / backward /
+gather replayed as a CUDA graph, then one all-reduce of the flat gradient and the optimizer) and 'graph+nccl' (the buckets'
+NCCL calls captured inside the step graph on a forked side stream) -- against ONE process on the concatenated batch.
+Reference behaviour: DistributedDataParallel gradient averaging (GA/train.py:505-515).  BatchNorm runs on its running statistics
+(model.eval() with gradients enabled), the only mode in which a sharded batch and the whole batch define the same function; fp32
+compute so the comparison is about the collective, not about rounding."""
 import os
 import socket
 
@@ -12,6 +14,9 @@ import torch.multiprocessing as mp
 
 from oracle import cases
 
+B_PER_RANK, STEPS, LR = 4, 4, 1e-3
+MODES = ('eager', 'graph', 'graph+nccl')
+
 
 def _free_port():
     s = socket.socket()
@@ -19,9 +24,6 @@ def _free_port():
     p = s.getsockname()[1]
     s.close()
     return p
-
-
-B_PER_RANK, STEPS, LR = 4, 5, 1e-3
 
 
 def _model():
@@ -36,70 +38,74 @@ def _model():
 
 
 def _batches(world):
-    g = torch.Generator().manual_seed(123)
     return [cases.ga_inputs_diverse(B_PER_RANK * world, seed=1000 + s) for s in range(STEPS)]
 
 
-def _worker(rank, world, port, use_graph, q):
+def _worker(rank, world, port, q):
+    import time
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       TORCH_NCCL_ASYNC_ERROR_HANDLING='0')
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world)
     from imagenet_models_b200.engine import TrainEngine
-    m = _model()
-    eng = TrainEngine(m, lr=LR, weight_decay=0.05, ema_decay=0.99, ga_lam=cases.GA_LAM, amp_dtype=None, cuda_graph=use_graph != 'eager',
-                      graph_warmup=2, bucket_mb=25.0, ddp_in_graph=use_graph == 'graph+nccl')
-    m.eval()
-    grads = []
-    for x, y in _batches(world):
-        xs = x[rank * B_PER_RANK:(rank + 1) * B_PER_RANK].cuda()
-        ys = y[rank * B_PER_RANK:(rank + 1) * B_PER_RANK].cuda()
-        eng.step(xs, ys)
-        grads.append((eng.opt.state.grad / world).cpu().clone())        # the optimizer folds 1/world into its gradient scale
-    torch.cuda.synchronize()
-    out = {'rank': rank, 'grads': [g.numpy() for g in grads], 'flat': eng.opt.state.flat.cpu().numpy(),
-           'graph': eng._graph is not None, 'nbuckets': len(eng.buckets.buckets)}
+    batches = _batches(world)
+    out = {'rank': rank}
+    try:
+        for mode in MODES:
+            m = _model()
+            eng = TrainEngine(m, lr=LR, weight_decay=0.05, ema_decay=0.99, ga_lam=cases.GA_LAM, amp_dtype=None, cuda_graph=mode != 'eager',
+                              graph_warmup=2, bucket_mb=25.0, ddp_in_graph=mode == 'graph+nccl')
+            m.eval()
+            first = None
+            for x, y in batches:
+                eng.step(x[rank * B_PER_RANK:(rank + 1) * B_PER_RANK].cuda(), y[rank * B_PER_RANK:(rank + 1) * B_PER_RANK].cuda())
+                if first is None:
+                    first = (eng.opt.state.grad / world).cpu().numpy()     # the optimizer folds 1/world into its gradient scale
+            torch.cuda.synchronize()
+            out[mode] = {'grad0': first, 'flat': eng.opt.state.flat.cpu().numpy(), 'graph': eng._graph is not None,
+                         'nbuckets': len(eng.buckets.buckets)}
+    except Exception as e:  # noqa: BLE001  (report instead of leaving the peer in a collective for ever)
+        out['error'] = repr(e)
     q.put(out)
-    dist.barrier()
-    torch.cuda.synchronize()
-    import time
-    time.sleep(2.0)            # let the queue's feeder thread hand the result over before the hard exit
+    time.sleep(3.0)            # let the queue's feeder thread hand the result over before the hard exit
     os._exit(0)                # not destroy_process_group(): it blocks once a CUDA graph holds NCCL kernels (scripts/nccl_graph_probe.py)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('use_graph', ['eager', 'graph', 'graph+nccl'])
-def test_two_rank_nccl_step_matches_one_process_on_the_whole_batch(use_graph):
+def test_two_rank_nccl_steps_match_one_process_on_the_whole_batch():
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs (gpurun --gpus 2)')
     world, port = 2, _free_port()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, use_graph, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    outs = sorted([q.get(timeout=600) for _ in range(world)], key=lambda o: o['rank'])
+    outs = sorted([q.get(timeout=420) for _ in range(world)], key=lambda o: o['rank'])
     for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+        p.join(timeout=60)
+    assert all('error' not in o for o in outs), [o.get('error') for o in outs]
     # single process, whole batch
     from imagenet_models_b200.engine import TrainEngine
     torch.cuda.set_device(0)
     m = _model()
     eng = TrainEngine(m, lr=LR, weight_decay=0.05, ema_decay=0.99, ga_lam=cases.GA_LAM, amp_dtype=None, cuda_graph=False)
     m.eval()
-    ref_grads = []
+    ref_grad0 = None
     for x, y in _batches(world):
         eng.step(x.cuda(), y.cuda())
-        ref_grads.append(eng.opt.state.grad.cpu().clone())
+        if ref_grad0 is None:
+            ref_grad0 = eng.opt.state.grad.cpu().clone()
     ref_flat = eng.opt.state.flat.cpu()
-    assert outs[0]['graph'] == (use_graph != 'eager') and outs[0]['nbuckets'] >= 2
-    for o in outs:
-        g0 = torch.from_numpy(o['grads'][0])
-        # step 1 starts from identical weights: reduced gradient == whole-batch gradient (summation order only)
-        assert (g0 - ref_grads[0]).norm().item() <= 2e-5 * ref_grads[0].norm().item(), (g0 - ref_grads[0]).norm().item() / ref_grads[0].norm().item()
-        # later steps start from weights that differ by optimizer round-off (AdamW turns 1e-7 gradient noise into +-lr on
-        # near-zero gradients), so the bound is per step: nobody moves more than lr per step away from the single process
-        assert (torch.from_numpy(o['flat']) - ref_flat).abs().max().item() <= STEPS * LR * 1.05
-    assert (torch.from_numpy(outs[0]['flat']) - torch.from_numpy(outs[1]['flat'])).abs().max().item() == 0.0   # replicas stay bit-identical
+    for mode in MODES:
+        assert outs[0][mode]['graph'] == (mode != 'eager') and outs[0][mode]['nbuckets'] >= 2
+        for o in outs:
+            g0 = torch.from_numpy(o[mode]['grad0'])
+            # step 1 starts from identical weights: reduced gradient == whole-batch gradient (summation order only)
+            err = (g0 - ref_grad0).norm().item() / ref_grad0.norm().item()
+            assert err <= 2e-5, (mode, err)
+            # later steps start from weights that differ by optimizer round-off (AdamW turns 1e-7 gradient noise into +-lr on
+            # near-zero gradients), so the bound is per step: nobody moves more than lr per step away from the single process
+            assert (torch.from_numpy(o[mode]['flat']) - ref_flat).abs().max().item() <= STEPS * LR * 1.05, mode
+        assert (torch.from_numpy(outs[0][mode]['flat']) - torch.from_numpy(outs[1][mode]['flat'])).abs().max().item() == 0.0, mode   # replicas stay bit-identical

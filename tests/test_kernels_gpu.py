@@ -442,3 +442,120 @@ def test_loss_and_adamw():
                                  L.f(1.0), L.stream()), 'adamw')
     assert rel(p, pr.detach()) < 1e-6 and rel(ema, ema_r) < 1e-6
     assert rel(p16.float(), p) < 4e-3
+
+
+def test_attnpool_attention_dropout():
+    """Attention dropout inside the pooling kernel (map.py:138): out = (softmax(qk) * mask) v, gradients through the mask."""
+    Q, N, H, E, nb, Bn = 3, 196, 12, 384, 2, 3
+    hd = E // H
+    q = rnd(nb, Bn, Q, E, seed=84, scale=0.3).requires_grad_(True)
+    kvc = rnd(nb, Bn, Q, 2 * E, seed=85).requires_grad_(True)
+    kvt = rnd(Bn * N, nb * 2 * E, seed=86).requires_grad_(True)
+    torch.manual_seed(5)
+    mask = ops.dropout_mask((nb, Bn, H, Q, Q + N), 0.25, DEV)
+    assert 0.6 < (mask > 0).float().mean().item() < 0.9 and abs(mask.max().item() - 1 / 0.75) < 1e-6
+    out = ops.attnpool(q, kvc, kvt, N, H, mask)
+    dout = rnd(*out.shape, seed=87)
+    out.backward(dout)
+    qr, kr, tr = q.detach().clone().requires_grad_(True), kvc.detach().clone().requires_grad_(True), kvt.detach().clone().requires_grad_(True)
+    outs = []
+    for k in range(nb):
+        t = tr[:, k * 2 * E:(k + 1) * 2 * E].view(Bn, N, 2 * E)
+        kk = torch.cat((kr[k][..., :E], t[..., :E]), 1).view(Bn, Q + N, H, hd).permute(0, 2, 1, 3)
+        vv = torch.cat((kr[k][..., E:], t[..., E:]), 1).view(Bn, Q + N, H, hd).permute(0, 2, 1, 3)
+        qq = qr[k].view(Bn, Q, H, hd).permute(0, 2, 1, 3)
+        a = torch.softmax(qq @ kk.transpose(-1, -2), -1) * mask[k]
+        outs.append((a @ vv).permute(0, 2, 1, 3).reshape(Bn, Q, E))
+    ref = torch.stack(outs)
+    ref.backward(dout)
+    assert rel(out, ref) < 1e-5
+    assert rel(q.grad, qr.grad) < 1e-5 and rel(kvc.grad, kr.grad) < 1e-5 and rel(kvt.grad, tr.grad) < 1e-5
+
+
+@pytest.mark.parametrize('bce', [False, True])
+@pytest.mark.parametrize('with_aux', [False, True])
+def test_dense_target_loss(bce, with_aux):
+    """Soft-target cross entropy / BCE-with-logits on dense targets (timm SoftTargetCrossEntropy, BinaryCrossEntropy) + the GA KL term
+    (+ MAP's self-distillation term), against their plain PyTorch definitions."""
+    nb, Bn, ncls, lam = 4, 6, 1000, -0.8
+    lg = rnd(nb, Bn, ncls, seed=91, scale=2.0).requires_grad_(True)
+    aux = rnd(nb, Bn, ncls, seed=92, scale=2.0).requires_grad_(True) if with_aux else None
+    y = torch.randint(0, ncls, (Bn,), device=DEV)
+    t = ops.smooth_one_hot(y, ncls, 0.1)
+    t = 0.7 * t + 0.3 * t.flip(0)                      # a mixup target
+    assert abs(t.sum(1).mean().item() - 1.0) < 1e-5
+    loss = ops.ga_soft_loss(lg, t, lam, aux=aux, bce=bce)
+    loss.backward()
+    lr = lg.detach().clone().requires_grad_(True)
+    ar = aux.detach().clone().requires_grad_(True) if with_aux else None
+    ref = 0
+    for k in range(nb):
+        if bce:
+            ref = ref + F.binary_cross_entropy_with_logits(lr[k], t)
+        else:
+            ref = ref + torch.sum(-t * F.log_softmax(lr[k], dim=-1), dim=-1).mean()
+        if with_aux:
+            ref = ref + F.kl_div(F.log_softmax(ar[k], dim=1), F.log_softmax(lr[k], dim=1).detach(), reduction='sum', log_target=True) / lr[k].numel()
+    mean = F.log_softmax(lr.detach().mean(0), dim=-1)
+    for k in range(nb):
+        ref = ref + F.kl_div(F.log_softmax(lr[k], dim=-1), mean, reduction='mean', log_target=True) * lam
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-6
+    assert rel(lg.grad, lr.grad) < 1e-5
+    if with_aux:
+        assert rel(aux.grad, ar.grad) < 1e-5
+    with pytest.raises(L.GaError):
+        ops.ga_loss(lg, t, lam)                          # dense targets must not be reinterpreted as int64 labels
+    with pytest.raises(L.GaError):
+        ops.ga_loss(lg, y.int(), lam)
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+def test_prep_batch_normalise_mixup_cutmix(mode):
+    """uint8 -> normalised fp32 (+ mixup / cutmix with the reversed batch) in one kernel vs the timm PrefetchLoader / Mixup maths."""
+    import ctypes as C
+    Bn, H, W = 6, 32, 48
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 256, (Bn, 3, H, W), dtype=torch.uint8, generator=g).cuda()
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    lam, box = 0.3, (5, 20, 8, 30)
+    out = torch.empty(Bn, 3, H, W, device=DEV)
+    L.check(L.load().ga_prep_batch(L.ptr(x), L.ptr(out), Bn, H, W, (C.c_float * 3)(*mean), (C.c_float * 3)(*std), mode, L.f(lam),
+                                   box[0], box[1], box[2], box[3], L.stream()), 'ga_prep_batch')
+    xf = x.float()
+    if mode == 1:
+        xf = lam * xf + (1 - lam) * xf.flip(0)
+    elif mode == 2:
+        xf = xf.clone()
+        xf[:, :, box[0]:box[1], box[2]:box[3]] = x.float().flip(0)[:, :, box[0]:box[1], box[2]:box[3]]
+    m = torch.tensor(mean, device=DEV).view(1, 3, 1, 1) * 255
+    s = torch.tensor(std, device=DEV).view(1, 3, 1, 1) * 255
+    assert torch.allclose(out, (xf - m) / s, atol=2e-5, rtol=1e-5)
+
+
+def test_adamw_global_norm_clip_matches_torch():
+    """ga_grad_clip_scale + ga_adamw_ema_dev against torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW over three steps."""
+    import torch.nn as nn
+    from imagenet_models_b200.optim import FusedAdamWEma
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Linear(37, 64), nn.GELU(), nn.Linear(64, 1000)).cuda()
+    ref = nn.Sequential(nn.Linear(37, 64), nn.GELU(), nn.Linear(64, 1000)).cuda()
+    ref.load_state_dict(net.state_dict())
+    decay = [p for n, p in ref.named_parameters() if p.ndim > 1]
+    no_decay = [p for n, p in ref.named_parameters() if p.ndim <= 1]
+    topt = torch.optim.AdamW([{'params': decay, 'weight_decay': 0.05}, {'params': no_decay, 'weight_decay': 0.0}], lr=1e-3)
+    opt = FusedAdamWEma(net, lr=1e-3, weight_decay=0.05, ema_decay=None)
+    opt.clip_grad = 0.5
+    g = torch.Generator().manual_seed(1)
+    for step in range(3):
+        scale = 10.0 if step != 1 else 1e-3               # steps 0 and 2 exceed the norm bound, step 1 does not
+        grads = [torch.randn(p.shape, generator=g).cuda() * scale for p in net.parameters()]
+        opt.zero_grad()
+        for p, r, gr in zip(net.parameters(), ref.parameters(), grads):
+            p.grad = gr.clone()
+            r.grad = gr.clone()
+        opt.step()
+        nn.utils.clip_grad_norm_(ref.parameters(), 0.5)
+        topt.step()
+    for (n, p), r in zip(net.named_parameters(), ref.parameters()):
+        assert (p - r).abs().max().item() <= 2e-6 + 1e-5 * r.abs().max().item(), n

@@ -70,6 +70,7 @@ def _build(name, dtype):
     m = create_model(name).cuda()
     m.load_state_dict({k: v.cuda() for k, v in MO.make_state(MO.SPECS[name], cases.STATE_SEED).items()}, strict=True)
     m.compute_dtype = dtype
+    m.head.drop = m.head.attn_drop = 0.0             # parity contract: every drop rate 0 (make_golden.py zeroes the reference's Dropouts)
     return m
 
 
