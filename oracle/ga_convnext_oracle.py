@@ -317,10 +317,12 @@ def ga_block(P: State, spec: GASpec, k: int, tokens: Tensor, cls: Tensor) -> Ten
     return cls + P[pre + 'gamma_2'] * group_conv_mlp(P, pre + 'mlp.', h, spec.mlp_groups)
 
 
-def aggregate(spec: GASpec, feats: List[Tensor], taps: List[Tensor]) -> Tensor:
-    """forward_features' multi-scale concat (ga_convnext.py:479-483): pool-to-14, taps, x2, bilinear x2."""
+def aggregate(spec: GASpec, feats: List[Tensor], taps: List[Tensor], pool: int = 14) -> Tensor:
+    """forward_features' multi-scale concat (ga_convnext.py:479-483): pool-to-14, taps, x2, bilinear x2.
+    pool: the reference hard-codes AdaptiveAvgPool2d(14) (:397), which is H/16 at 224; other input sizes only run with the pool
+    target set to H/16 (make_golden.py patches the module ATTRIBUTE of the unmodified reference for the 384 fixture)."""
     x0, x1, x2, x3 = feats
-    return torch.cat((F.adaptive_avg_pool2d(x0, 14), F.adaptive_avg_pool2d(x1, 14), *taps, x2,
+    return torch.cat((F.adaptive_avg_pool2d(x0, pool), F.adaptive_avg_pool2d(x1, pool), *taps, x2,
                       F.interpolate(x3, scale_factor=2, mode='bilinear')), dim=1)
 
 
@@ -333,7 +335,7 @@ def forward_features(P: State, spec: GASpec, x: Tensor, training: bool, relu_mas
         x, t = stage(P, spec, i, x)
         feats.append(x)
         taps += t
-    return bottleneck(P, aggregate(spec, feats, taps), training, relu_masks)
+    return bottleneck(P, aggregate(spec, feats, taps, pool=feats[2].shape[-1]), training, relu_masks)
 
 
 def branch(P: State, spec: GASpec, k: int, f: Tensor, training: bool) -> Tensor:

@@ -24,6 +24,7 @@ def main():
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'step_profile.txt'))
     ap.add_argument('--fwd-only', action='store_true')
     ap.add_argument('--model', default='ga_convnext_tiny_688')
+    ap.add_argument('--drop-path', type=float, default=0.2)
     args = ap.parse_args()
     from imagenet_models_b200 import ops
     from imagenet_models_b200.optim import FusedAdamWEma
@@ -33,7 +34,7 @@ def main():
     import imagenet_models_b200.map_convnext  # noqa: F401
     dev = torch.device('cuda')
     torch.manual_seed(0)
-    model = create_model(args.model).to(dev).train()
+    model = create_model(args.model, drop_path_rate=args.drop_path).to(dev).train()
     opt = FusedAdamWEma(model, lr=1e-3, weight_decay=0.05, ema_decay=0.9998)
     x = torch.randn(args.batch, 3, 224, 224, device=dev)
     y = torch.randint(0, 1000, (args.batch,), device=dev)

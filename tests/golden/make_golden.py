@@ -393,6 +393,31 @@ def golden_parity(family):
     torch.save(out, os.path.join(HERE, fam.golden))
 
 
+def golden_ga_384():
+    """BASELINE config 5 runs GA-ConvNeXt-B at 384x384 as well.  The reference hard-codes AdaptiveAvgPool2d(14) (ga_convnext.py:397,
+    = H/16 at 224) and cannot run other sizes; with that one module ATTRIBUTE replaced by AdaptiveAvgPool2d(H/16) on the
+    otherwise unmodified reference instance it does.  Eval logits of ga_convnext_base_976 and ga_convnext_tiny_688 at 384x384."""
+    import ga_convnext  # noqa: F401
+    import timm
+    out = {}
+    for name, B in (('ga_convnext_base_976', 1), ('ga_convnext_tiny_688', 2)):
+        spec = O.SPECS[name]
+        ref = timm.create_model(name)
+        P = O.make_state(spec, seed=cases.STATE_SEED, profile='trained')
+        ref.load_state_dict(P, strict=True)
+        ref.avg_pool = torch.nn.AdaptiveAvgPool2d(384 // 16)
+        ref.eval()
+        x, _ = cases.ga_inputs_diverse(B, size=384)
+        with torch.no_grad():
+            r = ref(x)
+            o = O.forward({k: v.clone() for k, v in P.items()}, spec, x, training=False)
+        for a, b in zip(o, r):
+            assert rel(a, b) < 2e-5, rel(a, b)
+        print(f'{name} at 384x384 (pool target 24): oracle==reference')
+        out[f'{name}/B{B}/384'] = [t.clone() for t in r]
+    torch.save(out, os.path.join(HERE, 'ga_convnext_384.pt'))
+
+
 def golden_cswin():
     """GA-CSWin (GA/ga_cswin.py) through the unmodified reference: CSWinBlock cases + two whole-model cases."""
     import ga_cswin as R
@@ -491,6 +516,8 @@ if __name__ == '__main__':
         golden_map_model()
     if 'cswin' in which:
         golden_cswin()
+    if 'ga384' in which:
+        golden_ga_384()
     for fam in ('ga', 'map', 'cswin'):
         if f'parity_{fam}' in which or 'parity' in which:
             golden_parity(fam)
