@@ -492,7 +492,7 @@ static int launch_conv(const Plan& p, const CUtensorMap& tm, const float* w, con
 // second-generation bf16 kernels (dwconv3.cu); GA_ERR_UNSUPPORTED = shape not taken, fall through to the kernels above
 int ga_dwconv7_ln_fwd_v3(const void* x, const float* w49c, const float* bias, void* y, float* rstd, int B, int H, int W, int C,
                          float eps, cudaStream_t st);
-int ga_dwconv7_bwd_v3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dxs, float* partial,
+int ga_dwconv7_bwd_v3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dxs, const float* dxs_scale, float* partial,
                       int nparts, int B, int H, int W, int C, int res_dtype, cudaStream_t st);
 // GA_DW_V3=0 (read once, immutable afterwards) keeps the first-generation kernels for A/B timing in scripts/kernel_bench.py
 static bool dw_v3_enabled() {
@@ -544,6 +544,9 @@ extern "C" int ga_dwconv7_bwd_parts(int B, int H, int W, int C) { return 32; }
 extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
                                float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype, int res_dtype,
                                ga_stream_t s);
+extern "C" int ga_dwconv7_bwd3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
+                               const float* shadow_rowscale, float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C,
+                               int dtype, int res_dtype, ga_stream_t s);
 extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, float* dw49c,
                               float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype, int res_dtype,
                               ga_stream_t s) {
@@ -552,6 +555,11 @@ extern "C" int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres
 extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
                                float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype, int res_dtype,
                                ga_stream_t s) {
+  return ga_dwconv7_bwd3(dconv, x, dres, w49c, dx, dx_shadow, nullptr, dw49c, dbias, dw_partial, B, H, W, C, dtype, res_dtype, s);
+}
+extern "C" int ga_dwconv7_bwd3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
+                               const float* shadow_rowscale, float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C,
+                               int dtype, int res_dtype, ga_stream_t s) {
   cudaStream_t st = (cudaStream_t)s;
   GA_REQUIRE(dconv && w49c && B > 0, GA_ERR_SHAPE, "ga_dwconv7_bwd: bad arguments");
   GA_REQUIRE(((uintptr_t)dconv & 15) == 0 && ((uintptr_t)w49c & 7) == 0, GA_ERR_ALIGN, "ga_dwconv7_bwd: misaligned operands");
@@ -563,7 +571,7 @@ extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dre
     // one fused kernel: data gradient (+ residual, + bf16 shadow), weight gradient and bias gradient from one staged dconv halo
     const int nparts = ga_dwconv7_bwd_parts(B, H, W, C);
     cudaMemsetAsync(dw_partial, 0, (size_t)nparts * 50 * C * sizeof(float), st);
-    rc = ga_dwconv7_bwd_v3(dconv, x, dres, w49c, dx, dx_shadow, dw_partial, nparts, B, H, W, C, res_dtype, st);
+    rc = ga_dwconv7_bwd_v3(dconv, x, dres, w49c, dx, dx_shadow, shadow_rowscale, dw_partial, nparts, B, H, W, C, res_dtype, st);
     if (rc == GA_OK) {
       const int n = 50 * C;
       dw::reduce_parts_kernel<<<(n + 255) / 256, 256, 0, st>>>(dw_partial, nparts, n, dw49c, 49 * C, dbias);
@@ -572,6 +580,7 @@ extern "C" int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dre
     }
     if (rc != GA_ERR_UNSUPPORTED) return rc;
   }
+  GA_REQUIRE(!shadow_rowscale, GA_ERR_UNSUPPORTED, "ga_dwconv7_bwd3: the scaled shadow is written by the fused bf16 kernel only");
   if (dx) {
     dw::Plan p;
     int nslice = 1;

@@ -248,7 +248,8 @@ dwconv7_ln_fwd3_kernel(const __grid_constant__ CUtensorMap tm, const float* __re
 template <int CB, int TW, int TH, typename TR>
 __global__ void __launch_bounds__(TH * (TW / 7) * (CB / 2), TH * (TW / 7) * (CB / 2) <= 384 ? 2 : 1)
 dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_constant__ CUtensorMap tmx, const float* __restrict__ w49c,
-                    const TR* __restrict__ dres, TR* __restrict__ dx, bf16* __restrict__ dxs, float* __restrict__ partial, int nparts,
+                    const TR* __restrict__ dres, TR* __restrict__ dx, bf16* __restrict__ dxs, const float* __restrict__ dxs_scale,
+                    float* __restrict__ partial, int nparts,
                     Geo3 g) {
   constexpr int P = CB / 2, NS = TW / 7, HW_ = TW + 6, RS = TH * NS, NT = RS * P;
   constexpr int PIXB = CB * 2, ROWB = HW_ * PIXB;
@@ -356,6 +357,9 @@ dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_consta
     const int oy = y0 + row;
     if (cvalid && oy < g.H && dx) {
       const size_t off0 = (((size_t)b * g.H + oy) * g.W + (x0 + strip * 7)) * g.C + c;
+      // the bf16 shadow may carry the consumer's DropPath factor of this image (it is the GEMM operand of the previous block's
+      // backward, whose branch gradient is ps[b] * dy): saves that block a full scale-rows pass
+      const float ssc = dxs_scale ? dxs_scale[b] : 1.f;
       float r0[7], r1[7];
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
@@ -371,7 +375,7 @@ dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_consta
           const float v0 = lo2(acc[i]) + r0[i], v1 = hi2(acc[i]) + r1[i];
           if (sizeof(TR) == 4) *reinterpret_cast<float2*>(dx + off0 + (size_t)i * g.C) = make_float2(v0, v1);
           else *reinterpret_cast<uint32_t*>(dx + off0 + (size_t)i * g.C) = pack_bf16(v0, v1);
-          if (dxs) *reinterpret_cast<uint32_t*>(dxs + off0 + (size_t)i * g.C) = pack_bf16(v0, v1);
+          if (dxs) *reinterpret_cast<uint32_t*>(dxs + off0 + (size_t)i * g.C) = pack_bf16(v0 * ssc, v1 * ssc);
         }
       }
     }
@@ -446,7 +450,7 @@ static int launch_fwd(const void* x, const float* w49c, const float* bias, void*
 }
 
 template <int CB, int TW, int TH, typename TR>
-static int launch_bwd(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dxs, float* partial,
+static int launch_bwd(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dxs, const float* dxs_scale, float* partial,
                       int nparts, int B, int H, int W, int C, cudaStream_t st) {
   constexpr int P = CB / 2, RS = TH * (TW / 7), NT = RS * P;
   constexpr size_t HALO = (size_t)(TH + 6) * (TW + 6) * CB * 2, CEN = (size_t)TH * TW * CB * 2;
@@ -473,7 +477,7 @@ static int launch_bwd(const void* dconv, const void* x, const void* dres, const 
   if (rc) return rc;
   auto k = dwconv7_bwd3_kernel<CB, TW, TH, TR>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-  k<<<dim3((unsigned)gx, g.nsl), NT, SMEM, st>>>(tmd, tmx, w49c, (const TR*)dres, (TR*)dx, (bf16*)dxs, partial, nparts, g);
+  k<<<dim3((unsigned)gx, g.nsl), NT, SMEM, st>>>(tmd, tmx, w49c, (const TR*)dres, (TR*)dx, (bf16*)dxs, dxs_scale, partial, nparts, g);
   ga_count_launch();
   return ga_check_launch("dwconv7_bwd3");
 }
@@ -497,15 +501,15 @@ int ga_dwconv7_ln_fwd_v3(const void* x, const float* w49c, const float* bias, vo
   return GA_ERR_UNSUPPORTED;
 }
 
-int ga_dwconv7_bwd_v3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dxs, float* partial,
+int ga_dwconv7_bwd_v3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dxs, const float* dxs_scale, float* partial,
                       int nparts, int B, int H, int W, int C, int res_dtype, cudaStream_t st) {
   if (C % 8 || C < 32) return GA_ERR_UNSUPPORTED;
   const int cb = dw3::pick_cb_bwd(C);
   const bool narrow = W <= 7;
 #define DW3_BWD(CB_, TR_)                                                                                                             \
   if (cb == CB_) {                                                                                                                    \
-    if (narrow) return dw3::launch_bwd<CB_, 7, 8, TR_>(dconv, x, dres, w49c, dx, dxs, partial, nparts, B, H, W, C, st);                \
-    return dw3::launch_bwd<CB_, 14, 4, TR_>(dconv, x, dres, w49c, dx, dxs, partial, nparts, B, H, W, C, st);                           \
+    if (narrow) return dw3::launch_bwd<CB_, 7, 8, TR_>(dconv, x, dres, w49c, dx, dxs, dxs_scale, partial, nparts, B, H, W, C, st);                \
+    return dw3::launch_bwd<CB_, 14, 4, TR_>(dconv, x, dres, w49c, dx, dxs, dxs_scale, partial, nparts, B, H, W, C, st);                           \
   }
   if (res_dtype == GA_F32) { DW3_BWD(96, float) DW3_BWD(128, float) }
   else { DW3_BWD(96, bf16) DW3_BWD(128, bf16) }

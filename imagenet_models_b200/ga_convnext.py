@@ -79,13 +79,15 @@ class ConvNeXtBlock(nn.Module):
         self.gamma = nn.Parameter(ls_init_value * torch.ones(dim)) if ls_init_value > 0 else None
         self.drop_prob = float(drop_path)
 
-    def run(self, x, xs, geom, T):
-        """x: residual stream (fp32 under bf16 compute, as in the autocast reference); xs: its bf16 shadow or None."""
+    def run(self, x, xs, geom, T, ps=False, ps_prev=None):
+        """x: residual stream (fp32 under bf16 compute, as in the autocast reference); xs: its bf16 shadow or None.
+        ps: this block's DropPath factors (drawn here when not given); ps_prev: those of the previous block (ops.convnext_block)."""
         p = _params(self)
         if self.gamma is None:
             p['gamma'] = torch.ones_like(p['norm.weight'])
-        ps = _path_scale(self.drop_prob, self.training, geom[0], x.device)
-        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T)
+        if ps is False:
+            ps = _path_scale(self.drop_prob, self.training, geom[0], x.device)
+        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T, ps_prev=ps_prev)
 
 
 class ConvNeXtStage(nn.Module):
@@ -120,8 +122,9 @@ class ConvNeXtStage(nn.Module):
         geom = (Bn, H, W)
         taps: List[torch.Tensor] = []
         n = len(self.blocks)
+        scales = [_path_scale(blk.drop_prob, blk.training, Bn, x.device) for blk in self.blocks]
         for i, blk in enumerate(self.blocks):
-            x, xs = blk.run(x, xs, geom, T)
+            x, xs = blk.run(x, xs, geom, T, ps=scales[i], ps_prev=scales[i - 1] if i > 0 else None)
             if n > 5 and (i + 1) % (n // (self.stage3_naggre + 1)) == 0 and len(taps) < self.stage3_naggre:
                 taps.append(xs if xs is not None else x)
         return x, xs, geom, taps

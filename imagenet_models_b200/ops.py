@@ -15,6 +15,7 @@ from . import lib as L
 from .lib import ACT_GELU, ACT_MUL, ACT_NONE, ACT_RELU, BF16, F32
 
 Function = torch.autograd.Function
+GA_ERR_UNSUPPORTED_ = 4      # GA_ERR_UNSUPPORTED of include/ga_sm100.h
 
 
 def _L():
@@ -362,36 +363,44 @@ def grouped_linear(A3, W3, bias=None, act=ACT_NONE, out_dtype=None):
 _shadow = {}
 
 
-def _offer_shadow(t, ts):
+def _offer_shadow(t, ts, scaled_by=None):
+    """scaled_by: the per-sample DropPath factors [B] the shadow was multiplied with (the consumer's own path_scale tensor)."""
     if ts is not None:
-        _shadow[id(t)] = (t, t._version, ts)
+        _shadow[id(t)] = (t, t._version, ts, scaled_by)
 
 
-def _take_shadow(t, T):
+def _take_shadow(t, T, want_scale=None):
+    """-> (compute-dtype copy of t, True when it already carries `want_scale`)."""
     ent = _shadow.pop(id(t), None)
     if ent is not None and ent[0] is t and ent[1] == t._version and ent[2].dtype == T:
-        return ent[2]
-    return convert(t, T)
+        if ent[3] is None:
+            return ent[2], False
+        if ent[3] is want_scale:
+            return ent[2], True
+    return convert(t, T), False
 
 
 def clear_shadows():
     _shadow.clear()
 
 
-def _stream_grad(dy, dys_in, M, Cc, RT, T, dev):
+def _stream_grad(dy, dys_in, M, Cc, RT, T, dev, want_scale=None):
     """Gradient of a block's two outputs (stream y in RT, shadow ys in T) -> (dy in RT, its T copy for the GEMM operands).
     The last block of a stage feeds only its shadow onward (next stage's LayerNorm, the aggregator): dy is then absent and
     the shadow gradient IS the gradient -- one widening copy instead of zero-fill + mixed-dtype add + narrowing copy."""
     if dy is None and dys_in is None:
         dy = torch.zeros(M, Cc, dtype=RT, device=dev)
-        return dy, (convert(dy, T) if RT != T else dy)
+        return dy, (convert(dy, T) if RT != T else dy), False
     if dy is None:
         dys = rowmat(dys_in) if dys_in.is_contiguous() else dys_in.contiguous()
-        return (convert(dys, RT) if RT != T else dys), dys
+        return (convert(dys, RT) if RT != T else dys), dys, False
     dy = dy.contiguous()
     if dys_in is not None:                      # tapped blocks: both outputs are consumed
         dy = dy + dys_in                        # type promotion keeps the sum in the stream dtype
-    return dy, (_take_shadow(dy, T) if RT != T else dy)
+    if RT == T:
+        return dy, dy, False
+    dys, scaled = _take_shadow(dy, T, want_scale)
+    return dy, dys, scaled
 
 
 class ConvNeXtBlockFn(Function):
@@ -407,7 +416,7 @@ class ConvNeXtBlockFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, xs, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, path_scale, geom, train, T):
+    def forward(ctx, x, xs, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, path_scale, geom, train, T, ps_prev=None):
         Bn, H, W_ = geom
         M, Cc = x.shape
         assert x.is_contiguous() and M == Bn * H * W_
@@ -434,6 +443,7 @@ class ConvNeXtBlockFn(Function):
         if train:
             ctx.save_for_backward(src, xhat, rstd, z, a, w49c, ln_w, ln_b, w1, w1f, b1, w2, b2, gamma, path_scale)
             ctx.geom, ctx.T, ctx.RT = geom, T, x.dtype
+            ctx.ps_prev = ps_prev       # DropPath factors of the block that consumes this block's dx (not a saved tensor: identity matters)
         return y, ys
 
     @staticmethod
@@ -445,8 +455,8 @@ class ConvNeXtBlockFn(Function):
         Hd = w1.shape[0]
         dev = src.device
         lib = _L()
-        dy, dys = _stream_grad(dy, dys_in, M, Cc, RT, T, dev)
-        if path_scale is not None:
+        dy, dys, prescaled = _stream_grad(dy, dys_in, M, Cc, RT, T, dev, path_scale)
+        if path_scale is not None and not prescaled:
             t = torch.empty_like(dys)
             L.check(lib.ga_scale_rows(L.ptr(dys), L.ptr(path_scale), L.ptr(t), L.ll(M), Cc, H * W_, L.dt(dys), L.stream()),
                     'ga_scale_rows')
@@ -482,20 +492,30 @@ class ConvNeXtBlockFn(Function):
         dxs = torch.empty(M, Cc, dtype=T, device=dev) if RT != T else None
         parts = lib.ga_dwconv7_bwd_parts(Bn, H, W_, Cc)
         ws = workspace(parts * 50 * Cc, dev, 'dwconv')
-        L.check(lib.ga_dwconv7_bwd2(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(dxs), L.ptr(d49), L.ptr(ddwb),
-                                    L.ptr(ws), Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream()), 'ga_dwconv7_bwd')
-        _offer_shadow(dx, dxs)
+        ps_prev = ctx.ps_prev if dxs is not None else None
+        rc = GA_ERR_UNSUPPORTED_
+        if ps_prev is not None:          # the shadow leaves the kernel already multiplied by the consumer's DropPath factors
+            rc = lib.ga_dwconv7_bwd3(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(dxs), L.ptr(ps_prev), L.ptr(d49),
+                                     L.ptr(ddwb), L.ptr(ws), Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream())
+            if rc not in (0, GA_ERR_UNSUPPORTED_):
+                L.check(rc, 'ga_dwconv7_bwd3')
+        if rc == GA_ERR_UNSUPPORTED_:
+            ps_prev = None
+            L.check(lib.ga_dwconv7_bwd2(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(dxs), L.ptr(d49), L.ptr(ddwb),
+                                        L.ptr(ws), Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream()), 'ga_dwconv7_bwd')
+        _offer_shadow(dx, dxs, ps_prev)
         d_dw_w = d49.view(49, Cc).t().reshape(Cc, 1, 7, 7)
-        return (dx, None, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None, None)
+        return (dx, None, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None, None, None)
 
 
-def convnext_block(x, p, geom, path_scale=None, train=True, xs=None, T=None):
+def convnext_block(x, p, geom, path_scale=None, train=True, xs=None, T=None, ps_prev=None):
     """p: dict with conv_dw.weight/bias, norm.weight/bias, mlp.fc1/fc2.weight/bias, gamma (reference key names).
+    ps_prev: the DropPath factors of the block whose backward consumes this block's stream gradient (the previous block).
     Returns (y, ys): the residual stream and its compute-dtype shadow (None when they coincide)."""
     T = T or (xs.dtype if xs is not None else x.dtype)
     return ConvNeXtBlockFn.apply(x, xs, p['conv_dw.weight'], p['conv_dw.bias'], p['norm.weight'], p['norm.bias'],
                                  p['mlp.fc1.weight'], p['mlp.fc1.bias'], p['mlp.fc2.weight'], p['mlp.fc2.bias'], p['gamma'],
-                                 path_scale, geom, train, T)
+                                 path_scale, geom, train, T, ps_prev)
 
 
 class ConvertFn(Function):
@@ -1158,7 +1178,7 @@ class CSWinBlockFn(Function):
         dev = xh1.device
         lib = _L()
         HW = R * R
-        dy, dys = _stream_grad(dy, dys_in, M, Cc, RT, T, dev)
+        dy, dys, _ = _stream_grad(dy, dys_in, M, Cc, RT, T, dev)
 
         def rows_scaled(t, ps):
             if ps is None:

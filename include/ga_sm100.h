@@ -98,6 +98,12 @@ int ga_dwconv7_bwd(const void* dconv, const void* x, const void* dres, const flo
 int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
                     float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C, int dtype,
                     int res_dtype, ga_stream_t s);
+/* same; shadow_rowscale [B] (may be NULL): dx_shadow = dx * shadow_rowscale[image] -- the DropPath factor of the block that consumes
+ * the shadow as its backward GEMM operand (timm DropPath on the residual branch, ga_convnext.py:111), so that block needs no
+ * separate row-scaling pass.  GA_ERR_UNSUPPORTED when the fused bf16 kernel does not take the shape (caller scales itself). */
+int ga_dwconv7_bwd3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
+                    const float* shadow_rowscale, float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C,
+                    int dtype, int res_dtype, ga_stream_t s);
 
 /* ---- row LayerNorm over the last dim (LayerNorm2d on NHWC rows, nn.LayerNorm)  (ga_convnext.py:51-67,233,237) */
 int ga_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,

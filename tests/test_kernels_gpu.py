@@ -559,3 +559,42 @@ def test_adamw_global_norm_clip_matches_torch():
         topt.step()
     for (n, p), r in zip(net.named_parameters(), ref.parameters()):
         assert (p - r).abs().max().item() <= 2e-6 + 1e-5 * r.abs().max().item(), n
+
+
+def test_stage_with_droppath_prescaled_shadow_vs_oracle():
+    """Three ConvNeXt blocks with DropPath factors (one sample dropped): the stream gradient's bf16 shadow leaves the fused depthwise
+    backward already multiplied by the consumer block's factors (ga_dwconv7_bwd3); every parameter gradient must still match the
+    oracle's x + ps * branch chain (ga_convnext.py:98-112 with timm DropPath)."""
+    from oracle import cases
+    from oracle import ga_convnext_oracle as O
+    C, H, Bn, nblk = 96, 14, 4, 3
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(Bn, C, H, H, generator=g)
+    dy = torch.randn(Bn, C, H, H, generator=g)
+    states = [cases.block_state(C, seed=100 + i) for i in range(nblk)]
+    for st in states:
+        st['gamma'] = st['gamma'] * 0.3
+    scales = [torch.tensor([1.25, 0.0, 1.25, 1.25]), torch.tensor([0.0, 1.25, 1.25, 1.25]), torch.tensor([1.25, 1.25, 1.25, 0.0])]
+    # oracle (fp32 CPU)
+    Ps = [{k: v.clone().requires_grad_(True) for k, v in st.items()} for st in states]
+    xo = x.clone().requires_grad_(True)
+    h = xo
+    for P, sc in zip(Ps, scales):
+        h = O.convnext_block(P, '', h, path_scale=sc)
+    h.backward(dy)
+    # implementation: fp32 stream + bf16 shadow, as the model runs it under autocast
+    T = torch.bfloat16
+    xr = x.permute(0, 2, 3, 1).reshape(-1, C).contiguous().cuda().requires_grad_(True)
+    xs = ops.to_dtype(xr, T)
+    Pg = [{k: v.clone().cuda().requires_grad_(True) for k, v in st.items()} for st in states]
+    sg = [s.cuda() for s in scales]
+    y, ys = xr, xs
+    for i in range(nblk):
+        y, ys = ops.convnext_block(y, Pg[i], (Bn, H, H), sg[i], True, xs=ys, T=T, ps_prev=sg[i - 1] if i > 0 else None)
+    y.backward(dy.permute(0, 2, 3, 1).reshape(-1, C).contiguous().cuda())
+    assert rel(y.detach().cpu(), h.detach().permute(0, 2, 3, 1).reshape(-1, C)) < 1e-2
+    assert rel(xr.grad.cpu(), xo.grad.permute(0, 2, 3, 1).reshape(-1, C)) < 1e-2
+    for i in range(nblk):
+        for k in Ps[i]:
+            e = rel(Pg[i][k].grad.cpu().reshape(-1), Ps[i][k].grad.reshape(-1))
+            assert e < 3e-2, (i, k, e)
