@@ -790,7 +790,7 @@ static int launch(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
     if (splits <= 0) {
       long long tiles = (long long)mt * nt * g->batch;
       int sms = ga_num_sms();
-      splits = (int)((2LL * sms + tiles - 1) / tiles);
+      splits = (int)(sms / tiles);                 // one balanced wave, see launch2
       int maxs = p.kb_total / 4; if (maxs < 1) maxs = 1;
       if (splits > maxs) splits = maxs;
       if (splits < 1) splits = 1;
@@ -842,8 +842,11 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   if (g->accumulate) {
     splits = g->splits;
     if (splits <= 0) {
+      // one balanced wave: tiles * splits <= #SMs.  Measured (scripts/kernel_bench.py, KB_SPLIT_SWEEP=1, B=256 weight-gradient
+      // shapes): against the former two-waves rule 56x56 156 -> 123 us (96 % of the HBM peak), 28x28 103 -> 82 / 139 -> 104,
+      // 14x14 74 -> 59, 7x7 64 -> 55; more splits only add red.v4 traffic on the [N, K] gradient tile.
       const long long tiles = (long long)mt * nt * g->batch;
-      splits = (int)((2LL * sms + tiles - 1) / tiles);
+      splits = (int)(sms / tiles);
       int maxs = p.kb_total / 4; if (maxs < 1) maxs = 1;
       if (splits > maxs) splits = maxs;
       if (splits < 1) splits = 1;

@@ -87,6 +87,16 @@ def gemm_cases():
         dgrad_gelu(f's{s}_dz', M, c, 4 * c)
         fwd(f's{s}_dxhat', M, 4 * c, c)
         wgrad(f's{s}_wgrad_fc2', M, c, 4 * c)
+    if os.environ.get('KB_SPLIT_SWEEP'):
+        for s_, (hw, c) in enumerate([(56, 96), (28, 192), (14, 384), (7, 688)]):
+            M = B * hw * hw
+            for (n_, k_, tag) in ((c, 4 * c, 'fc2'), (4 * c, c, 'fc1')):
+                dY = torch.randn(M, n_, device=DEV, dtype=bf)
+                X = torch.randn(M, k_, device=DEV, dtype=bf)
+                G = torch.zeros(n_, k_, device=DEV)
+                for sp in (0, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48):
+                    cases[f's{s_}_wgrad_{tag}_sp{sp}'] = (lambda dY=dY, X=X, G=G, sp=sp: ops.gemm(dY.t(), X.t(), G, accumulate=True, splits=sp),
+                                                         M * (n_ + k_) * 2, 2.0 * M * k_ * n_)
     fwd('kv_proj', B * 196, 688, 1680)
     fwd('bneck_conv1', B * 196, 2128, 172)
     return cases
