@@ -33,9 +33,10 @@ GA_LAM = -0.8
 # aggregate in `value`, so the line carries the training aggregate, `per_gpu` = value / n_gpus, and the roofline objects
 METRIC = 'train images/sec, whole job (BASELINE.json metric: train/infer images/sec/GPU at 1/2/4/8 B200 (224^2) + % roofline; per_gpu = value / n_gpus)'
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same call sites (profiles/)
-NCU_TRAFFIC = {('ga_gemm', (802816, 384, 96, 'gelu')): 1333.5e6, ('ga_gemm', (802816, 384, 96, 'mul')): 1360.3e6}
+NCU_TRAFFIC = {('ga_gemm', (802816, 384, 96, 'gelu')): 1333.5e6, ('ga_gemm', (802816, 384, 96, 'mul')): 1360.3e6}     # + dwconv entries below
 KERNEL_OF = {'ga_gemm': 'tc::gemm_tc2_kernel (tcgen05 persistent GEMM)', 'ga_dwconv7_ln_fwd': 'dw::dwconv7 forward (dw7x7 + bias + LayerNorm)',
-             'ga_dwconv7_bwd2': 'dw::dwconv7 backward (data gradient + weight gradient + bias gradient)'}
+             'ga_dwconv7_bwd2': 'dw3::dwconv7_bwd3_kernel (fused depthwise 7x7 backward: data gradient + residual + bf16 shadow, weight and bias gradient)',
+             'ga_dwconv7_bwd3': 'dw3::dwconv7_bwd3_kernel (fused depthwise 7x7 backward: data gradient + residual + bf16 shadow, weight and bias gradient)'}
 
 
 def call_bytes(name, sig):
@@ -52,7 +53,7 @@ def call_bytes(name, sig):
         B, H, W, C, dt = sig[:5]
         es = 2 if dt == 1 else 4
         return B * H * W * (2 * C * es + 4)
-    if name == 'ga_dwconv7_bwd2':
+    if name in ('ga_dwconv7_bwd2', 'ga_dwconv7_bwd3'):
         B, H, W, C, dt, rdt = sig[:6]
         es, rs = (2 if dt == 1 else 4), (2 if rdt == 1 else 4)
         return B * H * W * C * (2 * es + 2 * rs + (es if rs != es else 0))     # R dconv, R x, R dres, W dx (+ W bf16 shadow)
@@ -316,7 +317,11 @@ def main():
     step_resident()
     timer = L.start_timing() if rank == 0 else None
     ms_inst = timed(step_resident, n_inst)
-    calls = timer.summary() if rank == 0 else {}
+    calls = {}
+    for (nm, sg), (n, t) in (timer.summary() if rank == 0 else {}).items():
+        nm = 'ga_dwconv7_bwd2' if nm == 'ga_dwconv7_bwd3' else nm          # same kernel, with / without the DropPath-scaled shadow
+        n0_, t0_ = calls.get((nm, sg), (0, 0.0))
+        calls[(nm, sg)] = (n0_ + n, t0_ + t)
     L.stop_timing()
 
     # inference leg (BASELINE config 5 / validate.py loop body), CUDA-graph replay per batch, replicas only
@@ -361,7 +366,7 @@ def main():
     for (nm, sg), (n, t) in calls.items():
         k = 'gemm' if nm == 'ga_gemm' else 'dwconv7' if nm.startswith('ga_dwconv7') else 'other'
         fam[k] = fam.get(k, 0.0) + t / n_inst / ms_step_inst
-    tkey = None
+    tkey = (name, tuple(sig[:4])) if name.startswith('ga_dwconv7') else None
     if name == 'ga_gemm':
         tkey = (name, (sig[1], sig[2], sig[3], 'gelu' if sig[6] == 1 else 'mul' if sig[10] else 'lin'))
     line = {
