@@ -286,15 +286,27 @@ dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_consta
   const long long t_begin = (long long)blockIdx.x * g.tpc;
   const long long t_end = t_begin + g.tpc < g.total_tiles ? t_begin + g.tpc : g.total_tiles;
   uint32_t phase = 0;
+  auto issue_tile = [&](long long t) {               // one elected thread: stage the dconv halo and the x centre of tile t
+    const int tx = (int)(t % g.tiles_x);
+    const int ty = (int)((t / g.tiles_x) % g.tiles_y);
+    const int b = (int)(t / ((long long)g.tiles_x * g.tiles_y));
+    mbar_expect_tx(bar, HALO_BYTES + CEN_BYTES);
+    tma_load_4d(halo_s, &tmd, bar, c0, tx * TW - 3, ty * TH - 3, b);
+    tma_load_4d(cen_s, &tmx, bar, c0, tx * TW, ty * TH, b);
+  };
+  if (threadIdx.x == 0 && t_begin < t_end) issue_tile(t_begin);
   for (long long t = t_begin; t < t_end; ++t) {
     const int tx = (int)(t % g.tiles_x);
     const int ty = (int)((t / g.tiles_x) % g.tiles_y);
     const int b = (int)(t / ((long long)g.tiles_x * g.tiles_y));
     const int x0 = tx * TW, y0 = ty * TH;
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(bar, HALO_BYTES + CEN_BYTES);
-      tma_load_4d(halo_s, &tmd, bar, c0, x0 - 3, y0 - 3, b);
-      tma_load_4d(cen_s, &tmx, bar, c0, x0, y0, b);
+    // the residual-stream gradient of this thread's 7 pixels is only needed in the epilogue: pull its lines into L2 now
+    // (ncu: 19 % long-scoreboard stall, most of it on these loads)
+    if (dres && cvalid && y0 + row < g.H) {
+      const TR* rp = dres + (((size_t)b * g.H + (y0 + row)) * g.W + (x0 + strip * 7)) * g.C + c;
+#pragma unroll
+      for (int i = 0; i < 7; ++i)
+        if (x0 + strip * 7 + i < g.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)i * g.C));
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -353,6 +365,8 @@ dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_consta
       const float2 o = lds_f2(aa);
       sts_f2(aa, o.x + s0, o.y + s1);
     }
+    // every thread passed the barrier above after its last read of the staged tiles: the next tile's TMA can overlap the epilogue
+    if (threadIdx.x == 0 && t + 1 < t_end) issue_tile(t + 1);
     // data gradient + residual, stream dtype TR, optional bf16 shadow
     const int oy = y0 + row;
     if (cvalid && oy < g.H && dx) {
@@ -379,8 +393,8 @@ dwconv7_bwd3_kernel(const __grid_constant__ CUtensorMap tmd, const __grid_consta
         }
       }
     }
-    __syncthreads();       // halo / centre tiles free for the next TMA, accum updates ordered before the flush
   }
+  __syncthreads();         // accum updates of the last tile ordered before the flush
   // flush the CTA's sums: [50][C] slot (blockIdx.x % nparts)
   if (partial) {
     float* slot = partial + (size_t)(blockIdx.x % nparts) * 50 * g.C;
