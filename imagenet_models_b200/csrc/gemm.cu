@@ -791,6 +791,7 @@ static int launch(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
       long long tiles = (long long)mt * nt * g->batch;
       int sms = ga_num_sms();
       splits = (int)(sms / tiles);                 // one balanced wave, see launch2
+      if (splits == 6) splits = 8;
       int maxs = p.kb_total / 4; if (maxs < 1) maxs = 1;
       if (splits > maxs) splits = maxs;
       if (splits < 1) splits = 1;
@@ -847,6 +848,7 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
       // 14x14 74 -> 59, 7x7 64 -> 55; more splits only add red.v4 traffic on the [N, K] gradient tile.
       const long long tiles = (long long)mt * nt * g->batch;
       splits = (int)(sms / tiles);
+      if (splits == 6) splits = 8;       // 22..24 tiles: the sweep has 6 splits (K blocks of 131) at 104 us and 8 at 82 ([1536,384], K = 50176)
       int maxs = p.kb_total / 4; if (maxs < 1) maxs = 1;
       if (splits > maxs) splits = maxs;
       if (splits < 1) splits = 1;

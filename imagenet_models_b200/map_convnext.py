@@ -46,13 +46,14 @@ class Block(nn.Module):
         self.gamma = nn.Parameter(layer_scale_init_value * torch.ones(dim)) if layer_scale_init_value > 0 else None
         self.drop_prob = float(drop_path)
 
-    def run(self, x, xs, geom, T):
+    def run(self, x, xs, geom, T, ps=False, ps_prev=None):
         p = {'conv_dw.weight': self.dwconv.weight, 'conv_dw.bias': self.dwconv.bias, 'norm.weight': self.norm.weight,
              'norm.bias': self.norm.bias, 'mlp.fc1.weight': self.pwconv1.weight, 'mlp.fc1.bias': self.pwconv1.bias,
              'mlp.fc2.weight': self.pwconv2.weight, 'mlp.fc2.bias': self.pwconv2.bias,
              'gamma': self.gamma if self.gamma is not None else torch.ones_like(self.norm.weight)}
-        ps = _path_scale(self.drop_prob, self.training, geom[0], x.device)
-        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T)
+        if ps is False:
+            ps = _path_scale(self.drop_prob, self.training, geom[0], x.device)
+        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T, ps_prev=ps_prev)
 
 
 class ClassAttention(nn.Module):
@@ -285,8 +286,10 @@ class ConvNeXt(nn.Module):
                 geom = (Bn, geom[1] // 2, geom[2] // 2)
                 y = ops.linear(h, conv.weight.permute(0, 2, 3, 1).reshape(conv.out_channels, -1), conv.bias, out_dtype=RT)
                 ys = ops.to_dtype(y, T) if RT != T else None
-            for blk in self.stages[i]:
-                y, ys = blk.run(y, ys, geom, T)
+            blocks = list(self.stages[i])
+            scales = [_path_scale(blk.drop_prob, blk.training, Bn, y.device) for blk in blocks]     # DropPath factors of the stage
+            for j, blk in enumerate(blocks):
+                y, ys = blk.run(y, ys, geom, T, ps=scales[j], ps_prev=scales[j - 1] if j > 0 else None)
             feats.append(ys if ys is not None else y)
             geoms.append(geom)
         return feats, geoms

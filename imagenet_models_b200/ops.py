@@ -74,23 +74,7 @@ def _zeros(n, device):
 
 
 # ------------------------------------------------------------------------------------------------- raw kernels
-class GemmTimer:
-    """Optional CUDA-event instrumentation of every ga_gemm launch (bench.py's live per-kernel roofline).
-    Events are recorded on the launching stream around the single kernel launch; read with summary() after a sync."""
-
-    def __init__(self):
-        self.records = []
-
-    def summary(self):
-        agg = {}
-        for key, e0, e1 in self.records:
-            ms = e0.elapsed_time(e1)
-            n, t = agg.get(key, (0, 0.0))
-            agg[key] = (n + 1, t + ms)
-        return agg
-
-
-TIMER = None      # set to a GemmTimer() to time GEMM launches
+# (per-call timing of every C-ABI entry point, bench.py's live roofline: lib.start_timing() / lib.CallTimer)
 LAST_GEMM_BACKEND = 0   # lib.BACKEND_* the most recent gemm() ran on (reported by the call itself through GaGemm.backend_used)
 RELU_TAP = None   # tests set this to a list: every ReLU appends (kind, 0/1 decisions): ('bn', rows [M, C]) per fused BatchNorm+ReLU, ('se', [B, R]), ('gemm', rows [M, G*N]) per ReLU epilogue
 
@@ -176,19 +160,6 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
     global LAST_GEMM_BACKEND
     used = C.c_int(0)
     g.backend_used = C.pointer(used)
-    if TIMER is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        L.check(_L().ga_gemm(C.byref(g), L.stream()), 'ga_gemm')
-        e1.record()
-        kind = ('gelu' if act == ACT_GELU else 'relu' if act == ACT_RELU else 'lin') + ('+z' if save_z is not False and save_z is not None else '') + \
-            ('+res' if residual is not None else '') + ('+zin' if zin is not None else '') + ('+acc' if accumulate else '') + \
-            ('+shadow' if shadow is not None else '')
-        byts = nb * (M * K + N * K) * A3.element_size() + nb * M * N * D3.element_size() * (2 if (save_z is not False and save_z is not None) else 1) + \
-            (nb * M * N * D3.element_size() if residual is not None else 0) + (nb * M * N * D3.element_size() if zin is not None else 0) + \
-            (nb * M * N * 2 if shadow is not None else 0)
-        TIMER.records.append(((nb, M, N, K, str(A3.dtype).split('.')[-1], kind, byts), e0, e1))
-        return (out, Z) if (save_z is not False and save_z is not None) else out
     L.check(_L().ga_gemm(C.byref(g), L.stream()), 'ga_gemm')
     LAST_GEMM_BACKEND = used.value
     return (out, Z) if (save_z is not False and save_z is not None) else out
