@@ -561,10 +561,8 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
   return csum;
 }
 
-// NEW = epilogue warps: 16 (one CTA per SM, deep TMA ring) or 8 (BN = 128, short K: two CTAs per SM, so that the epilogues of two
-// tiles are in flight per SM -- with K <= 256 the main loop is two k-blocks and the tile time is the epilogue's latency chain)
-template <int BN, bool A_MN, bool B_MN, int EPI, int NEW = EPI_WARPS>
-__global__ void __launch_bounds__(64 + 32 * NEW, NEW == 8 ? 2 : 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                           const __grid_constant__ CUtensorMap tmB, Params p,
                                                                           EpiArgs e, int mt, int nt, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -572,10 +570,10 @@ __global__ void __launch_bounds__(64 + 32 * NEW, NEW == 8 ? 2 : 1) gemm_tc2_kern
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int SLICE = BN / (NEW / 4);        // columns per epilogue warp
+  constexpr int SLICE = BN / 4;                // columns per epilogue warp
   uint8_t* stage_base = smem;
-  float* staging = (float*)(smem + (size_t)p.stages * STAGE_BYTES);            // NEW x 32 x ST_LD floats
-  uint64_t* full_bar = (uint64_t*)((uint8_t*)staging + NEW * 32 * ST_LD * 4);
+  float* staging = (float*)(smem + (size_t)p.stages * STAGE_BYTES);            // EPI_WARPS x 32 x ST_LD floats
+  uint64_t* full_bar = (uint64_t*)((uint8_t*)staging + EPI_WARPS * 32 * ST_LD * 4);
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* tmem_full = empty_bar + 8;         // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
@@ -584,7 +582,7 @@ __global__ void __launch_bounds__(64 + 32 * NEW, NEW == 8 ? 2 : 1) gemm_tc2_kern
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NEW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -826,7 +824,7 @@ static int launch(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   return ga_check_launch("gemm_tc");
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, int NEW = EPI_WARPS>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   CUtensorMap ma, mb;
   int rc;
@@ -861,8 +859,8 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.splits = splits;
   constexpr int STAGE_BYTES = (BM + BN) * BK * 2;
-  constexpr size_t FIXED = 1024 + (size_t)NEW * 32 * ST_LD * 4 + 256;
-  int stages = (int)(((NEW == 8 ? 110 : 225) * 1024 - FIXED) / STAGE_BYTES);      // NEW == 8: two CTAs per SM
+  constexpr size_t FIXED = 1024 + (size_t)EPI_WARPS * 32 * ST_LD * 4 + 256;
+  int stages = (int)((225 * 1024 - FIXED) / STAGE_BYTES);
   static int stages_env = -1;
   if (stages_env < 0) { const char* sv = getenv("GA_GEMM_STAGES"); stages_env = sv ? atoi(sv) : 0; }
   if (stages_env > 0 && stages_env < stages) stages = stages_env;
@@ -874,14 +872,13 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   const size_t smem = FIXED + (size_t)stages * STAGE_BYTES;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_tc2_kernel<BN, A_MN, B_MN, EPI, NEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tc2_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_done = true;
   }
   const long long total = (long long)mt * nt * g->batch * splits;
   GA_REQUIRE(total < (1LL << 31), GA_ERR_SHAPE, "ga_gemm: too many tiles");
-  const long long slots = (long long)sms * (NEW == 8 ? 2 : 1);
-  const int grid = (int)(total < slots ? total : slots);
-  gemm_tc2_kernel<BN, A_MN, B_MN, EPI, NEW><<<grid, 64 + 32 * NEW, smem, st>>>(ma, mb, p, e, mt, nt, (int)total);
+  const int grid = (int)(total < sms ? total : sms);
+  gemm_tc2_kernel<BN, A_MN, B_MN, EPI><<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ma, mb, p, e, mt, nt, (int)total);
   ga_count_launch();
   return ga_check_launch("gemm_tc2");
 }
@@ -937,10 +934,6 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
     if (v1_env < 0) { const char* sv = getenv("GA_GEMM_V1"); v1_env = (sv && atoi(sv)) ? 1 : 0; }
     const bool wide = g->N > 32;   // N in (32, 64] also takes the persistent kernel (half of a BN=128 tile idle; these GEMMs are HBM-bound)
     const bool wide256 = (g->N >= 512) || (g->N % 256 == 0);
-    // K <= 256 with 128-column tiles (stage-0/1 fc1, x act', fc2 of GA-ConvNeXt): two 320-thread CTAs per SM.  GA_GEMM_2CTA=0 (read once)
-    // keeps one CTA per SM for A/B timing.
-    static const bool two_cta_on = [] { const char* ev = getenv("GA_GEMM_2CTA"); return !(ev && atoi(ev) == 0); }();
-    const bool two_cta = two_cta_on && g->K <= 256 && !g->accumulate && g->M >= 128 * 296;
     // compile-time specialised epilogues for the ConvNeXt-block GEMMs (vector path: widths and pitches multiples of 4)
     const bool v4 = ((g->N & 3) == 0) && ((g->ldd & 3) == 0) && e.d_cs == 1 && g->alpha == 1.0f;
     const bool bf_out = (g->out_dtype == GA_BF16);
@@ -963,7 +956,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
         ((uintptr_t)g->D & 15) == 0 && (g->d_bs & 3) == 0)
       epi = tc::EPI_ACCUM;
 #define GA_TC2(BN_, AM, BM_, EP) return tc::launch2<BN_, AM, BM_, EP>(g, e, st)
-#define GA_TC_BN(AM, BM_, EP) { if (wide256) GA_TC2(256, AM, BM_, EP); else if (two_cta && EP != tc::EPI_ACCUM && EP != tc::EPI_GENERIC) return tc::launch2<128, AM, BM_, EP, 8>(g, e, st); else GA_TC2(128, AM, BM_, EP); }
+#define GA_TC_BN(AM, BM_, EP) { if (wide256) GA_TC2(256, AM, BM_, EP); else GA_TC2(128, AM, BM_, EP); }
     GA_REQUIRE(!g->colsum || (epi == tc::EPI_ZIN_GELU && wide && !v1_env && g->batch == 1 && (((uintptr_t)g->colsum) & 15) == 0),
                GA_ERR_UNSUPPORTED, "ga_gemm: colsum is fused only into the tcgen05 x act' epilogue (bf16, N %% 4 == 0, N > 32)");
     if (wide && !v1_env) {
