@@ -139,17 +139,18 @@ __device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// y = gelu(x), dy = gelu'(x) for the pair (x0, x1); WANT_D = false skips the derivative
+// y = gelu(x), dy = gelu'(x) for the pair (x0, x1); WANT_D = false skips the derivative.
+// h = 1 - Phi(|x|) by Abramowitz-Stegun 26.2.17 (|error| < 7.5e-8), in packed fp32x2 arithmetic where the operands are pairs.
+// Sign handling is kept off the 64-bit integer path (every packed AND / XOR is two LOP3): |x| enters through the free source
+// modifier of a scalar FFMA, and with the derivative wanted Phi = 0.5 + copysign(0.5 - h, x) serves both outputs
+// (y = x Phi, dy = Phi + x phi): 21 instructions per pair instead of 28 in a kernel that is issue-bound.
 template <bool WANT_D>
 __device__ __forceinline__ void gelu_pair(float x0, float x1, float* y0, float* y1, float* d0, float* d1) {
-  const f32x2_t SIGN = 0x8000000080000000ull;
   const f32x2_t x = f2_pack(x0, x1);
-  const f32x2_t u = x & ~SIGN;                                                  // |x|
-  const f32x2_t tin = f2_fma(f2_splat(0.23164189f), u, f2_splat(1.f));
   float t0, t1, e0, e1;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(f2_lo(tin)));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(f2_hi(tin)));
-  const f32x2_t ein = f2_mul(f2_mul(u, u), f2_splat(-0.72134752f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.23164189f, fabsf(x0), 1.f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.23164189f, fabsf(x1), 1.f)));
+  const f32x2_t ein = f2_mul(f2_mul(x, x), f2_splat(-0.72134752f));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(f2_lo(ein)));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(f2_hi(ein)));
   const f32x2_t t = f2_pack(t0, t1), ex = f2_pack(e0, e1);
@@ -158,14 +159,17 @@ __device__ __forceinline__ void gelu_pair(float x0, float x1, float* y0, float* 
   poly = f2_fma(poly, t, f2_splat(-0.142248368f));
   poly = f2_fma(poly, t, f2_splat(0.127414796f));
   const f32x2_t h = f2_mul(f2_mul(poly, t), ex);
-  const f32x2_t yv = f2_fma(u ^ SIGN, h, f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));   // relu(x) - |x| h
-  *y0 = f2_lo(yv); *y1 = f2_hi(yv);
   if (WANT_D) {
-    // Phi = x >= 0 ? 1 - h : h  =  0.5 + copysign(0.5 - h, x)   (0 < h <= 0.5)
-    const f32x2_t q = f2_fma(h, f2_splat(-1.f), f2_splat(0.5f));
-    const f32x2_t cdf = f2_add(q ^ (x & SIGN), f2_splat(0.5f));
+    const f32x2_t q = f2_fma(h, f2_splat(-1.f), f2_splat(0.5f));                // 0.5 - h  in [0, 0.5)
+    const f32x2_t cdf = f2_add(f2_pack(copysignf(f2_lo(q), x0), copysignf(f2_hi(q), x1)), f2_splat(0.5f));
+    const f32x2_t yv = f2_mul(x, cdf);
     const f32x2_t dv = f2_fma(f2_mul(x, f2_splat(0.39894228040143268f)), ex, cdf);
+    *y0 = f2_lo(yv); *y1 = f2_hi(yv);
     *d0 = f2_lo(dv); *d1 = f2_hi(dv);
+  } else {
+    const float h0 = f2_lo(h), h1 = f2_hi(h);
+    *y0 = fmaf(-fabsf(x0), h0, fmaxf(x0, 0.f));                                 // relu(x) - |x| h
+    *y1 = fmaf(-fabsf(x1), h1, fmaxf(x1, 0.f));
   }
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {

@@ -279,6 +279,7 @@ struct Params {
   int stages;
   uint32_t idesc;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;  // descriptor byte offsets (host-selected so they can be probed)
+  uint32_t wait_ns;                     // persistent kernel: suspend-time hint of the mbarrier waits (0 = poll + nanosleep)
 };
 
 // grid: (m tiles, n tiles, batch*splits).  192 threads: warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue.
@@ -433,21 +434,39 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// control-warp wait: back off between polls so the spinning thread does not steal issue slots from the epilogue warps
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+// Wait used by every role of the persistent kernel: mbarrier.try_wait with a suspend-time hint parks the thread in hardware
+// until the phase completes (or the hint expires), so a waiting warp issues ~3 instructions per microsecond instead of per
+// 20 ns -- the polling loops were 14 % of all issued instructions of the short-K GEMMs (profiles/r02_ncu_gemm_epilogue.txt).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t done = 0;
-  for (;;) {
+  const uint32_t addr = smem_u32(bar);
+  if (hint_ns == 0) {
+    while (true) {
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n"
+          "}\n"
+          : "=r"(done)
+          : "r"(addr), "r"(parity)
+          : "memory");
+      if (done) break;
+      __nanosleep(40);
+    }
+    return;
+  }
+  while (true) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(hint_ns)
         : "memory");
     if (done) break;
-    __nanosleep(40);
   }
 }
 
@@ -495,40 +514,55 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
   if (EPI == EPI_RES_F32_SHADOW) {
     if (e.colscale) cs4 = *reinterpret_cast<const float4*>(e.colscale + (long long)batch * e.colscale_bs + n);
   }
-  const long long dbase = (long long)batch * e.d_bs + n;
+  // Address arithmetic is hoisted: ONE 64-bit element offset per chunk, then a 32-bit row offset (it * 4 * ldd) widened into
+  // each base pointer; staging rows sit at compile-time offsets from one shared-space address.  The integer work was half of
+  // the instructions this kernel issued (profiles/r02_ncu_gemm_epilogue.txt).
+  const int m_first = m_base + r0;
+  const long long eoff = (long long)batch * e.d_bs + (long long)m_first * e.ldd + n;
+  float* const d32 = (float*)e.D + eoff;
+  bf16* const d16 = (bf16*)e.D + eoff;
+  bf16* const z16 = (bf16*)e.Z + eoff;
+  const float* const r32 = (const float*)e.R + ((long long)batch * e.r_bs + (long long)m_first * e.ldr + n);
+  const bf16* const zin16 = (const bf16*)e.Zin + ((long long)batch * e.z_bs + (long long)m_first * e.ldz + n);
+  const uint32_t dstep = 4u * (uint32_t)e.ldd, rstep = 4u * (uint32_t)e.ldr, zstep = 4u * (uint32_t)e.ldz;
+  const float* const stl = st + (r0 * ST_LD + cl);
+  const int z_shadow = e.z_shadow;
+  const bool mul_mode = (e.zmode == GA_ACT_MUL);
+  const bool has_z = (e.Z != nullptr);
+  const float* const rowscale = e.rowscale;
 #pragma unroll
   for (int g4 = 0; g4 < 2; ++g4) {
     float4 pre[4];
     if (EPI == EPI_RES_F32_SHADOW || EPI == EPI_ZIN_GELU) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int m = m_base + r0 + 4 * (g4 * 4 + j);
+        const uint32_t it = g4 * 4 + j;
         pre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (FULL || m < e.M) {
-          if (EPI == EPI_RES_F32_SHADOW) pre[j] = ld4((const float*)e.R + (long long)batch * e.r_bs + (long long)m * e.ldr + n);
-          else if (zraw) { const uint2 u = zraw[g4 * 4 + j]; pre[j] = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y)); }
-          else pre[j] = ld4((const bf16*)e.Zin + (long long)batch * e.z_bs + (long long)m * e.ldz + n);
+        if (FULL || m_first + 4 * (int)it < e.M) {
+          if (EPI == EPI_RES_F32_SHADOW) pre[j] = ld4(r32 + it * rstep);
+          else if (zraw) { const uint2 u = zraw[it]; pre[j] = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y)); }
+          else pre[j] = ld4(zin16 + it * zstep);
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int rl = r0 + 4 * (g4 * 4 + j);
-      const int m = m_base + rl;
+      const uint32_t it = g4 * 4 + j;
+      const int m = m_first + 4 * (int)it;
       if (!FULL && m >= e.M) continue;
-      const float4 acc = *reinterpret_cast<const float4*>(st + rl * ST_LD + cl);
-      const long long off = dbase + (long long)m * e.ldd;
+      const float4 acc = *reinterpret_cast<const float4*>(stl + it * (4 * ST_LD));
+      const uint32_t off = it * dstep;
       float v[4] = {acc.x, acc.y, acc.z, acc.w};
       if (EPI == EPI_BIAS_GELU_Z || EPI == EPI_BIAS_GELU) {
         v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
         if (EPI == EPI_BIAS_GELU_Z) {
-          if (e.z_shadow == 2) {       // save gelu'(z) instead of z: the backward epilogue becomes one multiply
+          if (z_shadow == 2) {         // save gelu'(z) instead of z: the backward epilogue becomes one multiply
             float gd[4];
             gelu_pair<true>(v[0], v[1], &v[0], &v[1], &gd[0], &gd[1]);
             gelu_pair<true>(v[2], v[3], &v[2], &v[3], &gd[2], &gd[3]);
-            st4((bf16*)e.Z + off, make_float4(gd[0], gd[1], gd[2], gd[3]));
+            st4(z16 + off, make_float4(gd[0], gd[1], gd[2], gd[3]));
           } else {
-            st4((bf16*)e.Z + off, make_float4(v[0], v[1], v[2], v[3]));
+            st4(z16 + off, make_float4(v[0], v[1], v[2], v[3]));
             gelu_pair<false>(v[0], v[1], &v[0], &v[1], nullptr, nullptr);
             gelu_pair<false>(v[2], v[3], &v[2], &v[3], nullptr, nullptr);
           }
@@ -536,25 +570,25 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
           gelu_pair<false>(v[0], v[1], &v[0], &v[1], nullptr, nullptr);
           gelu_pair<false>(v[2], v[3], &v[2], &v[3], nullptr, nullptr);
         }
-        st4((bf16*)e.D + off, make_float4(v[0], v[1], v[2], v[3]));
+        st4(d16 + off, make_float4(v[0], v[1], v[2], v[3]));
       } else if (EPI == EPI_RES_F32_SHADOW) {
         float rs = 1.f;
-        if (e.rowscale) rs = e.rowscale[m / e.rows_per_scale];
+        if (rowscale) rs = rowscale[m / e.rows_per_scale];
         v[0] = fmaf((v[0] + bias4.x) * cs4.x, rs, pre[j].x); v[1] = fmaf((v[1] + bias4.y) * cs4.y, rs, pre[j].y);
         v[2] = fmaf((v[2] + bias4.z) * cs4.z, rs, pre[j].z); v[3] = fmaf((v[3] + bias4.w) * cs4.w, rs, pre[j].w);
         const float4 o = make_float4(v[0], v[1], v[2], v[3]);
-        st4((float*)e.D + off, o);
-        if (e.Z) st4((bf16*)e.Z + off, o);
+        st4(d32 + off, o);
+        if (has_z) st4(z16 + off, o);
       } else if (EPI == EPI_ZIN_GELU) {
         const float zz[4] = {pre[j].x, pre[j].y, pre[j].z, pre[j].w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] *= (e.zmode == GA_ACT_MUL) ? zz[i] : gelu_grad_f(zz[i]);
-        st4((bf16*)e.D + off, make_float4(v[0], v[1], v[2], v[3]));
+        for (int i = 0; i < 4; ++i) v[i] *= mul_mode ? zz[i] : gelu_grad_f(zz[i]);
+        st4(d16 + off, make_float4(v[0], v[1], v[2], v[3]));
         csum.x += v[0]; csum.y += v[1]; csum.z += v[2]; csum.w += v[3];
       } else if (EPI == EPI_PLAIN_BF16) {
-        st4((bf16*)e.D + off, make_float4(v[0] + bias4.x, v[1] + bias4.y, v[2] + bias4.z, v[3] + bias4.w));
+        st4(d16 + off, make_float4(v[0] + bias4.x, v[1] + bias4.y, v[2] + bias4.z, v[3] + bias4.w));
       } else if (EPI == EPI_ACCUM) {
-        atomicAdd(reinterpret_cast<float4*>((float*)e.D + off), make_float4(v[0] * e.alpha, v[1] * e.alpha, v[2] * e.alpha, v[3] * e.alpha));
+        atomicAdd(reinterpret_cast<float4*>(d32 + off), make_float4(v[0] * e.alpha, v[1] * e.alpha, v[2] * e.alpha, v[3] * e.alpha));
       }
     }
   }
@@ -566,7 +600,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
                                                                           const __grid_constant__ CUtensorMap tmB, Params p,
                                                                           EpiArgs e, int mt, int nt, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // aligned by pointer arithmetic on the shared array (no integer round trip), so the compiler keeps the shared address space
+  // and the staging traffic of the epilogue compiles to LDS / STS instead of generic LD / ST
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -606,7 +642,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait_backoff(&empty_bar[s], ph ^ 1);
+          mbar_wait_backoff(&empty_bar[s], ph ^ 1, p.wait_ns);
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           uint8_t* sa = stage_base + (size_t)s * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
@@ -636,13 +672,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
         int kb1 = kb0 + p.kb_per_split;
         if (kb1 > p.kb_total) kb1 = p.kb_total;
         const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-        mbar_wait_backoff(&tmem_empty[buf], bph ^ 1);          // epilogue has drained this accumulator
+        mbar_wait_backoff(&tmem_empty[buf], bph ^ 1, p.wait_ns);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % p.stages;
           const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait_backoff(&full_bar[s], ph);
+          mbar_wait_backoff(&full_bar[s], ph, p.wait_ns);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)s * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
@@ -686,45 +722,68 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
     };
 #pragma unroll
     for (int c = 0; c < SLICE / EPI_C; ++c) csum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // x act'(z) epilogue: this warp's share of the saved derivative is fetched straight into registers.  With one chunk per
+    // warp (BN = 128) the loads run ONE TILE AHEAD, so their HBM latency hides behind a whole tile of work (issued at the top
+    // of the same tile they were exposed: long-scoreboard stalls were 3.3 cycles per issued instruction); with two chunks the
+    // registers do not allow that and the loads are issued before the wait for this tile's accumulator.
+    constexpr int NCH = SLICE / EPI_C;
+    constexpr bool IS_Z = (EPI == EPI_ZIN_GELU);
+    uint2 zraw[NCH][8], znext[(IS_Z && NCH == 1) ? 8 : 1];
+    auto load_z = [&](int t, int c, uint2* zr) {             // chunk c of tile t
+      const int n_t = t % nt, m_t = (t / nt) % mt, z = t / (nt * mt);
+      const int batch = z / p.splits;
+      const int m_first = m_t * BM + q * 32 + (lane >> 3);
+      const int ncol = n_t * BN + slice * SLICE + c * EPI_C + (lane & 7) * 4;
+      const bf16* zp = (const bf16*)e.Zin + ((long long)batch * e.z_bs + (long long)m_first * e.ldz + ncol);
+      const uint32_t zstep = 4u * (uint32_t)e.ldz;
+      const bool full = (m_t * BM + q * 32 + 32 <= e.M) && (ncol < e.N);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        zr[it] = make_uint2(0u, 0u);
+        if (full || (m_first + 4 * it < e.M && ncol < e.N)) zr[it] = *reinterpret_cast<const uint2*>(zp + (uint32_t)it * zstep);
+      }
+    };
+    constexpr bool z_ahead = IS_Z;
+    if (z_ahead && blockIdx.x < total_tiles) load_z(blockIdx.x, 0, NCH == 1 ? znext : zraw[0]);
+    float* const st_row = st + lane * ST_LD;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const int n_t = t % nt, m_t = (t / nt) % mt, z = t / (nt * mt);
       const int batch = z / p.splits;
       const int m0 = m_t * BM, n0 = n_t * BN;
       if (want_cs && n0 != cs_n0) { cs_flush(); cs_n0 = n0; }
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
-      // x act'(z) epilogue: fetch this warp's share of the saved derivative BEFORE waiting for the accumulator, so the
-      // HBM latency of the per-element operand hides behind the MMA of this tile (it was exposed once per chunk)
-      uint2 zraw[SLICE / EPI_C][8];
-      if (EPI == EPI_ZIN_GELU) {
+      // Prefetch schedule of the x act' operand (registers only).  One chunk per warp: the loads run one tile ahead through
+      // `znext`.  Two chunks: chunk 1 of this tile is fetched here (chunk 0's work covers it) and chunk 0 of the NEXT tile right
+      // after chunk 0 is consumed (chunk 1's work covers it), so no load is exposed and no extra registers are needed.
+      if (IS_Z) {
+        if (!z_ahead) {
 #pragma unroll
-        for (int c = 0; c < SLICE / EPI_C; ++c) {
-          const int ncol = n0 + slice * SLICE + c * EPI_C + (lane & 7) * 4;
+          for (int c = 0; c < NCH; ++c) load_z(t, c, zraw[c]);
+        } else if (NCH == 1) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int m = m0 + q * 32 + (lane >> 3) + 4 * it;
-            zraw[c][it] = make_uint2(0u, 0u);
-            if (m < e.M && ncol < e.N)
-              zraw[c][it] = *reinterpret_cast<const uint2*>((const bf16*)e.Zin + (long long)batch * e.z_bs + (long long)m * e.ldz + ncol);
-          }
+          for (int it = 0; it < 8; ++it) zraw[0][it] = znext[it];
+          if (t + (int)gridDim.x < total_tiles) load_z(t + (int)gridDim.x, 0, znext);
+        } else {
+#pragma unroll
+          for (int c = 1; c < NCH; ++c) load_z(t, c, zraw[c]);
         }
       }
-      mbar_wait_backoff(&tmem_full[buf], bph);
+      mbar_wait_backoff(&tmem_full[buf], bph, p.wait_ns);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-      for (int c = 0; c < SLICE / EPI_C; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         const int col0 = slice * SLICE + c * EPI_C;
         const bool live = (n0 + col0 < e.N);
-        const bool last = (c == SLICE / EPI_C - 1);
+        const bool last = (c == NCH - 1);
+        if (IS_Z && NCH > 1 && c == 1 && z_ahead && t + (int)gridDim.x < total_tiles) load_z(t + (int)gridDim.x, 0, zraw[0]);
         if (live) {
           uint32_t r[32];
           tmem_ld32(tacc + (uint32_t)col0, r);
-          float* row = st + lane * ST_LD;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(row + 4 * i) =
-                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                            __uint_as_float(r[4 * i + 3]));
+            *reinterpret_cast<float4*>(st_row + 4 * i) =
+                make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
         }
         if (last) {                           // all TMEM reads of this tile are done: hand the accumulator back
           tc_fence_before();
@@ -866,6 +925,9 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   if (stages_env > 0 && stages_env < stages) stages = stages_env;
   if (stages > 8) stages = 8;
   p.stages = stages;
+  static int wait_env = -1;
+  if (wait_env < 0) { const char* sv = getenv("GA_GEMM_WAIT_NS"); wait_env = sv ? atoi(sv) : 0; }
+  p.wait_ns = (uint32_t)wait_env;
   p.idesc = make_idesc(BM, BN, A_MN, B_MN);
   p.lbo_a = A_MN ? 64 * BK * 2 : 16; p.sbo_a = 1024;
   p.lbo_b = B_MN ? 64 * BK * 2 : 16; p.sbo_b = 1024;

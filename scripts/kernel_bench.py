@@ -177,9 +177,8 @@ def main():
     if args.what in ('rows', 'all'):
         cases.update(rows_cases())
     if args.one:
-        fn = cases[args.one][0]
-        for _ in range(3):
-            fn()
+        for name in args.one.split(','):          # one launch each (for an ncu capture); several names: comma-separated
+            cases[name][0]()
         torch.cuda.synchronize()
         return
     print(f'{"case":18s} {"us":>9s} {"GB/s":>8s} {"%hbm":>6s} {"TFLOP/s":>8s} {"%tc":>6s}')
