@@ -280,6 +280,7 @@ struct Params {
   uint32_t idesc;
   uint32_t lbo_a, sbo_a, lbo_b, sbo_b;  // descriptor byte offsets (host-selected so they can be probed)
   uint32_t wait_ns;                     // persistent kernel: suspend-time hint of the mbarrier waits (0 = poll + nanosleep)
+  int step_n, step_m, step_z;           // persistent kernel: gridDim.x decomposed over (n tiles, m tiles, batch*splits)
 };
 
 // grid: (m tiles, n tiles, batch*splits).  192 threads: warp0 TMA, warp1 MMA(+TMEM alloc), warps 2..5 epilogue.
@@ -530,6 +531,11 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
   const bool mul_mode = (e.zmode == GA_ACT_MUL);
   const bool has_z = (e.Z != nullptr);
   const float* const rowscale = e.rowscale;
+  // per-sample row scale (DropPath): one division per chunk; 32 consecutive rows span at most two samples when a sample has
+  // >= 32 rows (it has 49 at the least on this path), so row it's sample is q0 + (r0 + 4 it >= rows_per_scale)
+  int rs_q0 = 0, rs_r0 = 0;
+  const int rps = e.rows_per_scale;
+  if (EPI == EPI_RES_F32_SHADOW && rowscale) { rs_q0 = m_first / rps; rs_r0 = m_first - rs_q0 * rps; }
 #pragma unroll
   for (int g4 = 0; g4 < 2; ++g4) {
     float4 pre[4];
@@ -573,7 +579,10 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
         st4(d16 + off, make_float4(v[0], v[1], v[2], v[3]));
       } else if (EPI == EPI_RES_F32_SHADOW) {
         float rs = 1.f;
-        if (rowscale) rs = rowscale[m / e.rows_per_scale];
+        if (rowscale) {
+          const int rr = rs_r0 + 4 * (int)it;
+          rs = rowscale[rps >= 32 ? rs_q0 + (rr >= rps ? 1 : 0) : m / rps];
+        }
         v[0] = fmaf((v[0] + bias4.x) * cs4.x, rs, pre[j].x); v[1] = fmaf((v[1] + bias4.y) * cs4.y, rs, pre[j].y);
         v[2] = fmaf((v[2] + bias4.z) * cs4.z, rs, pre[j].z); v[3] = fmaf((v[3] + bias4.w) * cs4.w, rs, pre[j].w);
         const float4 o = make_float4(v[0], v[1], v[2], v[3]);
@@ -594,6 +603,26 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
   }
   return csum;
 }
+
+// Tile walk of the persistent kernel without per-tile divisions: t = blockIdx.x + k * gridDim.x decomposed as (n_t fastest,
+// m_t, z) and advanced by the decomposition of gridDim.x with carries.  Four integer divisions per tile and thread (~100
+// instructions) were a quarter of the epilogue warps' instruction stream (profiles/r02_ncu_gemm_epilogue.txt).
+struct TileIter {
+  int n_t, m_t, z;
+  __device__ __forceinline__ void init(int t0, int nt, int mt) {
+    n_t = t0 % nt; const int r = t0 / nt; m_t = r % mt; z = r / mt;
+  }
+  // the step (host-decomposed gridDim.x) and the extents stay in the constant bank: three registers per walker
+  __device__ __forceinline__ void next(const Params& p, int nt, int mt) {
+    n_t += p.step_n;
+    int c = (n_t >= nt) ? 1 : 0;
+    n_t -= c ? nt : 0;
+    m_t += p.step_m + c;
+    c = (m_t >= mt) ? 1 : 0;
+    m_t -= c ? mt : 0;
+    z += p.step_z + c;
+  }
+};
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -632,9 +661,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int n_t = t % nt, m_t = (t / nt) % mt, z = t / (nt * mt);
-        const int batch = z / p.splits, split = z % p.splits;
+      TileIter ti;
+      ti.init(blockIdx.x, nt, mt);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ti.next(p, nt, mt)) {
+        const int n_t = ti.n_t, m_t = ti.m_t, z = ti.z;
+        const int batch = (p.splits == 1) ? z : z / p.splits, split = (p.splits == 1) ? 0 : z % p.splits;
         const int kb0 = split * p.kb_per_split;
         int kb1 = kb0 + p.kb_per_split;
         if (kb1 > p.kb_total) kb1 = p.kb_total;
@@ -665,9 +696,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-        const int z = t / (nt * mt);
-        const int split = z % p.splits;
+      TileIter ti;
+      ti.init(blockIdx.x, nt, mt);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt, ti.next(p, nt, mt)) {
+        const int split = (p.splits == 1) ? 0 : ti.z % p.splits;
         const int kb0 = split * p.kb_per_split;
         int kb1 = kb0 + p.kb_per_split;
         if (kb1 > p.kb_total) kb1 = p.kb_total;
@@ -729,27 +761,34 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
     constexpr int NCH = SLICE / EPI_C;
     constexpr bool IS_Z = (EPI == EPI_ZIN_GELU);
     uint2 zraw[NCH][8], znext[(IS_Z && NCH == 1) ? 8 : 1];
-    auto load_z = [&](int t, int c, uint2* zr) {             // chunk c of tile t
-      const int n_t = t % nt, m_t = (t / nt) % mt, z = t / (nt * mt);
-      const int batch = z / p.splits;
-      const int m_first = m_t * BM + q * 32 + (lane >> 3);
-      const int ncol = n_t * BN + slice * SLICE + c * EPI_C + (lane & 7) * 4;
+    auto load_z = [&](const TileIter& w, int c, uint2* zr) {   // chunk c of the tile at w
+      const int batch = (p.splits == 1) ? w.z : w.z / p.splits;
+      const int m_first = w.m_t * BM + q * 32 + (lane >> 3);
+      const int ncol = w.n_t * BN + slice * SLICE + c * EPI_C + (lane & 7) * 4;
       const bf16* zp = (const bf16*)e.Zin + ((long long)batch * e.z_bs + (long long)m_first * e.ldz + ncol);
       const uint32_t zstep = 4u * (uint32_t)e.ldz;
-      const bool full = (m_t * BM + q * 32 + 32 <= e.M) && (ncol < e.N);
+      if ((w.m_t * BM + q * 32 + 32 <= e.M) && (ncol < e.N)) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        zr[it] = make_uint2(0u, 0u);
-        if (full || (m_first + 4 * it < e.M && ncol < e.N)) zr[it] = *reinterpret_cast<const uint2*>(zp + (uint32_t)it * zstep);
+        for (int it = 0; it < 8; ++it) zr[it] = *reinterpret_cast<const uint2*>(zp + (uint32_t)it * zstep);
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          zr[it] = make_uint2(0u, 0u);
+          if (m_first + 4 * it < e.M && ncol < e.N) zr[it] = *reinterpret_cast<const uint2*>(zp + (uint32_t)it * zstep);
+        }
       }
     };
     constexpr bool z_ahead = IS_Z;
-    if (z_ahead && blockIdx.x < total_tiles) load_z(blockIdx.x, 0, NCH == 1 ? znext : zraw[0]);
+    TileIter ti;
+    ti.init(blockIdx.x, nt, mt);
+    if (z_ahead && blockIdx.x < total_tiles) load_z(ti, 0, NCH == 1 ? znext : zraw[0]);
     float* const st_row = st + lane * ST_LD;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      const int n_t = t % nt, m_t = (t / nt) % mt, z = t / (nt * mt);
-      const int batch = z / p.splits;
-      const int m0 = m_t * BM, n0 = n_t * BN;
+      const int batch = (p.splits == 1) ? ti.z : ti.z / p.splits;
+      const int m0 = ti.m_t * BM, n0 = ti.n_t * BN;
+      const TileIter tc = ti;                 // this tile; ti moves on to the tile after it (the prefetch target)
+      ti.next(p, nt, mt);
+      const bool has_next = (t + (int)gridDim.x < total_tiles);
       if (want_cs && n0 != cs_n0) { cs_flush(); cs_n0 = n0; }
       const uint32_t buf = lt & 1, bph = (lt >> 1) & 1;
       // Prefetch schedule of the x act' operand (registers only).  One chunk per warp: the loads run one tile ahead through
@@ -758,14 +797,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
       if (IS_Z) {
         if (!z_ahead) {
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) load_z(t, c, zraw[c]);
+          for (int c = 0; c < NCH; ++c) load_z(tc, c, zraw[c]);
         } else if (NCH == 1) {
 #pragma unroll
           for (int it = 0; it < 8; ++it) zraw[0][it] = znext[it];
-          if (t + (int)gridDim.x < total_tiles) load_z(t + (int)gridDim.x, 0, znext);
+          if (has_next) load_z(ti, 0, znext);
         } else {
 #pragma unroll
-          for (int c = 1; c < NCH; ++c) load_z(t, c, zraw[c]);
+          for (int c = 1; c < NCH; ++c) load_z(tc, c, zraw[c]);
         }
       }
       mbar_wait_backoff(&tmem_full[buf], bph, p.wait_ns);
@@ -776,7 +815,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
         const int col0 = slice * SLICE + c * EPI_C;
         const bool live = (n0 + col0 < e.N);
         const bool last = (c == NCH - 1);
-        if (IS_Z && NCH > 1 && c == 1 && z_ahead && t + (int)gridDim.x < total_tiles) load_z(t + (int)gridDim.x, 0, zraw[0]);
+        if (IS_Z && NCH > 1 && c == 1 && z_ahead && has_next) load_z(ti, 0, zraw[0]);
         if (live) {
           uint32_t r[32];
           tmem_ld32(tacc + (uint32_t)col0, r);
@@ -940,6 +979,7 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   const long long total = (long long)mt * nt * g->batch * splits;
   GA_REQUIRE(total < (1LL << 31), GA_ERR_SHAPE, "ga_gemm: too many tiles");
   const int grid = (int)(total < sms ? total : sms);
+  p.step_n = grid % nt; p.step_m = (grid / nt) % mt; p.step_z = grid / (nt * mt);
   gemm_tc2_kernel<BN, A_MN, B_MN, EPI><<<grid, 64 + 32 * EPI_WARPS, smem, st>>>(ma, mb, p, e, mt, nt, (int)total);
   ga_count_launch();
   return ga_check_launch("gemm_tc2");

@@ -1051,6 +1051,62 @@ extern "C" int ga_fold_ln(const float* W, const float* ln_w, const float* ln_b, 
   else fold_ln_kernel<float><<<grid, 256, 0, (cudaStream_t)s>>>(W, ln_w, ln_b, bias, (float*)Wf, bf, N, K, ldw);
   return launch_ok("fold_ln");
 }
+// Operand preparation of EVERY ConvNeXt block of a model in one launch (was: a transpose copy, fold_ln, a cast and a
+// scale_matrix per block and step: 72 launches of a few microseconds each).  One warp per unit; a block with C channels
+// has 4C units for fc1 rows (W1 diag(ln_w) -> bf16, b1 + W1 ln_b), C units for fc2 rows (bf16 W2 and gamma[c] W2) and 49
+// units for the depthwise taps ([C,1,7,7] -> [49,C] fp32).  table: GA_BLOCK_PREP_WORDS int64 words per block (header).
+__global__ void __launch_bounds__(256) block_weight_prep_kernel(const long long* __restrict__ table, int nblocks, int total_units) {
+  const int lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (unit >= total_units) return;
+  int b = 0;
+  while (b + 1 < nblocks && unit >= (int)table[(long long)(b + 1) * GA_BLOCK_PREP_WORDS + 13]) ++b;
+  const long long* t = table + (long long)b * GA_BLOCK_PREP_WORDS;
+  const float* dw_w = (const float*)t[0];
+  const float* ln_w = (const float*)t[1];
+  const float* ln_b = (const float*)t[2];
+  const float* w1 = (const float*)t[3];
+  const float* b1 = (const float*)t[4];
+  const float* w2 = (const float*)t[5];
+  const float* gamma = (const float*)t[6];
+  float* w49c = (float*)t[7];
+  bf16* w1f = (bf16*)t[8];
+  float* b1f = (float*)t[9];
+  bf16* w2c = (bf16*)t[10];
+  bf16* w2s = (bf16*)t[11];
+  const int C = (int)t[12], H = 4 * C;
+  const int r = unit - (int)t[13];
+  if (r < H) {                                   // fc1 row r: K = C (multiple of 8 on this path)
+    const float* w = w1 + (long long)r * C;
+    float acc = 0.f;
+    for (int k = lane * 4; k < C; k += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(w + k);
+      const float4 gg = *reinterpret_cast<const float4*>(ln_w + k);
+      const float4 bb = *reinterpret_cast<const float4*>(ln_b + k);
+      acc = fmaf(v.x, bb.x, fmaf(v.y, bb.y, fmaf(v.z, bb.z, fmaf(v.w, bb.w, acc))));
+      st4(w1f + (long long)r * C + k, make_float4(v.x * gg.x, v.y * gg.y, v.z * gg.z, v.w * gg.w));
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) b1f[r] = acc + b1[r];
+  } else if (r < H + C) {                        // fc2 row c: K = 4C
+    const int c = r - H;
+    const float g = gamma ? gamma[c] : 1.f;
+    const float* w = w2 + (long long)c * H;
+    for (int k = lane * 4; k < H; k += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(w + k);
+      st4(w2c + (long long)c * H + k, v);
+      st4(w2s + (long long)c * H + k, make_float4(v.x * g, v.y * g, v.z * g, v.w * g));
+    }
+  } else {                                       // depthwise tap
+    const int tap = r - H - C;
+    for (int c = lane; c < C; c += 32) w49c[(long long)tap * C + c] = dw_w[(long long)c * 49 + tap];
+  }
+}
+extern "C" int ga_block_weight_prep(const void* table, int nblocks, int total_units, ga_stream_t s) {
+  GA_REQUIRE(table && nblocks > 0 && total_units > 0, GA_ERR_SHAPE, "ga_block_weight_prep: bad arguments");
+  block_weight_prep_kernel<<<(total_units + 7) / 8, 256, 0, (cudaStream_t)s>>>((const long long*)table, nblocks, total_units);
+  return launch_ok("block_weight_prep");
+}
 extern "C" int ga_cast_bf16(const float* src, void* dst, long long n, ga_stream_t s) {
   if (n == 0) return GA_OK;
   GA_REQUIRE(n < (1LL << 31), GA_ERR_SHAPE, "ga_cast_bf16: too large");

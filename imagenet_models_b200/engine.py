@@ -133,6 +133,8 @@ class TrainEngine:
                     self.opt.step(gathered=True, device_hyper=True)
             self.graph_launches = L.launch_count() - n0
             self._graph = g
+            from . import ops
+            ops.ZEROS.reset()
         else:
             self._sx.copy_(x, non_blocking=True)
             self._sy.copy_(y, non_blocking=True)

@@ -14,6 +14,8 @@ from __future__ import annotations
 import warnings
 from typing import List, Optional
 
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -43,6 +45,26 @@ def _params(mod: nn.Module) -> dict:
     return d
 
 
+_KEEP_CACHE = {}
+
+
+def _path_scales(probs, training: bool, batch: int, device):
+    """DropPath factors of several blocks from ONE uniform draw (was a bernoulli_ + div_ pair of launches per block):
+    floor(u + keep) / keep per sample, None where the rate is 0 or the module is in eval mode."""
+    probs = [float(p) for p in probs]
+    live = [i for i, p in enumerate(probs) if p > 0. and training]
+    out = [None] * len(probs)
+    if live:
+        key = (tuple(probs[i] for i in live), str(device))
+        keep = _KEEP_CACHE.get(key)
+        if keep is None:              # made once (eager warm-up): a host-to-device copy cannot be captured in a CUDA graph
+            keep = _KEEP_CACHE[key] = torch.tensor([1.0 - p for p in key[0]], dtype=torch.float32).clamp_min(1e-12).to(device)
+        m = torch.rand(len(live), batch, dtype=torch.float32, device=device).add_(keep[:, None]).floor_().div_(keep[:, None])
+        for j, i in enumerate(live):
+            out[i] = m[j]
+    return out
+
+
 def _path_scale(p: float, training: bool, batch: int, device) -> Optional[torch.Tensor]:
     """timm DropPath: per-sample bernoulli(keep)/keep multiplier on the residual branch (None = identity)."""
     if p == 0. or not training:
@@ -52,6 +74,29 @@ def _path_scale(p: float, training: bool, batch: int, device) -> Optional[torch.
     if keep > 0.0:
         m.div_(keep)
     return m
+
+
+def _block_params(blk):
+    """ConvNeXt block parameters under the reference's key names, `gamma` absent when the block has no layer scale."""
+    p = _params(blk)
+    if getattr(blk, 'gamma', None) is None:
+        p.pop('gamma', None)
+    return p
+
+
+# model -> ops.BlockWeights, held outside the module so deepcopy (EMA) and pickling see plain nn.Modules
+_BLOCK_WEIGHTS = weakref.WeakKeyDictionary()
+
+
+def block_weights(model, blocks, T):
+    """Refresh and return the prepared operands of `blocks` (all ConvNeXt blocks of `model`), or None when unsupported."""
+    if not blocks or not ops.BlockWeights.supported([_block_params(b) for b in blocks], T):
+        return None
+    bw = _BLOCK_WEIGHTS.get(model)
+    if bw is None:
+        bw = _BLOCK_WEIGHTS[model] = ops.BlockWeights(lambda: [_block_params(b) for b in blocks])
+    bw.refresh()
+    return [bw.get(j) for j in range(len(blocks))]
 
 
 class LayerNorm2d(nn.LayerNorm):
@@ -79,15 +124,16 @@ class ConvNeXtBlock(nn.Module):
         self.gamma = nn.Parameter(ls_init_value * torch.ones(dim)) if ls_init_value > 0 else None
         self.drop_prob = float(drop_path)
 
-    def run(self, x, xs, geom, T, ps=False, ps_prev=None):
+    def run(self, x, xs, geom, T, ps=False, ps_prev=None, prep=None):
         """x: residual stream (fp32 under bf16 compute, as in the autocast reference); xs: its bf16 shadow or None.
-        ps: this block's DropPath factors (drawn here when not given); ps_prev: those of the previous block (ops.convnext_block)."""
+        ps: this block's DropPath factors (drawn here when not given); ps_prev: those of the previous block; prep: this block's
+        prepared operands (ops.BlockWeights) or None."""
         p = _params(self)
         if self.gamma is None:
             p['gamma'] = torch.ones_like(p['norm.weight'])
         if ps is False:
             ps = _path_scale(self.drop_prob, self.training, geom[0], x.device)
-        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T, ps_prev=ps_prev)
+        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T, ps_prev=ps_prev, prep=prep)
 
 
 class ConvNeXtStage(nn.Module):
@@ -105,8 +151,9 @@ class ConvNeXtStage(nn.Module):
         self.blocks = nn.Sequential(*[ConvNeXtBlock(out_chs, drop_path=dp_rates[j], ls_init_value=ls_init_value)
                                       for j in range(depth)])
 
-    def run(self, x, xs, geom, T, RT):
+    def run(self, x, xs, geom, T, RT, scales=None, preps=None):
         """x / xs: residual stream (dtype RT) and its compute-dtype (T) shadow (None when RT == T).
+        scales / preps: per-block DropPath factors and prepared operands when the model made them for all stages at once.
         Returns (x, xs, geom, taps); taps hold the compute-dtype view of the tapped activations."""
         Bn, H, W = geom
         if not isinstance(self.downsample, nn.Identity):
@@ -122,9 +169,11 @@ class ConvNeXtStage(nn.Module):
         geom = (Bn, H, W)
         taps: List[torch.Tensor] = []
         n = len(self.blocks)
-        scales = [_path_scale(blk.drop_prob, blk.training, Bn, x.device) for blk in self.blocks]
+        if scales is None:
+            scales = _path_scales([blk.drop_prob for blk in self.blocks], self.training, Bn, x.device)
         for i, blk in enumerate(self.blocks):
-            x, xs = blk.run(x, xs, geom, T, ps=scales[i], ps_prev=scales[i - 1] if i > 0 else None)
+            x, xs = blk.run(x, xs, geom, T, ps=scales[i], ps_prev=scales[i - 1] if i > 0 else None,
+                            prep=preps[i] if preps is not None else None)
             if n > 5 and (i + 1) % (n // (self.stage3_naggre + 1)) == 0 and len(taps) < self.stage3_naggre:
                 taps.append(xs if xs is not None else x)
         return x, xs, geom, taps
@@ -311,7 +360,7 @@ class GA_ConvNeXt(nn.Module):
         if self.compute_dtype is not None:
             return self.compute_dtype
         if torch.is_autocast_enabled():
-            dt = torch.get_autocast_gpu_dtype()
+            dt = torch.get_autocast_dtype('cuda')
             if dt == torch.float16:
                 warnings.warn('fp16 autocast requested: the sm_100a kernels compute in bf16 (fp32 accumulate) instead', stacklevel=3)
             return torch.bfloat16
@@ -334,8 +383,17 @@ class GA_ConvNeXt(nn.Module):
             ys = ops.to_dtype(y, T) if RT != T else None
             geom = (Bn, H // k, W // k)
             feats, taps = [], []
+            # per-forward work shared by all 18 blocks: one DropPath draw, one operand-preparation launch
+            blocks = [blk for i in range(4) for blk in self.stages[i].blocks]
+            scales = _path_scales([blk.drop_prob for blk in blocks], self.training, Bn, x.device)
+            preps = None
+            preps = block_weights(self, blocks, T)
+            off = 0
             for i in range(4):
-                y, ys, geom, t = self.stages[i].run(y, ys, geom, T, RT)
+                n = len(self.stages[i].blocks)
+                y, ys, geom, t = self.stages[i].run(y, ys, geom, T, RT, scales=scales[off:off + n],
+                                                    preps=preps[off:off + n] if preps is not None else None)
+                off += n
                 feats.append((ys if ys is not None else y, geom))
                 taps += [(tt, geom) for tt in t]
             (x0, g0), (x1, g1), (x2, g2), (x3, g3) = feats

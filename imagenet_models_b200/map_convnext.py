@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import ops
 from .ga_convnext import GroupConvMlp as _GAGroupConvMlp
-from .ga_convnext import _apply_children_first, _init_weights, _path_scale
+from .ga_convnext import _BLOCK_WEIGHTS, _apply_children_first, _init_weights, _path_scale, _path_scales
 from .lib import ACT_RELU
 from .registry import register_model
 
@@ -46,14 +46,22 @@ class Block(nn.Module):
         self.gamma = nn.Parameter(layer_scale_init_value * torch.ones(dim)) if layer_scale_init_value > 0 else None
         self.drop_prob = float(drop_path)
 
-    def run(self, x, xs, geom, T, ps=False, ps_prev=None):
+    def params(self):
+        """Parameters under the key names ops.convnext_block / ops.BlockWeights use (`gamma` absent without layer scale)."""
         p = {'conv_dw.weight': self.dwconv.weight, 'conv_dw.bias': self.dwconv.bias, 'norm.weight': self.norm.weight,
              'norm.bias': self.norm.bias, 'mlp.fc1.weight': self.pwconv1.weight, 'mlp.fc1.bias': self.pwconv1.bias,
-             'mlp.fc2.weight': self.pwconv2.weight, 'mlp.fc2.bias': self.pwconv2.bias,
-             'gamma': self.gamma if self.gamma is not None else torch.ones_like(self.norm.weight)}
+             'mlp.fc2.weight': self.pwconv2.weight, 'mlp.fc2.bias': self.pwconv2.bias}
+        if self.gamma is not None:
+            p['gamma'] = self.gamma
+        return p
+
+    def run(self, x, xs, geom, T, ps=False, ps_prev=None, prep=None):
+        p = self.params()
+        if self.gamma is None:
+            p['gamma'] = torch.ones_like(self.norm.weight)
         if ps is False:
             ps = _path_scale(self.drop_prob, self.training, geom[0], x.device)
-        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T, ps_prev=ps_prev)
+        return ops.convnext_block(x, p, geom, ps, torch.is_grad_enabled(), xs=xs, T=T, ps_prev=ps_prev, prep=prep)
 
 
 class ClassAttention(nn.Module):
@@ -268,6 +276,17 @@ class ConvNeXt(nn.Module):
         feats, geoms = [], []
         y = ys = None
         geom = None
+        # per-forward work shared by every block: one DropPath draw, one operand-preparation launch
+        all_blocks = [blk for i in range(4) for blk in self.stages[i]]
+        all_scales = _path_scales([blk.drop_prob for blk in all_blocks], self.training, Bn, x.device)
+        all_preps = None
+        if T == torch.bfloat16 and all(blk.norm.weight.numel() % 8 == 0 for blk in all_blocks):
+            bw = _BLOCK_WEIGHTS.get(self)
+            if bw is None:
+                bw = _BLOCK_WEIGHTS[self] = ops.BlockWeights(lambda: [blk.params() for blk in all_blocks])
+            bw.refresh()
+            all_preps = [bw.get(j) for j in range(len(all_blocks))]
+        off = 0
         for i in range(4):
             ds = self.downsample_layers[i]
             if i == 0:
@@ -287,9 +306,11 @@ class ConvNeXt(nn.Module):
                 y = ops.linear(h, conv.weight.permute(0, 2, 3, 1).reshape(conv.out_channels, -1), conv.bias, out_dtype=RT)
                 ys = ops.to_dtype(y, T) if RT != T else None
             blocks = list(self.stages[i])
-            scales = [_path_scale(blk.drop_prob, blk.training, Bn, y.device) for blk in blocks]     # DropPath factors of the stage
+            scales = all_scales[off:off + len(blocks)]                                              # DropPath factors of the stage
             for j, blk in enumerate(blocks):
-                y, ys = blk.run(y, ys, geom, T, ps=scales[j], ps_prev=scales[j - 1] if j > 0 else None)
+                y, ys = blk.run(y, ys, geom, T, ps=scales[j], ps_prev=scales[j - 1] if j > 0 else None,
+                                prep=all_preps[off + j] if all_preps is not None else None)
+            off += len(blocks)
             feats.append(ys if ys is not None else y)
             geoms.append(geom)
         return feats, geoms

@@ -73,6 +73,57 @@ def _zeros(n, device):
     return _const_cache[k]
 
 
+class ZeroArena:
+    """One zero fill per training step instead of one per backward node.
+
+    Weight-gradient accumulators (split-K GEMMs, the depthwise backward, bias sums) need zeroed fp32 buffers: ~120 fill
+    launches of a few KB..MB each per step.  begin() (called where the step drops the old gradients, optim.zero_grad)
+    allocates ONE zeroed buffer sized by what the previous step asked for; zeros() hands out 256-byte aligned views of it
+    and falls back to torch.zeros when the arena is absent or exhausted (first step, plain nn.Module use, a second
+    backward).  The views keep the buffer alive for as long as any gradient made in it lives."""
+
+    def __init__(self):
+        self.buf, self.off, self.used, self.need = None, 0, 0, 0
+
+    @staticmethod
+    def _dev(device):
+        d = torch.device(device)
+        return torch.device('cuda', torch.cuda.current_device()) if (d.type == 'cuda' and d.index is None) else d
+
+    def begin(self, device):
+        self.need = self.used
+        self.used = self.off = 0
+        d = self._dev(device)
+        self.buf = torch.zeros(self.need, dtype=torch.uint8, device=d) if (self.need and d.type == 'cuda') else None
+
+    def reset(self):
+        """Forget the buffer (after a CUDA-graph capture it lives in the graph's private pool)."""
+        self.buf, self.off = None, 0
+
+    def take(self, numel, dtype, device):
+        nbytes = numel * dtype.itemsize
+        al = (nbytes + 255) // 256 * 256
+        self.used += al
+        buf = self.buf
+        if buf is not None and buf.device == self._dev(device) and self.off + al <= buf.numel():
+            v = buf[self.off:self.off + nbytes].view(dtype)
+            self.off += al
+            return v
+        return torch.zeros(numel, dtype=dtype, device=device)
+
+
+ZEROS = ZeroArena()
+
+
+def zeros(shape, dtype, device):
+    """Zero-filled tensor from the step's arena (ZeroArena); shape: int or tuple."""
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    n = 1
+    for d in shape:
+        n *= d
+    return ZEROS.take(n, dtype, device).view(shape)
+
+
 # ------------------------------------------------------------------------------------------------- raw kernels
 # (per-call timing of every C-ABI entry point, bench.py's live roofline: lib.start_timing() / lib.CallTimer)
 LAST_GEMM_BACKEND = 0   # lib.BACKEND_* the most recent gemm() ran on (reported by the call itself through GaGemm.backend_used)
@@ -309,7 +360,7 @@ class GemmFn(Function):
             dA = torch.empty(G, M, K, dtype=A.dtype, device=A.device) if (G > 1 or K % 8) else alloc_rows(M, K, A.dtype, A.device).unsqueeze(0)
             gemm(dD3, Wc.transpose(1, 2), dA)              # dA[g,m,k] = sum_n dD[g,m,n] W[g,n,k]
         if ctx.needs_input_grad[1]:
-            dW = torch.zeros(G, N, K, dtype=torch.float32, device=A.device)
+            dW = zeros((G, N, K), torch.float32, A.device)
             gemm(dD3.transpose(1, 2), A.transpose(1, 2), dW, accumulate=True)   # dW[g,n,k] = sum_m dD[g,m,n] A[g,m,k]
         if ctx.has_bias and ctx.needs_input_grad[2] and db is None:
             db = colsum(dout)
@@ -387,7 +438,7 @@ class ConvNeXtBlockFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, xs, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, path_scale, geom, train, T, ps_prev=None):
+    def forward(ctx, x, xs, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma, path_scale, geom, train, T, ps_prev=None, prep=None):
         Bn, H, W_ = geom
         M, Cc = x.shape
         assert x.is_contiguous() and M == Bn * H * W_
@@ -397,17 +448,24 @@ class ConvNeXtBlockFn(Function):
         assert src is not None and src.dtype == T and src.is_contiguous()
         dev = x.device
         lib = _L()
-        w49c = dw_w.reshape(Cc, 49).t().contiguous()
+        # prep: (taps [49,C], W1 diag(ln_w), b1 + W1 ln_b, W2, diag(gamma) W2) in the operand dtype, made for all blocks of the
+        # model by one launch (BlockWeights); without it the block prepares its own operands
+        w2s = None
+        if prep is not None:
+            w49c, w1f, b1f, w2c, w2s = prep
+        else:
+            w49c = dw_w.reshape(Cc, 49).t().contiguous()
         xhat = torch.empty(M, Cc, dtype=T, device=dev)
         rstd = torch.empty(M, dtype=torch.float32, device=dev)
         L.check(lib.ga_dwconv7_ln_fwd(L.ptr(src), L.ptr(w49c), L.ptr(dw_b), None, None, L.ptr(xhat), L.ptr(rstd), Bn, H, W_, Cc,
                                       L.f(1e-6), L.dt(src), L.stream()), 'ga_dwconv7_ln_fwd')
-        w1f, b1f = fold_ln(w1, b1, ln_w, ln_b, T)
+        if prep is None:
+            w1f, b1f = fold_ln(w1, b1, ln_w, ln_b, T)
+            w2c = cast_like(w2, T)
         if train:
             a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU, save_z='grad')
         else:
             a, z = gemm(xhat, w1f, bias=b1f, act=ACT_GELU), None
-        w2c = cast_like(w2, T)
         y = torch.empty(M, Cc, dtype=x.dtype, device=dev)
         ys = torch.empty(M, Cc, dtype=T, device=dev) if mixed else None
         gemm(a, w2c, y, bias=b2, colscale=gamma, rowscale=path_scale, rows_per_scale=H * W_, residual=x, shadow=ys)
@@ -415,6 +473,7 @@ class ConvNeXtBlockFn(Function):
             ctx.save_for_backward(src, xhat, rstd, z, a, w49c, ln_w, ln_b, w1, w1f, b1, w2, b2, gamma, path_scale)
             ctx.geom, ctx.T, ctx.RT = geom, T, x.dtype
             ctx.ps_prev = ps_prev       # DropPath factors of the block that consumes this block's dx (not a saved tensor: identity matters)
+            ctx.w2s = w2s               # persistent operand buffer (BlockWeights), valid until the next forward
         return y, ys
 
     @staticmethod
@@ -434,7 +493,7 @@ class ConvNeXtBlockFn(Function):
             dys = t
         # one zeroed slab for every parameter gradient of the block
         sizes = [49 * Cc, Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, Cc, Cc, Cc * Hd, Hd * Cc, Hd]
-        slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        slab = zeros(sum(sizes), torch.float32, dev)
         views, o = [], 0
         for n in sizes:
             views.append(slab[o:o + n])
@@ -448,7 +507,7 @@ class ConvNeXtBlockFn(Function):
         L.check(lib.ga_linear_grad_finalize(L.ptr(G2), L.ptr(s2), L.ptr(w2), L.ptr(b2), L.ptr(gamma), None, None, L.ptr(dw2),
                                             L.ptr(db2), L.ptr(dgam), None, None, Cc, Hd, L.stream()), 'linear_grad_finalize')
         # dz = (dys . (gamma*W2)) * gelu'(z)
-        w2s = scale_matrix(w2, gamma, None, T)
+        w2s = ctx.w2s if ctx.w2s is not None else scale_matrix(w2, gamma, None, T)
         dz, s1 = gemm_dz(dys, w2s.t(), z, s1buf)
         # fc1: G1 = dz^T xhat ; dW1 = G1*ln_w + s1 (x) ln_b ; db1 = s1 ; dln_w = coldot(W1, G1) ; dln_b = W1^T s1
         gemm(dz.t(), xhat.t(), G1.view(Hd, Cc), accumulate=True)
@@ -476,17 +535,74 @@ class ConvNeXtBlockFn(Function):
                                         L.ptr(ws), Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream()), 'ga_dwconv7_bwd')
         _offer_shadow(dx, dxs, ps_prev)
         d_dw_w = d49.view(49, Cc).t().reshape(Cc, 1, 7, 7)
-        return (dx, None, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None, None, None)
+        return (dx, None, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None, None, None, None)
 
 
-def convnext_block(x, p, geom, path_scale=None, train=True, xs=None, T=None, ps_prev=None):
+class BlockWeights:
+    """Operands of every ConvNeXt block of a model, prepared by ONE kernel per forward (ga_block_weight_prep): depthwise taps
+    as [49,C], W1 diag(ln_w) and b1 + W1 ln_b (LayerNorm affine folded into fc1), bf16 W2 and diag(gamma) W2 (layer scale folded
+    into the x act' GEMM of the backward).  The output buffers are persistent; a refresh overwrites them, so they are valid
+    from one forward to the next -- which covers that forward's backward.  bf16 operands, C % 8 == 0 only."""
+
+    def __init__(self, blocks_fn):
+        """blocks_fn() -> list of dicts with the reference's key names (conv_dw.weight, norm.weight/bias, mlp.fc1/fc2.weight/bias,
+        gamma), read afresh at every refresh so replaced parameters (.to(), load with assign) are noticed."""
+        self.blocks_fn = blocks_fn
+        self.blocks = None
+        self.table = None
+        self.ptrs = None
+        self.outs = []
+
+    @staticmethod
+    def supported(blocks, T):
+        return T == torch.bfloat16 and all(p['norm.weight'].numel() % 8 == 0 and p['mlp.fc1.weight'].shape[0] == 4 * p['norm.weight'].numel()
+                                           for p in blocks)
+
+    def _inputs(self, p):
+        return [p['conv_dw.weight'], p['norm.weight'], p['norm.bias'], p['mlp.fc1.weight'], p['mlp.fc1.bias'], p['mlp.fc2.weight'],
+                p.get('gamma')]
+
+    def _build(self):
+        dev = self.blocks[0]['norm.weight'].device
+        rows, self.outs, unit = [], [], 0
+        for p in self.blocks:
+            Cc = p['norm.weight'].numel()
+            Hd = 4 * Cc
+            o = (torch.empty(49, Cc, dtype=torch.float32, device=dev), torch.empty(Hd, Cc, dtype=torch.bfloat16, device=dev),
+                 torch.empty(Hd, dtype=torch.float32, device=dev), torch.empty(Cc, Hd, dtype=torch.bfloat16, device=dev),
+                 torch.empty(Cc, Hd, dtype=torch.bfloat16, device=dev))
+            ins = self._inputs(p)
+            for t in ins:
+                assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.device == dev)
+            rows.append([0 if t is None else t.data_ptr() for t in ins] + [t.data_ptr() for t in o] + [Cc, unit])
+            self.outs.append(o)
+            unit += 5 * Cc + 49
+        self.total_units = unit
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.ptrs = self._sig()
+
+    def _sig(self):
+        return [0 if t is None else t.data_ptr() for p in self.blocks for t in self._inputs(p)]
+
+    def refresh(self):
+        self.blocks = self.blocks_fn()
+        if self.table is None or self.ptrs != self._sig():      # first use, or the parameters moved (.to(), new tensors)
+            self._build()
+        L.check(_L().ga_block_weight_prep(L.ptr(self.table), len(self.blocks), self.total_units, L.stream()), 'ga_block_weight_prep')
+
+    def get(self, i):
+        return self.outs[i]
+
+
+def convnext_block(x, p, geom, path_scale=None, train=True, xs=None, T=None, ps_prev=None, prep=None):
     """p: dict with conv_dw.weight/bias, norm.weight/bias, mlp.fc1/fc2.weight/bias, gamma (reference key names).
     ps_prev: the DropPath factors of the block whose backward consumes this block's stream gradient (the previous block).
+    prep: this block's operands from BlockWeights.get (None: prepared here).
     Returns (y, ys): the residual stream and its compute-dtype shadow (None when they coincide)."""
     T = T or (xs.dtype if xs is not None else x.dtype)
     return ConvNeXtBlockFn.apply(x, xs, p['conv_dw.weight'], p['conv_dw.bias'], p['norm.weight'], p['norm.bias'],
                                  p['mlp.fc1.weight'], p['mlp.fc1.bias'], p['mlp.fc2.weight'], p['mlp.fc2.bias'], p['gamma'],
-                                 path_scale, geom, train, T, ps_prev)
+                                 path_scale, geom, train, T, ps_prev, prep)
 
 
 class ConvertFn(Function):
@@ -532,7 +648,7 @@ class LayerNormFn(Function):
         dx = alloc_rows(M, Cc, x.dtype, x.device)
         dw = db = ws = None
         if w is not None:
-            dwb = torch.zeros(2 * Cc, dtype=torch.float32, device=x.device)
+            dwb = zeros(2 * Cc, torch.float32, x.device)
             dw, db = dwb[:Cc], dwb[Cc:]
             ws = workspace(_L().ga_layernorm_bwd_parts(L.ll(M), Cc) * 2 * Cc, x.device, 'ln')
         L.check(_L().ga_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(dw), L.ptr(db),
@@ -953,14 +1069,14 @@ class GramEmbedFn(Function):
         a_hi = hi.view(Bn, G, gld)[:, :, :glen].transpose(0, 1)
         dW = None
         if ctx.needs_input_grad[1]:
-            dW = torch.zeros(G, N, glen, dtype=torch.float32, device=dev)
+            dW = zeros((G, N, glen), torch.float32, dev)
             gemm(dD3.transpose(1, 2), a_hi.transpose(1, 2), dW, accumulate=True)
             if lo is not None:
                 gemm(dD3.transpose(1, 2), lo.view(Bn, G, gld)[:, :, :glen].transpose(0, 1).transpose(1, 2), dW, accumulate=True)
         dx = None
         if ctx.needs_input_grad[0]:
             Wc = cast_like(W3, T)
-            dv = torch.zeros(Bn, G * gld, dtype=T, device=dev) if gld != glen else torch.empty(Bn, G * gld, dtype=T, device=dev)
+            dv = zeros((Bn, G * gld), T, dev) if gld != glen else torch.empty(Bn, G * gld, dtype=T, device=dev)
             gemm(dD3, Wc.transpose(1, 2), dv.view(Bn, G, gld)[:, :, :glen].transpose(0, 1))
             S = torch.empty(Bn, Cc, Cc, dtype=T, device=dev)
             if lo is not None:
@@ -1071,7 +1187,7 @@ class CSWinAttnFn(Function):
         dout = dout.contiguous()
         if dout.dtype != qkv.dtype:
             dout = convert(dout, qkv.dtype)
-        dl = torch.zeros(Cc * 10, dtype=torch.float32, device=qkv.device)
+        dl = zeros(Cc * 10, torch.float32, qkv.device)
         dqkv = _attn_bwd(dout, qkv, out, lse, lw, lb, dl[:Cc * 9], dl[Cc * 9:], Bn, R, Cc, split, nbr)
         return dqkv, dl[:Cc * 9].view(Cc, 9), dl[Cc * 9:], None, None, None, None
 
@@ -1159,7 +1275,7 @@ class CSWinBlockFn(Function):
             return o
 
         sizes = [Cc, Cc, 3 * Cc * Cc, 3 * Cc, 9 * Cc, Cc, Cc * Cc, Cc, Cc, Hd * Cc, Hd, Cc * Hd, 3 * Cc * Cc, Hd * Cc, Hd]
-        slab = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        slab = zeros(sum(sizes), torch.float32, dev)
         views, o = [], 0
         for n in sizes:
             views.append(slab[o:o + n])
@@ -1228,7 +1344,7 @@ class GALossFn(Function):
                             'soft targets (mixup / smoothing / BCE) go through ga_soft_loss')
         target = target.contiguous()
         logits = logits.contiguous().float()
-        loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        loss = zeros(1, torch.float32, logits.device)
         dl = torch.empty_like(logits)
         da = None
         if aux is not None:
@@ -1260,7 +1376,7 @@ class GADenseLossFn(Function):
             raise L.GaError(f'ga_soft_loss: dense targets must be a CUDA fp32 tensor of shape ({Bn}, {ncls})')
         target = target.contiguous()
         logits = logits.contiguous().float()
-        loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        loss = zeros(1, torch.float32, logits.device)
         dl = torch.empty_like(logits)
         da = None
         if aux is not None:

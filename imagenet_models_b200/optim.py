@@ -68,6 +68,7 @@ class FlatState:
             p.grad = None
         from . import ops
         ops.clear_shadows()
+        ops.ZEROS.begin(self.flat.device)       # one zero fill for every gradient accumulator of the coming backward
 
     def _table(self, members):
         key = tuple(members)

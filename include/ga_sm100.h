@@ -230,6 +230,16 @@ int ga_cast_bf16(const float* src, void* dst, long long n, ga_stream_t s);
  * Wf[n,k] = W[n,k]*ln_w[k] in dst_dtype (row pitch ldw), bf[n] = bias[n] + sum_k W[n,k]*ln_b[k] (bias may be NULL) */
 int ga_fold_ln(const float* W, const float* ln_w, const float* ln_b, const float* bias, void* Wf, float* bf, int N, int K,
                long long ldw, int dst_dtype, ga_stream_t s);
+/* Operand preparation of every ConvNeXt block of a model in ONE launch (the per-step work that GA/ga_convnext.py:100,105-111
+ * leaves to cuDNN/cuBLAS weight layouts): for block b, `table` holds GA_BLOCK_PREP_WORDS int64 words
+ *   [0] conv_dw.weight [C,1,7,7] f32   [1] norm.weight [C]   [2] norm.bias [C]   [3] fc1.weight [4C,C]   [4] fc1.bias [4C]
+ *   [5] fc2.weight [C,4C]   [6] gamma [C] or 0      (inputs, fp32)
+ *   [7] taps [49,C] f32   [8] fc1.weight*diag(norm.weight) bf16 [4C,C]   [9] fc1.bias + fc1.weight norm.bias f32 [4C]
+ *   [10] bf16 fc2.weight [C,4C]   [11] bf16 diag(gamma) fc2.weight [C,4C]      (outputs)
+ *   [12] C (multiple of 8)   [13] first unit of the block = sum over earlier blocks of (5C + 49)
+ * total_units = sum over all blocks of (5C + 49). */
+#define GA_BLOCK_PREP_WORDS 14
+int ga_block_weight_prep(const void* table, int nblocks, int total_units, ga_stream_t s);
 int ga_scale_matrix(const float* src, const float* rowscale, const float* colscale, void* dst, int rows, int cols,
                     int dst_dtype, ga_stream_t s);
 /* y[r,:] = x[r,:] * rowscale[r / rows_per_scale]  (DropPath mask applied to a gradient; timm drop_path) */

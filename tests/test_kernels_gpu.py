@@ -598,3 +598,57 @@ def test_stage_with_droppath_prescaled_shadow_vs_oracle():
         for k in Ps[i]:
             e = rel(Pg[i][k].grad.cpu().reshape(-1), Ps[i][k].grad.reshape(-1))
             assert e < 3e-2, (i, k, e)
+
+
+def test_block_weight_prep_matches_per_block_ops():
+    """ga_block_weight_prep (one launch for every ConvNeXt block of a model) against the per-block operand preparation it replaces
+    (transpose copy, ga_fold_ln, ga_cast_bf16, ga_scale_matrix) -- bit-identical bf16 operands, fp32 folded bias to 1e-6."""
+    torch.manual_seed(0)
+    blocks = []
+    for Cc, has_gamma in ((96, True), (192, True), (688, True), (384, False)):
+        p = {'conv_dw.weight': torch.randn(Cc, 1, 7, 7, device=DEV), 'norm.weight': torch.randn(Cc, device=DEV),
+             'norm.bias': torch.randn(Cc, device=DEV), 'mlp.fc1.weight': torch.randn(4 * Cc, Cc, device=DEV) * 0.1,
+             'mlp.fc1.bias': torch.randn(4 * Cc, device=DEV), 'mlp.fc2.weight': torch.randn(Cc, 4 * Cc, device=DEV) * 0.1}
+        if has_gamma:
+            p['gamma'] = torch.randn(Cc, device=DEV)
+        blocks.append(p)
+    T = torch.bfloat16
+    assert ops.BlockWeights.supported(blocks, T)
+    bw = ops.BlockWeights(lambda: blocks)
+    bw.refresh()
+    torch.cuda.synchronize()
+    for i, p in enumerate(blocks):
+        w49c, w1f, b1f, w2c, w2s = bw.get(i)
+        Cc = p['norm.weight'].numel()
+        assert torch.equal(w49c, p['conv_dw.weight'].reshape(Cc, 49).t().contiguous())
+        rf, rb = ops.fold_ln(p['mlp.fc1.weight'], p['mlp.fc1.bias'], p['norm.weight'], p['norm.bias'], T)
+        assert torch.equal(w1f, rf)
+        assert torch.allclose(b1f, rb, rtol=1e-6, atol=1e-6)
+        assert torch.equal(w2c, ops.cast_like(p['mlp.fc2.weight'], T))
+        g = p.get('gamma', torch.ones(Cc, device=DEV))
+        assert torch.equal(w2s, ops.scale_matrix(p['mlp.fc2.weight'], g, None, T))
+    # parameters updated in place are picked up by the next refresh; replaced tensors rebuild the table
+    blocks[0]['mlp.fc2.weight'].mul_(2.0)
+    blocks[1]['norm.weight'] = torch.randn(192, device=DEV)
+    bw.refresh()
+    assert torch.equal(bw.get(0)[3], ops.cast_like(blocks[0]['mlp.fc2.weight'], T))
+    assert torch.equal(bw.get(1)[1], ops.fold_ln(blocks[1]['mlp.fc1.weight'], blocks[1]['mlp.fc1.bias'], blocks[1]['norm.weight'],
+                                                 blocks[1]['norm.bias'], T)[0])
+
+
+def test_zero_arena_hands_out_disjoint_zeroed_views():
+    """ops.ZeroArena: one fill per step; views are zero, aligned, disjoint; exhaustion and first use fall back to torch.zeros."""
+    A = ops.ZeroArena()
+    A.begin(DEV)                                     # nothing known yet: every request is its own fill
+    a = A.take(1000, torch.float32, DEV)
+    b = A.take(77, torch.bfloat16, DEV)
+    assert a.sum() == 0 and b.sum() == 0 and A.buf is None
+    A.begin(DEV)                                     # sized by the previous step
+    assert A.buf is not None and A.buf.numel() == A.need == 4096 + 256
+    a = A.take(1000, torch.float32, DEV)
+    b = A.take(77, torch.bfloat16, DEV)
+    a.fill_(1.0)
+    assert b.float().sum() == 0 and a.data_ptr() % 256 == 0 and b.data_ptr() % 256 == 0
+    assert a.data_ptr() + 4000 <= b.data_ptr()
+    c = A.take(10, torch.float32, DEV)               # beyond the arena: fallback, still zero
+    assert c.sum() == 0 and not (A.buf.data_ptr() <= c.data_ptr() < A.buf.data_ptr() + A.buf.numel())
