@@ -38,6 +38,18 @@ class TrainEngine:
         else:
             raise ValueError(f"optimizer '{opt}': 'adamw' and 'lamb' are fused here")
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        if self.world > 1:
+            # DistributedDataParallel construction (GA/train.py:505-515) copies rank 0's parameters and buffers to every rank
+            # (the trainers seed with seed + rank, so the initialisations differ); the EMA copy and the bf16 shadows follow
+            st = self.opt.state
+            dist.broadcast(st.flat, 0)
+            if st.bufflat is not None and st.bufflat.numel():
+                dist.broadcast(st.bufflat, 0)
+            if getattr(self.opt, 'ema_flat', None) is not None:
+                self.opt.ema_flat.copy_(st.flat)
+                if getattr(self.opt, 'ema_bufflat', None) is not None and st.bufflat is not None:
+                    self.opt.ema_bufflat.copy_(st.bufflat)
+            st.refresh_shadows()
         self.buckets = GradBuckets(self.opt.state, bucket_mb=bucket_mb) if self.world > 1 else None
         # DistributedDataParallel(broadcast_buffers=True) (GA/train.py:514, --no-ddp-bb turns it off): rank 0's BatchNorm running
         # statistics replace every rank's before each forward.  All float buffers live in one flat tensor -> one small broadcast.
@@ -152,6 +164,8 @@ class TrainEngine:
     def step(self, x, y):
         """One micro-step; the optimizer (and the all-reduce) runs every `grad_accumulation` micro-steps.  Returns the loss tensor."""
         self._calls += 1
+        if self._graph is None and not self.opt.state.shadows_current():
+            self.opt.state.refresh_shadows()        # parameters were written from outside (load_state_dict before training)
         if self.cuda_graph and self._calls > self.graph_warmup:
             return self._graph_step(x, y)
         first = self.micro % self.accum == 0

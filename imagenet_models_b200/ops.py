@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import weakref
+
 import torch
 
 from . import lib as L
@@ -216,8 +218,22 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
     return (out, Z) if (save_z is not False and save_z is not None) else out
 
 
+# bf16 shadows of fp32 parameters kept current by the optimizer kernel (optim.FlatState.flat16): data_ptr -> (weakref to the
+# parameter, its version counter when registered, bf16 view).  A parameter changed behind the optimizer's back (copy_,
+# load_state_dict: version bump) or replaced (.to(): other pointer) no longer matches and is cast on the spot.
+_weight_shadows = {}
+
+
+def register_weight_shadows(params, offsets, flat16):
+    for k in [k for k, v in _weight_shadows.items() if v[0]() is None]:
+        del _weight_shadows[k]
+    for p_, o in zip(params, offsets):
+        _weight_shadows[p_.data_ptr()] = (weakref.ref(p_), p_._version, flat16[o:o + p_.numel()])
+
+
 def cast_like(w: torch.Tensor, like_dtype) -> torch.Tensor:
-    """fp32 parameter -> operand dtype (bf16 shadow made by the cast kernel; fp32 passes through)."""
+    """fp32 parameter -> operand dtype (fp32 passes through).  bf16: the shadow the optimizer step wrote, when `w` is a
+    registered parameter (or a same-size view of it); else made here by the cast kernel."""
     if like_dtype == torch.float32:
         return w
     w = w if w.is_contiguous() else w.contiguous()
@@ -227,6 +243,11 @@ def cast_like(w: torch.Tensor, like_dtype) -> torch.Tensor:
         L.check(_L().ga_copy_cols(L.ptr(w), L.ptr(o), L.ll(w.numel() // K), K, L.ll(K), L.ll(pad8(K)), F32, BF16, L.stream()),
                 'ga_copy_cols')
         return o[..., :K]
+    ent = _weight_shadows.get(w.data_ptr())
+    if ent is not None and like_dtype == torch.bfloat16:
+        p_ = ent[0]()
+        if p_ is not None and p_._version == ent[1] and w._version == ent[1] and w.numel() == ent[2].numel():
+            return ent[2].view(w.shape)
     o = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
     L.check(_L().ga_cast_bf16(L.ptr(w), L.ptr(o), L.ll(w.numel()), L.stream()), 'ga_cast_bf16')
     return o

@@ -51,6 +51,27 @@ class FlatState:
             p.grad = None
         # float buffers (BatchNorm running statistics) re-homed the same way, for a one-launch EMA of non-parameter state
         self.bufflat = _flatten_buffers(model, dev)
+        # bf16 shadow of every parameter at the same offsets: written by the optimizer kernel together with the fp32 update,
+        # so no forward or backward GEMM casts a weight again (ops.cast_like looks the parameter up)
+        self.flat16 = None
+        if dev.type == 'cuda':
+            self.flat16 = torch.empty(off, dtype=torch.bfloat16, device=dev)
+            self.refresh_shadows()
+
+    def refresh_shadows(self):
+        """Re-cast every parameter and re-register the shadows (construction; after parameters were written from outside the
+        optimizer, e.g. load_state_dict, whose version bump had un-registered them)."""
+        if self.flat16 is None:
+            return
+        from . import ops
+        L.check(L.load().ga_cast_bf16(L.ptr(self.flat), L.ptr(self.flat16), L.ll(self.numel), L.stream()), 'ga_cast_bf16')
+        ops.register_weight_shadows(self.params, self.offsets, self.flat16)
+
+    def shadows_current(self):
+        if self.flat16 is None:
+            return True
+        from . import ops
+        return all((e := ops._weight_shadows.get(p.data_ptr())) is not None and e[1] == p._version for p in self.params)
 
     def decay_flags(self, no_decay_1d: bool = True) -> torch.Tensor:
         """timm filter_bias_and_bn: 1-D tensors and biases get no weight decay."""
@@ -193,7 +214,7 @@ class FusedAdamWEma:
                                            L.ptr(self._clip_scratch), L.stream()), 'ga_grad_clip_scale')
         if device_hyper:
             L.check(lib.ga_adamw_ema_dev(L.ptr(self.state.flat), L.ptr(self.state.grad), L.ptr(self.m), L.ptr(self.v),
-                                         L.ptr(self.ema_flat), None, L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel),
+                                         L.ptr(self.ema_flat), L.ptr(self.state.flat16), L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel),
                                          L.ptr(self.hyper), L.f(b1), L.f(b2), L.f(self.eps), L.f(self.wd), L.f(ema_d), L.stream()),
                     'ga_adamw_ema_dev')
         else:
@@ -201,7 +222,7 @@ class FusedAdamWEma:
             t = self.step_count
             lr = self.param_groups[0]['lr']
             L.check(lib.ga_adamw_ema(L.ptr(self.state.flat), L.ptr(self.state.grad), L.ptr(self.m), L.ptr(self.v),
-                                     L.ptr(self.ema_flat), None, L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel), L.f(lr),
+                                     L.ptr(self.ema_flat), L.ptr(self.state.flat16), L.ptr(self.flags), SEG_SHIFT, L.ll(self.state.numel), L.f(lr),
                                      L.f(b1), L.f(b2), L.f(self.eps), L.f(self.wd), L.f(1 - b1 ** t), L.f(1 - b2 ** t), L.f(ema_d),
                                      L.f(grad_scale), L.stream()), 'ga_adamw_ema')
         if self.ema_model is not None:
@@ -242,6 +263,9 @@ class FusedLambEma(FusedAdamWEma):
                                      L.ptr(self._scratch), L.ptr(self.hyper), L.f(b1), L.f(b2), L.f(self.eps), L.f(self.wd),
                                      L.f(self.max_grad_norm), L.f(self.ema_decay if self.ema_decay is not None else 0.0), L.stream()),
                 'ga_lamb_ema')
+        if self.state.flat16 is not None:          # bf16 shadows of the updated parameters (the AdamW kernel writes them itself)
+            L.check(L.load().ga_cast_bf16(L.ptr(self.state.flat), L.ptr(self.state.flat16), L.ll(self.state.numel), L.stream()),
+                    'ga_cast_bf16')
         if self.ema_model is not None:
             L.check(L.load().ga_ema_lerp(L.ptr(self.ema_bufflat), L.ptr(self.state.bufflat), L.ll(self.ema_bufflat.numel()),
                                          L.f(self.ema_decay), L.stream()), 'ga_ema_lerp')

@@ -25,6 +25,8 @@ def main():
     ap.add_argument('--fwd-only', action='store_true')
     ap.add_argument('--model', default='ga_convnext_tiny_688')
     ap.add_argument('--drop-path', type=float, default=0.2)
+    ap.add_argument('--top', type=int, default=45)
+    ap.add_argument('--sequence', default=None, help='also write the ordered kernel list of the last profiled step here')
     args = ap.parse_args()
     from imagenet_models_b200 import ops
     from imagenet_models_b200.optim import FusedAdamWEma
@@ -71,9 +73,18 @@ def main():
             shapes[name].append(ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time)
     total = sum(v[1] for v in agg.values())
     lines = [f'batch {args.batch}, {args.steps} steps, total device time {total / 1e3 / args.steps:.3f} ms/step']
-    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:args.top]:
         top = sorted(shapes[k], reverse=True)[:3]
         lines.append(f'{t / total * 100:6.2f}%  {t / 1e3 / args.steps:8.3f} ms/step  n={c // args.steps:4d}  max {top[0]:8.1f} us  {k[:100]}')
+    nk = sum(c for c, _ in agg.values()) // args.steps
+    ours = sum(c for k, (c, _) in agg.items() if not (k.startswith('at::') or 'Memcpy' in k or 'Memset' in k or k.startswith('cub::'))) // args.steps
+    lines.insert(1, f'{nk} kernel launches per step: {ours} from libga_sm100.so, {nk - ours} ATen / memcpy / memset')
+    if args.sequence:
+        evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+        evs = evs[len(evs) - len(evs) // args.steps:]
+        with open(args.sequence, 'w') as f:
+            for ev in evs:
+                f.write(f'{(ev.device_time if hasattr(ev, "device_time") else ev.cuda_time):9.1f}  {re.sub("^void ", "", ev.name).split(chr(40))[0][:110]}\n')
     txt = '\n'.join(lines)
     print(txt)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

@@ -652,3 +652,34 @@ def test_zero_arena_hands_out_disjoint_zeroed_views():
     assert a.data_ptr() + 4000 <= b.data_ptr()
     c = A.take(10, torch.float32, DEV)               # beyond the arena: fallback, still zero
     assert c.sum() == 0 and not (A.buf.data_ptr() <= c.data_ptr() < A.buf.data_ptr() + A.buf.numel())
+
+
+def test_weight_shadows_follow_the_optimizer():
+    """optim.FlatState.flat16: the AdamW kernel writes the bf16 copy of every parameter; ops.cast_like returns that copy for a
+    registered parameter (and its same-size views), casts afresh once the parameter was written from outside, and is
+    re-registered by refresh_shadows()."""
+    from imagenet_models_b200.optim import FusedAdamWEma
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(64, 48), torch.nn.Linear(48, 8)).to(DEV)
+    opt = FusedAdamWEma(m, lr=1e-2, weight_decay=0.05, ema_decay=None)
+    st = opt.state
+    lo, hi = st.flat16.data_ptr(), st.flat16.data_ptr() + st.flat16.numel() * 2
+    w = m[0].weight
+    s0 = ops.cast_like(w, torch.bfloat16)
+    assert lo <= s0.data_ptr() < hi and torch.equal(s0, w.detach().bfloat16())
+    assert ops.cast_like(w.unsqueeze(0), torch.bfloat16).data_ptr() == s0.data_ptr()        # view of the parameter
+    for p in m.parameters():
+        p.grad = torch.randn_like(p)
+    opt.step()
+    torch.cuda.synchronize()
+    s1 = ops.cast_like(w, torch.bfloat16)
+    assert s1.data_ptr() == s0.data_ptr() and torch.equal(s1, w.detach().bfloat16())        # refreshed by the step kernel
+    assert st.shadows_current()
+    with torch.no_grad():
+        w.copy_(torch.randn_like(w))                                                        # written behind the optimizer's back
+    assert not st.shadows_current()
+    s2 = ops.cast_like(w, torch.bfloat16)
+    assert not (lo <= s2.data_ptr() < hi) and torch.equal(s2, w.detach().bfloat16())
+    st.refresh_shadows()
+    s3 = ops.cast_like(w, torch.bfloat16)
+    assert lo <= s3.data_ptr() < hi and torch.equal(s3, w.detach().bfloat16()) and st.shadows_current()
