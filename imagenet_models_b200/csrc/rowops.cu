@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
                                                             const float* __restrict__ w, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, T* __restrict__ dx,
                                                             float* __restrict__ partial, long long M, int C, long long lddy,
-                                                            long long ldx, long long lddx, int x_is_hat, int rows_per_cta) {
+                                                            long long ldx, long long lddx, int x_is_hat, int rows_per_cta,
+                                                            float* __restrict__ adw, float* __restrict__ adb) {
   extern __shared__ float sacc[];  // [2][C] per CTA when partial != NULL
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (partial) {
@@ -207,7 +208,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * C + i] = sacc[i];
+    if (adw || adb) {          // single-kernel mode: this CTA's sums go straight into the (pre-zeroed or accumulating) gradients
+      for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float* o = i < C ? (adw ? adw + i : nullptr) : (adb ? adb + (i - C) : nullptr);
+        if (o) atomicAdd(o, sacc[i]);
+      }
+    } else {
+      for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * C + i] = sacc[i];
+    }
   }
 }
 
@@ -217,7 +225,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_narrow_kernel(const T* __re
                                                                    const float* __restrict__ w, const float* __restrict__ mean,
                                                                    const float* __restrict__ rstd, T* __restrict__ dx,
                                                                    float* __restrict__ partial, long long M, int C, long long lddy,
-                                                                   long long ldx, long long lddx, int x_is_hat, int rows_per_cta) {
+                                                                   long long ldx, long long lddx, int x_is_hat, int rows_per_cta,
+                                                                   float* __restrict__ adw, float* __restrict__ adb) {
   extern __shared__ float sacc[];  // [2][C]
   constexpr int G = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -281,7 +290,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_narrow_kernel(const T* __re
       atomicAdd(&sacc[C + c], dbv.x); atomicAdd(&sacc[C + c + 1], dbv.y); atomicAdd(&sacc[C + c + 2], dbv.z); atomicAdd(&sacc[C + c + 3], dbv.w);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * C + i] = sacc[i];
+    if (adw || adb) {          // single-kernel mode: this CTA's sums go straight into the (pre-zeroed or accumulating) gradients
+      for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float* o = i < C ? (adw ? adw + i : nullptr) : (adb ? adb + (i - C) : nullptr);
+        if (o) atomicAdd(o, sacc[i]);
+      }
+    } else {
+      for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * C + i] = sacc[i];
+    }
   }
 }
 
@@ -328,7 +344,13 @@ extern "C" int ga_layernorm_bwd(const void* dy, const void* x, const float* w, c
   GA_REQUIRE(C <= 2048, GA_ERR_UNSUPPORTED, "ga_layernorm_bwd: C=%d > 2048", C);
   if (M == 0) return GA_OK;
   const bool want_param = (dw || db);
-  GA_REQUIRE(!want_param || partial, GA_ERR_SHAPE, "ga_layernorm_bwd: parameter gradients need the partial workspace");
+  // partial == NULL: single-kernel mode, every CTA adds its sums to dw / db with fp32 atomics (no second launch; the order
+  // of the additions, hence the last bits, varies from run to run).  With the workspace the reduction is a second,
+  // deterministic kernel.  Either way dw / db are ACCUMULATED onto.
+  const bool atomic_out = want_param && !partial;
+  float* const adw = atomic_out ? dw : nullptr;
+  float* const adb = atomic_out ? db : nullptr;
+  if (atomic_out) partial = dw ? dw : db;          // non-null marker: the kernels test `partial` for "parameter gradients wanted"
   int parts = row_parts(M);
   if (!want_param) {                      // no partial buffers needed: one warp-row per slot, many CTAs in flight
     long long p = (M + 15) / 16;
@@ -338,18 +360,18 @@ extern "C" int ga_layernorm_bwd(const void* dy, const void* x, const float* w, c
   const int rows_per_cta = (int)((M + parts - 1) / parts);
   const size_t smem = want_param ? (size_t)2 * C * sizeof(float) : 0;
   const int x_is_hat = (mean == nullptr);
-#define GA_LNB_NARROW(LPR) layernorm_bwd_narrow_kernel<T, LPR, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta)
+#define GA_LNB_NARROW(LPR) layernorm_bwd_narrow_kernel<T, LPR, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb)
   DISPATCH_T(dtype, {
     if (C <= 32) GA_LNB_NARROW(8);
     else if (C <= 64) GA_LNB_NARROW(16);
     else if (C <= 128) GA_LNB_NARROW(32);
-    else if (C <= 512) layernorm_bwd_kernel<T, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
-    else if (C <= 1024) layernorm_bwd_kernel<T, 8><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
-    else layernorm_bwd_kernel<T, 16><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta);
+    else if (C <= 512) layernorm_bwd_kernel<T, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb);
+    else if (C <= 1024) layernorm_bwd_kernel<T, 8><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb);
+    else layernorm_bwd_kernel<T, 16><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb);
   });
 #undef GA_LNB_NARROW
   int rc = launch_ok("layernorm_bwd");
-  if (rc || !want_param) return rc;
+  if (rc || !want_param || atomic_out) return rc;
   reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, dw, C, db, 1);
   return launch_ok("layernorm_bwd_reduce");
 }
@@ -721,7 +743,8 @@ __global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, 
                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
                                                        float* __restrict__ partial, long long M, int C, long long ldx,
                                                        long long lddy, long long ldy, int rows_per_cta, int relu,
-                                                       float* __restrict__ pivot_out = nullptr) {
+                                                       float* __restrict__ pivot_out = nullptr, float* __restrict__ out0 = nullptr,
+                                                       float* __restrict__ out1 = nullptr) {
   __shared__ float4 sh[2][8][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + lane * 4;
@@ -772,7 +795,12 @@ __global__ void __launch_bounds__(256) colstats_kernel(const T* __restrict__ x, 
     float4 t = sh[wid][0][lane];
 #pragma unroll
     for (int k = 1; k < 8; ++k) { float4 u = sh[wid][k][lane]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
-    *reinterpret_cast<float4*>(partial + ((size_t)blockIdx.y * 2 + wid) * C + c) = t;
+    if (partial) {
+      *reinterpret_cast<float4*>(partial + ((size_t)blockIdx.y * 2 + wid) * C + c) = t;
+    } else {                   // single-kernel mode: add to the (pre-zeroed or accumulating) outputs
+      float* o = wid == 0 ? out0 : out1;
+      if (o) atomicAdd(reinterpret_cast<float4*>(o + c), t);
+    }
   }
 }
 
@@ -787,13 +815,14 @@ extern "C" int ga_colstats_parts(long long M, int C) {
 
 extern "C" int ga_colstats(const void* x, float* sum, float* sumsq, float* partial, long long M, int C, long long ldx,
                            int accumulate, int dtype, ga_stream_t s) {
-  GA_REQUIRE(x && partial && (C & 3) == 0 && (ldx & 3) == 0, GA_ERR_ALIGN, "ga_colstats: C=%d ldx=%lld must be multiples of 4", C, ldx);
+  GA_REQUIRE(x && (C & 3) == 0 && (ldx & 3) == 0, GA_ERR_ALIGN, "ga_colstats: C=%d ldx=%lld must be multiples of 4", C, ldx);
+  GA_REQUIRE(partial || accumulate, GA_ERR_SHAPE, "ga_colstats: without the workspace the sums are added atomically: pass accumulate = 1 and zeroed outputs");
   const int parts = ga_colstats_parts(M, C);
   const int rows_per_cta = (int)((M + parts - 1) / parts);
   dim3 grid((C + 127) / 128, parts);
-  DISPATCH_T(dtype, { colstats_kernel<T, 0><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, partial, M, C, ldx, 0, 0, rows_per_cta, 0); });
+  DISPATCH_T(dtype, { colstats_kernel<T, 0><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, partial, M, C, ldx, 0, 0, rows_per_cta, 0, nullptr, sum, sumsq); });
   int rc = launch_ok("colstats");
-  if (rc) return rc;
+  if (rc || !partial) return rc;
   reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, sum, C, sumsq, accumulate);
   return launch_ok("colstats_reduce");
 }
@@ -801,14 +830,14 @@ extern "C" int ga_colstats(const void* x, float* sum, float* sumsq, float* parti
 // sums of (x - pivot) and (x - pivot)^2 with pivot = row 0 (pivot[C] written), for ga_bn_finalize(pivot != NULL)
 extern "C" int ga_colstats_shifted(const void* x, float* pivot, float* sum, float* sumsq, float* partial, long long M, int C,
                                    long long ldx, int dtype, ga_stream_t s) {
-  GA_REQUIRE(x && pivot && sum && sumsq && partial && M > 0 && (C & 3) == 0 && (ldx & 3) == 0, GA_ERR_ALIGN,
+  GA_REQUIRE(x && pivot && sum && sumsq && M > 0 && (C & 3) == 0 && (ldx & 3) == 0, GA_ERR_ALIGN,
              "ga_colstats_shifted: C=%d ldx=%lld must be multiples of 4", C, ldx);
   const int parts = ga_colstats_parts(M, C);
   const int rows_per_cta = (int)((M + parts - 1) / parts);
   dim3 grid((C + 127) / 128, parts);
-  DISPATCH_T(dtype, { colstats_kernel<T, 2><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, partial, M, C, ldx, 0, 0, rows_per_cta, 0, pivot); });
+  DISPATCH_T(dtype, { colstats_kernel<T, 2><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, nullptr, nullptr, nullptr, nullptr, partial, M, C, ldx, 0, 0, rows_per_cta, 0, pivot, sum, sumsq); });
   int rc = launch_ok("colstats_shifted");
-  if (rc) return rc;
+  if (rc || !partial) return rc;          // partial == NULL: sum / sumsq were zero and now hold the atomically added sums
   reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, sum, C, sumsq, 0);
   return launch_ok("colstats_reduce");
 }
@@ -892,15 +921,15 @@ extern "C" int ga_affine_act(const void* x, const float* scale, const float* shi
 extern "C" int ga_bn_bwd_reduce(const void* dy, const void* x, const void* y, const float* mean, const float* invstd, float* c1,
                                 float* c2, float* partial, long long M, int C, long long lddy, long long ldx, long long ldy,
                                 int relu, int dtype, ga_stream_t s) {
-  GA_REQUIRE(dy && x && mean && invstd && partial && (C & 3) == 0 && (ldx & 3) == 0 && (lddy & 3) == 0, GA_ERR_ALIGN,
+  GA_REQUIRE(dy && x && mean && invstd && (C & 3) == 0 && (ldx & 3) == 0 && (lddy & 3) == 0, GA_ERR_ALIGN,
              "ga_bn_bwd_reduce: bad arguments");
   GA_REQUIRE(!relu || (y && (ldy & 3) == 0), GA_ERR_SHAPE, "ga_bn_bwd_reduce: relu mask needs y");
   const int parts = ga_colstats_parts(M, C);
   const int rows_per_cta = (int)((M + parts - 1) / parts);
   dim3 grid((C + 127) / 128, parts);
-  DISPATCH_T(dtype, { colstats_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)dy, (const T*)y, mean, invstd, partial, M, C, ldx, lddy, ldy, rows_per_cta, relu); });
+  DISPATCH_T(dtype, { colstats_kernel<T, 1><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)dy, (const T*)y, mean, invstd, partial, M, C, ldx, lddy, ldy, rows_per_cta, relu, nullptr, c1, c2); });
   int rc = launch_ok("bn_bwd_reduce");
-  if (rc) return rc;
+  if (rc || !partial) return rc;          // partial == NULL: c1 / c2 were zero and now hold the atomically added sums
   reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, c1, C, c2, 0);
   return launch_ok("bn_bwd_reduce2");
 }

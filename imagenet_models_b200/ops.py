@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
 import weakref
 
 import torch
@@ -73,6 +74,13 @@ def _zeros(n, device):
     if k not in _const_cache:
         _const_cache[k] = torch.zeros(n, dtype=torch.float32, device=device)
     return _const_cache[k]
+
+
+# Column reductions (bias / BatchNorm / LayerNorm-affine sums) in ONE kernel: every CTA adds its partial sums to zeroed outputs
+# with fp32 atomics instead of writing them to a workspace that a second launch reduces (~100 launches of 2 us per step).
+# The additions commute only up to rounding, so the last bits vary between runs; GA_ATOMIC_REDUCE=0 restores the two-kernel
+# deterministic order.
+ATOMIC_REDUCE = os.environ.get('GA_ATOMIC_REDUCE', '1') == '1'
 
 
 class ZeroArena:
@@ -294,6 +302,11 @@ def colsum(x: torch.Tensor, sumsq: bool = False):
         s = gemm(x.t(), ones, out_dtype=torch.float32).reshape(Cc)
         assert not sumsq
         return s
+    if ATOMIC_REDUCE:          # one kernel: CTAs add into zeroed outputs (step arena); see ATOMIC_REDUCE
+        sq = zeros((2, Cc) if sumsq else (1, Cc), torch.float32, x.device)
+        s, q = sq[0], (sq[1] if sumsq else None)
+        L.check(_L().ga_colstats(L.ptr(x), L.ptr(s), L.ptr(q), None, L.ll(M), Cc, L.ll(ld), 1, L.dt(x), L.stream()), 'ga_colstats')
+        return (s, q) if sumsq else s
     s = torch.empty(Cc, dtype=torch.float32, device=x.device)
     q = torch.empty(Cc, dtype=torch.float32, device=x.device) if sumsq else None
     parts = _L().ga_colstats_parts(L.ll(M), Cc)
@@ -671,7 +684,7 @@ class LayerNormFn(Function):
         if w is not None:
             dwb = zeros(2 * Cc, torch.float32, x.device)
             dw, db = dwb[:Cc], dwb[Cc:]
-            ws = workspace(_L().ga_layernorm_bwd_parts(L.ll(M), Cc) * 2 * Cc, x.device, 'ln')
+            ws = None if ATOMIC_REDUCE else workspace(_L().ga_layernorm_bwd_parts(L.ll(M), Cc) * 2 * Cc, x.device, 'ln')
         L.check(_L().ga_layernorm_bwd(L.ptr(dy), L.ptr(x), L.ptr(w), L.ptr(mean), L.ptr(rstd), L.ptr(dx), L.ptr(dw), L.ptr(db),
                                       L.ptr(ws), L.ll(M), Cc, L.ll(dy.stride(0)), L.ll(x.stride(0)), L.ll(dx.stride(0)),
                                       L.dt(x), L.stream()), 'ga_layernorm_bwd')
@@ -767,6 +780,8 @@ def _bn_stats(x, w, b, rm, rv, training, momentum, eps):
     if training:
         # sums of (x - row 0): the variance then has no E[x^2] - E[x]^2 cancellation (the gram_embedding BatchNorm sees a batch
         # whose rows differ by ~5 % of their magnitude; the plain form cost 2e-5 on the fp32 logits)
+        # forward statistics stay on the two-kernel, fixed-order reduction: a train-mode BatchNorm over a handful of rows turns
+        # last-bit differences of its mean into visible output differences, and the forward should repeat bit for bit
         sq = torch.empty(3, Cc, dtype=torch.float32, device=dev)
         pv, s, q = sq[0], sq[1], sq[2]
         ws = workspace(_L().ga_colstats_parts(L.ll(M), Cc) * 2 * Cc, dev, 'colstats')
@@ -818,9 +833,9 @@ class BatchNormFn(Function):
                 outs += [act_bwd(dy, y, ACT_RELU) if ctx.relu else dy, None, None]
                 continue
             M, Cc = xi.shape
-            cc = torch.empty(2, Cc, dtype=torch.float32, device=xi.device)
+            cc = zeros((2, Cc), torch.float32, xi.device) if ATOMIC_REDUCE else torch.empty(2, Cc, dtype=torch.float32, device=xi.device)
             parts = _L().ga_colstats_parts(L.ll(M), Cc)
-            ws = workspace(parts * 2 * Cc, xi.device, 'colstats')
+            ws = None if ATOMIC_REDUCE else workspace(parts * 2 * Cc, xi.device, 'colstats')
             L.check(_L().ga_bn_bwd_reduce(L.ptr(dy), L.ptr(xi), L.ptr(y), L.ptr(sti[0]), L.ptr(sti[1]), L.ptr(cc[0]), L.ptr(cc[1]),
                                           L.ptr(ws), L.ll(M), Cc, L.ll(dy.stride(0)), L.ll(xi.stride(0)),
                                           L.ll(y.stride(0)) if y is not None else L.ll(0), int(ctx.relu), L.dt(xi), L.stream()),

@@ -108,7 +108,8 @@ int ga_dwconv7_bwd3(const void* dconv, const void* x, const void* dres, const fl
 /* ---- row LayerNorm over the last dim (LayerNorm2d on NHWC rows, nn.LayerNorm)  (ga_convnext.py:51-67,233,237) */
 int ga_layernorm_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,
                      long long M, int C, long long ldx, long long ldy, float eps, int dtype, ga_stream_t s);
-/* dx = LN backward (mean == NULL: x already holds xhat); dw/db accumulated (+=) via a [parts][2][C] workspace */
+/* dx = LN backward (mean == NULL: x already holds xhat); dw/db accumulated (+=) via a [parts][2][C] workspace, or, with
+ * partial == NULL, by fp32 atomics from the one kernel (no second launch; summation order, hence the last bits, not fixed) */
 int ga_layernorm_bwd_parts(long long M, int C);
 int ga_layernorm_bwd(const void* dy, const void* x, const float* w, const float* mean, const float* rstd,
                      void* dx, float* dw, float* db, float* partial, long long M, int C, long long lddy,
@@ -134,7 +135,10 @@ int ga_stem_im2col3(const float* x, void* y, int B, int H, int W, int stride, lo
 
 /* ---- column statistics over rows of [M,C]: BatchNorm2d (ga_convnext.py:261,270,276,283,409,420), bias grads --- */
 int ga_colstats_parts(long long M, int C);
-/* sum[c] (=|+=) sum_m x[m,c]; sumsq[c] likewise with x^2 (either may be NULL); partial: [parts][2][C] */
+/* sum[c] (=|+=) sum_m x[m,c]; sumsq[c] likewise with x^2 (either may be NULL); partial: [parts][2][C].
+ * partial == NULL (here, in ga_colstats_shifted and in ga_bn_bwd_reduce): single-kernel mode -- every CTA adds its partial sums
+ * to the outputs with fp32 atomics, so the outputs must be zero (or hold the value to add to; ga_colstats then needs
+ * accumulate = 1) and the summation order is not fixed; with the workspace a second kernel reduces in a fixed order. */
 int ga_colstats(const void* x, float* sum, float* sumsq, float* partial, long long M, int C, long long ldx,
                 int accumulate, int dtype, ga_stream_t s);
 /* the same sums of (x - pivot), pivot[c] = x[0,c] (written): BatchNorm statistics without the E[x^2] - E[x]^2 cancellation */
