@@ -33,7 +33,11 @@ GA_LAM = -0.8
 # aggregate in `value`, so the line carries the training aggregate, `per_gpu` = value / n_gpus, and the roofline objects
 METRIC = 'train images/sec, whole job (BASELINE.json metric: train/infer images/sec/GPU at 1/2/4/8 B200 (224^2) + % roofline; per_gpu = value / n_gpus)'
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same call sites (profiles/)
-NCU_TRAFFIC = {('ga_gemm', (802816, 384, 96, 'gelu')): 1333.5e6, ('ga_gemm', (802816, 384, 96, 'mul')): 1360.3e6}     # + dwconv entries below
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the same call sites
+# (profiles/r02_ncu_gemm_epilogue.txt, profiles/r02_ncu_dwconv3.txt)
+NCU_TRAFFIC = {('ga_gemm', (802816, 384, 96, 'gelu')): 1334.0e6, ('ga_gemm', (802816, 384, 96, 'mul')): 1353.0e6,
+               ('ga_dwconv7_bwd2', (256, 56, 56, 96)): 1194.6e6, ('ga_dwconv7_bwd3', (256, 56, 56, 96)): 1194.6e6,
+               ('ga_dwconv7_bwd2', (256, 14, 14, 384)): 264.0e6, ('ga_dwconv7_bwd3', (256, 14, 14, 384)): 264.0e6}
 KERNEL_OF = {'ga_gemm': 'tc::gemm_tc2_kernel (tcgen05 persistent GEMM)', 'ga_dwconv7_ln_fwd': 'dw::dwconv7 forward (dw7x7 + bias + LayerNorm)',
              'ga_dwconv7_bwd2': 'dw3::dwconv7_bwd3_kernel (fused depthwise 7x7 backward: data gradient + residual + bf16 shadow, weight and bias gradient)',
              'ga_dwconv7_bwd3': 'dw3::dwconv7_bwd3_kernel (fused depthwise 7x7 backward: data gradient + residual + bf16 shadow, weight and bias gradient)'}

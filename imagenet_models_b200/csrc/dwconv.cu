@@ -567,8 +567,17 @@ extern "C" int ga_dwconv7_bwd3(const void* dconv, const void* x, const void* dre
   // GA_DW_BWD3 = 0 (read once) keeps the two first-generation kernels for A/B timing (scripts/kernel_bench.py)
   static const int bwd3_mode = [] { const char* e = getenv("GA_DW_BWD3"); return e ? atoi(e) : -1; }();
   const bool bwd3 = bwd3_mode != 0;
-  if (dtype == GA_BF16 && dx && x && dw_partial && (dw49c || dbias) && ((uintptr_t)x & 15) == 0 && dw_v3_enabled() && bwd3) {
+  // dw_partial == NULL with dbias == dw49c + 49 C (one [50][C] accumulator, as the callers' gradient slabs are laid out):
+  // the fused kernel adds its per-CTA sums straight into dw49c / dbias (fp32 atomics, ACCUMULATING: the caller zeroes them) --
+  // no workspace clear and no reduction launch.  Only the fused bf16 kernel supports it; otherwise GA_ERR_UNSUPPORTED.
+  const bool direct = !dw_partial && dw49c && dbias == dw49c + (size_t)49 * C;
+  if (dtype == GA_BF16 && dx && x && (dw_partial || direct) && (dw49c || dbias) && ((uintptr_t)x & 15) == 0 && dw_v3_enabled() && bwd3) {
     // one fused kernel: data gradient (+ residual, + bf16 shadow), weight gradient and bias gradient from one staged dconv halo
+    if (direct) {
+      rc = ga_dwconv7_bwd_v3(dconv, x, dres, w49c, dx, dx_shadow, shadow_rowscale, dw49c, 1, B, H, W, C, res_dtype, st);
+      GA_REQUIRE(rc != GA_ERR_UNSUPPORTED, GA_ERR_UNSUPPORTED, "ga_dwconv7_bwd: this shape needs the partial workspace");
+      return rc;
+    }
     const int nparts = ga_dwconv7_bwd_parts(B, H, W, C);
     cudaMemsetAsync(dw_partial, 0, (size_t)nparts * 50 * C * sizeof(float), st);
     rc = ga_dwconv7_bwd_v3(dconv, x, dres, w49c, dx, dx_shadow, shadow_rowscale, dw_partial, nparts, B, H, W, C, res_dtype, st);
@@ -581,6 +590,7 @@ extern "C" int ga_dwconv7_bwd3(const void* dconv, const void* x, const void* dre
     if (rc != GA_ERR_UNSUPPORTED) return rc;
   }
   GA_REQUIRE(!shadow_rowscale, GA_ERR_UNSUPPORTED, "ga_dwconv7_bwd3: the scaled shadow is written by the fused bf16 kernel only");
+  GA_REQUIRE(dw_partial || !(dw49c || dbias), GA_ERR_UNSUPPORTED, "ga_dwconv7_bwd: this configuration needs the partial workspace");
   if (dx) {
     dw::Plan p;
     int nslice = 1;

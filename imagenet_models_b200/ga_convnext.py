@@ -410,7 +410,14 @@ class GA_ConvNeXt(nn.Module):
         conv, bn = self.gram_contraction[k][0], self.gram_contraction[k][1]
         g = ops.linear(f, conv.weight.reshape(self.gram_dim, f.shape[1]), conv.bias)
         g = ops.batchnorm(g, _params(bn), self.training)
-        g, _, _, _ = self.gram_layer[k].run(g, None, geom, g.dtype, g.dtype)
+        aux = self.__dict__.get('_gram_layer_aux')
+        nblk = len(self.gram_layer[k].blocks)
+        if aux is not None and g.dtype == torch.bfloat16 and len(aux[0]) == nblk * len(self.gram_layer):
+            sc = aux[0][k * nblk:(k + 1) * nblk]
+            pr = aux[1][k * nblk:(k + 1) * nblk] if aux[1] is not None else None
+            g, _, _, _ = self.gram_layer[k].run(g, None, geom, g.dtype, g.dtype, scales=sc, preps=pr)
+        else:
+            g, _, _, _ = self.gram_layer[k].run(g, None, geom, g.dtype, g.dtype)
         return g
 
     def _heads(self, f, geom):
@@ -459,9 +466,10 @@ class GA_ConvNeXt(nn.Module):
         return outs
 
     def forward(self, x):
-        f, geom = self.forward_features(x)
-        with torch.autocast('cuda', enabled=False):
-            return self._heads(f, geom)
+        with ops.collect_bn_counters():
+            f, geom = self.forward_features(x)
+            with torch.autocast('cuda', enabled=False):
+                return self._heads(f, geom)
 
 
 def _create_convnext(variant, pretrained=False, **kwargs):

@@ -257,9 +257,10 @@ class GA_CSWinTransformer(nn.Module):
         return (ys if ys is not None else y), (Bn, Ro, Ro)
 
     def forward(self, x):
-        f, geom = self.forward_features(x)
-        with torch.autocast('cuda', enabled=False):
-            return self._heads(f, geom)
+        with ops.collect_bn_counters():
+            f, geom = self.forward_features(x)
+            with torch.autocast('cuda', enabled=False):
+                return self._heads(f, geom)
 
 
 @register_model

@@ -317,7 +317,7 @@ class ConvNeXt(nn.Module):
 
     def forward(self, x):
         T = self._dtype()                                   # read the autocast state before disabling it for the glue ops
-        with torch.autocast('cuda', enabled=False):
+        with torch.autocast('cuda', enabled=False), ops.collect_bn_counters():
             feats, geoms = self.forward_features(x, T)
             return self.head.run(feats, geoms, T, self.training)
 

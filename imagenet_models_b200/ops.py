@@ -554,19 +554,22 @@ class ConvNeXtBlockFn(Function):
                 'ga_ln_bwd_rows')
         dx = torch.empty(M, Cc, dtype=RT, device=dev)
         dxs = torch.empty(M, Cc, dtype=T, device=dev) if RT != T else None
-        parts = lib.ga_dwconv7_bwd_parts(Bn, H, W_, Cc)
-        ws = workspace(parts * 50 * Cc, dev, 'dwconv')
+        # Preferred first: the shadow leaves the kernel already multiplied by the consumer's DropPath factors (ps_prev), and the
+        # weight / bias sums go straight into d49 / ddwb (one [50][C] piece of the zeroed slab) without a workspace; each
+        # variant the library does not support for this shape answers GA_ERR_UNSUPPORTED before launching anything.
         ps_prev = ctx.ps_prev if dxs is not None else None
-        rc = GA_ERR_UNSUPPORTED_
-        if ps_prev is not None:          # the shadow leaves the kernel already multiplied by the consumer's DropPath factors
-            rc = lib.ga_dwconv7_bwd3(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(dxs), L.ptr(ps_prev), L.ptr(d49),
+        variants = [(ps, direct) for ps in ((ps_prev, None) if ps_prev is not None else (None,))
+                    for direct in ((True, False) if ATOMIC_REDUCE else (False,))]
+        for ps, direct in variants:
+            ws = None
+            if not direct:
+                ws = workspace(lib.ga_dwconv7_bwd_parts(Bn, H, W_, Cc) * 50 * Cc, dev, 'dwconv')
+            rc = lib.ga_dwconv7_bwd3(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(dxs), L.ptr(ps), L.ptr(d49),
                                      L.ptr(ddwb), L.ptr(ws), Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream())
-            if rc not in (0, GA_ERR_UNSUPPORTED_):
+            if rc != GA_ERR_UNSUPPORTED_ or (ps, direct) == variants[-1]:
                 L.check(rc, 'ga_dwconv7_bwd3')
-        if rc == GA_ERR_UNSUPPORTED_:
-            ps_prev = None
-            L.check(lib.ga_dwconv7_bwd2(L.ptr(dconv), L.ptr(src), L.ptr(dy), L.ptr(w49c), L.ptr(dx), L.ptr(dxs), L.ptr(d49), L.ptr(ddwb),
-                                        L.ptr(ws), Bn, H, W_, Cc, L.dt(dconv), L.dt(dx), L.stream()), 'ga_dwconv7_bwd')
+                ps_prev = ps
+                break
         _offer_shadow(dx, dxs, ps_prev)
         d_dw_w = d49.view(49, Cc).t().reshape(Cc, 1, 7, 7)
         return (dx, None, d_dw_w, ddwb, dlnw, dlnb, dw1.view(Hd, Cc), db1, dw2.view(Cc, Hd), db2, dgam, None, None, None, None, None, None)
@@ -906,12 +909,45 @@ def scale_rows(x, scale, rows_per_scale):
     return ScaleRowsFn.apply(x, scale, rows_per_scale)
 
 
-def batchnorm(x, bn, training, relu=False, xb=None, bnb=None):
-    """bn / bnb: dicts with weight, bias, running_mean, running_var, num_batches_tracked (reference key names)."""
+BN_COUNTERS = None      # a list while a model forward collects its BatchNorm counters (collect_bn_counters)
+
+
+class collect_bn_counters:
+    """with ops.collect_bn_counters(): ...   every train-mode ops.batchnorm inside advances its num_batches_tracked in ONE
+    multi-tensor launch at exit instead of one add kernel per BatchNorm (14 per GA-ConvNeXt step)."""
+
+    def __enter__(self):
+        global BN_COUNTERS
+        self.prev, BN_COUNTERS = BN_COUNTERS, []
+        return self
+
+    def __exit__(self, *exc):
+        global BN_COUNTERS
+        cur, BN_COUNTERS = BN_COUNTERS, self.prev
+        bump_counters(cur)
+        return False
+
+
+def bump_counters(counters):
+    """num_batches_tracked += 1 for every collected BatchNorm, one multi-tensor launch."""
+    if counters:
+        torch._foreach_add_(counters, 1)
+        counters.clear()
+
+
+def batchnorm(x, bn, training, relu=False, xb=None, bnb=None, counters=None):
+    """bn / bnb: dicts with weight, bias, running_mean, running_var, num_batches_tracked (reference key names).
+    counters: a list that collects the num_batches_tracked buffers to advance; the caller then advances all of them in one
+    launch (bump_counters) instead of one add per BatchNorm."""
     if training:
-        bn['num_batches_tracked'].add_(1)
-        if bnb is not None:
-            bnb['num_batches_tracked'].add_(1)
+        for d in (bn, bnb):
+            if d is not None:
+                if counters is None:
+                    counters = BN_COUNTERS
+                if counters is not None:
+                    counters.append(d['num_batches_tracked'])
+                else:
+                    d['num_batches_tracked'].add_(1)
     return BatchNormFn.apply(x, bn['weight'], bn['bias'], bn['running_mean'], bn['running_var'], xb,
                              bnb['weight'] if bnb else None, bnb['bias'] if bnb else None,
                              bnb['running_mean'] if bnb else None, bnb['running_var'] if bnb else None,

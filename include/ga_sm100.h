@@ -100,7 +100,9 @@ int ga_dwconv7_bwd2(const void* dconv, const void* x, const void* dres, const fl
                     int res_dtype, ga_stream_t s);
 /* same; shadow_rowscale [B] (may be NULL): dx_shadow = dx * shadow_rowscale[image] -- the DropPath factor of the block that consumes
  * the shadow as its backward GEMM operand (timm DropPath on the residual branch, ga_convnext.py:111), so that block needs no
- * separate row-scaling pass.  GA_ERR_UNSUPPORTED when the fused bf16 kernel does not take the shape (caller scales itself). */
+ * separate row-scaling pass.  GA_ERR_UNSUPPORTED when the fused bf16 kernel does not take the shape (caller scales itself).
+ * dw_partial == NULL with dbias == dw49c + 49 C: the per-CTA sums are added straight into dw49c / dbias (fp32 atomics; no workspace
+ * clear, no reduction launch); GA_ERR_UNSUPPORTED when the shape needs the workspace.  Nothing is launched before that answer. */
 int ga_dwconv7_bwd3(const void* dconv, const void* x, const void* dres, const float* w49c, void* dx, void* dx_shadow,
                     const float* shadow_rowscale, float* dw49c, float* dbias, float* dw_partial, int B, int H, int W, int C,
                     int dtype, int res_dtype, ga_stream_t s);
