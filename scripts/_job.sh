@@ -1,7 +1,5 @@
 cd /root/repo
-timeout 2400 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 900 python bench.py --steps 10 --warmup 3 --no-infer --no-cpu-baseline --sustained 0 > gpurun_out/bench13.log 2>&1
+GA_TEST_PROGRESS=/root/repo/gpurun_out/nccl_progress timeout 480 python -m pytest tests/test_ddp_nccl_gpu.py -x -q -m gpu > gpurun_out/nccl_test.log 2>&1
 echo rc=$?
-python -c "import json; d=json.loads([l for l in open('gpurun_out/bench13.log') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], d['gpu_launches'], d['e2e']['value'])"
-timeout 600 python scripts/profile_step.py --top 300 --out gpurun_out/step_profile_d.txt --sequence gpurun_out/step_sequence_d.txt > /dev/null 2>gpurun_out/prof_err.txt
-head -2 gpurun_out/step_profile_d.txt
+tail -5 gpurun_out/nccl_test.log
+cat gpurun_out/nccl_progress.rank0

@@ -41,8 +41,10 @@ def _batches(world):
     return [cases.ga_inputs_diverse(B_PER_RANK * world, seed=1000 + s) for s in range(STEPS)]
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, outdir):
     import time
+
+    import numpy as np
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       TORCH_NCCL_ASYNC_ERROR_HANDLING='0')
@@ -51,8 +53,16 @@ def _worker(rank, world, port, q):
     from imagenet_models_b200.engine import TrainEngine
     batches = _batches(world)
     out = {'rank': rank}
+    progress = os.environ.get('GA_TEST_PROGRESS')          # optional: a file prefix that receives one line per finished stage
+
+    def note(msg):
+        if progress:
+            with open(f'{progress}.rank{rank}', 'a') as f:
+                f.write(f'{time.time():.1f} {msg}\n')
+    note('process group up')
     try:
         for mode in MODES:
+            note(f'{mode}: start')
             m = _model()
             eng = TrainEngine(m, lr=LR, weight_decay=0.05, ema_decay=0.99, ga_lam=cases.GA_LAM, amp_dtype=None, cuda_graph=mode != 'eager',
                               graph_warmup=2, bucket_mb=25.0, ddp_in_graph=mode == 'graph+nccl')
@@ -63,29 +73,43 @@ def _worker(rank, world, port, q):
                 if first is None:
                     first = (eng.opt.state.grad / world).cpu().numpy()     # the optimizer folds 1/world into its gradient scale
             torch.cuda.synchronize()
-            out[mode] = {'grad0': first, 'flat': eng.opt.state.flat.cpu().numpy(), 'graph': eng._graph is not None,
-                         'nbuckets': len(eng.buckets.buckets)}
+            note(f'{mode}: {len(batches)} steps done')
+            # the arrays (190 MB each) go through files: a multiprocessing queue would still be feeding them through its pipe
+            # when this process takes its hard exit below
+            np.save(os.path.join(outdir, f'grad0_{mode}_{rank}.npy'), first)
+            np.save(os.path.join(outdir, f'flat_{mode}_{rank}.npy'), eng.opt.state.flat.cpu().numpy())
+            out[mode] = {'graph': eng._graph is not None, 'nbuckets': len(eng.buckets.buckets)}
     except Exception as e:  # noqa: BLE001  (report instead of leaving the peer in a collective for ever)
         out['error'] = repr(e)
+    note('results written: ' + ('error ' + out['error'] if 'error' in out else 'ok'))
     q.put(out)
-    time.sleep(3.0)            # let the queue's feeder thread hand the result over before the hard exit
+    time.sleep(2.0)            # let the queue's feeder thread hand the (small) result over before the hard exit
     os._exit(0)                # not destroy_process_group(): it blocks once a CUDA graph holds NCCL kernels (scripts/nccl_graph_probe.py)
 
 
 @pytest.mark.gpu
-def test_two_rank_nccl_steps_match_one_process_on_the_whole_batch():
+def test_two_rank_nccl_steps_match_one_process_on_the_whole_batch(tmp_path):
+    import numpy as np
     if torch.cuda.device_count() < 2:
         pytest.skip('needs two GPUs (gpurun --gpus 2)')
     world, port = 2, _free_port()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, str(tmp_path))) for r in range(world)]
     for p in procs:
         p.start()
-    outs = sorted([q.get(timeout=420) for _ in range(world)], key=lambda o: o['rank'])
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        outs = sorted([q.get(timeout=300) for _ in range(world)], key=lambda o: o['rank'])
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+            if p.is_alive():
+                p.kill()               # the exact processes this test started
     assert all('error' not in o for o in outs), [o.get('error') for o in outs]
+    for o in outs:
+        for mode in MODES:
+            o[mode]['grad0'] = np.load(tmp_path / f"grad0_{mode}_{o['rank']}.npy")
+            o[mode]['flat'] = np.load(tmp_path / f"flat_{mode}_{o['rank']}.npy")
     # single process, whole batch
     from imagenet_models_b200.engine import TrainEngine
     torch.cuda.set_device(0)
