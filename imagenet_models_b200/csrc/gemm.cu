@@ -26,6 +26,7 @@ struct EpiArgs {
   const void* Zin; long long ldz, z_bs; int zmode;
   int z_shadow;  // Z receives a bf16 copy of the final value instead of the pre-activation
   float* colsum;  // x act' epilogue only: colsum[n] += sum_m D[m,n] (the bias gradient of the layer whose dz this GEMM produces)
+  const void* ln_xhat; long long ld_xhat; const float* ln_rstd;   // fused LayerNorm backward of the output rows (EPI_LNBWD)
   int M, N;
 };
 
@@ -476,7 +477,8 @@ constexpr int EPI_C = 32;                 // columns per epilogue chunk (one tcg
 constexpr int ST_LD = EPI_C + 4;          // staging row pitch (floats): conflict-free float4 writes and reads
 
 enum { EPI_GENERIC = 0, EPI_BIAS_GELU_Z = 1, EPI_BIAS_GELU = 2, EPI_RES_F32_SHADOW = 3, EPI_ZIN_GELU = 4, EPI_PLAIN_BF16 = 5,
-       EPI_ACCUM = 6 };
+       EPI_ACCUM = 6, EPI_LNBWD = 7 };
+constexpr int LNBWD_XCH_BYTES = 2 * 4 * 4 * 32 * 2 * 4;     // [tile parity][row quadrant][column slice][row][2] fp32
 
 // one 32-row x 32-column chunk held in this warp's staging buffer -> global memory
 template <int EPI, bool FULL>
@@ -604,6 +606,57 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
   return csum;
 }
 
+// EPI_LNBWD: the GEMM produces dxhat (gradient w.r.t. a LayerNorm's normalised output, affine folded away) and the row's
+// LayerNorm backward   dconv = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat))   is applied before anything is written,
+// so dxhat never reaches HBM (ga_ln_bwd_rows re-read it and xhat: 3 x M x C x 2 bytes).  Needs the whole row in one tile
+// (N <= BN = 128).  Within a row quadrant the up-to-four warps that own the row's 32-column slices exchange their two partial
+// sums per row through shared memory (double-buffered by tile parity) and meet at a named barrier (ids 1..4, one per quadrant).
+__device__ __forceinline__ void epilogue_lnbwd(const EpiArgs& e, const float* st, float* xch, int lane, int q, int slice, int nlive,
+                                               int m_base, int n, const uint2* xraw, const float* rsv) {
+  const int cl = (lane & 7) * 4, r0 = lane >> 3;
+  const float* const stl = st + (r0 * ST_LD + cl);
+  float s1[8], s2[8];
+  float4 xh[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const float4 g = *reinterpret_cast<const float4*>(stl + it * (4 * ST_LD));
+    const uint2 u = xraw[it];
+    xh[it] = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
+    s1[it] = (g.x + g.y) + (g.z + g.w);
+    s2[it] = (g.x * xh[it].x + g.y * xh[it].y) + (g.z * xh[it].z + g.w * xh[it].w);
+  }
+#pragma unroll
+  for (int o = 1; o <= 4; o <<= 1) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      s1[it] += __shfl_xor_sync(0xffffffffu, s1[it], o);
+      s2[it] += __shfl_xor_sync(0xffffffffu, s2[it], o);
+    }
+  }
+  float2* const mine = reinterpret_cast<float2*>(xch) + ((q * 4 + slice) * 32);
+  if ((lane & 7) == 0) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) mine[r0 + 4 * it] = make_float2(s1[it], s2[it]);
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "r"(32 * nlive) : "memory");
+  const float2* const quad = reinterpret_cast<const float2*>(xch) + (q * 4) * 32;
+  const float invN = 1.f / (float)e.N;
+  const long long eoff = (long long)(m_base + r0) * e.ldd + n;
+  bf16* const d16 = (bf16*)e.D + eoff;
+  const uint32_t dstep = 4u * (uint32_t)e.ldd;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = r0 + 4 * it;
+    float t1 = 0.f, t2 = 0.f;
+    for (int sl = 0; sl < nlive; ++sl) { const float2 v = quad[sl * 32 + row]; t1 += v.x; t2 += v.y; }
+    if (m_base + row >= e.M || n >= e.N) continue;
+    const float m1 = t1 * invN, m2 = t2 * invN, rs = rsv[it];
+    const float4 g = *reinterpret_cast<const float4*>(stl + it * (4 * ST_LD));
+    st4(d16 + (uint32_t)it * dstep, make_float4(rs * (g.x - m1 - xh[it].x * m2), rs * (g.y - m1 - xh[it].y * m2),
+                                                 rs * (g.z - m1 - xh[it].z * m2), rs * (g.w - m1 - xh[it].w * m2)));
+  }
+}
+
 // Tile walk of the persistent kernel without per-tile divisions: t = blockIdx.x + k * gridDim.x decomposed as (n_t fastest,
 // m_t, z) and advanced by the decomposition of gridDim.x with carries.  Four integer divisions per tile and thread (~100
 // instructions) were a quarter of the epilogue warps' instruction stream (profiles/r02_ncu_gemm_epilogue.txt).
@@ -638,7 +691,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
   constexpr int SLICE = BN / 4;                // columns per epilogue warp
   uint8_t* stage_base = smem;
   float* staging = (float*)(smem + (size_t)p.stages * STAGE_BYTES);            // EPI_WARPS x 32 x ST_LD floats
-  uint64_t* full_bar = (uint64_t*)((uint8_t*)staging + EPI_WARPS * 32 * ST_LD * 4);
+  float* xch_base = (float*)((uint8_t*)staging + EPI_WARPS * 32 * ST_LD * 4);  // EPI_LNBWD only (LNBWD_XCH_BYTES)
+  uint64_t* full_bar = (uint64_t*)((uint8_t*)xch_base + (EPI == EPI_LNBWD ? LNBWD_XCH_BYTES : 0));
   uint64_t* empty_bar = full_bar + 8;
   uint64_t* tmem_full = empty_bar + 8;         // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
@@ -807,6 +861,21 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
           for (int c = 1; c < NCH; ++c) load_z(tc, c, zraw[c]);
         }
       }
+      // EPI_LNBWD: this warp's xhat values (the layout of the store phase) and the rows' rstd, fetched before the accumulator wait
+      uint2 xraw[EPI == EPI_LNBWD ? 8 : 1];
+      float rsv[EPI == EPI_LNBWD ? 8 : 1];
+      if (EPI == EPI_LNBWD) {
+        const int m_first = m0 + q * 32 + (lane >> 3);
+        const int ncol = n0 + slice * SLICE + (lane & 7) * 4;
+        const bf16* xp = (const bf16*)e.ln_xhat + ((long long)m_first * e.ld_xhat + ncol);
+        const uint32_t xstep = 4u * (uint32_t)e.ld_xhat;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const bool ok = (m_first + 4 * it < e.M) && (ncol < e.N);
+          xraw[it] = ok ? *reinterpret_cast<const uint2*>(xp + (uint32_t)it * xstep) : make_uint2(0u, 0u);
+          rsv[it] = (m_first + 4 * it < e.M) ? e.ln_rstd[m_first + 4 * it] : 0.f;
+        }
+      }
       mbar_wait_backoff(&tmem_full[buf], bph, p.wait_ns);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16);
@@ -830,6 +899,12 @@ __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1) gemm_tc2_kernel(const 
         }
         if (!live) continue;
         __syncwarp();
+        if (EPI == EPI_LNBWD) {        // one chunk per warp (BN = 128); slices with columns >= N are not live and skip the barrier
+          epilogue_lnbwd(e, st, xch_base + (lt & 1) * (LNBWD_XCH_BYTES / 8), lane, q, slice, (e.N + SLICE - 1) / SLICE, m0 + q * 32,
+                         n0 + col0 + (lane & 7) * 4, xraw, rsv);
+          __syncwarp();
+          continue;
+        }
         float4 cs;
         if (m0 + q * 32 + 32 <= e.M) cs = epilogue_chunk<EPI, true>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4, EPI == EPI_ZIN_GELU ? zraw[c] : nullptr);
         else cs = epilogue_chunk<EPI, false>(e, st, lane, batch, m0 + q * 32, n0 + col0 + (lane & 7) * 4, EPI == EPI_ZIN_GELU ? zraw[c] : nullptr);
@@ -957,7 +1032,7 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.splits = splits;
   constexpr int STAGE_BYTES = (BM + BN) * BK * 2;
-  constexpr size_t FIXED = 1024 + (size_t)EPI_WARPS * 32 * ST_LD * 4 + 256;
+  constexpr size_t FIXED = 1024 + (size_t)EPI_WARPS * 32 * ST_LD * 4 + 256 + (EPI == EPI_LNBWD ? LNBWD_XCH_BYTES : 0);
   int stages = (int)((225 * 1024 - FIXED) / STAGE_BYTES);
   static int stages_env = -1;
   if (stages_env < 0) { const char* sv = getenv("GA_GEMM_STAGES"); stages_env = sv ? atoi(sv) : 0; }
@@ -1022,6 +1097,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
   e.R = g->R; e.ldr = g->ldr; e.r_bs = g->r_bs;
   e.Zin = g->Zin; e.ldz = g->ldz; e.z_bs = g->z_bs; e.zmode = g->zmode; e.z_shadow = g->z_shadow;
   e.colsum = g->colsum;
+  e.ln_xhat = g->ln_xhat; e.ld_xhat = g->ld_xhat; e.ln_rstd = g->ln_rstd;
   e.M = g->M; e.N = g->N;
 
   bool a_mn = false, b_mn = false;
@@ -1057,6 +1133,13 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
     if (((g->N & 3) == 0) && ((g->ldd & 3) == 0) && e.d_cs == 1 && !v1_env && wide && a_mn && b_mn && g->accumulate &&
         ((uintptr_t)g->D & 15) == 0 && (g->d_bs & 3) == 0)
       epi = tc::EPI_ACCUM;
+    if (g->ln_xhat) {
+      GA_REQUIRE(epi == tc::EPI_PLAIN_BF16 && !g->bias && g->N <= 128 && g->batch == 1 && g->ln_rstd && (g->ld_xhat & 3) == 0 &&
+                     ((uintptr_t)g->ln_xhat & 7) == 0,
+                 GA_ERR_UNSUPPORTED, "ga_gemm: the fused LayerNorm backward needs a plain bf16 GEMM with the whole row in one tile (32 < N <= 128, N %% 4 == 0)");
+      if (b_mn) return tc::launch2<128, false, true, tc::EPI_LNBWD>(g, e, st);
+      return tc::launch2<128, false, false, tc::EPI_LNBWD>(g, e, st);
+    }
 #define GA_TC2(BN_, AM, BM_, EP) return tc::launch2<BN_, AM, BM_, EP>(g, e, st)
 #define GA_TC_BN(AM, BM_, EP) { if (wide256) GA_TC2(256, AM, BM_, EP); else GA_TC2(128, AM, BM_, EP); }
     GA_REQUIRE(!g->colsum || (epi == tc::EPI_ZIN_GELU && wide && !v1_env && g->batch == 1 && (((uintptr_t)g->colsum) & 15) == 0),
@@ -1086,6 +1169,7 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
 #undef GA_TC_CASE
   }
   GA_REQUIRE(!g->colsum, GA_ERR_UNSUPPORTED, "ga_gemm: colsum is fused only into the tcgen05 x act' epilogue");
+  GA_REQUIRE(!g->ln_xhat, GA_ERR_UNSUPPORTED, "ga_gemm: the fused LayerNorm backward exists on the tcgen05 path only");
   if (g->backend_used) *g->backend_used = GA_BACKEND_SIMT;
   dim3 grid((g->M + 63) / 64, (g->N + 63) / 64, g->batch);
   GA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, GA_ERR_SHAPE, "ga_gemm(simt): grid too large");

@@ -39,6 +39,7 @@ class GaGemm(C.Structure):
         ('backend', C.c_int), ('splits', C.c_int), ('z_shadow', C.c_int),
         ('backend_used', C.POINTER(C.c_int)),
         ('colsum', C.c_void_p),
+        ('ln_xhat', C.c_void_p), ('ld_xhat', C.c_longlong), ('ln_rstd', C.c_void_p),
     ]
 
 

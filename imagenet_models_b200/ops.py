@@ -81,6 +81,7 @@ def _zeros(n, device):
 # The additions commute only up to rounding, so the last bits vary between runs; GA_ATOMIC_REDUCE=0 restores the two-kernel
 # deterministic order.
 ATOMIC_REDUCE = os.environ.get('GA_ATOMIC_REDUCE', '1') == '1'
+FUSE_LN_BWD = os.environ.get('GA_FUSE_LN_BWD', '1') == '1'      # LayerNorm backward inside the dxhat GEMM where the row fits one tile
 
 
 class ZeroArena:
@@ -142,12 +143,14 @@ RELU_TAP = None   # tests set this to a list: every ReLU appends (kind, 0/1 deci
 
 def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None, rowscale=None, rows_per_scale=1,
          residual=None, zin=None, zmode=ACT_NONE, alpha=1.0, accumulate=False, out_dtype=None, backend=L.BACKEND_AUTO,
-         splits=0, shadow=None, colsum=None):
+         splits=0, shadow=None, colsum=None, ln_bwd=None):
     """D[b,m,n] = epi(alpha * sum_k A[b,m,k] * B[b,n,k]);  A:[M,K]|[b,M,K], B:[N,K]|[b,N,K], arbitrary strides.
 
     A batch stride of 0 (expanded tensor) broadcasts that operand.  `out` may be any strided [.., M, N] view.
     save_z: True -> also return the pre-activation; 'grad' -> return act'(pre-activation) instead (apply it in backward
     with zin=..., zmode=ACT_MUL: the derivative is evaluated once, next to the activation, where exp / rcp are shared).
+    ln_bwd=(xhat [M,N], rstd [M]): the product is the gradient w.r.t. a LayerNorm's normalised rows and the LayerNorm backward
+    is applied in the epilogue (raises GaError code 4 = unsupported when the library cannot fuse it for this shape).
     """
     batched = A.dim() == 3 or B.dim() == 3
     A3 = A if A.dim() == 3 else A.unsqueeze(0)
@@ -214,6 +217,10 @@ def gemm(A, B, out=None, *, bias=None, act=ACT_NONE, save_z=False, colscale=None
     if shadow is not None:                       # bf16 copy of the final value, same row layout as D
         assert save_z is False and shadow.dtype == torch.bfloat16 and shadow.stride() == out.stride()
         g.Z, g.z_shadow = shadow.data_ptr(), 1
+    if ln_bwd is not None:
+        xh_, rs_ = ln_bwd
+        assert xh_.dtype == A3.dtype and xh_.shape == (M, N) and xh_.stride(1) == 1 and rs_.dtype == torch.float32 and rs_.numel() == M
+        g.ln_xhat, g.ld_xhat, g.ln_rstd = xh_.data_ptr(), xh_.stride(0), rs_.data_ptr()
     if colsum is not None:                       # fp32 [N], zeroed by the caller: += column sums of D (x act' epilogue only)
         assert colsum.dtype == torch.float32 and colsum.numel() == N and colsum.is_contiguous()
         g.colsum = colsum.data_ptr()
@@ -547,11 +554,16 @@ class ConvNeXtBlockFn(Function):
         gemm(dz.t(), xhat.t(), G1.view(Hd, Cc), accumulate=True)
         L.check(lib.ga_linear_grad_finalize(L.ptr(G1), L.ptr(s1), L.ptr(w1), None, None, L.ptr(ln_w), L.ptr(ln_b), L.ptr(dw1),
                                             L.ptr(db1), None, L.ptr(dlnw), L.ptr(dlnb), Hd, Cc, L.stream()), 'linear_grad_finalize')
-        dxhat = gemm(dz, w1f.t())
-        del dz
-        dconv = torch.empty(M, Cc, dtype=T, device=dev)
-        L.check(lib.ga_ln_bwd_rows(L.ptr(dxhat), L.ptr(xhat), L.ptr(rstd), L.ptr(dconv), L.ll(M), Cc, L.dt(dconv), L.stream()),
-                'ga_ln_bwd_rows')
+        if T == torch.bfloat16 and 32 < Cc <= 128 and Cc % 4 == 0 and FUSE_LN_BWD:
+            # the row fits one GEMM tile: LayerNorm backward in the epilogue, dxhat never written (gemm.cu EPI_LNBWD)
+            dconv = gemm(dz, w1f.t(), ln_bwd=(xhat, rstd))
+            del dz
+        else:
+            dxhat = gemm(dz, w1f.t())
+            del dz
+            dconv = torch.empty(M, Cc, dtype=T, device=dev)
+            L.check(lib.ga_ln_bwd_rows(L.ptr(dxhat), L.ptr(xhat), L.ptr(rstd), L.ptr(dconv), L.ll(M), Cc, L.dt(dconv), L.stream()),
+                    'ga_ln_bwd_rows')
         dx = torch.empty(M, Cc, dtype=RT, device=dev)
         dxs = torch.empty(M, Cc, dtype=T, device=dev) if RT != T else None
         # Preferred first: the shadow leaves the kernel already multiplied by the consumer's DropPath factors (ps_prev), and the

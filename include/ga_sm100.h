@@ -71,6 +71,10 @@ typedef struct GaGemm {
   int* backend_used; /* optional out: GA_BACKEND_* this call ran on */
   float* colsum;  /* optional, with Zin on the tcgen05 path only: colsum[n] += sum_m D[m,n] (fp32, 16-byte aligned; the bias
                      gradient of the layer whose dz this GEMM produces); GA_ERR_UNSUPPORTED when it cannot be fused */
+  /* optional fused LayerNorm backward of the output rows (the dxhat GEMM of a ConvNeXt block, ga_convnext.py:105-107 backward):
+     D = rstd * (P - mean_n(P) - xhat * mean_n(P * xhat)) with P = A B^T, xhat [M,N] in the operand dtype (row pitch ld_xhat),
+     rstd [M] fp32.  tcgen05 path, bf16, 32 < N <= 128, no bias / activation; otherwise GA_ERR_UNSUPPORTED (nothing launched) */
+  const void* ln_xhat; long long ld_xhat; const float* ln_rstd;
 } GaGemm;
 int ga_gemm(const GaGemm* p, ga_stream_t s);
 

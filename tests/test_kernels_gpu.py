@@ -683,3 +683,33 @@ def test_weight_shadows_follow_the_optimizer():
     st.refresh_shadows()
     s3 = ops.cast_like(w, torch.bfloat16)
     assert lo <= s3.data_ptr() < hi and torch.equal(s3, w.detach().bfloat16()) and st.shadows_current()
+
+
+@pytest.mark.parametrize('M,N,K', [(1000, 96, 384), (4096, 128, 512), (130, 64, 256), (802816 // 16, 96, 384)])
+@pytest.mark.parametrize('b_mn', [True, False])
+def test_gemm_fused_layernorm_backward(M, N, K, b_mn):
+    """ga_gemm with ln_xhat / ln_rstd (EPI_LNBWD): D = LN'(A B^T) against the unfused pair (GEMM, then ga_ln_bwd_rows) and an
+    fp32 torch evaluation of the same formula.  Rows beyond the last full 128-row tile, 2..4 live column slices, both operand
+    layouts of B (the block's backward passes W1'.t(), an MN-major view)."""
+    torch.manual_seed(M + N)
+    bf = torch.bfloat16
+    A = torch.randn(M, K, device=DEV, dtype=bf)
+    W = (torch.randn(K, N, device=DEV) * 0.05).to(bf)            # [K, N]: W.t() is the MN-major [N, K] operand
+    Bop = W.t() if b_mn else W.t().contiguous()
+    xhat = torch.randn(M, N, device=DEV, dtype=bf)
+    rstd = torch.rand(M, device=DEV) + 0.5
+    fused = ops.gemm(A, Bop, ln_bwd=(xhat, rstd))
+    assert L.BACKEND_TCGEN05 == ops.LAST_GEMM_BACKEND
+    P = ops.gemm(A, Bop)                                          # bf16-rounded product, as the unfused path stores it
+    unfused = torch.empty_like(P)
+    L.check(L.load().ga_ln_bwd_rows(L.ptr(P), L.ptr(xhat), L.ptr(rstd), L.ptr(unfused), L.ll(M), N, L.dt(P), L.stream()), 'ga_ln_bwd_rows')
+    Pf = A.float() @ W.float()
+    xf = xhat.float()
+    ref = rstd[:, None] * (Pf - Pf.mean(1, keepdim=True) - xf * (Pf * xf).mean(1, keepdim=True))
+    err_f = ((fused.float() - ref).norm() / ref.norm()).item()
+    err_u = ((unfused.float() - ref).norm() / ref.norm()).item()
+    assert err_f <= 4e-3, err_f                                   # one bf16 rounding of the result
+    assert err_f <= err_u * 1.05 + 1e-4, (err_f, err_u)           # never worse than the path that rounds the product first
+    with pytest.raises(L.GaError):                                # a row wider than one tile cannot be fused
+        ops.gemm(torch.randn(256, 64, device=DEV, dtype=bf), torch.randn(192, 64, device=DEV, dtype=bf),
+                 ln_bwd=(torch.randn(256, 192, device=DEV, dtype=bf), torch.rand(256, device=DEV)))
