@@ -375,8 +375,8 @@ extern "C" int ga_cswin_attn_bwd(const void* dout, const void* qkv, const void* 
                           bper, nchunk, st);
 #define GA_ATTN_BWD(T, NT)                                                                                                   \
   do {                                                                                                                       \
-    static bool attr = false;                                                                                                \
-    if (!attr) { cudaFuncSetAttribute(cswin_attn_bwd_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; } \
+    static GaPerDevice attr;                                                                                                 \
+    if (ga_first_on_device(attr)) cudaFuncSetAttribute(cswin_attn_bwd_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
     cswin_attn_bwd_kernel<T, NT><<<grid, NT, smem, st>>>((const T*)dout, (const T*)qkv, (const T*)out, lse, lepe_w, lepe_b, (T*)dqkv, \
                                                          dlepe_w, dlepe_b, B, bper, R, C, split, nbr, ldq, ldo, lddo, lddq, scale); \
   } while (0)
@@ -1076,8 +1076,8 @@ int ga_attn_fwd_tc5(const void* qkv, const float* lw, const float* lb, void* out
   rc = ga_tensor_map(&tm1, GA_BF16, 4, qkv, dims, strides, box1, 1);
   if (rc) return rc;
   const size_t smem = 1024 + 5 * (size_t)tc5::TILE_BYTES + (10 * 64) * sizeof(float) + 64;
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tc5::attn_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  static GaPerDevice attr;
+  if (ga_first_on_device(attr)) cudaFuncSetAttribute(tc5::attn_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int hb = C / nbr / HD, hp = (hb + 1) / 2;
   const dim3 grid(nbr == 1 ? hp : 2 * (R / split) * hp, B);      // one CTA per pair of heads
   tc5::attn_fwd_tc5_kernel<<<grid, 256, smem, st>>>(tm0, tm1, lw, lb, (bf16*)out, lse, R, C, split, nbr, ldo, scale * LOG2E);

@@ -18,6 +18,10 @@ typedef __nv_bfloat16 bf16;
 void ga_set_error(const char* fmt, ...);
 int ga_check_launch(const char* what);
 int ga_num_sms();
+// per call site, per device "first time" flag: opt-ins such as cudaFuncAttributeMaxDynamicSharedMemorySize are per device,
+// so a process that drives several GPUs must repeat them on each
+struct GaPerDevice { bool done[64] = {}; };
+bool ga_first_on_device(GaPerDevice& s);
 void ga_count_launch();
 // cached cuTensorMapEncodeTiled: rank<=5, dims/box innermost first, strides in BYTES for dims 1..rank-1
 struct CUtensorMap_st;

@@ -986,11 +986,9 @@ static int launch(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   p.lbo_a = A_MN ? 64 * BK * 2 : 16; p.sbo_a = 1024;
   p.lbo_b = B_MN ? 64 * BK * 2 : 16; p.sbo_b = 1024;
   size_t smem = 1024 + (size_t)stages * STAGE_BYTES + 4 * 32 * STAGE_LD * 4 + 256;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static GaPerDevice attr_once;
+  if (ga_first_on_device(attr_once))
     cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_done = true;
-  }
   dim3 grid(mt, nt, g->batch * splits);
   gemm_tc_kernel<BN, A_MN, B_MN><<<grid, 192, smem, st>>>(ma, mb, p, e);
   ga_count_launch();
@@ -1046,11 +1044,9 @@ static int launch2(const GaGemm* g, const EpiArgs& e, cudaStream_t st) {
   p.lbo_a = A_MN ? 64 * BK * 2 : 16; p.sbo_a = 1024;
   p.lbo_b = B_MN ? 64 * BK * 2 : 16; p.sbo_b = 1024;
   const size_t smem = FIXED + (size_t)stages * STAGE_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static GaPerDevice attr_once;
+  if (ga_first_on_device(attr_once))
     cudaFuncSetAttribute(gemm_tc2_kernel<BN, A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_done = true;
-  }
   const long long total = (long long)mt * nt * g->batch * splits;
   GA_REQUIRE(total < (1LL << 31), GA_ERR_SHAPE, "ga_gemm: too many tiles");
   const int grid = (int)(total < sms ? total : sms);

@@ -32,14 +32,23 @@ int ga_check_launch(const char* what) {
 }
 
 int ga_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = sms[dev & 63];
+  if (!v) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
   }
-  return sms;
+  return v;
+}
+bool ga_first_on_device(GaPerDevice& s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& d = s.done[dev & 63];
+  if (d) return false;
+  d = true;
+  return true;
 }
 
 extern "C" int ga_version(void) { return 100; }
