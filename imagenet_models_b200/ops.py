@@ -660,10 +660,13 @@ class ConvertFn(Function):
     @staticmethod
     def forward(ctx, x, dtype):
         ctx.src_dtype = x.dtype
+        ctx.set_materialize_grads(False)        # an unused copy must not cost a zero fill, a widening copy and an add
         return convert(x, dtype)
 
     @staticmethod
     def backward(ctx, dy):
+        if dy is None:                           # e.g. the shadow a ConvNeXt block reads: its gradient is folded into the stream's
+            return None, None
         return convert(rowmat(dy), ctx.src_dtype), None
 
 
