@@ -137,8 +137,11 @@ extern "C" int ga_layernorm_fwd(const void* x, const float* w, const float* b, v
 
 // backward.  xhat either given directly (x_is_hat) or recomputed from x, mean, rstd.
 // dx = rstd * (g - mean(g) - xhat*mean(g*xhat)),  g = dy*w ; per-CTA partial dw/db -> partial[blockIdx][2][C]
-template <typename T, int MAXV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+// HAS_PARAM = false (no affine gradients wanted) drops the per-lane dw / db accumulators: 214 -> ~100 registers at MAXV = 8, so
+// two CTAs fit an SM; MAXV <= 4 is capped at 80 registers for three.  The kernel keeps one row per warp in flight, so resident
+// warps are what hides the HBM latency (ncu-free reasoning from the launch list: 1.1-1.5 TB/s before).
+template <typename T, int MAXV, bool HAS_PARAM>
+__global__ void __launch_bounds__(256, MAXV <= 4 ? 3 : (HAS_PARAM ? 1 : 2)) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ w, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, T* __restrict__ dx,
                                                             float* __restrict__ partial, long long M, int C, long long lddy,
@@ -146,13 +149,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
                                                             float* __restrict__ adw, float* __restrict__ adb) {
   extern __shared__ float sacc[];  // [2][C] per CTA when partial != NULL
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  if (partial) {
+  if (HAS_PARAM) {
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
   }
-  float4 dwv[MAXV], dbv[MAXV];
+  float4 dwv[HAS_PARAM ? MAXV : 1], dbv[HAS_PARAM ? MAXV : 1];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) { dwv[i] = make_float4(0, 0, 0, 0); dbv[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < (HAS_PARAM ? MAXV : 1); ++i) { dwv[i] = make_float4(0, 0, 0, 0); dbv[i] = make_float4(0, 0, 0, 0); }
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long row_end = r0 + rows_per_cta;
   if (row_end > M) row_end = M;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
         float4 d = ld4(dy + row * lddy + c);
         float4 xv = ld4(x + row * ldx + c);
         if (!x_is_hat) { xv.x = (xv.x - mu) * rs; xv.y = (xv.y - mu) * rs; xv.z = (xv.z - mu) * rs; xv.w = (xv.w - mu) * rs; }
-        if (partial) {
+        if (HAS_PARAM) {
           dwv[i].x += d.x * xv.x; dwv[i].y += d.y * xv.y; dwv[i].z += d.z * xv.z; dwv[i].w += d.w * xv.w;
           dbv[i].x += d.x; dbv[i].y += d.y; dbv[i].z += d.z; dbv[i].w += d.w;
         }
@@ -198,7 +201,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
       }
     }
   }
-  if (partial) {
+  if (HAS_PARAM) {
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int c = (i * 32 + lane) * 4;
@@ -328,9 +331,13 @@ __global__ void __launch_bounds__(256) reduce_parts2_kernel(const float* __restr
 }
 
 static inline int row_parts(long long M) {
-  long long p = (M + 63) / 64;  // >= 64 rows per CTA
+  long long p = (M + 63) / 64;  // >= 64 rows per CTA ...
   const long long cap = 8LL * 148;
   if (p > cap) p = cap;
+  if (p < 148) {                // ... unless that leaves most SMs idle: the class-token rows of the heads ([256, 688]: 4 CTAs,
+    p = (M + 7) / 8;            // 36 us for 700 KB) get one row per warp instead
+    if (p > 148) p = 148;
+  }
   if (p < 1) p = 1;
   return (int)p;
 }
@@ -360,16 +367,26 @@ extern "C" int ga_layernorm_bwd(const void* dy, const void* x, const float* w, c
   const int rows_per_cta = (int)((M + parts - 1) / parts);
   const size_t smem = want_param ? (size_t)2 * C * sizeof(float) : 0;
   const int x_is_hat = (mean == nullptr);
+#define GA_LNB_WIDE(MV)                                                                                                        \
+  do {                                                                                                                         \
+    if (want_param)                                                                                                            \
+      layernorm_bwd_kernel<T, MV, true><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, partial, M, C, \
+                                                                                lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb);           \
+    else                                                                                                                       \
+      layernorm_bwd_kernel<T, MV, false><<<parts, 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, nullptr, M, C,  \
+                                                                              lddy, ldx, lddx, x_is_hat, rows_per_cta, nullptr, nullptr);     \
+  } while (0)
 #define GA_LNB_NARROW(LPR) layernorm_bwd_narrow_kernel<T, LPR, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb)
   DISPATCH_T(dtype, {
     if (C <= 32) GA_LNB_NARROW(8);
     else if (C <= 64) GA_LNB_NARROW(16);
     else if (C <= 128) GA_LNB_NARROW(32);
-    else if (C <= 512) layernorm_bwd_kernel<T, 4><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb);
-    else if (C <= 1024) layernorm_bwd_kernel<T, 8><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb);
-    else layernorm_bwd_kernel<T, 16><<<parts, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)x, w, mean, rstd, (T*)dx, want_param ? partial : nullptr, M, C, lddy, ldx, lddx, x_is_hat, rows_per_cta, adw, adb);
+    else if (C <= 512) GA_LNB_WIDE(4);
+    else if (C <= 1024) GA_LNB_WIDE(8);
+    else GA_LNB_WIDE(16);
   });
 #undef GA_LNB_NARROW
+#undef GA_LNB_WIDE
   int rc = launch_ok("layernorm_bwd");
   if (rc || !want_param || atomic_out) return rc;
   reduce_parts2_kernel<<<(2 * C + 31) / 32, 256, 0, (cudaStream_t)s>>>(partial, parts, 2 * C, dw, C, db, 1);
