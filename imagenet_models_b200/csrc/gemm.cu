@@ -477,7 +477,7 @@ constexpr int EPI_C = 32;                 // columns per epilogue chunk (one tcg
 constexpr int ST_LD = EPI_C + 4;          // staging row pitch (floats): conflict-free float4 writes and reads
 
 enum { EPI_GENERIC = 0, EPI_BIAS_GELU_Z = 1, EPI_BIAS_GELU = 2, EPI_RES_F32_SHADOW = 3, EPI_ZIN_GELU = 4, EPI_PLAIN_BF16 = 5,
-       EPI_ACCUM = 6, EPI_LNBWD = 7 };
+       EPI_ACCUM = 6, EPI_LNBWD = 7, EPI_PLAIN_F32 = 8 };
 constexpr int LNBWD_XCH_BYTES = 2 * 4 * 4 * 32 * 2 * 4;     // [tile parity][row quadrant][column slice][row][2] fp32
 
 // one 32-row x 32-column chunk held in this warp's staging buffer -> global memory
@@ -511,7 +511,7 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
   }
   if (n >= e.N) return csum;
   float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (EPI == EPI_BIAS_GELU_Z || EPI == EPI_BIAS_GELU || EPI == EPI_RES_F32_SHADOW || EPI == EPI_PLAIN_BF16) {
+  if (EPI == EPI_BIAS_GELU_Z || EPI == EPI_BIAS_GELU || EPI == EPI_RES_F32_SHADOW || EPI == EPI_PLAIN_BF16 || EPI == EPI_PLAIN_F32) {
     if (e.bias) bias4 = *reinterpret_cast<const float4*>(e.bias + (long long)batch * e.bias_bs + n);
   }
   if (EPI == EPI_RES_F32_SHADOW) {
@@ -598,6 +598,8 @@ __device__ __forceinline__ float4 epilogue_chunk(const EpiArgs& e, const float* 
         csum.x += v[0]; csum.y += v[1]; csum.z += v[2]; csum.w += v[3];
       } else if (EPI == EPI_PLAIN_BF16) {
         st4(d16 + off, make_float4(v[0] + bias4.x, v[1] + bias4.y, v[2] + bias4.z, v[3] + bias4.w));
+      } else if (EPI == EPI_PLAIN_F32) {
+        st4(d32 + off, make_float4(v[0] + bias4.x, v[1] + bias4.y, v[2] + bias4.z, v[3] + bias4.w));
       } else if (EPI == EPI_ACCUM) {
         atomicAdd(reinterpret_cast<float4*>(d32 + off), make_float4(v[0] * e.alpha, v[1] * e.alpha, v[2] * e.alpha, v[3] * e.alpha));
       }
@@ -1125,6 +1127,8 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
         epi = tc::EPI_ZIN_GELU;
       else if (!a_mn && bf_out && g->act == GA_ACT_NONE && plain)
         epi = tc::EPI_PLAIN_BF16;
+      else if (!a_mn && !bf_out && g->act == GA_ACT_NONE && plain && ((uintptr_t)g->D & 15) == 0 && (g->d_bs & 3) == 0)
+        epi = tc::EPI_PLAIN_F32;        // fp32 outputs of bf16 GEMMs: the heads' q / k / v / proj / fc linears, stem and downsample convs
     }
     if (((g->N & 3) == 0) && ((g->ldd & 3) == 0) && e.d_cs == 1 && !v1_env && wide && a_mn && b_mn && g->accumulate &&
         ((uintptr_t)g->D & 15) == 0 && (g->d_bs & 3) == 0)
@@ -1149,6 +1153,8 @@ extern "C" int ga_gemm(const GaGemm* g, ga_stream_t s) {
         case tc::EPI_ACCUM: GA_TC_BN(true, true, tc::EPI_ACCUM)
         case tc::EPI_PLAIN_BF16:
           if (b_mn) GA_TC_BN(false, true, tc::EPI_PLAIN_BF16) else GA_TC_BN(false, false, tc::EPI_PLAIN_BF16)
+        case tc::EPI_PLAIN_F32:
+          if (b_mn) GA_TC_BN(false, true, tc::EPI_PLAIN_F32) else GA_TC_BN(false, false, tc::EPI_PLAIN_F32)
         default: break;
       }
     }
