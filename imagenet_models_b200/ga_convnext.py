@@ -11,6 +11,7 @@ Reference lines are cited per method; construction order mirrors ga_convnext.py:
 """
 from __future__ import annotations
 
+import os
 import warnings
 from typing import List, Optional
 
@@ -455,6 +456,8 @@ class GA_ConvNeXt(nn.Module):
         q = torch.stack(qs).view(nb, Bn, 1, E)
         kvc = torch.stack(kvcs).view(nb, Bn, 1, 2 * E)
         o = ops.attnpool(q, kvc, kv_tok, HW, heads)                                # [nb, B, 1, E]
+        if self._can_batch_heads(T):
+            return self._heads_tail_batched(o, cls, T)
         outs = []
         for k in range(nb):
             blk = self.ga[k]
@@ -464,6 +467,49 @@ class GA_ConvNeXt(nn.Module):
             c = c + blk.gamma_2 * blk.mlp.run(h, T)
             outs.append(ops.linear(ops.to_dtype(c, T), self.fc[k].weight, self.fc[k].bias, out_dtype=torch.float32))
         return outs
+
+    def _can_batch_heads(self, T):
+        """The branch-batched class-token tail needs bf16 operands and 16-byte group pitches; GA_BATCH_HEADS=0 keeps the per-branch
+        form (the fp32 parity path always uses it)."""
+        if T != torch.bfloat16 or os.environ.get('GA_BATCH_HEADS', '1') != '1' or self.branches < 2:
+            return False
+        m = self.ga[0].mlp
+        g = m.groups
+        # group widths: 4-element multiples for the vector epilogues (172 = 688 / 4 is padded to a 16-byte pitch below)
+        return (m.fc1.in_channels // g) % 4 == 0 and (m.fc1.out_channels // g) % 8 == 0 and self.ga[0].attn.dim_embed % 8 == 0
+
+    def _heads_tail_batched(self, o, cls, T):
+        """Everything after the attention pooling (ga_convnext.py:240-248, 503) for all branches at once: the class tokens are
+        [B, C] rows, so per branch every Linear is a 12-CTA GEMM; stacked over the branches each layer is one grouped launch
+        forward, one for the data gradient and one for the weight gradient (ops.StackedLinearFn).  Per-branch parameters
+        (layer scales, norm2 affine) are stacked by torch and applied to the [nb, B, C] tensor."""
+        nb, Bn = o.shape[0], o.shape[1]
+        blks = list(self.ga)
+        Cc = cls[0].shape[1]
+        E = o.shape[-1]
+        c = torch.stack(cls)                                                       # [nb, B, C] fp32
+        t = ops.stacked_linear(ops.to_dtype(o.reshape(nb * Bn, E), T).view(nb, Bn, E), [b.attn.proj.weight for b in blks],
+                               [b.attn.proj.bias for b in blks], out_dtype=torch.float32)
+        c = torch.addcmul(c, torch.stack([b.gamma_1 for b in blks]).unsqueeze(1), t)
+        eps = blks[0].norm2.eps
+        h = ops.layernorm(c.view(nb * Bn, Cc), None, None, eps).view(nb, Bn, Cc)
+        h = torch.addcmul(torch.stack([b.norm2.bias for b in blks]).unsqueeze(1), h, torch.stack([b.norm2.weight for b in blks]).unsqueeze(1))
+        # GroupConvMlp: grouped 1x1 -> GELU -> channel shuffle -> grouped 1x1; groups of all branches side by side
+        g = blks[0].mlp.groups
+        hid = blks[0].mlp.fc1.out_channels
+        cg, hg = Cc // g, hid // g
+        a3 = torch.empty(nb * g, Bn, ops.pad8(cg), dtype=T, device=c.device)[:, :, :cg]
+        a3.view(nb, g, Bn, cg).copy_(h.view(nb, Bn, g, cg).permute(0, 2, 1, 3))
+        h1 = ops.stacked_linear(a3, [b.mlp.fc1.weight for b in blks], [b.mlp.fc1.bias for b in blks], act=GroupConvMlp.ACT, sub=g)
+        # channel_shuffle (ga_convnext.py:557-566): the second conv's group a reads hidden channels {b * g + a}
+        hrow = h1.view(nb, g, Bn, hg).permute(0, 2, 1, 3).reshape(nb, Bn, hg, g)   # rows [B, hid] per branch, viewed as (hg, g)
+        a3 = torch.empty(nb, g, Bn, hg, dtype=T, device=c.device).copy_(hrow.permute(0, 3, 1, 2)).view(nb * g, Bn, hg)
+        m = ops.stacked_linear(a3, [b.mlp.fc2.weight for b in blks], [b.mlp.fc2.bias for b in blks], out_dtype=torch.float32, sub=g)
+        m = m.view(nb, g, Bn, cg).permute(0, 2, 1, 3).reshape(nb, Bn, Cc)          # back to rows [B, C] (group-major columns)
+        c = torch.addcmul(c, torch.stack([b.gamma_2 for b in blks]).unsqueeze(1), m)
+        out = ops.stacked_linear(ops.to_dtype(c.view(nb * Bn, Cc), T).view(nb, Bn, Cc), [fc.weight for fc in self.fc], [fc.bias for fc in self.fc],
+                                 out_dtype=torch.float32)
+        return list(out.unbind(0))
 
     def forward(self, x):
         with ops.collect_bn_counters():

@@ -198,6 +198,8 @@ class GA_CSWinTransformer(nn.Module):
     # -- execution ----------------------------------------------------------------------------------------------------
     _dtype = GA_ConvNeXt._dtype
     _heads = GA_ConvNeXt._heads
+    _can_batch_heads = GA_ConvNeXt._can_batch_heads
+    _heads_tail_batched = GA_ConvNeXt._heads_tail_batched
 
     def _gram_features(self, k, f, geom):
         """Grouped (g=8) 1x1 contraction + BN + one CSWinBlock at gram_dim (ga_cswin.py:557-576, 676-677)."""

@@ -408,6 +408,82 @@ class GemmFn(Function):
         return dA, dW, db, None, None
 
 
+class StackedLinearFn(Function):
+    """out[g] = act(A[g] W_g^T + b_g) for several same-shaped Linear / grouped-1x1 layers in ONE grouped GEMM each way.
+
+    The GA heads evaluate `branches` copies of every class-token layer on [B, C] rows: per branch that is a 12-CTA GEMM on a
+    148-SM GPU plus its cast / bias-sum / weight-gradient launches.  Here the weights stay separate parameters (their
+    gradients come back as slices of one accumulator), the operands are stacked from the optimizer's bf16 shadows by one
+    copy, and forward, data gradient and weight gradient are one launch each over all branches.
+    A3: [G, M, K] (any strides); params: n weights, each viewable as [sub, N, K] (G = n * sub; sub > 1 = a grouped conv), then
+    n biases [sub * N] when has_bias.  Output [G, M, N], contiguous."""
+
+    @staticmethod
+    def forward(ctx, A3, act, out_dtype, has_bias, sub, N, *params):
+        G, M, K = A3.shape
+        n = len(params) // 2 if has_bias else len(params)
+        ws, bs = params[:n], params[n:]
+        assert n * sub == G
+        T = A3.dtype
+        if K % 8 and T != torch.float32:       # 16-byte row pitch for TMA: stack the fp32 weights, then one padded cast
+            Wc = cast_like(torch.stack([w.view(sub, N, K) for w in ws]).view(G, N, K), T)
+        else:
+            Wc = torch.stack([cast_like(w.view(sub, N, K), T) for w in ws]).view(G, N, K)
+        bias = torch.cat([b.reshape(-1) for b in bs]).view(G, N) if has_bias else None
+        odt = out_dtype or T
+        out = torch.empty(G, M, N, dtype=odt, device=A3.device)
+        z = None
+        if act == ACT_GELU:
+            z = torch.empty(G, M, N, dtype=odt, device=A3.device)
+            gemm(A3, Wc, out, bias=bias, act=act, save_z=z)
+        else:
+            gemm(A3, Wc, out, bias=bias, act=act)
+        ctx.save_for_backward(A3, Wc, z if z is not None else (out if act == ACT_RELU else None))
+        ctx.act, ctx.has_bias, ctx.sub, ctx.n, ctx.wshapes = act, has_bias, sub, n, [w.shape for w in ws]
+        ctx.bshapes = [b.shape for b in bs]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        A3, Wc, zy = ctx.saved_tensors
+        G, M, K = A3.shape
+        N = Wc.shape[1]
+        dout = dout.contiguous()
+        d2 = dout.view(G * M, N)
+        if dout.dtype != A3.dtype:
+            d2 = convert(d2, A3.dtype)                     # alloc_rows: 16-byte row pitch also when N % 8 != 0
+        if ctx.act != ACT_NONE:
+            d2 = act_bwd(d2, zy.view(G * M, N), ctx.act)
+        if N % 8 and d2.dtype == torch.bfloat16 and d2.stride(0) == N:
+            t_ = alloc_rows(G * M, N, d2.dtype, d2.device)
+            d2 = t_.copy_(d2)                              # re-pitch so both backward GEMMs stay on tcgen05
+        dD = d2.as_strided((G, M, N), (M * d2.stride(0), d2.stride(0), 1), d2.storage_offset())
+        db = ()
+        if ctx.has_bias:
+            # column sums per group in one launch: ones[1, M] x dD[g] on the fp32 SIMT kernel (exact fp32 accumulation)
+            src = dout if (ctx.act == ACT_NONE and dout.dtype == torch.float32) else dD.float().contiguous()
+            ones = _ones(M, dout.device).view(1, 1, M).expand(G, 1, M)
+            dbias = gemm(ones, src.transpose(1, 2), out_dtype=torch.float32).view(ctx.n, ctx.sub * N)
+            db = tuple(dbias[i].view(ctx.bshapes[i]) for i in range(ctx.n))
+        dA = None
+        if ctx.needs_input_grad[0]:
+            dA = torch.empty(G, M, K, dtype=A3.dtype, device=A3.device)
+            gemm(dD, Wc.transpose(1, 2), dA)
+        dW = zeros((G, N, K), torch.float32, A3.device)
+        gemm(dD.transpose(1, 2), A3.transpose(1, 2), dW, accumulate=True)
+        dWn = dW.view(ctx.n, ctx.sub * N * K)
+        dws = tuple(dWn[i].view(ctx.wshapes[i]) for i in range(ctx.n))
+        return (dA, None, None, None, None, None) + dws + db
+
+
+def stacked_linear(A3, weights, biases=None, act=ACT_NONE, out_dtype=None, sub=1):
+    """[G, M, K] x per-layer weights -> [G, M, N] (see StackedLinearFn).  weights: list of parameters viewable as [sub, N, K]."""
+    K = A3.shape[2]
+    N = weights[0].numel() // (sub * K)
+    params = tuple(weights) + (tuple(biases) if biases is not None else ())
+    return StackedLinearFn.apply(A3, act, out_dtype, biases is not None, sub, N, *params)
+
+
 def linear(x2, W, bias=None, act=ACT_NONE, out_dtype=None):
     """y = act(x W^T + b) on a row matrix x2 [M,K]; W [N,K] fp32."""
     x2 = rowmat(x2)
