@@ -434,11 +434,17 @@ class GA_ConvNeXt(nn.Module):
         E = self.ga[0].attn.dim_embed
         heads = self.ga[0].attn.num_heads
         fhat = ops.layernorm(f, None, None, self.ga[0].norm1.eps)
-        wkv = torch.cat([torch.cat((g.attn.k.weight, g.attn.v.weight), 0) * g.norm1.weight[None, :] for g in self.ga], 0)
-        bkv = torch.cat([torch.cat((g.attn.k.weight, g.attn.v.weight), 0) @ g.norm1.bias for g in self.ga], 0)
+        # norm1's affine folded into the token-side k / v projection of every branch: W diag(w) and W b.  Elementwise + row sums on
+        # the stacked [nb, 2E, C] weights (no library GEMV on the path); autograd carries the four parameter gradients
+        w_kv = torch.stack([torch.cat((g.attn.k.weight, g.attn.v.weight), 0) for g in self.ga])          # [nb, 2E, C]
+        n1w = torch.stack([g.norm1.weight for g in self.ga]).unsqueeze(1)
+        n1b = torch.stack([g.norm1.bias for g in self.ga]).unsqueeze(1)
+        wkv = (w_kv * n1w).view(nb * 2 * E, Cc)
+        bkv = (w_kv * n1b).sum(-1).view(nb * 2 * E)
         # k / v of the 196 tokens are kept in fp32 (0.3 GB more traffic per step at B=256): the softmax backward subtracts
         # nearly equal terms (dP - sum P dP), which turns a bf16 rounding of k / v into 2e-2 on the q / k weight gradients
         kv_tok = ops.linear(fhat, wkv, bkv, out_dtype=torch.float32)               # [B*HW, nb*2E]
+        batched = self._can_batch_heads(T)
         cls, qs, kvcs = [], [], []
         for k in range(nb):
             g = self._gram_features(k, f, geom)
@@ -447,17 +453,33 @@ class GA_ConvNeXt(nn.Module):
             glen = emb.weight.shape[1]
             c = ops.gram_embed(g, emb.weight.view(G, Cc // G, glen), emb.bias, Bn, HW, float(H))   # get_gram + embedding, [B, C] fp32
             c = ops.batchnorm(c, _params(ebn), tr)
+            cls.append(c)
+            if batched:
+                continue
             blk = self.ga[k]
             cn = ops.layernorm(c, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
             cn_t = ops.to_dtype(cn, T)       # like autocast: fp32 LayerNorm output, bf16 operands for the Linear
             qs.append(ops.linear(cn_t, blk.attn.q.weight * blk.attn.scale, out_dtype=torch.float32))
             kvcs.append(ops.linear(cn_t, torch.cat((blk.attn.k.weight, blk.attn.v.weight), 0), out_dtype=torch.float32))
-            cls.append(c)
-        q = torch.stack(qs).view(nb, Bn, 1, E)
-        kvc = torch.stack(kvcs).view(nb, Bn, 1, 2 * E)
+        cst = None
+        if batched:
+            # norm1 + q / k / v of the class tokens for all branches at once (see _heads_tail_batched)
+            blks = list(self.ga)
+            cst = torch.stack(cls)                                                     # [nb, B, C] fp32
+            cn = ops.layernorm(cst.view(nb * Bn, Cc), None, None, blks[0].norm1.eps).view(nb, Bn, Cc)
+            cn = torch.addcmul(torch.stack([b.norm1.bias for b in blks]).unsqueeze(1), cn,
+                               torch.stack([b.norm1.weight for b in blks]).unsqueeze(1))
+            cn_t = ops.to_dtype(cn.view(nb * Bn, Cc), T).view(nb, Bn, Cc)
+            q = ops.stacked_linear(cn_t, [b.attn.q.weight for b in blks], out_dtype=torch.float32, alpha=blks[0].attn.scale).view(nb, Bn, 1, E)
+            kc = ops.stacked_linear(cn_t, [b.attn.k.weight for b in blks], out_dtype=torch.float32)
+            vc = ops.stacked_linear(cn_t, [b.attn.v.weight for b in blks], out_dtype=torch.float32)
+            kvc = torch.cat((kc, vc), -1).view(nb, Bn, 1, 2 * E)
+        else:
+            q = torch.stack(qs).view(nb, Bn, 1, E)
+            kvc = torch.stack(kvcs).view(nb, Bn, 1, 2 * E)
         o = ops.attnpool(q, kvc, kv_tok, HW, heads)                                # [nb, B, 1, E]
-        if self._can_batch_heads(T):
-            return self._heads_tail_batched(o, cls, T)
+        if batched:
+            return self._heads_tail_batched(o, cst, T)
         outs = []
         for k in range(nb):
             blk = self.ga[k]
@@ -485,9 +507,9 @@ class GA_ConvNeXt(nn.Module):
         (layer scales, norm2 affine) are stacked by torch and applied to the [nb, B, C] tensor."""
         nb, Bn = o.shape[0], o.shape[1]
         blks = list(self.ga)
-        Cc = cls[0].shape[1]
+        c = cls                                                                    # [nb, B, C] fp32, the stacked class tokens
+        Cc = c.shape[2]
         E = o.shape[-1]
-        c = torch.stack(cls)                                                       # [nb, B, C] fp32
         t = ops.stacked_linear(ops.to_dtype(o.reshape(nb * Bn, E), T).view(nb, Bn, E), [b.attn.proj.weight for b in blks],
                                [b.attn.proj.bias for b in blks], out_dtype=torch.float32)
         c = torch.addcmul(c, torch.stack([b.gamma_1 for b in blks]).unsqueeze(1), t)

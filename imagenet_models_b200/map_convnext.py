@@ -181,7 +181,7 @@ class MAPHead(nn.Module):
             a = c.attention[0]
             w = torch.cat((a.attn.k.weight, a.attn.v.weight), 0)
             wkv.append(w * a.norm1.weight[None, :])
-            bkv.append(w @ a.norm1.bias + torch.cat((a.attn.k.bias, a.attn.v.bias), 0))
+            bkv.append((w * a.norm1.bias[None, :]).sum(-1) + torch.cat((a.attn.k.bias, a.attn.v.bias), 0))   # W b without a library GEMV
         kv_tok = ops.linear(fhat, torch.cat(wkv, 0), torch.cat(bkv, 0), out_dtype=torch.float32)   # [B*HW, nb*2E]; fp32 like GA_ConvNeXt._heads
         cls_all, qs, kvcs = [], [], []
         for c in caps:

@@ -419,7 +419,7 @@ class StackedLinearFn(Function):
     n biases [sub * N] when has_bias.  Output [G, M, N], contiguous."""
 
     @staticmethod
-    def forward(ctx, A3, act, out_dtype, has_bias, sub, N, *params):
+    def forward(ctx, A3, act, out_dtype, has_bias, sub, N, alpha, *params):
         G, M, K = A3.shape
         n = len(params) // 2 if has_bias else len(params)
         ws, bs = params[:n], params[n:]
@@ -435,10 +435,12 @@ class StackedLinearFn(Function):
         z = None
         if act == ACT_GELU:
             z = torch.empty(G, M, N, dtype=odt, device=A3.device)
+            assert alpha == 1.0
             gemm(A3, Wc, out, bias=bias, act=act, save_z=z)
         else:
-            gemm(A3, Wc, out, bias=bias, act=act)
+            gemm(A3, Wc, out, bias=bias, act=act, alpha=alpha)
         ctx.save_for_backward(A3, Wc, z if z is not None else (out if act == ACT_RELU else None))
+        ctx.alpha = alpha
         ctx.act, ctx.has_bias, ctx.sub, ctx.n, ctx.wshapes = act, has_bias, sub, n, [w.shape for w in ws]
         ctx.bshapes = [b.shape for b in bs]
         return out
@@ -468,20 +470,21 @@ class StackedLinearFn(Function):
         dA = None
         if ctx.needs_input_grad[0]:
             dA = torch.empty(G, M, K, dtype=A3.dtype, device=A3.device)
-            gemm(dD, Wc.transpose(1, 2), dA)
+            gemm(dD, Wc.transpose(1, 2), dA, alpha=ctx.alpha)
         dW = zeros((G, N, K), torch.float32, A3.device)
-        gemm(dD.transpose(1, 2), A3.transpose(1, 2), dW, accumulate=True)
+        gemm(dD.transpose(1, 2), A3.transpose(1, 2), dW, accumulate=True, alpha=ctx.alpha)
         dWn = dW.view(ctx.n, ctx.sub * N * K)
         dws = tuple(dWn[i].view(ctx.wshapes[i]) for i in range(ctx.n))
-        return (dA, None, None, None, None, None) + dws + db
+        return (dA, None, None, None, None, None, None) + dws + db
 
 
-def stacked_linear(A3, weights, biases=None, act=ACT_NONE, out_dtype=None, sub=1):
-    """[G, M, K] x per-layer weights -> [G, M, N] (see StackedLinearFn).  weights: list of parameters viewable as [sub, N, K]."""
+def stacked_linear(A3, weights, biases=None, act=ACT_NONE, out_dtype=None, sub=1, alpha=1.0):
+    """[G, M, K] x per-layer weights -> [G, M, N] (see StackedLinearFn).  weights: list of parameters viewable as [sub, N, K];
+    alpha scales the product (not the bias)."""
     K = A3.shape[2]
     N = weights[0].numel() // (sub * K)
     params = tuple(weights) + (tuple(biases) if biases is not None else ())
-    return StackedLinearFn.apply(A3, act, out_dtype, biases is not None, sub, N, *params)
+    return StackedLinearFn.apply(A3, act, out_dtype, biases is not None, sub, N, float(alpha), *params)
 
 
 def linear(x2, W, bias=None, act=ACT_NONE, out_dtype=None):
