@@ -386,9 +386,11 @@ class GA_ConvNeXt(nn.Module):
             feats, taps = [], []
             # per-forward work shared by all 18 blocks: one DropPath draw, one operand-preparation launch
             blocks = [blk for i in range(4) for blk in self.stages[i].blocks]
+            n_stage_blocks = len(blocks)
+            blocks += [blk for gl in self.gram_layer for blk in gl.blocks]      # the heads' gram layers ride along
             scales = _path_scales([blk.drop_prob for blk in blocks], self.training, Bn, x.device)
-            preps = None
             preps = block_weights(self, blocks, T)
+            self.__dict__['_gram_layer_aux'] = (scales[n_stage_blocks:], preps[n_stage_blocks:] if preps is not None else None)
             off = 0
             for i in range(4):
                 n = len(self.stages[i].blocks)
@@ -406,10 +408,19 @@ class GA_ConvNeXt(nn.Module):
             f = self.stages[4].run(cat, (Bn, Ho, Wo))
         return f, (Bn, Ho, Wo)
 
-    def _gram_features(self, k, f, geom):
-        """Branch k's contraction conv + BN + gram layer on the shared feature rows -> [B*HW, gram_dim]."""
+    def _gram_contractions(self, f):
+        """The `branches` 1x1 contraction convs as ONE GEMM of width branches * gram_dim on the shared feature rows: the
+        features are read once instead of per branch, and the data gradient is one K = branches * gram_dim GEMM instead of
+        five GEMMs whose [M, C] results autograd has to add up.  Returns the per-branch column slices (strided views)."""
+        w = torch.cat([gc[0].weight.reshape(self.gram_dim, f.shape[1]) for gc in self.gram_contraction], 0)
+        b = torch.cat([gc[0].bias for gc in self.gram_contraction], 0)
+        return ops.linear(f, w, b).split(self.gram_dim, dim=1)
+
+    def _gram_features(self, k, f, geom, g=None):
+        """Branch k's contraction conv (unless its output `g` is given) + BN + gram layer on the shared feature rows -> [B*HW, gram_dim]."""
         conv, bn = self.gram_contraction[k][0], self.gram_contraction[k][1]
-        g = ops.linear(f, conv.weight.reshape(self.gram_dim, f.shape[1]), conv.bias)
+        if g is None:
+            g = ops.linear(f, conv.weight.reshape(self.gram_dim, f.shape[1]), conv.bias)
         g = ops.batchnorm(g, _params(bn), self.training)
         aux = self.__dict__.get('_gram_layer_aux')
         nblk = len(self.gram_layer[k].blocks)
@@ -445,9 +456,12 @@ class GA_ConvNeXt(nn.Module):
         # nearly equal terms (dP - sum P dP), which turns a bf16 rounding of k / v into 2e-2 on the q / k weight gradients
         kv_tok = ops.linear(fhat, wkv, bkv, out_dtype=torch.float32)               # [B*HW, nb*2E]
         batched = self._can_batch_heads(T)
+        gpre = None
+        if batched and type(self)._gram_features is GA_ConvNeXt._gram_features and self.gram_dim % 8 == 0:
+            gpre = self._gram_contractions(f)
         cls, qs, kvcs = [], [], []
         for k in range(nb):
-            g = self._gram_features(k, f, geom)
+            g = self._gram_features(k, f, geom, gpre[k]) if gpre is not None else self._gram_features(k, f, geom)
             emb, ebn = self.gram_embedding[k][0], self.gram_embedding[k][1]
             G = self.embed_groups
             glen = emb.weight.shape[1]
