@@ -431,6 +431,7 @@ class StackedLinearFn(Function):
             Wc = torch.stack([cast_like(w.view(sub, N, K), T) for w in ws]).view(G, N, K)
         bias = torch.cat([b.reshape(-1) for b in bs]).view(G, N) if has_bias else None
         odt = out_dtype or T
+        assert act == ACT_NONE or odt == T, 'an activation keeps the operand dtype (its backward re-reads the saved input in it)'
         out = torch.empty(G, M, N, dtype=odt, device=A3.device)
         z = None
         if act == ACT_GELU:

@@ -713,3 +713,42 @@ def test_gemm_fused_layernorm_backward(M, N, K, b_mn):
     with pytest.raises(L.GaError):                                # a row wider than one tile cannot be fused
         ops.gemm(torch.randn(256, 64, device=DEV, dtype=bf), torch.randn(192, 64, device=DEV, dtype=bf),
                  ln_bwd=(torch.randn(256, 192, device=DEV, dtype=bf), torch.rand(256, device=DEV)))
+
+
+@pytest.mark.parametrize('sub,K,N,act,has_bias,alpha', [(1, 688, 168, 'none', False, 0.1543), (1, 168, 688, 'none', True, 1.0),
+                                                        (4, 172, 688, 'gelu', True, 1.0), (4, 688, 172, 'none', True, 1.0)])
+def test_stacked_linear_matches_per_layer_linears(sub, K, N, act, has_bias, alpha):
+    """ops.StackedLinearFn (one grouped GEMM per direction for several same-shaped layers whose weights stay separate parameters)
+    against the per-layer ops.linear / grouped_linear it replaces in the GA heads: outputs, input gradient, every weight and bias
+    gradient.  Shapes of the GA-ConvNeXt-T heads (q, proj, GroupConvMlp fc1 / fc2 with 172-wide groups: padded operand pitches)."""
+    torch.manual_seed(sub * 1000 + K)
+    nl, M = 5, 64
+    G = nl * sub
+    T = torch.bfloat16
+    ACT = L.ACT_GELU if act == 'gelu' else L.ACT_NONE
+    ws = [torch.nn.Parameter(torch.randn(sub * N, K, device=DEV) * 0.05) for _ in range(nl)]
+    bs = [torch.nn.Parameter(torch.randn(sub * N, device=DEV) * 0.1) for _ in range(nl)] if has_bias else None
+    a_pad = torch.zeros(G, M, ops.pad8(K), device=DEV, dtype=T)
+    A3 = a_pad[:, :, :K].copy_(torch.randn(G, M, K, device=DEV)).detach().requires_grad_(True)
+    odt = None if act == 'gelu' else torch.float32          # an activation keeps the operand dtype (its saved input is re-read in it)
+    out = ops.stacked_linear(A3, ws, bs, act=ACT, out_dtype=odt, sub=sub, alpha=alpha)
+    assert out.shape == (G, M, N)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    got = [A3.grad.clone()] + [w.grad.clone() for w in ws] + ([b.grad.clone() for b in bs] if has_bias else [])
+    A3.grad = None
+    for p in ws + (bs or []):
+        p.grad = None
+    # reference: one grouped_linear per layer (sub groups each) on the same operands
+    outs = []
+    for i in range(nl):
+        o = ops.grouped_linear(A3[i * sub:(i + 1) * sub], ws[i].view(sub, N, K) * alpha, bs[i] if has_bias else None, act=ACT,
+                               out_dtype=odt)                                 # [M, sub*N]
+        outs.append(o.view(M, sub, N).permute(1, 0, 2))
+    ref = torch.cat(outs, 0)
+    ref.backward(dout)
+    want = [A3.grad] + [w.grad for w in ws] + ([b.grad for b in bs] if has_bias else [])
+    # the reference rounds alpha * W to bf16, the stacked form applies alpha to the fp32 product: one operand rounding apart
+    assert (out.float() - ref.float()).norm() <= 4e-3 * ref.float().norm()
+    for g_, w_ in zip(got, want):
+        assert (g_.float() - w_.float()).norm() <= 1e-2 * w_.float().norm() + 1e-6, ((g_.float() - w_.float()).norm() / w_.float().norm()).item()
