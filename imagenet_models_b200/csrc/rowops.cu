@@ -520,10 +520,31 @@ __global__ void patchify_kernel(const T* __restrict__ x, T* __restrict__ y, int 
     if (!inverse) st4(y + po, ld4(x + xo)); else st4(y + xo, ld4(x + po));
   }
 }
+// the same gather with 16-byte accesses (bf16, C % 8 == 0): half the threads and half the index arithmetic per byte moved
+__global__ void patchify8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int C8, int k, int inverse) {
+  const long long total = (long long)B * H * W * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long p = i / C8;
+    const int xx = (int)(p % W); p /= W;
+    const int yy = (int)(p % H);
+    const int b = (int)(p / H);
+    const int oy = yy / k, ky = yy - oy * k, ox = xx / k, kx = xx - ox * k;
+    const long long row = ((long long)b * (H / k) + oy) * (W / k) + ox;
+    const long long po = row * ((long long)k * k * C8) + (long long)(ky * k + kx) * C8 + c8;
+    if (!inverse) y[po] = x[i]; else y[i] = x[po];
+  }
+}
 extern "C" int ga_patchify(const void* x, void* y, int B, int H, int W, int C, int k, int inverse, int dtype, ga_stream_t s) {
   GA_REQUIRE(x && y && (C & 3) == 0 && H % k == 0 && W % k == 0, GA_ERR_SHAPE, "ga_patchify: bad shape H=%d W=%d C=%d k=%d", H, W, C, k);
   const long long total = (long long)B * H * W * (C >> 2);
   if (total == 0) return GA_OK;
+  if (dtype == GA_BF16 && (C & 7) == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    const long long t8 = total >> 1;
+    const int grid8 = (int)((t8 + 255) / 256 > 148 * 16 ? 148 * 16 : (t8 + 255) / 256);
+    patchify8_kernel<<<grid8, 256, 0, (cudaStream_t)s>>>((const uint4*)x, (uint4*)y, B, H, W, C >> 3, k, inverse);
+    return launch_ok("patchify8");
+  }
   const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
   DISPATCH_T(dtype, { patchify_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, B, H, W, C, k, inverse); });
   return launch_ok("patchify");
@@ -546,11 +567,46 @@ __global__ void stem_patchify_kernel(const float* __restrict__ x, T* __restrict_
     st_f(y + i, x[b * sb + c * sc + (long long)(oy * k + ky) * sy + (long long)(ox * k + kx) * sx]);
   }
 }
+// k = 4 on an image whose rows are contiguous (NCHW storage): one thread per output row.  The 3 x 4 source segments of a patch
+// are 16 contiguous bytes each and adjacent for adjacent patches (12 coalesced 128-bit loads per thread); the 48 outputs of a
+// row are contiguous (bf16: six 128-bit stores).  The element-per-thread kernel above reads 4 bytes per thread from three
+// channel planes at once: 0.9 TB/s at 224^2 (profiles/r02_step_profile_torchprofiler.txt), this form streams.
+template <typename T>
+__global__ void __launch_bounds__(128) stem_patchify4_kernel(const float* __restrict__ x, T* __restrict__ y, int B, int H, int W, long long sb,
+                                                             long long sc, long long sy) {
+  const int Ho = H >> 2, Wo = W >> 2;
+  const long long rows = (long long)B * Ho * Wo;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(r % Wo);
+    long long p = r / Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const float* src = x + b * sb + (long long)(oy * 4) * sy + ox * 4;
+    float v[48];                                   // column (ky * 4 + kx) * 3 + c
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+        const float4 q = *reinterpret_cast<const float4*>(src + c * sc + ky * sy);
+        v[(ky * 4 + 0) * 3 + c] = q.x; v[(ky * 4 + 1) * 3 + c] = q.y; v[(ky * 4 + 2) * 3 + c] = q.z; v[(ky * 4 + 3) * 3 + c] = q.w;
+      }
+    T* dst = y + r * 48;
+#pragma unroll
+    for (int j = 0; j < 48; j += 4) st4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+  }
+}
+
 extern "C" int ga_stem_patchify(const float* x, void* y, int B, int H, int W, int k, long long sb, long long sc, long long sy,
                                 long long sx, int dtype, ga_stream_t s) {
   GA_REQUIRE(x && y && H % k == 0 && W % k == 0, GA_ERR_SHAPE, "ga_stem_patchify: bad shape");
   const long long total = (long long)B * (H / k) * (W / k) * k * k * 3;
   if (total == 0) return GA_OK;
+  if (k == 4 && sx == 1 && ((uintptr_t)x & 15) == 0 && ((sb | sc | sy) & 3) == 0 && ((uintptr_t)y & 15) == 0) {
+    const long long rows = total / 48;
+    const int grid4 = (int)((rows + 127) / 128 > 148 * 32 ? 148 * 32 : (rows + 127) / 128);
+    DISPATCH_T(dtype, { stem_patchify4_kernel<T><<<grid4, 128, 0, (cudaStream_t)s>>>(x, (T*)y, B, H, W, sb, sc, sy); });
+    return launch_ok("stem_patchify4");
+  }
   const int grid = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
   DISPATCH_T(dtype, { stem_patchify_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>(x, (T*)y, B, H, W, k, sb, sc, sy, sx); });
   return launch_ok("stem_patchify");
