@@ -65,3 +65,40 @@ def test_convnext_block_at_bench_batch_vs_fp32_torch(C, HW):
     assert errs['shadow'] <= 1e-2, errs                                   # the bf16 shadow of the stream
     bad = {k: v for k, v in errs.items() if k not in ('y', 'shadow') and not v <= TOL}
     assert not bad, (bad, errs)
+
+
+@pytest.mark.parametrize('R,split,C', [(14, 7, 256), (56, 1, 64)])
+def test_cswin_stripe_attention_at_bench_batch_vs_oracle(R, split, C):
+    """K6 (LePE stripe attention, ga_cswin.py:110-136) at GA-CSWin-T's batch 128: stage 3 (14 x 14 tokens, 7-wide stripes, 256
+    channels; the tcgen05 forward) and stage 1 (56 x 56, 1-wide stripes, 64 channels), both branches, forward + backward in bf16
+    against the fp32 oracle evaluated on the same (bf16-rounded) operands on the GPU."""
+    from oracle import ga_cswin_oracle as CO
+    B, nbr = 128, 2
+    g = torch.Generator().manual_seed(R * 100 + C)
+    qkv = torch.randn(B, R * R, 3 * C, generator=g).to(DEV)
+    dy = torch.randn(B, R * R, C, generator=g).to(DEV)
+    cb = C // nbr
+    P = {f'{i}.get_v.weight': (torch.randn(cb, 1, 3, 3, generator=g) * 0.3).to(DEV) for i in range(nbr)}
+    P.update({f'{i}.get_v.bias': (torch.randn(cb, generator=g) * 0.1).to(DEV) for i in range(nbr)})
+    P = {k: v.requires_grad_(True) for k, v in P.items()}
+    qo = qkv.to(torch.bfloat16).float().requires_grad_(True)
+    q, k, v = qo[..., :C], qo[..., C:2 * C], qo[..., 2 * C:]
+    h = C // 2
+    o = torch.cat((CO.lepe_attention(P, '0.', q[..., :h], k[..., :h], v[..., :h], R, R, split, h // 32),
+                   CO.lepe_attention(P, '1.', q[..., h:], k[..., h:], v[..., h:], R, split, R, h // 32)), 2)
+    o.backward(dy.to(torch.bfloat16).float())
+    lw = torch.cat([P[f'{i}.get_v.weight'].detach().reshape(cb, 9) for i in range(nbr)]).requires_grad_(True)
+    lb = torch.cat([P[f'{i}.get_v.bias'].detach() for i in range(nbr)]).requires_grad_(True)
+    qg = qkv.reshape(-1, 3 * C).to(torch.bfloat16).requires_grad_(True)
+    og = ops.cswin_attention(qg, lw, lb, B, R, split, nbr)
+    og.backward(dy.reshape(-1, C).to(torch.bfloat16))
+    torch.cuda.synchronize()
+    dw = torch.cat([P[f'{i}.get_v.weight'].grad.reshape(cb, 9) for i in range(nbr)])
+    db = torch.cat([P[f'{i}.get_v.bias'].grad for i in range(nbr)])
+    errs = {'out': rel(og.detach().float().reshape(o.shape), o.detach()), 'dqkv': rel(qg.grad.float().reshape(qo.shape), qo.grad),
+            'dlepe_w': rel(lw.grad, dw), 'dlepe_b': rel(lb.grad, db)}
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(out):
+        json.dump({'B': B, 'R': R, 'split': split, 'C': C, 'rel_err_vs_fp32_oracle': errs}, open(os.path.join(out, f'bench_shape_attn_R{R}.json'), 'w'), indent=1)
+    bad = {k_: v_ for k_, v_ in errs.items() if not v_ <= 2e-2}
+    assert not bad, (bad, errs)
