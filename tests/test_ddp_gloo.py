@@ -104,3 +104,39 @@ def test_flat_state_keeps_values_and_decay_flags():
     # weights decay, biases do not (timm filter_bias_and_bn)
     for name, p, o in zip(st.names, st.params, st.offsets):
         assert int(flags[o >> 4]) == (0 if name.endswith('.bias') else 1)
+
+
+def _engine_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from imagenet_models_b200.engine import TrainEngine
+    torch.manual_seed(1000 + rank)                           # the trainers seed with seed + rank (GA/train.py:402): different initialisations
+    net = nn.Sequential(nn.Linear(16, 32), nn.BatchNorm1d(32), nn.GELU(), nn.Linear(32, 10))
+    net[1].running_mean.add_(float(rank) + 1.0)              # buffers differ too
+    before = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()
+    eng = TrainEngine(net, lr=1e-3, ema_decay=0.99, amp_dtype=None, cuda_graph=False)
+    after = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+    ema = torch.cat([p.detach().reshape(-1) for p in eng.model_ema.parameters()])
+    q.put((rank, before.tolist(), after.tolist(), ema.tolist(), net[1].running_mean.tolist(), eng.model_ema[1].running_mean.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_engine_construction_copies_rank0_parameters_and_buffers():
+    """TrainEngine with several ranks starts every replica (and its EMA copy) from rank 0's parameters and buffers, as
+    DistributedDataParallel does when it wraps a module (GA/train.py:505-515)."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_engine_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, b0, a0, e0, rm0, erm0), (_, b1, a1, e1, rm1, erm1) = out
+    assert b0 != b1                                          # the initialisations did differ
+    assert a0 == b0 and a1 == b0                             # both replicas hold rank 0's parameters
+    assert e0 == b0 and e1 == b0                             # ... and so do their EMA copies
+    assert rm0 == rm1 == erm0 == erm1 and abs(rm0[0] - 1.0) < 1e-6      # buffers (rank 0 had added 1.0)
